@@ -1,0 +1,413 @@
+"""
+make_golden.py — run the REFERENCE ITSELF (imported unmodified from /root/reference) on small
+seeded inputs and store inputs + outputs as fixtures under tests/golden/.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+
+What is executed is the reference's own code: empanada/inference/postprocess.py and engines.py
+as they are; empanada/inference/rle.py through the skimage/zarr shim of oracle/ref_shim.py;
+data/utils/target_creation.py (loaded by path) for the 256x256 test fixture of the reference's
+tests/test_data_post.py.  The tests (tests/test_oracle_golden.py on CPU, tests/test_gpu_*.py on
+the B200) compare the oracle and the CUDA path with these files bit for bit.
+"""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+
+import torch  # noqa: E402
+from empanada.inference import postprocess as rpp  # noqa: E402  (reference)
+from empanada.inference import engines as reng  # noqa: E402  (reference)
+from empanada.inference import rle as rrle  # noqa: E402  (reference, via shim)
+from empanada_b200.synth import synth_tile  # noqa: E402
+
+torch.set_num_threads(8)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **arrays)
+    print(f'{name}: {os.path.getsize(path) / 1024:.0f} KiB')
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+# ---------------------------------------------------------------------------------------------
+# post-processing cases
+# ---------------------------------------------------------------------------------------------
+def run_pp(name, sem, hm, off, thing_list, L, stuff_area, void, thr=0.1, k=7, steps=(1.0, 4.0)):
+    sem, hm, off = (np.ascontiguousarray(a) for a in (sem, hm, off))
+    out = {'in_sem': sem, 'in_hm': hm, 'in_off': off,
+           'params': json.dumps(dict(thing_list=list(thing_list), label_divisor=L,
+                                     stuff_area=stuff_area, void_label=void,
+                                     threshold=thr, nms_kernel=k))}
+    ctr = rpp.find_instance_center(t(hm), thr, k)
+    out['out_centers'] = ctr.numpy()
+    if ctr.size(0) > 0:
+        for s in steps:
+            out[f'out_ids_step{int(s)}'] = rpp.group_pixels(ctr, t(off), step=float(s)).numpy()
+    ins, c2 = rpp.get_instance_segmentation(t(sem), t(hm), t(off), list(thing_list), thr, k)
+    out['out_ins'] = ins.numpy()
+    pan, c3 = rpp.get_panoptic_segmentation(t(sem), t(hm), t(off), list(thing_list), L,
+                                            stuff_area, void, thr, k)
+    out['out_pan'] = pan.numpy()
+    assert c3.shape[1] == ctr.shape[0]
+    print(f'  {name}: K={ctr.size(0)} pan shape {tuple(pan.shape)}')
+    save(name, **out)
+
+
+def fixture256():
+    """The reference's own test fixture (tests/test_data_post.py:13-36): GT mask ->
+    sem / heat-map / offsets exactly as data/panoptic_dataset.py:72-95 builds them."""
+    import cv2
+    spec = importlib.util.spec_from_file_location(
+        'ref_target_creation',
+        os.path.join(ref_shim.REFERENCE_ROOT, 'empanada/data/utils/target_creation.py'))
+    tc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tc)
+    mask = cv2.imread(os.path.join(ref_shim.REFERENCE_ROOT,
+                                   'tests/test_data/panoptic/dataset1/masks/pan_seg.tiff'),
+                      cv2.IMREAD_UNCHANGED)
+    labels, things, L = [1, 2, 3], [2], 1000
+    thing_seg = np.zeros_like(mask)
+    sem_seg = np.zeros_like(mask)
+    for c in labels:
+        inside = (mask >= c * L) * (mask < (c + 1) * L)
+        sem_seg[inside] = c
+        if c in things:
+            thing_seg[inside] = mask[inside]
+    hm, off = tc.heatmap_and_offsets(thing_seg, 6)
+    sem = sem_seg.astype(np.int32).astype(np.int64)[None, None]
+    run_pp('pp_fixture256', sem, hm[None], off[None], things, L, 0, 0, 0.1, 7)
+    np.savez_compressed(os.path.join(HERE, 'fixture256_mask.npz'), mask=mask)
+
+
+def pp_cases():
+    fixture256()
+
+    d = synth_tile(96, 128, 9, seed=1, semi_axes=(6, 14))
+    run_pp('pp_small_k_le_20', d['sem'], d['ctr_hmp'], d['offsets'], [1], 1000, 64, 0)
+
+    d = synth_tile(128, 160, 70, seed=2, semi_axes=(4, 9), sigma=2.0)
+    run_pp('pp_chunked_k_gt_20', d['sem'], d['ctr_hmp'], d['offsets'], [1], 1000, 64, 0, 0.1, 3)
+
+    # exact ties: zero offsets on a lattice of centers, and integer / half-integer offsets
+    rng = np.random.default_rng(3)
+    H, W = 64, 80
+    hm = np.zeros((H, W), np.float32)
+    hm[8::16, 8::16] = 1.0
+    off = np.zeros((2, H, W), np.float32)
+    sem = np.ones((1, 1, H, W), np.int64)
+    run_pp('pp_ties_zero_offsets', sem, hm[None, None], off[None], [1], 1000, 0, 0, 0.1, 7)
+    off = rng.integers(-12, 13, (2, H, W)).astype(np.float32)
+    run_pp('pp_ties_int_offsets', sem, hm[None, None], off[None], [1], 1000, 0, 0, 0.1, 7)
+    off = (rng.integers(-24, 25, (2, H, W)) * 0.5).astype(np.float32)
+    hm2 = np.zeros((H, W), np.float32)
+    hm2[4::8, 4::8] = 1.0                       # 80 centers -> chunked path with many ties
+    run_pp('pp_ties_half_offsets', sem, hm2[None, None], off[None], [1], 1000, 0, 0, 0.1, 3)
+
+    # plateaus / duplicated maxima, several kernels (even one included) and thresholds
+    for k, thr in ((1, 0.3), (3, 0.1), (4, 0.5), (7, -0.2), (5, 0.1)):
+        hm = (rng.integers(0, 6, (48, 56)) / 5.0).astype(np.float32)
+        hm[10:14, 20:25] = 1.0
+        hm[0, 0] = 1.0
+        hm[-1, -1] = 1.0
+        hm[30, :] = 0.8
+        off = rng.normal(0, 3, (2, 48, 56)).astype(np.float32)
+        sem = (rng.random((1, 1, 48, 56)) < 0.7).astype(np.int64)
+        run_pp(f'pp_plateau_k{k}', sem, hm[None, None], off[None], [1], 1000, 16, 0, thr, k,
+               steps=(1.0,))
+
+    # 1e5 sentinel: K = 21 (> chunksize) and offsets pushing a region beyond 1e5 -> id 0
+    H, W = 40, 64
+    hm = np.zeros((H, W), np.float32)
+    hm[4::8, 4::8][:3, :7] = 1.0              # 21 centers
+    off = rng.normal(0, 2, (2, H, W)).astype(np.float32)
+    off[:, 10:20, 10:30] += 2e5
+    sem = np.ones((1, 1, H, W), np.int64)
+    run_pp('pp_sentinel_k21', sem, hm[None, None], off[None], [1], 1000, 0, 0, 0.1, 7)
+    hm[4::8, 4::8][:3, :7] = 0
+    hm[4::8, 4::8][:2, :5] = 1.0              # 10 centers: no sentinel
+    run_pp('pp_no_sentinel_k10', sem, hm[None, None], off[None], [1], 1000, 0, 0, 0.1, 7)
+
+    # multi-class: 2 thing classes + 2 stuff classes, vote ties, void labels, stuff thresholds
+    for i, (void, sa) in enumerate(((0, 0), (-1, 64), (7, 200))):
+        d = synth_tile(96, 112, 30, seed=10 + i, semi_axes=(5, 12), sigma=2.5,
+                       thing_classes=(1, 3), stuff_classes=(2, 4))
+        sem = d['sem'].copy()
+        # scramble classes inside instances so that votes are contested (incl. exact ties)
+        noise = rng.integers(0, 5, sem.shape)
+        flip = rng.random(sem.shape) < 0.45
+        sem[flip] = noise[flip]
+        sem[0, 0, 40:44, 40:60] = 1
+        sem[0, 0, 44:48, 40:60] = 3
+        run_pp(f'pp_multiclass_{i}', sem, d['ctr_hmp'], d['offsets'], [1, 3], 1000, sa, void,
+               0.1, 5, steps=(1.0,))
+
+    # no centers at all
+    d = synth_tile(32, 48, 4, seed=20, semi_axes=(4, 8))
+    run_pp('pp_k0', d['sem'], d['ctr_hmp'] * 0.05, d['offsets'], [1], 1000, 8, 0)
+
+    # instances touching all borders, non-multiple-of-anything shape
+    d = synth_tile(67, 93, 40, seed=21, semi_axes=(5, 15), sigma=3.0)
+    run_pp('pp_odd_shape', d['sem'], d['ctr_hmp'], d['offsets'], [1], 20000, 32, 0, 0.1, 3)
+
+
+def merge_cases():
+    rng = np.random.default_rng(30)
+    for i, (shape_sem, shape_ins) in enumerate((((1, 50, 60), (1, 50, 60)),
+                                                ((1, 1, 50, 60), (1, 50, 60)),
+                                                ((1, 37, 41), (1, 37, 41)))):
+        H, W = shape_sem[-2:]
+        sem = rng.integers(0, 5, shape_sem).astype(np.int64)
+        ins = np.zeros((H, W), np.int64)
+        for j in range(1, 40):
+            y0, x0 = rng.integers(0, H - 4), rng.integers(0, W - 4)
+            ins[y0:y0 + rng.integers(1, 9), x0:x0 + rng.integers(1, 9)] = j * (3 if i == 2 else 1)
+        ins = ins.reshape(shape_ins)
+        for void, sa, things in ((0, 64, [1, 2]), (-1, 0, [3]), (7, 200, [1, 2, 4])):
+            pan = rpp.merge_semantic_and_instance(t(sem), t(ins), 1000, things, sa, void).numpy()
+            save(f'merge_{i}_void{void}_sa{sa}', in_sem=sem, in_ins=ins, out_pan=pan,
+                 params=json.dumps(dict(label_divisor=1000, thing_list=things, stuff_area=sa,
+                                        void_label=void)))
+
+
+# ---------------------------------------------------------------------------------------------
+# engines: fake models that replay precomputed head tensors through the reference engines
+# ---------------------------------------------------------------------------------------------
+class ReplayModel(torch.nn.Module):
+    def __init__(self, outputs):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.outputs = outputs
+        self.i = 0
+
+    def forward(self, image, render_steps=None, interpolate_ins=None):
+        out = {k: v.clone() for k, v in self.outputs[self.i].items()}
+        self.i += 1
+        return out
+
+
+def logit(p):
+    return np.log(p / (1 - p)).astype(np.float32)
+
+
+def stack_inputs(D, H, W, seed, coarse, n_classes=1):
+    """Per-slice head tensors for a drifting blob field (small, deterministic)."""
+    outs = []
+    for z in range(D):
+        d = synth_tile(H, W, 14, seed=seed, semi_axes=(5 + 0.3 * z, 11 + 0.3 * z), sigma=2.5,
+                       prob=True)
+        rng = np.random.default_rng([seed, z])
+        prob = np.clip(d['sem_prob'] + rng.normal(0, 0.25, d['sem_prob'].shape), 0.02, 0.98).astype(np.float32)
+        if n_classes == 1:
+            sem_logits = logit(prob)
+        else:
+            sem_logits = rng.normal(0, 1, (1, n_classes, H, W)).astype(np.float32)
+            sem_logits[:, 1] += 3 * (d['ins'] > 0)
+        if coarse == 1:
+            hm, off = d['ctr_hmp'], d['offsets']
+        else:
+            dd = synth_tile(H // coarse, W // coarse, 14, seed=seed, semi_axes=(2, 4), sigma=1.2)
+            hm, off = dd['ctr_hmp'], dd['offsets'] * coarse
+        outs.append({'sem_logits': sem_logits, 'ctr_hmp': hm.astype(np.float32), 'offsets': off.astype(np.float32)})
+    return outs
+
+
+def engine_cases():
+    # 2D engine
+    ins2d = stack_inputs(2, 64, 80, seed=40, coarse=1)
+    model = ReplayModel([{k: t(v) for k, v in o.items()} for o in ins2d])
+    eng = reng.PanopticDeepLabEngine(model, [1], 1000, 16, 0, 0.1, 3, 0.5)
+    res = {}
+    for z, o in enumerate(ins2d):
+        res[f'out_{z}'] = eng(torch.zeros(1, 1, 64, 80)).numpy()
+        for k, v in o.items():
+            res[f'in_{z}_{k}'] = v
+    save('engine2d', params=json.dumps(dict(thing_list=[1], label_divisor=1000, stuff_area=16,
+                                            void_label=0, nms_threshold=0.1, nms_kernel=3,
+                                            confidence_thr=0.5, n=2)), **res)
+
+    # 3D engines: (name, class, ks, classes, coarse, upsampling, D)
+    for name, ks, ncls, D in (('engine3d_ks3', 3, 1, 7), ('engine3d_ks5_mc', 5, 3, 8),
+                              ('engine3d_ks1', 1, 1, 3), ('engine3d_short', 3, 1, 2)):
+        ins = stack_inputs(D, 48, 64, seed=41, coarse=1, n_classes=ncls)
+        model = ReplayModel([{k: t(v) for k, v in o.items()} for o in ins])
+        things = [1] if ncls == 1 else [1, 2]
+        eng = reng.PanopticDeepLabEngine3d(model, things, 1000, 16, 0, 0.1, 3, 0.3, ks)
+        res, emitted = {}, []
+        for z, o in enumerate(ins):
+            for k, v in o.items():
+                res[f'in_{z}_{k}'] = v
+            out = eng(torch.zeros(1, 1, 48, 64))
+            if out is not None:
+                res[f'out_{sum(emitted)}'] = out.numpy()
+            emitted.append(out is not None)
+        tail = eng.end()
+        n_call = sum(emitted)
+        for j, out in enumerate(tail):
+            res[f'out_{n_call + j}'] = out.numpy()
+        save(name, params=json.dumps(dict(thing_list=things, label_divisor=1000, stuff_area=16,
+                                          void_label=0, nms_threshold=0.1, nms_kernel=3,
+                                          confidence_thr=0.3, median_kernel_size=ks, n=D,
+                                          emitted=emitted, n_tail=len(tail))), **res)
+
+    for name, ks, coarse, up, D, size in (('render3d_coarse', 3, 4, 1, 6, (60, 75)),
+                                          ('render3d_fine_up2', 3, 1, 2, 5, (64, 80)),
+                                          ('render3d_coarse_up2', 1, 4, 2, 3, (64, 80))):
+        H, W = 64, 80                       # padded size (multiple of padding_factor 16)
+        # model output res: sem at (H*up, W*up); ctr/offsets at (H*up/coarse... ) — the model
+        # sees the padded image and render_steps; here we simply replay tensors of the shapes
+        # the quantizable PR models emit (quantization/panoptic_deeplab.py:221-250)
+        ins = []
+        base = stack_inputs(D, H * up, W * up, seed=42, coarse=1)
+        for z in range(D):
+            o = dict(base[z])
+            if coarse == 4:
+                dd = synth_tile(H // 4, W // 4, 10, seed=43, semi_axes=(2, 4), sigma=1.2)
+                o['ctr_hmp'] = dd['ctr_hmp'].astype(np.float32)
+                o['offsets'] = (dd['offsets'] * 4).astype(np.float32)
+            else:
+                dd = synth_tile(H, W, 14, seed=43, semi_axes=(5, 11), sigma=2.5)
+                o['ctr_hmp'] = dd['ctr_hmp'].astype(np.float32)
+                o['offsets'] = dd['offsets'].astype(np.float32)
+            ins.append(o)
+        model = ReplayModel([{k: t(v) for k, v in o.items()} for o in ins])
+        eng = reng.PanopticDeepLabRenderEngine3d(model, [1], 20000, 32, 0, 0.1, 3, 0.3, ks, 16,
+                                                 coarse_boundaries=(coarse == 4))
+        res, emitted = {}, []
+        for z, o in enumerate(ins):
+            for k, v in o.items():
+                res[f'in_{z}_{k}'] = v
+            out = eng(torch.zeros(1, 1, size[0], size[1]), size, up)
+            if out is not None:
+                res[f'out_{sum(emitted)}'] = out.numpy()
+            emitted.append(out is not None)
+        tail = eng.end(up)
+        n_call = sum(emitted)
+        for j, out in enumerate(tail):
+            res[f'out_{n_call + j}'] = out.numpy()
+        save(name, params=json.dumps(dict(thing_list=[1], label_divisor=20000, stuff_area=32,
+                                          void_label=0, nms_threshold=0.1, nms_kernel=3,
+                                          confidence_thr=0.3, median_kernel_size=ks,
+                                          padding_factor=16, coarse_boundaries=(coarse == 4),
+                                          upsampling=up, size=list(size), n=D,
+                                          emitted=emitted, n_tail=len(tail))), **res)
+
+
+# ---------------------------------------------------------------------------------------------
+# RLE
+# ---------------------------------------------------------------------------------------------
+def flatten_rle(rle_seg):
+    inst, starts, runs = [], [], []
+    for cls, attrs in rle_seg.items():
+        for lab, a in attrs.items():
+            inst.append([cls, lab, *a['box'], len(a['starts'])])
+            starts.append(np.asarray(a['starts'], np.int64))
+            runs.append(np.asarray(a['runs'], np.int64))
+    inst = np.asarray(inst, np.int64).reshape(-1, 7)
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
+    return inst, cat(starts), cat(runs)
+
+
+def rle_case(name, pan, labels, L, things, fc):
+    pan = np.ascontiguousarray(pan)
+    seg = rrle.pan_seg_to_rle_seg(pan, labels, L, things, fc)
+    inst, starts, runs = flatten_rle(seg)
+    back = rrle.rle_seg_to_pan_seg(seg, pan.shape)
+    save(name, in_pan=pan.astype(np.int64), out_inst=inst, out_starts=starts, out_runs=runs,
+         out_back=back,
+         params=json.dumps(dict(labels=labels, label_divisor=L, thing_list=things,
+                                force_connected=fc)))
+    print(f'  {name}: {inst.shape[0]} instances, {starts.size} runs')
+
+
+def matcher_target():
+    seg = np.zeros((200, 200), dtype=np.uint32)     # tests/test_matcher.py:6-19 known-answer map
+    seg[:16, :16] = 1001
+    seg[30:50, 30:50] = 1002
+    seg[:10, -10:] = 1003
+    seg[-50:, :50] = 1004
+    seg[-30:, -30:] = 1005
+    seg[100:130, 90:110] = 1006
+    return seg
+
+
+def rle_cases():
+    rle_case('rle_matcher_target', matcher_target(), [1], 1000, [1], False)
+    rle_case('rle_matcher_target_fc', matcher_target(), [1], 1000, [1], True)
+
+    # SURVEY A5 example: separated blocks of one label, an 8-connected chain, row wrap
+    pan = np.zeros((8, 10), np.int64)
+    pan[0:2, 0:2] = 1001
+    pan[0:2, 5:7] = 1001
+    pan[4, 3:8] = 1002
+    pan[5, 3:8] = 1002
+    pan[6, 8] = 1002
+    pan[7, 9] = 1002
+    rle_case('rle_a5_fc', pan, [1], 1000, [1], True)
+    rle_case('rle_a5_nofc', pan, [1], 1000, [1], False)
+
+    # runs wrapping row ends + full rows + stuff class + two thing classes
+    rng = np.random.default_rng(50)
+    pan = np.zeros((40, 33), np.int64)
+    pan[3:6, :] = 2000                      # stuff class 2 spanning full rows -> one long run
+    pan[10, 20:] = 1001
+    pan[11, :7] = 1001                      # wraps from col W-1 into col 0 (not 8-connected!)
+    pan[20:24, 30:] = 3002
+    pan[21:25, :3] = 3002
+    pan[30:35, 5:25] = 1007
+    pan[31:34, 10:20] = 3001                # hole filled by another class
+    pan[38, 1::2] = 1009                    # many single-pixel runs
+    pan[39, 0::2] = 1009                    # diagonal 8-connectivity
+    rle_case('rle_wrap_fc', pan, [1, 2, 3], 1000, [1, 3], True)
+    rle_case('rle_wrap_nofc', pan, [1, 2, 3], 1000, [1, 3], False)
+    rle_case('rle_wrap_subset', pan, [3, 1], 1000, [3], True)
+
+    # random blobs: panoptic output of the reference on a synthetic tile, two classes
+    d = synth_tile(96, 120, 40, seed=51, semi_axes=(4, 12), sigma=2.5, thing_classes=(1, 2),
+                   stuff_classes=(3,))
+    pan, _ = rpp.get_panoptic_segmentation(t(d['sem']), t(d['ctr_hmp']), t(d['offsets']), [1, 2],
+                                           1000, 16, 0, 0.1, 5)
+    pan = pan.numpy()[0, 0]
+    rle_case('rle_synth_fc', pan, [1, 2, 3], 1000, [1, 2], True)
+    rle_case('rle_synth_nofc', pan, [1, 2, 3], 1000, [1, 2], False)
+
+    # salt-and-pepper: worst case for CCL / run counts
+    pan = np.where(rng.random((50, 64)) < 0.5, 1001, 0).astype(np.int64)
+    pan[rng.random((50, 64)) < 0.2] = 1002
+    rle_case('rle_noise_fc', pan, [1], 1000, [1], True)
+    # spiral / U shapes that need many union-find merges
+    pan = np.zeros((41, 41), np.int64)
+    for r in range(0, 20, 2):
+        pan[r, r:41 - r] = 1001
+        pan[40 - r, r:41 - r] = 1001
+        pan[r:41 - r, r] = 1001
+        pan[r + 2:41 - r, 40 - r] = 1001
+    rle_case('rle_spiral_fc', pan, [1], 1000, [1], True)
+    rle_case('rle_empty', np.zeros((16, 16), np.int64), [1, 2], 1000, [1], True)
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle']
+    if 'pp' in which:
+        pp_cases()
+    if 'merge' in which:
+        merge_cases()
+    if 'engine' in which:
+        engine_cases()
+    if 'rle' in which:
+        rle_cases()

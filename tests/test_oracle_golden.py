@@ -1,0 +1,144 @@
+"""CPU: the oracle (oracle/oracle.c + oracle/__init__.py) against fixtures produced by running
+the reference itself (tests/golden/make_golden.py).  Bit-exact everywhere."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_names, load_golden
+
+
+@pytest.mark.parametrize('name', golden_names('pp_'))
+def test_postprocess_matches_reference(name):
+    g = load_golden(name)
+    p = g['params']
+    ctr = oracle.find_instance_center(g['in_hm'], p['threshold'], p['nms_kernel'])
+    np.testing.assert_array_equal(ctr, g['out_centers'])
+    for step in (1, 4):
+        key = f'out_ids_step{step}'
+        if key in g:
+            ids = oracle.group_pixels(ctr, g['in_off'], step=float(step))
+            np.testing.assert_array_equal(ids, g[key])
+    ins, c = oracle.get_instance_segmentation(g['in_sem'], g['in_hm'], g['in_off'], p['thing_list'],
+                                              p['threshold'], p['nms_kernel'])
+    np.testing.assert_array_equal(ins, g['out_ins'])
+    pan, c = oracle.get_panoptic_segmentation(g['in_sem'], g['in_hm'], g['in_off'], p['thing_list'],
+                                              p['label_divisor'], p['stuff_area'], p['void_label'],
+                                              p['threshold'], p['nms_kernel'])
+    assert pan.shape == g['out_pan'].shape and pan.dtype == np.int64
+    np.testing.assert_array_equal(pan, g['out_pan'])
+
+
+@pytest.mark.parametrize('name', golden_names('merge_'))
+def test_merge_matches_reference(name):
+    g = load_golden(name)
+    p = g['params']
+    pan = oracle.merge_semantic_and_instance(g['in_sem'], g['in_ins'], p['label_divisor'],
+                                             p['thing_list'], p['stuff_area'], p['void_label'])
+    assert pan.shape == g['out_pan'].shape
+    np.testing.assert_array_equal(pan, g['out_pan'])
+
+
+def _sigmoid_or_softmax(logits):
+    import torch          # engines.logits_to_prob (engines.py:22-30) stays a torch op in the product too
+    t = torch.from_numpy(logits)
+    return (torch.softmax(t, 1) if t.size(1) > 1 else torch.sigmoid(t)).numpy()
+
+
+@pytest.mark.parametrize('name', golden_names('engine3d_'))
+def test_median_queue_and_engine3d(name):
+    g = load_golden(name)
+    p = g['params']
+    q = oracle.MedianQueue(p['median_kernel_size'])
+    outs = []
+
+    def post(entry):
+        sem = oracle.harden_seg(entry['sem'], p['confidence_thr'])
+        pan, _ = oracle.get_panoptic_segmentation(sem, entry['ctr_hmp'], entry['offsets'], p['thing_list'],
+                                                  p['label_divisor'], p['stuff_area'], p['void_label'],
+                                                  p['nms_threshold'], p['nms_kernel'])
+        return pan
+
+    emitted = []
+    for z in range(p['n']):
+        e = {'sem': _sigmoid_or_softmax(g[f'in_{z}_sem_logits']), 'ctr_hmp': g[f'in_{z}_ctr_hmp'],
+             'offsets': g[f'in_{z}_offsets']}
+        q.enqueue(e)
+        o = q.get_next(['sem'])
+        emitted.append(o is not None)
+        if o is not None:
+            outs.append(post(o))
+    for e in q.end():
+        outs.append(post(e))
+    assert emitted == p['emitted']
+    assert len(outs) == sum(p['emitted']) + p['n_tail']
+    for i, o in enumerate(outs):
+        np.testing.assert_array_equal(o, g[f'out_{i}'])
+
+
+@pytest.mark.parametrize('name', golden_names('render3d_'))
+def test_render_engine3d(name):
+    g = load_golden(name)
+    p = g['params']
+    q = oracle.MedianQueue(p['median_kernel_size'])
+    step = 4 if p['coarse_boundaries'] else 1
+    up = p['upsampling']
+    h, w = p['size']
+    outs = []
+
+    def post(entry):
+        ctr = oracle.find_instance_center(entry['ctr_hmp'], p['nms_threshold'], p['nms_kernel'])
+        if ctr.shape[0] == 0:
+            cells = np.zeros(entry['ctr_hmp'].shape[-2:], np.int64)
+        else:
+            cells = oracle.group_pixels(ctr, entry['offsets'], step=float(step))[0]
+        cells = oracle.nearest_upsample(cells, int(up * step))
+        sem = oracle.harden_seg(entry['sem'], p['confidence_thr'])[0]       # (1,H,W)
+        thing = np.isin(sem, p['thing_list'])
+        ins = np.where(thing, cells[None], 0)
+        pan = oracle.merge_semantic_and_instance(sem, ins, p['label_divisor'], p['thing_list'],
+                                                 p['stuff_area'], p['void_label'])
+        return pan[..., :h, :w]
+
+    for z in range(p['n']):
+        e = {'sem': _sigmoid_or_softmax(g[f'in_{z}_sem_logits']), 'ctr_hmp': g[f'in_{z}_ctr_hmp'],
+             'offsets': g[f'in_{z}_offsets']}
+        q.enqueue(e)
+        o = q.get_next(['sem'])
+        if o is not None:
+            outs.append(post(o))
+    for e in q.end():
+        outs.append(post(e))
+    assert len(outs) == sum(p['emitted']) + p['n_tail']
+    for i, o in enumerate(outs):
+        assert o.shape == g[f'out_{i}'].shape
+        np.testing.assert_array_equal(o, g[f'out_{i}'])
+
+
+@pytest.mark.parametrize('name', golden_names('rle_'))
+def test_rle_matches_reference(name):
+    g = load_golden(name)
+    p = g['params']
+    seg = oracle.pan_seg_to_rle_seg(g['in_pan'], p['labels'], p['label_divisor'], p['thing_list'],
+                                    p['force_connected'])
+    inst, starts, runs = [], [], []
+    assert list(seg.keys()) == p['labels']
+    for cls, attrs in seg.items():
+        for lab, a in attrs.items():
+            inst.append([cls, lab, *a['box'], len(a['starts'])])
+            starts += list(a['starts'])
+            runs += list(a['runs'])
+    np.testing.assert_array_equal(np.asarray(inst, np.int64).reshape(-1, 7), g['out_inst'])
+    np.testing.assert_array_equal(np.asarray(starts, np.int64), g['out_starts'])
+    np.testing.assert_array_equal(np.asarray(runs, np.int64), g['out_runs'])
+    np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg(seg, g['in_pan'].shape), g['out_back'])
+
+
+def test_sigmoid_cpu_matches_goldens_engine2d():
+    g = load_golden('engine2d')
+    p = g['params']
+    for z in range(p['n']):
+        sem = oracle.harden_seg(_sigmoid_or_softmax(g[f'in_{z}_sem_logits']), p['confidence_thr'])
+        pan, _ = oracle.get_panoptic_segmentation(sem, g[f'in_{z}_ctr_hmp'], g[f'in_{z}_offsets'],
+                                                  p['thing_list'], p['label_divisor'], p['stuff_area'],
+                                                  p['void_label'], p['nms_threshold'], p['nms_kernel'])
+        np.testing.assert_array_equal(pan, g[f'out_{z}'])
