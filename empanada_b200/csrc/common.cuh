@@ -1,0 +1,118 @@
+// common.cuh — shared helpers for libempanada_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/empanada_b200.h"
+
+#define EMP_API extern "C" __attribute__((visibility("default")))
+
+namespace emp {
+
+void set_error(const char* fmt, ...);
+
+#define EMP_CUDA_CHECK(expr)                                                          \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            emp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                           __FILE__, __LINE__);                                       \
+            return EMP_ERR_CUDA;                                                      \
+        }                                                                             \
+    } while (0)
+
+#define EMP_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            emp::set_error(__VA_ARGS__);        \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// code-map conventions (see DESIGN.md "code map"):
+//   0                      -> void
+//   1 .. CLS_BASE-1        -> instance id (index into the label LUT)
+//   CLS_BASE + c           -> stuff pixel of semantic class c (index into the class LUT)
+constexpr uint32_t kClsBase16 = 0xF000u;
+constexpr uint32_t kClsBase32 = 0xFFFFF000u;
+constexpr int kNumClasses = EMP_MAX_CLASSES;
+
+// Per-tile workspace layout.  Everything in [0, zero_bytes) is cleared by one memset per call.
+struct WsLayout {
+    size_t status, rowcnt, areas, votes, zero_bytes;
+    size_t mask, centers, lut, clut, codes, total;
+    int wd;          // mask words per row
+    bool code16;
+};
+
+static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
+{
+    WsLayout L;
+    if (n_things < 1) n_things = 1;
+    L.wd = (W + 31) / 32;
+    L.code16 = (uint32_t)k_cap < kClsBase16;
+    size_t o = 0;
+    L.status = o; o = align_up(o + sizeof(int32_t) * EMP_ST_WORDS, 256);
+    L.rowcnt = o; o = align_up(o + sizeof(uint32_t) * (size_t)H, 256);
+    L.areas = o;  o = align_up(o + sizeof(uint32_t) * kNumClasses, 256);
+    L.votes = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1) * n_things, 256);
+    L.zero_bytes = o;
+    L.mask = o;    o = align_up(o + sizeof(uint32_t) * (size_t)H * L.wd, 256);
+    L.centers = o; o = align_up(o + sizeof(int2) * ((size_t)k_cap + 1), 256);
+    L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
+    L.clut = o;    o = align_up(o + sizeof(int64_t) * kNumClasses, 256);
+    L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
+    L.total = o;
+    return L;
+}
+
+struct Things {
+    long long v[EMP_MAX_THINGS];   // ascending, unique
+    int n;
+};
+
+int make_things(const int64_t* list, int n, Things* out);
+
+// Optional per-stage device timing (emp_profile_enable / emp_profile_read): one CUDA event pair
+// around each kernel launch on the launching stream.  Off by default (no events recorded).
+enum { ST_NMS = 0, ST_EMIT = 1, ST_ASSIGN = 2, ST_LUT = 3, ST_APPLY = 4, ST_MEDIAN = 5, ST_RLE_MARK = 6,
+       ST_RLE_RUNS = 7, ST_COUNT = 8 };
+struct ProfScope {
+    ProfScope(int stage, cudaStream_t st);
+    ~ProfScope();
+    int idx;
+    cudaStream_t st;
+};   // sorts + dedups; EMP_ERR_INVALID if > max
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ int thing_index(long long c, const Things& th)
+{
+    int t = -1;
+#pragma unroll
+    for (int i = 0; i < EMP_MAX_THINGS; ++i)
+        if (i < th.n && th.v[i] == c) t = i;
+    return t;
+}
+
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total)
+{
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+}  // namespace emp

@@ -1,0 +1,179 @@
+/*
+ * empanada_b200.h — C ABI of libempanada_b200.so: B200 (sm_100a) replacement for empanada's
+ * panoptic post-processing, 3D median/harden and pan_seg -> RLE path.
+ *
+ * The reference has no FFI layer (it is pure Python on torch ops); its boundary for this path is
+ * the call surface of empanada/inference/{postprocess,engines,rle}.py.  Each entry point below
+ * names the reference function (file:line under the reference tree) it replaces.  The Python
+ * package empanada_b200.inference mirrors those functions name for name and reaches this library
+ * through ctypes with tensor.data_ptr() / torch.cuda.current_stream().cuda_stream — no torch
+ * types cross this interface.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless it says "host";
+ *   - all work is enqueued on `stream` (a cudaStream_t); no entry point synchronises or allocates
+ *     device memory — the caller passes a workspace of emp_workspace_bytes() bytes per tile, 256-B
+ *     aligned (the Python shim allocates it with torch.empty so the caching allocator owns it);
+ *   - dynamic results (number of centers, runs, instances) are written to a device status block
+ *     at the start of the workspace (see EMP_ST_*); the caller reads it back when it needs them;
+ *   - images are row-major contiguous planes; batched entry points take B tiles laid out
+ *     back to back (tile stride = plane size) and B workspaces back to back;
+ *   - return value: EMP_OK or an EMP_ERR_* code; emp_last_error() gives a thread-local message.
+ *   - data-dependent problems (class id out of range, more centers than k_cap) cannot be known at
+ *     enqueue time; they are reported through EMP_ST_FLAGS in the status block.
+ */
+#ifndef EMPANADA_B200_H
+#define EMPANADA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMP_OK 0
+#define EMP_ERR_INVALID 1   /* bad argument (null pointer, size, too many thing classes ...) */
+#define EMP_ERR_CUDA 2      /* a CUDA runtime call failed; see emp_last_error() */
+#define EMP_ERR_WORKSPACE 3 /* workspace too small or misaligned */
+
+#define EMP_MAX_THINGS 16    /* thing classes per call */
+#define EMP_MAX_CLASSES 4096 /* semantic class ids must lie in [0, EMP_MAX_CLASSES) */
+#define EMP_MAX_LABELS 64    /* classes per emp_rle call */
+
+/* status block: int32 words at the start of each tile's workspace */
+#define EMP_ST_K 0          /* number of centers found (may exceed k_cap; then only k_cap are used) */
+#define EMP_ST_FLAGS 1      /* EMP_FLAG_* bits */
+#define EMP_ST_NROWRUNS 2   /* rle: row-runs found */
+#define EMP_ST_NRUNS 3      /* rle: final runs */
+#define EMP_ST_NINST 4      /* rle: instances (distinct output labels) */
+#define EMP_ST_WORDS 16
+
+#define EMP_FLAG_K_OVERFLOW 1     /* more centers than k_cap: result invalid, retry with larger cap */
+#define EMP_FLAG_CLASS_RANGE 2    /* a semantic class id outside [0, EMP_MAX_CLASSES) was seen */
+#define EMP_FLAG_ID_RANGE 4       /* an instance id outside [0, max_id] was seen (emp_merge) */
+#define EMP_FLAG_RLE_OVERFLOW 8   /* rle run / instance capacity exceeded */
+
+int emp_version(void);
+const char* emp_last_error(void);
+
+/* Optional per-stage device timing for benchmarks: while enabled, every kernel launch is
+ * bracketed by a CUDA event pair on its stream.  emp_profile_read() waits for the recorded events
+ * and returns, per stage (0 nms_peaks, 1 emit_centers, 2 assign, 3 build_lut, 4 apply_lut,
+ * 5 median_harden, 6 rle_mark, 7 rle run kernels), the summed milliseconds and the number of
+ * launches since the last read.  Both arrays have 8 entries (host). */
+int emp_profile_enable(int on);
+int emp_profile_read(double* ms_per_stage, int* launches_per_stage);
+
+/* Bytes of workspace ONE tile of H x W needs when at most k_cap centers (or, for emp_merge,
+ * instance ids up to k_cap) and n_things thing classes are in play. */
+size_t emp_workspace_bytes(int H, int W, int k_cap, int n_things);
+
+/* find_instance_center — empanada/inference/postprocess.py:38-76.
+ * Fused threshold + k x k stride-1 max-pool NMS + ordered (row-major) stream compaction; there is
+ * no top-k in the reference (every NMS peak is kept, in row-major order).
+ *   hm        (H,W) float32 heat-map
+ *   ctr_out   (cap,2) int64 rows (y,x), may be NULL; rows beyond cap are dropped
+ *   status[EMP_ST_K] receives K. */
+int emp_find_centers(const float* hm, int H, int W, float threshold, int nms_kernel,
+                     int64_t* ctr_out, int cap, void* ws, size_t ws_bytes, void* stream);
+
+/* group_pixels (+ chunked_pixel_grouping) — postprocess.py:118-169, :78-116.
+ * Offset-shifted nearest-center argmin over ALL pixels, exact fp32 distance
+ * sqrt_rn(fma(dx,dx,rn(dy*dy))), ties to the lowest center index, 1e5 sentinel when K > chunksize.
+ *   ctr (K,2) int64 (y,x); off (2,H,W) float32 (ch0 = dy, ch1 = dx)
+ *   ids_out (H,W) int64, or int32 if ids_i32 != 0 (the Render engines' coarse id map). */
+int emp_group_pixels(const int64_t* ctr, int K, const float* off, int H, int W, float step,
+                     int chunksize, void* ids_out, int ids_i32, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* get_instance_segmentation — postprocess.py:171-221: centers, then nearest-center ids on
+ * thing pixels only (0 elsewhere).
+ *   sem (H,W) int64; ins_out (H,W) int64; ctr_out as in emp_find_centers. */
+int emp_instance_segmentation(const int64_t* sem, const float* hm, const float* off, int H, int W,
+                              const int64_t* thing_list /* host */, int n_things, float threshold,
+                              int nms_kernel, int64_t* ins_out, int64_t* ctr_out, int cap,
+                              int k_cap, void* ws, size_t ws_bytes, void* stream);
+
+/* merge_semantic_and_instance — postprocess.py:223-296 (majority vote per instance, per-class
+ * renumbering in ascending id order, stuff-area filter).
+ *   sem, ins, pan_out (H,W) int64; instance ids must lie in [0, max_id]. */
+int emp_merge(const int64_t* sem, const int64_t* ins, int H, int W, int64_t label_divisor,
+              const int64_t* thing_list /* host */, int n_things, int64_t stuff_area,
+              int64_t void_label, int64_t max_id, int64_t* pan_out, void* ws, size_t ws_bytes,
+              void* stream);
+
+/* Render-engine merge — engines.py:277-292 with get_instance_cells' nearest upsample
+ * (engines.py:257-275) folded in: ins[Y,X] = thing(sem[Y,X]) ? coarse_ids[Y>>shift, X>>shift] : 0.
+ *   sem (H,W) int64 or uint8 (sem_u8 != 0); coarse_ids (hc,wc) int32 with ids in [0, max_id]. */
+int emp_merge_coarse(const void* sem, int sem_u8, const int32_t* coarse_ids, int hc, int wc,
+                     int shift, int H, int W, int64_t label_divisor,
+                     const int64_t* thing_list /* host */, int n_things, int64_t stuff_area,
+                     int64_t void_label, int64_t max_id, const int32_t* k_dev /* device, may be NULL:
+                     number of ids actually in use (<= max_id), bounds the label-LUT build */,
+                     int64_t* pan_out, void* ws, size_t ws_bytes, void* stream);
+
+/* get_instance_cells before the upsample — engines.py:257-272: centers of the (coarse) heat-map,
+ * then group_pixels(step) over ALL pixels, without a host round trip for K.
+ *   hm (h,w) f32; off (2,h,w) f32; ids_out (h,w) int32 (all 0 when there is no center);
+ *   status[EMP_ST_K] = K (a device pointer to it is ws + 0). */
+int emp_coarse_ids(const float* hm, const float* off, int h, int w, float threshold, int nms_kernel,
+                   float step, int32_t* ids_out, int k_cap, void* ws, size_t ws_bytes, void* stream);
+
+/* get_panoptic_segmentation — postprocess.py:298-356, fused, B tiles per call:
+ * centers -> nearest-center ids on thing pixels -> votes -> label LUT -> panoptic map.
+ *   sem (B,H,W) int64 or uint8; hm (B,H,W) f32; off (B,2,H,W) f32; pan_out (B,H,W) int64
+ *   ctr_out (B,cap,2) int64 or NULL;  ws: B workspaces of emp_workspace_bytes(H,W,k_cap,n) each.
+ *   Per tile status[EMP_ST_K] = K, status[EMP_ST_FLAGS] = flags. */
+int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float* hm, const float* off,
+                         int H, int W, const int64_t* thing_list /* host */, int n_things,
+                         int64_t label_divisor, int64_t stuff_area, int64_t void_label,
+                         float threshold, int nms_kernel, int64_t* pan_out, int64_t* ctr_out,
+                         int cap, int k_cap, void* ws, size_t ws_bytes_per_tile, void* stream);
+
+/* Same pipeline with HOST buffers (pinned or pageable): tiles are streamed host->device, processed
+ * and streamed back on internal streams (copy/compute overlap); this is the end-to-end entry the
+ * benchmark's e2e figure times.  dev_scratch: device buffer of emp_host_scratch_bytes(). Blocks
+ * until the batch is complete.  k_out (host, B int32) receives K per tile, flags_out the flags. */
+size_t emp_host_scratch_bytes(int H, int W, int k_cap, int n_things);
+int emp_panoptic_batched_host(int B, const int64_t* sem_h, const float* hm_h, const float* off_h,
+                              int H, int W, const int64_t* thing_list, int n_things,
+                              int64_t label_divisor, int64_t stuff_area, int64_t void_label,
+                              float threshold, int nms_kernel, int64_t* pan_out_h, int32_t* k_out,
+                              int32_t* flags_out, int k_cap, void* dev_scratch,
+                              size_t dev_scratch_bytes);
+
+/* _MedianQueue.get_median + _harden_seg — engines.py:59-66, :114-121.
+ * Median (middle order statistic) over ks odd planes of (C,H,W) float32, optionally written back
+ * (the reference stores it into the queued entry, which makes the filter recursive), then
+ * hardened: C > 1 first-argmax over C, C == 1 `>= thr`.  ks == 1 hardens planes[0] directly.
+ *   planes: HOST array of ks device pointers;  median_out (C,H,W) f32 or NULL;
+ *   sem_out (H,W) int64, or uint8 if sem_u8 != 0, or NULL. */
+int emp_median_harden(const float* const* planes /* host array */, int ks, int C, int H, int W,
+                      float confidence_thr, float* median_out, void* sem_out, int sem_u8,
+                      void* stream);
+
+/* pan_seg_to_rle_seg — empanada/inference/rle.py:26-86 (+ connected_components :18-24,
+ * array_utils.rle_encode array_utils.py:209-235).  One pass over the pixels extracts row-runs
+ * (maximal horizontal segments of one selected value); everything after that works on runs:
+ * run-based 8-connected union-find for thing classes when force_connected (root = first run in
+ * raster order, so components number themselves in raster-first order), instance slots in the
+ * reference's output order (class order of `labels`, then ascending instance label), run merging
+ * across row ends (a run continues from column W-1 into column 0 of the next row), boxes.
+ *   pan (H,W) int64;  labels / thing_list: host arrays; labels >= 0, 0 < label_divisor <= 2^22.
+ * Results (device, capacity-bounded; true counts in status[EMP_ST_NROWRUNS/NRUNS/NINST], and
+ * EMP_FLAG_RLE_OVERFLOW is set if a capacity was exceeded — retry with the counts):
+ *   runs_out  (run_cap,3) int64: start (flat index), length, instance slot — ascending start
+ *   inst_out  (inst_cap,8) int64: class label, instance label, y0, x0, y1, x1, n runs, 0 —
+ *             slot order IS the reference's dict order; a stable group-by-slot of runs_out gives
+ *             each instance's starts / runs arrays. */
+size_t emp_rle_workspace_bytes(int H, int W, int run_cap, int n_labels, int64_t label_divisor);
+int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, int n_labels,
+            int64_t label_divisor, const int64_t* thing_list /* host */, int n_things,
+            int force_connected, int64_t* runs_out, int run_cap, int64_t* inst_out, int inst_cap,
+            void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMPANADA_B200_H */

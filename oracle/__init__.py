@@ -51,6 +51,8 @@ def lib():
         L.orc_find_centers.argtypes = [vp, i32, i32, f32, i32, vp, i64]
         L.orc_group_pixels.restype = None
         L.orc_group_pixels.argtypes = [vp, i64, vp, i32, i32, f32, i32, vp]
+        L.orc_group_pixels_masked.restype = None
+        L.orc_group_pixels_masked.argtypes = [vp, i64, vp, i32, i32, f32, i32, vp, vp]
         L.orc_merge.restype = i32
         L.orc_merge.argtypes = [vp, vp, i64, i64, vp, i32, i64, i64, vp]
         L.orc_median.restype = None
@@ -112,12 +114,18 @@ def get_instance_segmentation(sem_seg, ctr_hmp, offsets, thing_list, threshold=0
     sem = _c(sem_seg, np.int64)
     assert sem.shape[0] == 1
     sem = sem[0]
-    thing = np.isin(sem, np.asarray(list(thing_list), np.int64)).astype(np.int64)
+    thing = np.ascontiguousarray(np.isin(sem, np.asarray(list(thing_list), np.int64)).astype(np.uint8))
     ctr = find_instance_center(ctr_hmp, threshold, nms_kernel)
     if ctr.shape[0] == 0:
         return np.zeros_like(sem), ctr[None]
-    ids = group_pixels(ctr, offsets)
-    return thing * ids, ctr[None]
+    off = _c(offsets, np.float32)
+    if off.ndim == 4:
+        off = np.ascontiguousarray(off[0])
+    _, H, W = off.shape
+    ids = np.empty((1, H, W), np.int64)
+    # search only thing pixels: the others are multiplied by 0 anyway (postprocess.py:221)
+    lib().orc_group_pixels_masked(_p(ctr), ctr.shape[0], _p(off), H, W, np.float32(1.0), 20, _p(thing), _p(ids))
+    return ids, ctr[None]
 
 
 def merge_semantic_and_instance(sem_seg, ins_seg, label_divisor, thing_list, stuff_area, void_label):

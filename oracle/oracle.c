@@ -67,8 +67,19 @@ ORC_API int64_t orc_find_centers(const float* hm, int H, int W, float thr, int k
  *   K <= chunksize : id = 1 + argmin_k d_k (first minimum)
  *   K  > chunksize : running strict-< minimum from 1e5 -> id 0 if every d_k >= 1e5
  * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_group_pixels_masked(const int64_t* ctr, int64_t K, const float* off, int H, int W,
+                                     float step, int chunksize, const uint8_t* mask, int64_t* ids);
+
 ORC_API void orc_group_pixels(const int64_t* ctr, int64_t K, const float* off, int H, int W,
                               float step, int chunksize, int64_t* ids)
+{
+    orc_group_pixels_masked(ctr, K, off, H, W, step, chunksize, NULL, ids);
+}
+
+/* mask != NULL: only pixels with mask[p] != 0 are searched, the rest get id 0 (what
+ * get_instance_segmentation's `instance_seg * instance_id` keeps, postprocess.py:221). */
+ORC_API void orc_group_pixels_masked(const int64_t* ctr, int64_t K, const float* off, int H, int W,
+                                     float step, int chunksize, const uint8_t* mask, int64_t* ids)
 {
     const int64_t HW = (int64_t)H * W;
     float* cy = (float*)malloc(sizeof(float) * (size_t)(K > 0 ? K : 1));
@@ -83,6 +94,7 @@ ORC_API void orc_group_pixels(const int64_t* ctr, int64_t K, const float* off, i
         const float fy = (float)y * step;
         for (int x = 0; x < W; ++x) {
             const int64_t p = (int64_t)y * W + x;
+            if (mask && !mask[p]) { ids[p] = 0; continue; }
             const float ly = fy + off[p];
             const float lx = (float)x * step + off[HW + p];
             float best = chunked ? 1e5f : 0.0f;

@@ -1,0 +1,103 @@
+"""B200: the engine classes (median queue, hardening, fused post-processing, Render-engine coarse
+path) replaying the head tensors of reference-generated fixtures through a fake model."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from empanada_b200.inference import engines as eng
+
+pytestmark = pytest.mark.gpu
+
+
+class ReplayModel(torch.nn.Module):
+    def __init__(self, outputs, device):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1, device=device))
+        self.outputs = outputs
+        self.i = 0
+
+    def forward(self, image, render_steps=None, interpolate_ins=None):
+        out = {k: v.clone() for k, v in self.outputs[self.i].items()}
+        self.i += 1
+        return out
+
+
+def _inputs(g, n, dev):
+    return [{k: torch.from_numpy(g[f'in_{z}_{k}']).to(dev) for k in ('sem_logits', 'ctr_hmp', 'offsets')}
+            for z in range(n)]
+
+
+def _mismatch(got, want):
+    got = got.cpu().numpy()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return int((got != want).sum())
+
+
+def test_engine2d(cuda_device):
+    g = load_golden('engine2d')
+    p = g['params']
+    model = ReplayModel(_inputs(g, p['n'], cuda_device), cuda_device)
+    e = eng.PanopticDeepLabEngine(model, p['thing_list'], p['label_divisor'], p['stuff_area'], p['void_label'],
+                                  p['nms_threshold'], p['nms_kernel'], p['confidence_thr'])
+    for z in range(p['n']):
+        out = e(torch.zeros(1, 1, 64, 80))
+        assert out.dtype == torch.int64
+        assert _mismatch(out, g[f'out_{z}']) == 0
+
+
+@pytest.mark.parametrize('name', golden_names('engine3d_'))
+def test_engine3d(name, cuda_device):
+    g = load_golden(name)
+    p = g['params']
+    model = ReplayModel(_inputs(g, p['n'], cuda_device), cuda_device)
+    e = eng.PanopticDeepLabEngine3d(model, p['thing_list'], p['label_divisor'], p['stuff_area'], p['void_label'],
+                                    p['nms_threshold'], p['nms_kernel'], p['confidence_thr'], p['median_kernel_size'])
+    outs, emitted = [], []
+    for z in range(p['n']):
+        o = e(torch.zeros(1, 1, 48, 64))
+        emitted.append(o is not None)
+        if o is not None:
+            outs.append(o)
+    outs += e.end()
+    assert emitted == p['emitted'] and len(outs) == sum(p['emitted']) + p['n_tail']
+    for i, o in enumerate(outs):
+        assert _mismatch(o, g[f'out_{i}']) == 0, f'slice {i}'
+
+
+@pytest.mark.parametrize('name', golden_names('render3d_'))
+def test_render_engine3d(name, cuda_device):
+    g = load_golden(name)
+    p = g['params']
+    size, up = tuple(p['size']), p['upsampling']
+    for mode in ('fused', 'reference_methods'):
+        model = ReplayModel(_inputs(g, p['n'], cuda_device), cuda_device)
+        e = eng.PanopticDeepLabRenderEngine3d(model, p['thing_list'], p['label_divisor'], p['stuff_area'],
+                                              p['void_label'], p['nms_threshold'], p['nms_kernel'],
+                                              p['confidence_thr'], p['median_kernel_size'], p['padding_factor'],
+                                              p['coarse_boundaries'])
+        outs = []
+        if mode == 'fused':
+            for z in range(p['n']):
+                o = e(torch.zeros(1, 1, *size), size, up)
+                if o is not None:
+                    outs.append(o)
+            outs += e.end(up)
+        else:       # the reference-shaped public methods: get_instance_cells -> postprocess
+            from empanada_b200.inference.postprocess import factor_pad
+            for z in range(p['n']):
+                image = e.to_model_device(factor_pad(torch.zeros(1, 1, *size), e.padding_factor))
+                mo = e.infer(image, 2)
+                mo['size'] = size
+                e.enqueue(mo)
+                m = e.get_next(keys=['sem'])
+                if m is not None:
+                    cells = e.get_instance_cells(m['ctr_hmp'], m['offsets'], up)
+                    assert cells.dtype == torch.float32 and cells.dim() == 4
+                    outs.append(e.postprocess(m['sem'], cells)[..., :size[0], :size[1]])
+            for mo in list(e.median_queue)[e.mid_idx + 1:]:
+                cells = e.get_instance_cells(mo['ctr_hmp'], mo['offsets'], up)
+                outs.append(e.postprocess(mo['sem'], cells)[..., :size[0], :size[1]])
+        assert len(outs) == sum(p['emitted']) + p['n_tail']
+        for i, o in enumerate(outs):
+            assert _mismatch(o, g[f'out_{i}']) == 0, f'{mode} slice {i}'

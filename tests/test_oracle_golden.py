@@ -142,3 +142,18 @@ def test_sigmoid_cpu_matches_goldens_engine2d():
                                                   p['thing_list'], p['label_divisor'], p['stuff_area'],
                                                   p['void_label'], p['nms_threshold'], p['nms_kernel'])
         np.testing.assert_array_equal(pan, g[f'out_{z}'])
+
+
+@pytest.mark.parametrize('name', ['pp_fixture256', 'pp_chunked_k_gt_20', 'pp_ties_half_offsets', 'pp_multiclass_1',
+                                  'pp_sentinel_k21', 'pp_plateau_k4', 'pp_k0'])
+def test_torch_port_matches_reference(name):
+    """The op-sequence port that bench.py times as the CPU baseline gives the reference's results."""
+    import torch
+    from oracle import torch_port
+    g = load_golden(name)
+    p = g['params']
+    pan, ctr = torch_port.panoptic(torch.from_numpy(g['in_sem']), torch.from_numpy(g['in_hm']),
+                                   torch.from_numpy(g['in_off']), p['thing_list'], p['label_divisor'],
+                                   p['stuff_area'], p['void_label'], p['threshold'], p['nms_kernel'])
+    np.testing.assert_array_equal(ctr[0].numpy(), g['out_centers'])
+    np.testing.assert_array_equal(pan.numpy(), g['out_pan'])
