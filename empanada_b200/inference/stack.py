@@ -1,0 +1,180 @@
+"""
+Z-sharded stack inference: the part of the reference's 3D path between "CNN heads produced
+sem / ctr_hmp / offsets for slice z" and "the host tracker receives slice z's RLE dict"
+(reference scripts/pdl_inference3d.py:163-176 + empanada/inference/patterns.py:68-100, and the
+multi-GPU recipe patterns.forward_multigpu :279-350), one process per GPU.
+
+Sharding.  Slices are independent except for the recursive median queue (engines.py:47-90):
+    m_i = median(f_{i-mid}, ..., f_{i-1}, s_i, s_{i+1}, ..., s_{i+mid}),   f_j = m_j (j >= mid) else s_j
+for mid <= i < D - mid, raw s_i otherwise.  Rank r owns the contiguous block [z0, z1).  It needs
+  * a look-ahead halo: the raw probabilities of slices z1 .. z1+mid-1 (it runs the CNN on them too);
+  * a carry: the filtered planes f_{z0-mid} .. f_{z0-1} from rank r-1 (one send/recv of `mid`
+    (C,H,W) fp32 planes over NCCL/NVLink), available once r-1 has run its — elementwise, cheap —
+    median chain.  The CNN forwards, which dominate, never wait on it.
+With median_kernel_size == 1 nothing is exchanged.
+
+Labels.  Every slice numbers its instances 1..n per class.  So that labels from different ranks
+never collide before the host-side cross-slice matcher renumbers them, ranks all-gather their
+per-class maximum instance count (one int64 per class) and add the exclusive prefix as an offset;
+rank 0 keeps offset 0, which is what the reference's matcher sees for the first slice.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+__all__ = ['partition_slices', 'halo_range', 'median_chain', 'exchange_carry', 'label_offsets',
+           'apply_label_offset', 'StackShard']
+
+
+def partition_slices(depth, world_size, rank):
+    """Contiguous z-block [z0, z1) of `rank`: the first depth % world_size ranks get one extra slice."""
+    base, extra = divmod(depth, world_size)
+    z0 = rank * base + min(rank, extra)
+    return z0, z0 + base + (1 if rank < extra else 0)
+
+
+def halo_range(depth, world_size, rank, median_kernel_size):
+    """Slices whose head tensors `rank` must compute: its block plus the look-ahead halo."""
+    z0, z1 = partition_slices(depth, world_size, rank)
+    mid = (median_kernel_size - 1) // 2
+    return z0, min(depth, z1 + mid)
+
+
+def median_chain(raw, z0, z1, depth, ks, carry, median_fn):
+    """Recursive median over the block [z0, z1).
+
+    raw      dict {z: sem plane} for z in [z0, min(depth, z1 + mid))
+    carry    list of the `mid` planes f_{z0-mid} .. f_{z0-1} (filtered where z >= mid, else raw);
+             ignored for z0 == 0
+    median_fn(list of ks planes) -> plane   (libempanada_b200's emp_median_harden on the GPU,
+             any odd-count median on the CPU in tests)
+    Returns (filtered {z: plane} for z in [z0, z1), carry for the next rank).
+    """
+    mid = (ks - 1) // 2
+    assert depth >= ks, 'stack shallower than the median kernel'
+    f = {}
+    if z0 > 0:
+        assert len(carry) == mid
+        for j, p in enumerate(carry):
+            f[z0 - mid + j] = p
+    for z in range(z0, z1):
+        if z < mid or z >= depth - mid or ks == 1:
+            f[z] = raw[z]                                   # queue still filling / end(): raw
+        else:
+            window = [f[j] for j in range(z - mid, z)] + [raw[j] for j in range(z, z + mid + 1)]
+            f[z] = median_fn(window)
+    out = {z: f[z] for z in range(z0, z1)}
+    nxt = [f[z] for z in range(z1 - mid, z1)] if mid > 0 else []
+    return out, nxt
+
+
+def exchange_carry(chain_fn, rank, world_size, mid, plane_like, group=None):
+    """Run `chain_fn(carry) -> (result, next_carry)` on every rank in rank order, handing the
+    carry planes from rank r to r+1 with point-to-point send/recv (NCCL on CUDA tensors, gloo on
+    CPU tensors).  plane_like: a tensor with the carry planes' shape / dtype / device."""
+    carry = []
+    if mid > 0 and rank > 0 and world_size > 1:
+        carry = [torch.empty_like(plane_like) for _ in range(mid)]
+        for p in carry:
+            dist.recv(p, src=rank - 1, group=group)
+    result, nxt = chain_fn(carry)
+    if mid > 0 and rank + 1 < world_size:
+        for p in nxt:
+            dist.send(p.contiguous(), dst=rank + 1, group=group)
+    return result
+
+
+def label_offsets(max_counts, group=None):
+    """max_counts: int64 tensor (n_classes,) — this rank's largest per-slice instance count per
+    class.  All-gathers it (NCCL over NVLink for CUDA tensors) and returns this rank's exclusive
+    prefix (n_classes,) plus the gathered (world, n_classes) table."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return torch.zeros_like(max_counts), max_counts[None].clone()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = [torch.zeros_like(max_counts) for _ in range(world)]
+    dist.all_gather(gathered, max_counts, group=group)
+    table = torch.stack(gathered)
+    return table[:rank].sum(0), table
+
+
+def apply_label_offset(rle_seg, offsets_by_class, label_divisor, thing_list):
+    """Shift the instance labels of thing classes in one slice's rle dict by this rank's offset."""
+    out = {}
+    for cls, attrs in rle_seg.items():
+        off = int(offsets_by_class.get(cls, 0)) if cls in thing_list else 0
+        if off == 0:
+            out[cls] = attrs
+            continue
+        shifted = {}
+        for lab, a in attrs.items():
+            new = lab + off
+            if new >= (cls + 1) * label_divisor:
+                raise ValueError(f'label {lab} + offset {off} leaves class {cls}\'s range; '
+                                 f'raise label_divisor (reference default for 3D is 20000)')
+            shifted[new] = a
+        out[cls] = shifted
+    return out
+
+
+class StackShard:
+    """One rank's share of a stack: feed it the head tensors of its slices (block + halo) in z
+    order, then `finish()` returns {z: rle_seg} for the block.
+
+    engine: a PanopticDeepLabRenderEngine(3d) (its post-processing parameters and fused kernels
+    are used; its own median queue is bypassed in favour of the sharded chain above).
+    """
+
+    def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
+                 upsampling=1, force_connected=True, group=None):
+        assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
+        assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
+        self.engine, self.labels, self.depth = engine, list(labels), depth
+        self.rank, self.world, self.ks = rank, world_size, median_kernel_size
+        self.mid = (median_kernel_size - 1) // 2
+        self.upsampling, self.force_connected, self.group = upsampling, force_connected, group
+        self.z0, self.z1 = partition_slices(depth, world_size, rank)
+        _, self.z_halo = halo_range(depth, world_size, rank, median_kernel_size)
+        self.heads = {}
+
+    def slices(self):
+        """z indices this rank must run the CNN on, in order."""
+        return range(self.z0, self.z_halo)
+
+    def add(self, z, sem_prob, ctr_hmp=None, offsets=None, size=None):
+        """Head tensors of slice z: sem_prob (1,C,H,W) probabilities; ctr_hmp/offsets only needed
+        for z inside the block (halo slices contribute their probabilities only)."""
+        assert self.z0 <= z < self.z_halo
+        self.heads[z] = {'sem': sem_prob, 'ctr_hmp': ctr_hmp, 'offsets': offsets, 'size': size}
+
+    def finish(self):
+        from empanada_b200.inference import engines as eng
+        from empanada_b200.inference import rle
+
+        raw = {z: h['sem'] for z, h in self.heads.items()}
+
+        def med(window):
+            return eng.median_harden(window, 0.0)[0]
+
+        def chain(carry):
+            return median_chain(raw, self.z0, self.z1, self.depth, self.ks, carry, med)
+
+        filtered = exchange_carry(chain, self.rank, self.world, self.mid, raw[self.z0], self.group)
+        e = self.engine
+        out, max_counts = {}, {c: 0 for c in self.labels}
+        for z in range(self.z0, self.z1):
+            h = self.heads[z]
+            pan = e._fused_postprocess(filtered[z], h['ctr_hmp'], h['offsets'], self.upsampling)
+            if h['size'] is not None:
+                pan = pan[..., :h['size'][0], :h['size'][1]]
+            seg = rle.pan_seg_to_rle_seg(pan, self.labels, e.label_divisor, e.thing_list, self.force_connected)
+            for c in self.labels:
+                if c in e.thing_list and seg[c]:
+                    max_counts[c] = max(max_counts[c], max(seg[c]) - c * e.label_divisor)
+            out[z] = seg
+        counts = torch.tensor([max_counts[c] for c in self.labels], dtype=torch.int64, device=raw[self.z0].device)
+        offs, _ = label_offsets(counts, self.group)
+        offs = {c: int(o) for c, o in zip(self.labels, offs.tolist())}
+        self.label_offsets_ = offs
+        return {z: apply_label_offset(s, offs, e.label_divisor, e.thing_list) for z, s in out.items()}

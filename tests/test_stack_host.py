@@ -1,0 +1,120 @@
+"""CPU: host-side logic of the z-sharded stack path — slice partitioning, the recursive median
+chain with its rank-to-rank carry, and the label-offset all-gather — with world_size-2/3 gloo
+process groups.  The sharded result must equal the sequential _MedianQueue semantics (oracle)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from empanada_b200.inference import stack
+
+
+def test_partition_covers_everything():
+    for depth in (1, 7, 8, 512, 513):
+        for world in (1, 2, 3, 8):
+            blocks = [stack.partition_slices(depth, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == depth
+            for a, b in zip(blocks, blocks[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    assert stack.halo_range(512, 8, 0, 3) == (0, 65)
+    assert stack.halo_range(512, 8, 7, 3) == (448, 512)
+    assert stack.halo_range(512, 8, 3, 1) == (192, 256)
+
+
+def _sequential(planes, ks):
+    """What the reference's queue emits for every slice (engines.py:68-90), via the oracle."""
+    q = oracle.MedianQueue(ks)
+    out = []
+    for p in planes:
+        q.enqueue({'sem': p})
+        o = q.get_next(['sem'])
+        if o is not None:
+            out.append(o['sem'])
+    out += [e['sem'] for e in q.end()]
+    return out
+
+
+def _tmedian(window):
+    return torch.median(torch.stack(window), dim=0).values
+
+
+@pytest.mark.parametrize('ks', [1, 3, 5, 7])
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_median_chain_single_process(ks, world):
+    rng = np.random.default_rng(ks * 10 + world)
+    D = 13
+    planes = [rng.random((1, 2, 5, 6), dtype=np.float32) for _ in range(D)]
+    want = _sequential([p.copy() for p in planes], ks)
+    assert len(want) == D
+    carry = []
+    for r in range(world):
+        z0, z1 = stack.partition_slices(D, world, r)
+        _, zh = stack.halo_range(D, world, r, ks)
+        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
+        got, carry = stack.median_chain(raw, z0, z1, D, ks, carry, _tmedian)
+        for z in range(z0, z1):
+            np.testing.assert_array_equal(got[z].numpy(), want[z])
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ks, D, seed, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]      # same on all ranks
+        z0, z1 = stack.partition_slices(D, world, rank)
+        _, zh = stack.halo_range(D, world, rank, ks)
+        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
+        mid = (ks - 1) // 2
+        got = stack.exchange_carry(lambda c: stack.median_chain(raw, z0, z1, D, ks, c, _tmedian),
+                                   rank, world, mid, raw[z0])
+        counts = torch.tensor([10 * (rank + 1), 3 + rank], dtype=torch.int64)
+        offs, table = stack.label_offsets(counts)
+        ret[rank] = ({z: got[z].numpy() for z in got}, offs.tolist(), table.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,ks', [(2, 3), (2, 5), (3, 3)])
+def test_sharded_chain_and_offsets_gloo(world, ks):
+    D, seed = 11, 5
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ks, D, seed, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]
+    want = _sequential(planes, ks)
+    seen = set()
+    for r in range(world):
+        got, offs, table = ret[r]
+        for z, p in got.items():
+            np.testing.assert_array_equal(p, want[z])
+            seen.add(z)
+        assert offs == [sum(10 * (q + 1) for q in range(r)), sum(3 + q for q in range(r))]
+        assert table == [[10 * (q + 1), 3 + q] for q in range(world)]
+    assert seen == set(range(D))
+
+
+def test_apply_label_offset():
+    seg = {1: {1001: {'box': (0, 0, 1, 1)}, 1002: {'box': (1, 1, 2, 2)}}, 2: {2000: {'box': (0, 0, 4, 4)}}}
+    out = stack.apply_label_offset(seg, {1: 40, 2: 7}, 1000, [1])
+    assert list(out[1]) == [1041, 1042] and list(out[2]) == [2000]
+    with pytest.raises(ValueError):
+        stack.apply_label_offset(seg, {1: 998}, 1000, [1])
