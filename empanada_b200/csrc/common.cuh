@@ -42,7 +42,7 @@ constexpr int kNumClasses = EMP_MAX_CLASSES;
 // Per-tile workspace layout.  Everything in [0, zero_bytes) is cleared by one memset per call.
 struct WsLayout {
     size_t status, rowcnt, areas, votes, zero_bytes;
-    size_t mask, centers, lut, clut, codes, total;
+    size_t mask, centers, lut, codes, total;
     int wd;          // mask words per row
     bool code16;
 };
@@ -60,9 +60,8 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     L.votes = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1) * n_things, 256);
     L.zero_bytes = o;
     L.mask = o;    o = align_up(o + sizeof(uint32_t) * (size_t)H * L.wd, 256);
-    L.centers = o; o = align_up(o + sizeof(int2) * ((size_t)k_cap + 1), 256);
+    L.centers = o; o = align_up(o + sizeof(float2) * ((size_t)k_cap + 1), 256);
     L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
-    L.clut = o;    o = align_up(o + sizeof(int64_t) * kNumClasses, 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
     L.total = o;
     return L;

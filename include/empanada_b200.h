@@ -47,6 +47,7 @@ extern "C" {
 #define EMP_ST_NROWRUNS 2   /* rle: row-runs found */
 #define EMP_ST_NRUNS 3      /* rle: final runs */
 #define EMP_ST_NINST 4      /* rle: instances (distinct output labels) */
+#define EMP_ST_TICKET 5     /* internal: CTA completion counter of the assign kernel */
 #define EMP_ST_WORDS 16
 
 #define EMP_FLAG_K_OVERFLOW 1     /* more centers than k_cap: result invalid, retry with larger cap */
