@@ -82,14 +82,11 @@ int make_things(const int64_t* list, int n, Things* out)
 //   peak(y,x)  <=>  v > thr  and  v > 0  and  v >= every value in rows y-lo..y+hi, cols x-lo..x+hi
 // (clipped; lo = k/2, hi = k-1-lo).  Thresholding neighbours to -1 first (F.threshold) cannot
 // change the comparison because v itself is > thr.  NaNs compare false both ways, like -1.
-// One lane per pixel column, 32 rows (+1 halo row above and below) per warp, all held in
-// registers.  A row in which some lane is above threshold first checks the 3x3 neighbourhood with
-// register / shuffle operands only (that alone rejects every slope pixel of a smooth heat-map);
-// only 3x3-maxima walk the rest of the k x k window through L1.  Output: one ballot word per 32
-// pixels and a per-row popcount.
+// A streaming pass flags pixels above threshold (a few % of an EM heat-map); only words holding a
+// flagged pixel check neighbours, 3x3 first (that alone rejects every slope pixel of a smooth
+// heat-map), the full k x k window only for 3x3 maxima.  Output: one ballot word per 32 pixels
+// and a per-row popcount.
 // ---------------------------------------------------------------------------------------------
-constexpr int kNmsRows = 32;
-
 __device__ __forceinline__ bool window_is_peak(const float* __restrict__ hm, int H, int W, int y,
                                                int x, float v, int lo, int hi)
 {
@@ -111,6 +108,40 @@ __device__ __forceinline__ bool window_is_peak(const float* __restrict__ hm, int
     return true;
 }
 
+// Called by a whole (converged) warp for one 32-pixel word of one row in which some lane is above
+// threshold (a few % of all words).  Neighbour values come through L1 here (the streaming loop does
+// not keep them): 3x3 neighbourhood first, the rest of the k x k window only for 3x3 maxima.
+__device__ __noinline__ unsigned nms_word_check(const float* __restrict__ hm, int H, int W, int y, int x,
+                                                bool cand, float thr, int lo, int hi)
+{
+    bool peak = false;
+    if (cand) {
+        const float c = __ldg(hm + (size_t)y * W + x);
+        const bool before = lo >= 1, after = hi >= 1;   // window reaches to -1 / +1 at all?
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dy == 0 && dx == 0) continue;
+                if ((dy < 0 || dx < 0) && !before) continue;
+                if ((dy > 0 || dx > 0) && !after) continue;
+                const int yy = y + dy, xx = x + dx;
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m = fmaxf(m, __ldg(hm + (size_t)yy * W + xx));
+            }
+        }
+        peak = !(m > c);
+        if (peak && lo >= 2) peak = window_is_peak(hm, H, W, y, x, c, lo, hi);
+    }
+    return __ballot_sync(0xffffffffu, peak);
+}
+
+// One warp owns 4 rows x 256 pixels = 4 full 32-byte sectors of the peak mask, so it needs no
+// shared memory and no barrier: lane l streams pixels 32j + l (j = 0..7) of each row (128-byte
+// coalesced loads), keeps one "above threshold" flag per pixel, and only words with a flagged
+// lane take the neighbourhood check.
+constexpr int kNmsRows = 4, kNmsWords = 8;
+
 __global__ void __launch_bounds__(256)
 nms_peaks_kernel(const float* __restrict__ hm_base, size_t hm_stride, int H, int W, float thr,
                  int lo, int hi, char* __restrict__ ws_base, size_t ws_stride, size_t o_mask,
@@ -122,57 +153,45 @@ nms_peaks_kernel(const float* __restrict__ hm_base, size_t hm_stride, int H, int
     uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + o_rowcnt);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wordcol = blockIdx.x * 4 + (warp & 3);
-    const int y0 = blockIdx.y * (2 * kNmsRows) + (warp >> 2) * kNmsRows;
-    const int x = wordcol * 32 + lane;
-    const bool xin = x < W;
-    if (wordcol >= wd || y0 >= H) return;       // warp-uniform
-    const bool before = lo >= 1, after = hi >= 1;   // window reaches to -1 / +1 at all?
+    const int w0 = blockIdx.x * kNmsWords;                          // first mask word of this warp
+    const int y0 = (blockIdx.y * 8 + warp) * kNmsRows;
+    if (y0 >= H) return;                                            // warp-uniform
+    const int x0 = w0 * 32 + lane;
 
-    float v[kNmsRows + 2];                      // v[i] = row y0 - 1 + i
+    unsigned cm = 0;                                                // bit 8*r + j: pixel (y0+r, x0+32j) is a candidate
+    const long long Wl = W;
+    const float* p = hm + (long long)y0 * Wl + x0;
 #pragma unroll
-    for (int i = 0; i < kNmsRows + 2; ++i) {
-        const int y = y0 - 1 + i;
-        v[i] = (xin && y >= 0 && y < H) ? __ldg(hm + (size_t)y * W + x) : -CUDART_INF_F;
+    for (int r = 0; r < kNmsRows; ++r) {
+        const bool rin = y0 + r < H;
+#pragma unroll
+        for (int j = 0; j < kNmsWords; ++j) {
+            float v = -CUDART_INF_F;
+            if (rin && x0 + 32 * j < W) v = __ldcs(p + 32 * j);
+            cm |= ((v > thr && v > 0.0f) ? 1u : 0u) << (8 * r + j);
+        }
+        p += Wl;
     }
-    unsigned myword = 0;
+    unsigned mine[kNmsRows] = {0, 0, 0, 0};                         // lane j (< 8) ends up with word j of each row
+    unsigned todo = __reduce_or_sync(0xffffffffu, cm);              // (row, word) pairs with any candidate
+    while (todo) {                                                  // warp-uniform
+        const int bit = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int r = bit >> 3, j = bit & 7;
+        const unsigned word = nms_word_check(hm, H, W, y0 + r, x0 + 32 * j, (cm >> bit) & 1u, thr, lo, hi);
+        if (lane == j) {
+            if (r == 0) mine[0] = word; else if (r == 1) mine[1] = word; else if (r == 2) mine[2] = word; else mine[3] = word;
+        }
+    }
 #pragma unroll
     for (int r = 0; r < kNmsRows; ++r) {
         const int y = y0 + r;
-        const float c = v[r + 1];
-        const bool cand = xin && c > thr && c > 0.0f;      // rows beyond H hold -inf
-        bool peak = false;
-        if (__any_sync(0xffffffffu, cand)) {
-            const float up = v[r], dn = v[r + 2];
-            float l = __shfl_up_sync(0xffffffffu, c, 1), rt = __shfl_down_sync(0xffffffffu, c, 1);
-            float ul = __shfl_up_sync(0xffffffffu, up, 1), ur = __shfl_down_sync(0xffffffffu, up, 1);
-            float dl = __shfl_up_sync(0xffffffffu, dn, 1), dr = __shfl_down_sync(0xffffffffu, dn, 1);
-            if (cand && (lane == 0 || lane == 31)) {
-                const int xx = lane == 0 ? x - 1 : x + 1;
-                float e[3];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int yy = y - 1 + d;
-                    e[d] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? __ldg(hm + (size_t)yy * W + xx) : -CUDART_INF_F;
-                }
-                if (lane == 0) { ul = e[0]; l = e[1]; dl = e[2]; }
-                else { ur = e[0]; rt = e[1]; dr = e[2]; }
-            }
-            float m = -CUDART_INF_F;
-            if (before) { m = fmaxf(m, fmaxf(l, up)); m = fmaxf(m, ul); if (after) m = fmaxf(m, fmaxf(ur, dl)); }
-            if (after) { m = fmaxf(m, fmaxf(rt, dn)); m = fmaxf(m, dr); }
-            peak = cand && !(m > c);
-            if (lo >= 2 && __any_sync(0xffffffffu, peak)) {
-                if (peak) peak = window_is_peak(hm, H, W, y, x, c, lo, hi);
-            }
+        if (y < H) {                                                // warp-uniform
+            const bool wl = lane < kNmsWords && w0 + lane < wd;
+            if (wl) mask[(size_t)y * wd + w0 + lane] = mine[r];
+            const unsigned cnt = __reduce_add_sync(0xffffffffu, wl ? (unsigned)__popc(mine[r]) : 0u);
+            if (cnt && lane == 0) atomicAdd(rowcnt + y, cnt);
         }
-        const unsigned word = __ballot_sync(0xffffffffu, peak);
-        if (lane == r) myword = word;
-    }
-    const int yw = y0 + lane;
-    if (yw < H) {
-        mask[(size_t)yw * wd + wordcol] = myword;
-        if (myword) atomicAdd(rowcnt + yw, (uint32_t)__popc(myword));
     }
 }
 
@@ -307,6 +326,13 @@ constexpr int kAreaBins = 64, kVoteSlots = 64;
 constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
 
+struct LutScratch {
+    int run[EMP_MAX_THINGS];
+    int wcnt[8];
+};
+
+constexpr int kSmemLut = 2048;      // ids whose label LUT apply_lut rebuilds in shared memory
+
 struct AssignSmem {
     float cy[kCandCap], cx[kCandCap];
     int ck[kCandCap];
@@ -315,11 +341,13 @@ struct AssignSmem {
     int wcnt[8];
     unsigned area[kAreaBins];
     unsigned vkey[kVoteSlots], vcnt[kVoteSlots];
-    int run[EMP_MAX_THINGS];
+    LutScratch lut;
     int last;
+    int kshared;
 };
 
-__device__ __forceinline__ void vote_insert(AssignSmem& sm, uint32_t* votes, unsigned key, int cnt)
+// Rare paths are kept out of line so that the per-pixel code stays small and branch-light.
+__device__ __noinline__ void vote_insert(AssignSmem& sm, uint32_t* votes, unsigned key, int cnt)
 {
     unsigned h = (key * 2654435761u) >> 26;
 #pragma unroll 1
@@ -339,7 +367,7 @@ __device__ __forceinline__ void area_insert(AssignSmem& sm, uint32_t* areas, uns
 
 // 16-bit info word of one pixel: thing -> kInfoThing | thing index, stuff -> class id,
 // class outside [0, 4096) -> kInfoBad (reported through EMP_FLAG_CLASS_RANGE).
-__device__ __forceinline__ unsigned classify(long long v, const AssignArgs& a)
+__device__ __noinline__ unsigned classify_slow(long long v, const AssignArgs& a)
 {
     if ((unsigned long long)v < 64ull) {
         const unsigned c = (unsigned)v;
@@ -355,21 +383,27 @@ __device__ __forceinline__ unsigned classify(long long v, const AssignArgs& a)
     return (unsigned)v;
 }
 
-// merge_semantic_and_instance's bookkeeping (postprocess.py:263-281) by the last CTA of the grid:
+// class ids known to be < 64: one shift / mask, no branches
+__device__ __forceinline__ unsigned classify_small(unsigned c, unsigned long long tbits, bool multi)
+{
+    const unsigned th = (unsigned)(tbits >> c) & 1u;
+    const unsigned t = multi ? (unsigned)__popcll(tbits & ((1ull << c) - 1ull)) : 0u;
+    return th ? (kInfoThing | t) : c;
+}
+
+// merge_semantic_and_instance's bookkeeping (postprocess.py:263-281), by one 256-thread CTA:
 //   id -> majority thing class (ties -> smallest class, torch.mode) * L + 1-based rank among voted
-//   ids of that class in ascending id order.
-__device__ void build_lut_tail(const AssignArgs& a, AssignSmem& sm, const int32_t* status,
-                               const uint32_t* votes, long long* lut)
+//   ids of that class in ascending id order.  `lut` may point to shared or global memory.
+__device__ void build_label_lut(long long K, const uint32_t* votes, const Things& things, long long label_divisor,
+                                long long void_label, long long* lut, LutScratch& sc)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = a.things.n;
+    const int nt = things.n;
     const int T = nt > 0 ? nt : 1;
-    long long K = a.k_fixed >= 0 ? (long long)a.k_fixed : (long long)min(__ldcg(status + EMP_ST_K), a.k_cap);
-    if (a.k_dev) K = min(K, (long long)max(__ldcg(a.k_dev), 0));
-    if (tid < EMP_MAX_THINGS) sm.run[tid] = 0;
-    if (tid == 0) lut[0] = a.void_label;
+    if (tid < EMP_MAX_THINGS) sc.run[tid] = 0;
+    if (tid == 0) lut[0] = void_label;
     __syncthreads();
-    for (long long base = 1; base <= K; base += kAssignThreads) {
+    for (long long base = 1; base <= K; base += 256) {
         const long long id = base + tid;
         int t = -1;
         if (id <= K) {
@@ -378,27 +412,35 @@ __device__ void build_lut_tail(const AssignArgs& a, AssignSmem& sm, const int32_
                 const uint32_t v = __ldcg(votes + (size_t)id * T + c);
                 if (v > best) { best = v; t = c; }
             }
-            if (t < 0) lut[id] = a.void_label;
+            if (t < 0) lut[id] = void_label;
         }
         for (int c = 0; c < nt; ++c) {
             const bool f = (t == c);
             const unsigned bal = __ballot_sync(0xffffffffu, f);
-            if (lane == 0) sm.wcnt[warp] = __popc(bal);
+            if (lane == 0) sc.wcnt[warp] = __popc(bal);
             __syncthreads();
             int woff = 0, tot = 0;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) { const int x = sm.wcnt[w]; if (w < warp) woff += x; tot += x; }
-            if (f) lut[id] = a.things.v[c] * a.label_divisor + (long long)(sm.run[c] + woff + __popc(bal & lanemask_lt()) + 1);
+            for (int w8 = 0; w8 < 8; ++w8) { const int x = sc.wcnt[w8]; if (w8 < warp) woff += x; tot += x; }
+            if (f) lut[id] = things.v[c] * label_divisor + (long long)(sc.run[c] + woff + __popc(bal & lanemask_lt()) + 1);
             __syncthreads();
-            if (tid == 0) sm.run[c] += tot;
+            if (tid == 0) sc.run[c] += tot;
         }
         __syncthreads();
     }
 }
 
+// number of instance ids the label LUT must cover (device-side counts resolved here)
+__device__ __forceinline__ long long lut_extent(int k_fixed, int k_cap, const int32_t* status, const int32_t* k_dev)
+{
+    long long K = k_fixed >= 0 ? (long long)k_fixed : (long long)min(__ldcg(status + EMP_ST_K), k_cap);
+    if (k_dev) K = min(K, (long long)max(__ldcg(k_dev), 0));
+    return K;
+}
+
 template <int SEM, int IDM, int OUT>
 __global__ void __launch_bounds__(kAssignThreads, 3)
-assign_kernel(const AssignArgs a)
+assign_kernel(const __grid_constant__ AssignArgs a)
 {
     constexpr bool kCodes = (OUT == OUT_CODE16 || OUT == OUT_CODE32);
     constexpr uint32_t kClsBase = (OUT == OUT_CODE16) ? kClsBase16 : kClsBase32;
@@ -414,153 +456,145 @@ assign_kernel(const AssignArgs a)
     uint32_t* votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
     uint32_t* areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
     const int T = a.things.n > 0 ? a.things.n : 1;
+    const bool multi = a.things.n > 1;
 
-    // K is needed only after the first barrier: issue its load now so the latency overlaps
-    int K = 0;
-    if (IDM == ID_ARGMIN) K = a.k_fixed >= 0 ? a.k_fixed : min(__ldg(status + EMP_ST_K), a.k_cap);
+    // Thread <-> pixel map: warp w owns tile rows 4w..4w+3, lane l owns columns 2l, 2l+1 of each,
+    // so one warp-wide access covers one whole 64-pixel tile row: 512 B of int64 sem (LDG.128),
+    // 256 B of an offset plane (LDG.64), 128 B of uint16 codes (STG.32) — always full sectors.
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+    const int col0 = tx0 + 2 * lane;
+    const int row0 = ty0 + 4 * warp;
+    const bool cin = col0 < W;
+    const bool c1in = col0 + 1 < W;
 
+    // ---- phase 1a: issue every load of the tile before anything depends on one --------------
+    int Kld = 0;                // thread 0 resolves the device-side id count for the whole CTA
+    if ((IDM == ID_ARGMIN || kCodes) && tid == 0) Kld = (int)lut_extent(a.k_fixed, a.k_cap, status, a.k_dev);
     if (kCodes) {
         if (tid < kAreaBins) sm.area[tid] = 0;
         if (tid < kVoteSlots) { sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0; }
     }
-
-    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
-    const int col0 = tx0 + (tid & 15) * 4;
-    const int rowA = ty0 + (tid >> 4);              // second row group is rowA + 16
-    const bool cin = col0 < W;
-
-    // ---- phase 1: load sem / ids, classify --------------------------------------------------
-    unsigned inb = 0;           // bit p: pixel p is inside the image
-    unsigned thing = 0;         // bit p: pixel p takes an instance id
-    unsigned info[kPx / 2];     // two 16-bit info words per register
-    int idv[kPx];               // instance id (ID_DENSE / ID_COARSE) or argmin result
-    int flags = 0;
+    long long sv[kPx];
+    long long iv[kPx];
 #pragma unroll
-    for (int q = 0; q < kPx / 2; ++q) info[q] = 0;
+    for (int p = 0; p < kPx; ++p) { sv[p] = 0; iv[p] = 0; }
 #pragma unroll
-    for (int p = 0; p < kPx; ++p) idv[p] = 0;
-
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int row = rowA + i * 16;
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + i;
         const bool rin = row < H && cin;
-        const size_t rbase = (size_t)row * W;
-        unsigned w4[4] = {0, 0, 0, 0};
-        if (SEM == SEM_NONE) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) w4[j] = kInfoThing;
-        } else if (SEM == SEM_I64) {
-            const long long* sp = reinterpret_cast<const long long*>(a.sem) + (size_t)b * a.sem_stride + rbase + col0;
-            long long sv[4] = {0, 0, 0, 0};
-            if (rin && a.vec) {
-                const longlong2 u0 = __ldcs(reinterpret_cast<const longlong2*>(sp));
-                const longlong2 u1 = __ldcs(reinterpret_cast<const longlong2*>(sp) + 1);
-                sv[0] = u0.x; sv[1] = u0.y; sv[2] = u1.x; sv[3] = u1.y;
-            } else if (rin) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (col0 + j < W) sv[j] = __ldcs(sp + j);
-            }
-            const unsigned long long any = (unsigned long long)(sv[0] | sv[1] | sv[2] | sv[3]);
-            if (any == 0ull) {
-                // all background: class 0 (a thing only if 0 is in thing_list)
-                const unsigned w0 = (a.thing_bits & 1ull) ? kInfoThing : 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w4[j] = w0;
+        const size_t e = (size_t)row * W + col0;
+        if (SEM == SEM_I64) {
+            const long long* sp = reinterpret_cast<const long long*>(a.sem) + (size_t)b * a.sem_stride + e;
+            if (a.vec) {
+                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w4[j] = classify(sv[j], a);
+                if (rin) sv[2 * i] = __ldcs(sp);
+                if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
             }
-        } else {
-            const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + (size_t)b * a.sem_stride + rbase + col0;
-            unsigned u = 0;
-            if (rin && a.vec) {
-                u = __ldcs(reinterpret_cast<const unsigned*>(sp));
-            } else if (rin) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (col0 + j < W) u |= (unsigned)sp[j] << (8 * j);
-            }
-            if (u == 0u) {
-                const unsigned w0 = (a.thing_bits & 1ull) ? kInfoThing : 0u;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w4[j] = w0;
+        } else if (SEM == SEM_U8) {
+            const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + (size_t)b * a.sem_stride + e;
+            if (a.vec) {
+                if (rin) { const unsigned u = __ldcs(reinterpret_cast<const unsigned short*>(sp)); sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8; }
             } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) w4[j] = classify((long long)((u >> (8 * j)) & 255u), a);
+                if (rin) sv[2 * i] = sp[0];
+                if (rin && c1in) sv[2 * i + 1] = sp[1];
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = i * 4 + j;
-            const bool in = rin && (col0 + j < W);
-            if (!in) w4[j] = 0;
-            else inb |= 1u << p;
-            if (w4[j] & kInfoThing) thing |= 1u << p;
-            if (w4[j] & kInfoBad) flags |= EMP_FLAG_CLASS_RANGE;
-        }
-        info[i * 2] = w4[0] | (w4[1] << 16);
-        info[i * 2 + 1] = w4[2] | (w4[3] << 16);
-
         if (IDM == ID_DENSE) {
-            const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride + rbase + col0;
-            long long iv[4] = {0, 0, 0, 0};
-            if (rin && a.vec) {
-                const longlong2 u0 = __ldcs(reinterpret_cast<const longlong2*>(ip));
-                const longlong2 u1 = __ldcs(reinterpret_cast<const longlong2*>(ip) + 1);
-                iv[0] = u0.x; iv[1] = u0.y; iv[2] = u1.x; iv[3] = u1.y;
-            } else if (rin) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (col0 + j < W) iv[j] = __ldcs(ip + j);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (iv[j] < 0 || iv[j] > a.max_id) { flags |= EMP_FLAG_ID_RANGE; iv[j] = 0; }
-                idv[i * 4 + j] = (int)iv[j];
+            const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride + e;
+            if (a.vec) {
+                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(ip)); iv[2 * i] = u.x; iv[2 * i + 1] = u.y; }
+            } else {
+                if (rin) iv[2 * i] = __ldcs(ip);
+                if (rin && c1in) iv[2 * i + 1] = __ldcs(ip + 1);
             }
         } else if (IDM == ID_COARSE) {
             const int* ip = reinterpret_cast<const int*>(a.ids_in) + (size_t)b * a.ids_stride;
-            if (rin) {
-                const size_t crow = (size_t)(row >> a.shift) * a.wc;
+            const size_t crow = (size_t)(row >> a.shift) * a.wc;
+            if (rin) iv[2 * i] = __ldg(ip + crow + (col0 >> a.shift));
+            if (rin && c1in) iv[2 * i + 1] = __ldg(ip + crow + ((col0 + 1) >> a.shift));
+        }
+    }
+
+    // ---- phase 1b: classify ------------------------------------------------------------------
+    unsigned inb = 0;           // bit p: pixel p = 2*i + j is inside the image
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (col0 + j < W) {
-                        int v = __ldg(ip + crow + ((col0 + j) >> a.shift));
-                        if (v < 0 || v > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v = 0; }
-                        idv[i * 4 + j] = v;
-                    }
-                }
+    for (int i = 0; i < 4; ++i) {
+        const bool rin = (row0 + i) < H && cin;
+        if (rin) inb |= 1u << (2 * i);
+        if (rin && c1in) inb |= 2u << (2 * i);
+    }
+    unsigned long long orall = 0ull, orid = 0ull;
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) { orall |= (unsigned long long)sv[p]; orid |= (unsigned long long)iv[p]; }
+    // Fast path: the thread's 8 pixels are all in the image, all background class 0 (not a thing
+    // class) and carry no instance id that could void them — the bulk of an EM tile.
+    const bool pure_bg = SEM != SEM_NONE && inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull) &&
+                         (IDM != ID_DENSE || orid == 0ull);
+    unsigned w[kPx];            // 16-bit info word per pixel
+    unsigned thing = 0;         // bit p: pixel p takes an instance id
+    unsigned bad = 0;
+    int flags = 0;
+    int idv[kPx];               // instance id (ID_DENSE / ID_COARSE) or argmin result
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) { w[p] = 0; idv[p] = 0; }
+    if (!pure_bg) {
+        if (SEM == SEM_NONE) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) w[p] = kInfoThing;
+        } else if (orall < 64ull) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a);
+        }
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) {
+            w[p] = ((inb >> p) & 1u) ? w[p] : 0u;
+            thing |= ((w[p] >> 15) & 1u) << p;
+            bad |= ((w[p] >> 14) & 1u) << p;
+        }
+        if (bad) flags |= EMP_FLAG_CLASS_RANGE;
+        if (IDM != ID_ARGMIN) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) {
+                long long v = iv[p];
+                if (v < 0 || v > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v = 0; }
+                idv[p] = (int)v;
             }
         }
     }
 
     // ---- phase 2: nearest center over the culled candidate list ------------------------------
+    if ((IDM == ID_ARGMIN || kCodes) && tid == 0) sm.kshared = Kld;
     if (IDM == ID_ARGMIN) {
         const int any = __syncthreads_or(thing != 0);       // also publishes the smem tables
+        const int K = sm.kshared;
         if (any && K > 0) {                                 // block-uniform
             float ly[kPx], lx[kPx];
+            {
+                float2 fy[4], fx[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int row = rowA + i * 16;
-                float fy[4] = {0.f, 0.f, 0.f, 0.f}, fx[4] = {0.f, 0.f, 0.f, 0.f};
-                if ((thing >> (4 * i)) & 15u) {
-                    const float* oy = a.off + (size_t)b * a.off_stride + (size_t)row * W + col0;
+                for (int i = 0; i < 4; ++i) {
+                    fy[i] = make_float2(0.f, 0.f); fx[i] = make_float2(0.f, 0.f);
+                    const float* oy = a.off + (size_t)b * a.off_stride + (size_t)(row0 + i) * W + col0;
                     const float* ox = oy + HW;
+                    const unsigned t2 = (thing >> (2 * i)) & 3u;
                     if (a.vec) {
-                        const float4 u = __ldcs(reinterpret_cast<const float4*>(oy));
-                        const float4 w = __ldcs(reinterpret_cast<const float4*>(ox));
-                        fy[0] = u.x; fy[1] = u.y; fy[2] = u.z; fy[3] = u.w;
-                        fx[0] = w.x; fx[1] = w.y; fx[2] = w.z; fx[3] = w.w;
+                        if (t2) { fy[i] = __ldcs(reinterpret_cast<const float2*>(oy)); fx[i] = __ldcs(reinterpret_cast<const float2*>(ox)); }
                     } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (col0 + j < W) { fy[j] = __ldcs(oy + j); fx[j] = __ldcs(ox + j); }
-                        }
+                        if (t2 & 1u) { fy[i].x = __ldcs(oy); fx[i].x = __ldcs(ox); }
+                        if (t2 & 2u) { fy[i].y = __ldcs(oy + 1); fx[i].y = __ldcs(ox + 1); }
                     }
                 }
-                const float ycoord = __fmul_rn((float)row, a.step);     // arange(0, H*step, step)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ly[i * 4 + j] = __fadd_rn(ycoord, fy[j]);
-                    lx[i * 4 + j] = __fadd_rn(__fmul_rn((float)(col0 + j), a.step), fx[j]);
+                for (int i = 0; i < 4; ++i) {
+                    const float ycoord = __fmul_rn((float)(row0 + i), a.step);     // arange(0, H*step, step)
+                    ly[2 * i] = __fadd_rn(ycoord, fy[i].x);
+                    ly[2 * i + 1] = __fadd_rn(ycoord, fy[i].y);
+                    lx[2 * i] = __fadd_rn(__fmul_rn((float)col0, a.step), fx[i].x);
+                    lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
                 }
             }
             float by0 = CUDART_INF_F, by1 = -CUDART_INF_F, bx0 = CUDART_INF_F, bx1 = -CUDART_INF_F;
@@ -587,10 +621,10 @@ assign_kernel(const AssignArgs a)
             }
             __syncthreads();
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                by0 = fminf(by0, sm.red[w][0]); by1 = fmaxf(by1, sm.red[w][1]);
-                bx0 = fminf(bx0, sm.red[w][2]); bx1 = fmaxf(bx1, sm.red[w][3]);
-                nonfinite |= sm.redi[w];
+            for (int w8 = 0; w8 < 8; ++w8) {
+                by0 = fminf(by0, sm.red[w8][0]); by1 = fmaxf(by1, sm.red[w8][1]);
+                bx0 = fminf(bx0, sm.red[w8][2]); bx1 = fmaxf(bx1, sm.red[w8][3]);
+                nonfinite |= sm.redi[w8];
             }
 
             // sweep 1: U2 = min_k maxdist^2(box, c_k)
@@ -607,7 +641,7 @@ assign_kernel(const AssignArgs a)
             if (lane == 0) sm.red[warp][0] = u2;
             __syncthreads();
 #pragma unroll
-            for (int w = 0; w < 8; ++w) u2 = fminf(u2, sm.red[w][0]);
+            for (int w8 = 0; w8 < 8; ++w8) u2 = fminf(u2, sm.red[w8][0]);
             const float thr2 = nonfinite ? CUDART_INF_F : u2 * 1.001f + 1e-6f;
 
             float best_s[kPx];
@@ -632,7 +666,7 @@ assign_kernel(const AssignArgs a)
                 __syncthreads();
                 int woff = 0, tot = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) { const int cc = sm.wcnt[w]; if (w < warp) woff += cc; tot += cc; }
+                for (int w8 = 0; w8 < 8; ++w8) { const int cc = sm.wcnt[w8]; if (w8 < warp) woff += cc; tot += cc; }
                 if (keep) {
                     const int pos = n_list + woff + __popc(bal & lanemask_lt());
                     sm.cy[pos] = c.x; sm.cx[pos] = c.y; sm.ck[pos] = k;
@@ -641,6 +675,7 @@ assign_kernel(const AssignArgs a)
                 __syncthreads();
                 if (n_list > kCandCap - kAssignThreads || base + kAssignThreads >= K) {
                     if (thing != 0) {
+#pragma unroll 1
                         for (int j = 0; j < n_list; ++j) {
                             const float ccy = sm.cy[j], ccx = sm.cx[j];
                             const int ck = sm.ck[j];
@@ -649,10 +684,10 @@ assign_kernel(const AssignArgs a)
                                 if (thing & (1u << p)) {
                                     const float dy = __fsub_rn(ccy, ly[p]);
                                     const float dx = __fsub_rn(ccx, lx[p]);
-                                    const float s = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-                                    if (s < best_s[p]) {
-                                        if (__fsqrt_rn(s) < __fsqrt_rn(best_s[p])) best_k[p] = ck;
-                                        best_s[p] = s;
+                                    const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+                                    if (s2 < best_s[p]) {
+                                        if (__fsqrt_rn(s2) < __fsqrt_rn(best_s[p])) best_k[p] = ck;
+                                        best_s[p] = s2;
                                     }
                                 }
                             }
@@ -677,102 +712,116 @@ assign_kernel(const AssignArgs a)
         __syncthreads();                                    // publish the smem tables
     }
 
-    // ---- phase 3: outputs, votes, stuff areas --------------------------------------------------
+    // ---- phase 3: outputs, votes (postprocess.py:263-273), stuff areas (:284-291) ---------------
+    unsigned code[kPx];
     unsigned vkey = kEmptyKey, akey = kEmptyKey;
     int vcnt = 0, acnt = 0;
+    if (pure_bg) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int row = rowA + i * 16;
-        unsigned code[4] = {0, 0, 0, 0};
-        long long idout[4] = {0, 0, 0, 0};
+        for (int p = 0; p < kPx; ++p) code[p] = kCodes ? kClsBase : 0u;
+        akey = 0u; acnt = kPx;
+    } else {
+        unsigned voted = 0, stuff = 0;      // bit p: pixel p votes for its instance / counts as stuff area
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = i * 4 + j;
-            if (!(inb & (1u << p))) continue;
-            const unsigned w = (info[p >> 1] >> (16 * (p & 1))) & 0xFFFFu;
-            const bool th = (w & kInfoThing) != 0;
+        for (int p = 0; p < kPx; ++p) {
+            const bool in = (inb >> p) & 1u;
+            const bool th = (thing >> p) & 1u;
+            const bool bd = (bad >> p) & 1u;
             const int id = idv[p];
-            if (!kCodes) { idout[j] = th ? id : 0; continue; }
-            if (th) {
-                if (id != 0) {
-                    code[j] = (unsigned)id;
-                    const unsigned key = (unsigned)id * (unsigned)T + (w & 15u);
-                    if (key == vkey) ++vcnt;
-                    else { if (vcnt) vote_insert(sm, votes, vkey, vcnt); vkey = key; vcnt = 1; }
-                }
-            } else if (!(IDM == ID_DENSE && id > 0) && !(w & kInfoBad)) {
-                code[j] = kClsBase + w;
-                if (w == akey) ++acnt;
-                else { if (acnt) area_insert(sm, areas, akey, acnt); akey = w; acnt = 1; }
-            }
+            const bool v = th && id != 0;
+            const bool st = in && !th && !bd && !(IDM == ID_DENSE && id > 0);
+            voted |= (v ? 1u : 0u) << p;
+            stuff |= (st ? 1u : 0u) << p;
+            if (kCodes) code[p] = v ? (unsigned)id : (st ? kClsBase + w[p] : 0u);
+            else code[p] = th ? (unsigned)id : 0u;
         }
-        if (row < H && cin) {
-            const size_t o = (size_t)b * a.out_stride + (size_t)row * W + col0;
-            if (OUT == OUT_CODE16) {
-                unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
-                if (a.vec) {
-                    *reinterpret_cast<uint2*>(op) = make_uint2(code[0] | (code[1] << 16), code[2] | (code[3] << 16));
-                } else {
+        if (kCodes) {
+            // key of the thread's first voting / stuff pixel and how many of its pixels share it;
+            // stragglers with another key take the out-of-line insert
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col0 + j < W) op[j] = (unsigned short)code[j];
-                }
-            } else if (OUT == OUT_CODE32) {
-                unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
-                if (a.vec) {
-                    *reinterpret_cast<uint4*>(op) = make_uint4(code[0], code[1], code[2], code[3]);
-                } else {
+            for (int p = kPx - 1; p >= 0; --p) {
+                if ((voted >> p) & 1u) vkey = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
+                if ((stuff >> p) & 1u) akey = w[p];
+            }
+            unsigned vrest = 0, arest = 0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col0 + j < W) op[j] = code[j];
-                }
-            } else if (OUT == OUT_IDS64) {
-                long long* op = reinterpret_cast<long long*>(a.out) + o;
-                if (a.vec) {
-                    __stcs(reinterpret_cast<longlong2*>(op), make_longlong2(idout[0], idout[1]));
-                    __stcs(reinterpret_cast<longlong2*>(op) + 1, make_longlong2(idout[2], idout[3]));
-                } else {
+            for (int p = 0; p < kPx; ++p) {
+                const unsigned kv = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
+                const bool isv = (voted >> p) & 1u, isa = (stuff >> p) & 1u;
+                vcnt += (isv && kv == vkey) ? 1 : 0;
+                vrest |= ((isv && kv != vkey) ? 1u : 0u) << p;
+                acnt += (isa && w[p] == akey) ? 1 : 0;
+                arest |= ((isa && w[p] != akey) ? 1u : 0u) << p;
+            }
+            if (vrest | arest) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col0 + j < W) op[j] = idout[j];
-                }
-            } else {
-                int* op = reinterpret_cast<int*>(a.out) + o;
-                if (a.vec) {
-                    *reinterpret_cast<int4*>(op) = make_int4((int)idout[0], (int)idout[1], (int)idout[2], (int)idout[3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) if (col0 + j < W) op[j] = (int)idout[j];
+                for (int p = 0; p < kPx; ++p) {
+                    if ((vrest >> p) & 1u) vote_insert(sm, votes, (unsigned)idv[p] * (unsigned)T + (w[p] & 15u), 1);
+                    if ((arest >> p) & 1u) area_insert(sm, areas, w[p], 1);
                 }
             }
         }
     }
-
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = row0 + i;
+        if (row < H && cin) {
+            const size_t o = (size_t)b * a.out_stride + (size_t)row * W + col0;
+            const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
+            if (OUT == OUT_CODE16) {
+                unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
+                if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
+                else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
+            } else if (OUT == OUT_CODE32) {
+                unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
+                if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
+                else { op[0] = c0; if (c1in) op[1] = c1; }
+            } else if (OUT == OUT_IDS64) {
+                long long* op = reinterpret_cast<long long*>(a.out) + o;
+                if (a.vec) __stcs(reinterpret_cast<longlong2*>(op), make_longlong2((long long)c0, (long long)c1));
+                else { op[0] = (long long)c0; if (c1in) op[1] = (long long)c1; }
+            } else {
+                int* op = reinterpret_cast<int*>(a.out) + o;
+                if (a.vec) *reinterpret_cast<int2*>(op) = make_int2((int)c0, (int)c1);
+                else { op[0] = (int)c0; if (c1in) op[1] = (int)c1; }
+            }
+        }
+    }
     if (flags) atomicOr(status + EMP_ST_FLAGS, flags);
+
     if (kCodes) {
-        // warp-aggregated flush of each thread's last run, then one global atomic per live bin
+        // one warp-aggregated insert per distinct key, then one global atomic per live bin per CTA
         {
             const unsigned peers = __match_any_sync(0xffffffffu, vkey);
             const int sum = __reduce_add_sync(peers, vcnt);
-            if (vkey != kEmptyKey && sum > 0 && lane == __ffs(peers) - 1) vote_insert(sm, votes, vkey, sum);
+            if (vkey != kEmptyKey && lane == __ffs(peers) - 1) vote_insert(sm, votes, vkey, sum);
         }
         {
             const unsigned peers = __match_any_sync(0xffffffffu, akey);
             const int sum = __reduce_add_sync(peers, acnt);
-            if (akey != kEmptyKey && sum > 0 && lane == __ffs(peers) - 1) area_insert(sm, areas, akey, sum);
+            if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(sm, areas, akey, sum);
         }
         __syncthreads();
         if (tid < kAreaBins && sm.area[tid]) atomicAdd(areas + tid, sm.area[tid]);
         if (tid < kVoteSlots && sm.vkey[tid] != kEmptyKey && sm.vcnt[tid]) atomicAdd(votes + sm.vkey[tid], sm.vcnt[tid]);
 
-        // last CTA of this tile builds the label LUT (threadFenceReduction pattern)
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            const int total = (int)(gridDim.x * gridDim.y);
-            sm.last = (atomicAdd(status + EMP_ST_TICKET, 1) == total - 1) ? 1 : 0;
-        }
-        __syncthreads();
-        if (sm.last) {
-            __threadfence();
-            build_lut_tail(a, sm, status, votes, reinterpret_cast<long long*>(ws + a.o_lut));
+        // Label LUT.  Up to kSmemLut ids apply_lut rebuilds it in shared memory per CTA and nothing
+        // is left to do here.  Beyond that the last CTA of the tile builds it in global memory: the
+        // barrier orders every thread's atomics before thread 0's device-scope fence (fences are
+        // cumulative), which orders them before the ticket; votes are then read from L2 (__ldcg).
+        if (sm.kshared > kSmemLut) {                        // block-uniform
+            __syncthreads();
+            if (tid == 0) {
+                __threadfence();
+                const int total = (int)(gridDim.x * gridDim.y);
+                sm.last = (atomicAdd(status + EMP_ST_TICKET, 1) == total - 1) ? 1 : 0;
+            }
+            __syncthreads();
+            if (sm.last) {
+                __threadfence();
+                build_label_lut((long long)sm.kshared, votes, a.things, a.label_divisor, a.void_label,
+                                reinterpret_cast<long long*>(ws + a.o_lut), sm.lut);
+            }
         }
     }
 }
@@ -781,106 +830,111 @@ assign_kernel(const AssignArgs a)
 // K5  apply_lut — code map -> int64 panoptic labels (postprocess.py:281, :287-294).
 //   code 0 -> void; 1..CLS_BASE-1 -> lut[id]; CLS_BASE + c -> c*L if area[c] >= stuff_area else void
 // (a thing-class pixel never carries a class code, so no thing test is needed here).
-// 16 codes per thread per iteration; a vector of identical codes (background) decodes once.
+// 16 codes per thread per iteration; a thread whose codes are all equal (background) decodes once.
 // ---------------------------------------------------------------------------------------------
 struct ApplyArgs {
     char* ws; size_t ws_stride;
-    size_t o_codes, o_lut, o_areas;
+    size_t o_status, o_codes, o_lut, o_areas, o_votes;
+    const int32_t* k_dev;
+    int k_cap, k_fixed;
     long long* pan; size_t n_px;
     long long label_divisor, stuff_area, void_label;
     int vec;
+    Things things;
 };
 
 template <bool C16>
-__device__ __forceinline__ long long decode(unsigned code, const long long* __restrict__ lut,
-                                            const uint32_t* __restrict__ areas, const ApplyArgs& a)
+__device__ __forceinline__ long long decode(unsigned code, const long long* lut, const uint32_t* __restrict__ areas,
+                                            const ApplyArgs& a)
 {
     constexpr uint32_t base = C16 ? kClsBase16 : kClsBase32;
     if (code >= base) {
         const unsigned c = code - base;
         return ((long long)__ldg(areas + c) >= a.stuff_area) ? (long long)c * a.label_divisor : a.void_label;
     }
-    return __ldg(lut + code);
+    return lut[code];
 }
 
-template <bool C16>
-__device__ __forceinline__ void decode_store8(const unsigned (&w)[C16 ? 4 : 8], long long* out,
-                                              const long long* __restrict__ lut,
-                                              const uint32_t* __restrict__ areas, const ApplyArgs& a)
-{
-    longlong2* op = reinterpret_cast<longlong2*>(out);
-    if (C16) {
-        const unsigned w0 = w[0];
-        if (w[1] == w0 && w[2] == w0 && w[3] == w0 && (w0 >> 16) == (w0 & 0xFFFFu)) {
-            const long long v = decode<true>(w0 & 0xFFFFu, lut, areas, a);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) __stcs(op + q, make_longlong2(v, v));
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                __stcs(op + q, make_longlong2(decode<true>(w[q] & 0xFFFFu, lut, areas, a),
-                                              decode<true>(w[q] >> 16, lut, areas, a)));
-        }
-    } else {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            __stcs(op + q, make_longlong2(decode<false>(w[2 * q], lut, areas, a),
-                                          decode<false>(w[2 * q + 1], lut, areas, a)));
-    }
-}
-
+// Persistent CTAs (a few per SM).  Each first rebuilds the label LUT in shared memory from the
+// vote table (cheap: K is a few hundred) — or, beyond kSmemLut ids, uses the global LUT the assign
+// kernel's last CTA built — then streams: a warp handles 512 consecutive pixels per iteration, in
+// step q (0..7) lane l owns pixels 64q + 2l, 64q + 2l + 1, so each warp-wide load (128 B of uint16
+// codes) and store (512 B of int64 labels) is one contiguous run of full sectors.
 template <bool C16>
 __global__ void __launch_bounds__(256)
-apply_lut_kernel(const ApplyArgs a)
+apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
+    __shared__ long long s_lut[kSmemLut + 1];
+    __shared__ LutScratch s_sc;
+    __shared__ long long s_k;
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
-    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
+    const int32_t* status = reinterpret_cast<const int32_t*>(ws + a.o_status);
     const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
-    const size_t n16 = a.vec ? a.n_px / 16 : 0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint4* cp = reinterpret_cast<const uint4*>(ws + a.o_codes);
+    const int lane = threadIdx.x & 31;
 
-    if (C16) {
-        for (size_t i = t0; i < n16; i += stride) {
-            const uint4 u0 = __ldcs(cp + 2 * i), u1 = __ldcs(cp + 2 * i + 1);
-            const unsigned wa[4] = {u0.x, u0.y, u0.z, u0.w};
-            const unsigned wb[4] = {u1.x, u1.y, u1.z, u1.w};
-            decode_store8<true>(wa, pan + i * 16, lut, areas, a);
-            decode_store8<true>(wb, pan + i * 16 + 8, lut, areas, a);
+    if (threadIdx.x == 0) s_k = lut_extent(a.k_fixed, a.k_cap, status, a.k_dev);
+    __syncthreads();
+    const long long K = s_k;
+    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
+    if (K <= kSmemLut) {                                    // block-uniform
+        build_label_lut(K, reinterpret_cast<const uint32_t*>(ws + a.o_votes), a.things, a.label_divisor,
+                        a.void_label, s_lut, s_sc);
+        __syncthreads();
+        lut = s_lut;
+    }
+
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t n512 = a.vec ? a.n_px / 512 : 0;
+    for (size_t g = warp_global; g < n512; g += n_warps) {
+        const size_t base = g * 512;
+        unsigned c0[8], c1[8];
+        if (C16) {
+            const unsigned* cp = reinterpret_cast<const unsigned*>(ws + a.o_codes) + base / 2 + lane;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const unsigned u = __ldcs(cp + q * 32); c0[q] = u & 0xFFFFu; c1[q] = u >> 16; }
+        } else {
+            const uint2* cp = reinterpret_cast<const uint2*>(ws + a.o_codes) + base / 2 + lane;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const uint2 u = __ldcs(cp + q * 32); c0[q] = u.x; c1[q] = u.y; }
         }
-        const unsigned short* cs = reinterpret_cast<const unsigned short*>(ws + a.o_codes);
-        for (size_t i = n16 * 16 + t0; i < a.n_px; i += stride) pan[i] = decode<true>(cs[i], lut, areas, a);
-    } else {
-        for (size_t i = t0; i < n16; i += stride) {
-            const uint4 u0 = __ldcs(cp + 4 * i), u1 = __ldcs(cp + 4 * i + 1);
-            const uint4 u2 = __ldcs(cp + 4 * i + 2), u3 = __ldcs(cp + 4 * i + 3);
-            const unsigned wa[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-            const unsigned wb[8] = {u2.x, u2.y, u2.z, u2.w, u3.x, u3.y, u3.z, u3.w};
-            decode_store8<false>(wa, pan + i * 16, lut, areas, a);
-            decode_store8<false>(wb, pan + i * 16 + 8, lut, areas, a);
+        longlong2* op = reinterpret_cast<longlong2*>(pan + base) + lane;
+        bool same = true;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) same = same && (c0[q] == c0[0]) && (c1[q] == c0[0]);
+        if (same) {
+            const long long v = decode<C16>(c0[0], lut, areas, a);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) __stcs(op + q * 32, make_longlong2(v, v));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                __stcs(op + q * 32, make_longlong2(decode<C16>(c0[q], lut, areas, a), decode<C16>(c1[q], lut, areas, a)));
         }
-        const unsigned* cs = reinterpret_cast<const unsigned*>(ws + a.o_codes);
-        for (size_t i = n16 * 16 + t0; i < a.n_px; i += stride) pan[i] = decode<false>(cs[i], lut, areas, a);
+    }
+    // tail (and the whole image when it is not 512-divisible / aligned): one pixel per thread
+    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = n512 * 512 + t0; i < a.n_px; i += stride) {
+        const unsigned code = C16 ? (unsigned)reinterpret_cast<const unsigned short*>(ws + a.o_codes)[i]
+                                  : reinterpret_cast<const unsigned*>(ws + a.o_codes)[i];
+        pan[i] = decode<C16>(code, lut, areas, a);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-
 static int sm_count()
 {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        g_sm_count = n;
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n = v;
     }
-    return g_sm_count;
+    return n;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -897,7 +951,7 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
                    char* ws, size_t ws_stride, int k_cap, int64_t* ctr_out, int cap, cudaStream_t st)
 {
     const int lo = k / 2, hi = k - 1 - lo;
-    dim3 g1((L.wd + 3) / 4, (H + 2 * kNmsRows - 1) / (2 * kNmsRows), B);
+    dim3 g1((L.wd + kNmsWords - 1) / kNmsWords, (H + 8 * kNmsRows - 1) / (8 * kNmsRows), B);
     {
         ProfScope ps(ST_NMS, st);
         nms_peaks_kernel<<<g1, 256, 0, st>>>(hm, (size_t)H * W, H, W, thr, lo, hi, ws, ws_stride, L.mask, L.rowcnt, L.wd);
@@ -958,18 +1012,24 @@ void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th, long
     a.void_label = void_label;
 }
 
-int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long label_divisor, long long stuff_area,
-                 long long void_label, int64_t* pan_out, size_t n_px, cudaStream_t st)
+int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, int k_cap, int k_fixed, const int32_t* k_dev,
+                 const Things& things, long long label_divisor, long long stuff_area, long long void_label,
+                 int64_t* pan_out, size_t n_px, cudaStream_t st)
 {
     ApplyArgs a;
+    memset(&a, 0, sizeof(a));
     a.ws = ws; a.ws_stride = ws_stride;
-    a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas;
+    a.o_status = L.status; a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas; a.o_votes = L.votes;
+    a.k_dev = k_dev; a.k_cap = k_cap; a.k_fixed = k_fixed;
     a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = n_px;
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
-    a.vec = aligned16(pan_out) && (n_px % 16 == 0);
-    // one 16-pixel item per thread: short CTAs, so the last partial wave costs almost nothing
-    size_t blocks = ((a.vec ? n_px / 16 : n_px) + 255) / 256;
-    if (blocks > (1u << 30)) blocks = 1u << 30;
+    a.vec = aligned16(pan_out);
+    a.things = things;
+    // persistent: up to 6 CTAs of 8 warps per SM, each warp striding over 512-pixel groups
+    const size_t groups = a.vec ? n_px / 512 : 0;
+    size_t blocks = groups ? (groups + 7) / 8 : (n_px + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 6;
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
@@ -1149,8 +1209,8 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.max_id = max_id; a.k_dev = k_dev;
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
     if ((rc = launch_assign(1, sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-    return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out,
-                        (size_t)H * W, st);
+    return launch_apply(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, stuff_area,
+                        void_label, pan_out, (size_t)H * W, st);
 }
 
 EMP_API int emp_merge(const int64_t* sem, const int64_t* ins, int H, int W, int64_t label_divisor,
@@ -1212,8 +1272,8 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
         a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
         a.vec = (W % 4 == 0) && aligned16(a.sem) && aligned16(a.off);
         if ((rc = launch_assign(1, sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-        if ((rc = launch_apply(1, L, wst, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
-                               pan_out + (size_t)b * n_px, n_px, st))) return rc;
+        if ((rc = launch_apply(1, L, wst, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, stuff_area,
+                               void_label, pan_out + (size_t)b * n_px, n_px, st))) return rc;
     }
     return EMP_OK;
 }
