@@ -65,7 +65,7 @@ def lib():
     return _lib
 
 
-STAGES = ('nms_peaks', 'emit_centers', 'assign', 'build_lut', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs')
+STAGES = ('nms_peaks', 'emit_centers', 'classify', 'argmin_tiles', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs')
 
 
 def profile_enable(on):

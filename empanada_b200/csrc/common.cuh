@@ -42,7 +42,7 @@ constexpr int kNumClasses = EMP_MAX_CLASSES;
 // Per-tile workspace layout.  Everything in [0, zero_bytes) is cleared by one memset per call.
 struct WsLayout {
     size_t status, rowcnt, areas, votes, zero_bytes;
-    size_t mask, centers, lut, codes, total;
+    size_t mask, centers, lut, worklist, codes, total;
     int wd;          // mask words per row
     bool code16;
 };
@@ -52,16 +52,17 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     WsLayout L;
     if (n_things < 1) n_things = 1;
     L.wd = (W + 31) / 32;
-    L.code16 = (uint32_t)k_cap < kClsBase16;
+    L.code16 = (uint32_t)k_cap < 0xEFF0u;     // ids must stay below the "pending" codes (kPend16)
     size_t o = 0;
     L.status = o; o = align_up(o + sizeof(int32_t) * EMP_ST_WORDS, 256);
     L.rowcnt = o; o = align_up(o + sizeof(uint32_t) * (size_t)H, 256);
-    L.areas = o;  o = align_up(o + sizeof(uint32_t) * kNumClasses, 256);
+    L.areas = o;  o = align_up(o + sizeof(uint32_t) * (kNumClasses + 1), 256);   // [kNumClasses]: pixels that are not class-0 stuff
     L.votes = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1) * n_things, 256);
     L.zero_bytes = o;
     L.mask = o;    o = align_up(o + sizeof(uint32_t) * (size_t)H * L.wd, 256);
     L.centers = o; o = align_up(o + sizeof(float2) * ((size_t)k_cap + 1), 256);
     L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
+    L.worklist = o; o = align_up(o + sizeof(uint32_t) * (size_t)((W + 63) / 64) * (size_t)((H + 31) / 32), 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
     L.total = o;
     return L;

@@ -331,8 +331,6 @@ struct LutScratch {
     int wcnt[8];
 };
 
-constexpr int kSmemLut = 2048;      // ids whose label LUT apply_lut rebuilds in shared memory
-
 struct AssignSmem {
     float cy[kCandCap], cx[kCandCap];
     int ck[kCandCap];
@@ -359,24 +357,25 @@ __device__ __noinline__ void vote_insert(AssignSmem& sm, uint32_t* votes, unsign
     atomicAdd(votes + key, (uint32_t)cnt);      // table full: straight to global
 }
 
-__device__ __forceinline__ void area_insert(AssignSmem& sm, uint32_t* areas, unsigned cls, int cnt)
+__device__ __forceinline__ void area_insert(unsigned* s_area, uint32_t* areas, unsigned cls, int cnt)
 {
-    if (cls < (unsigned)kAreaBins) atomicAdd(&sm.area[cls], (unsigned)cnt);
+    if (cls < (unsigned)kAreaBins) atomicAdd(&s_area[cls], (unsigned)cnt);
     else atomicAdd(areas + cls, (uint32_t)cnt);
 }
 
 // 16-bit info word of one pixel: thing -> kInfoThing | thing index, stuff -> class id,
 // class outside [0, 4096) -> kInfoBad (reported through EMP_FLAG_CLASS_RANGE).
-__device__ __noinline__ unsigned classify_slow(long long v, const AssignArgs& a)
+__device__ __noinline__ unsigned classify_slow(long long v, unsigned long long thing_bits, int things_small,
+                                               const Things& things)
 {
     if ((unsigned long long)v < 64ull) {
         const unsigned c = (unsigned)v;
-        if ((a.thing_bits >> c) & 1ull)
-            return kInfoThing | (unsigned)__popcll(a.thing_bits & ((1ull << c) - 1ull));
+        if ((thing_bits >> c) & 1ull)
+            return kInfoThing | (unsigned)__popcll(thing_bits & ((1ull << c) - 1ull));
         return c;
     }
-    if (!a.things_small) {
-        const int t = thing_index(v, a.things);
+    if (!things_small) {
+        const int t = thing_index(v, things);
         if (t >= 0) return kInfoThing | (unsigned)t;
     }
     if (v < 0 || v >= kNumClasses) return kInfoBad;
@@ -436,6 +435,157 @@ __device__ __forceinline__ long long lut_extent(int k_fixed, int k_cap, const in
     long long K = k_fixed >= 0 ? (long long)k_fixed : (long long)min(__ldcg(status + EMP_ST_K), k_cap);
     if (k_dev) K = min(K, (long long)max(__ldcg(k_dev), 0));
     return K;
+}
+
+// Exact nearest center for the CTA's thing pixels (8 per thread): CTA-level cull of all K centers
+// against the box of shifted locations, ordered compaction of the survivors into shared memory,
+// warp-level cull against the warp's own box, then the reference's fp32 distance on what is left.
+// Must be called by all threads of the CTA (it synchronises).  idv[p] receives the 1-based id.
+__device__ __forceinline__ void nearest_center_8px(AssignSmem& sm, const float2* __restrict__ centers, int K,
+                                                   int chunksize, unsigned thing, const float (&ly)[kPx],
+                                                   const float (&lx)[kPx], int (&idv)[kPx])
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float by0 = CUDART_INF_F, by1 = -CUDART_INF_F, bx0 = CUDART_INF_F, bx1 = -CUDART_INF_F;
+    int nonfinite = 0;
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) {
+        if (thing & (1u << p)) {
+            by0 = fminf(by0, ly[p]); by1 = fmaxf(by1, ly[p]);
+            bx0 = fminf(bx0, lx[p]); bx1 = fmaxf(bx1, lx[p]);
+            if (!isfinite(ly[p]) || !isfinite(lx[p])) nonfinite = 1;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+    }
+    nonfinite = __any_sync(0xffffffffu, nonfinite) ? 1 : 0;
+    const float wy0 = by0, wy1 = by1, wx0 = bx0, wx1 = bx1;    // this warp's own box (4 x 64 px)
+    const bool wnf = nonfinite != 0;
+    const bool warp_has_thing = __any_sync(0xffffffffu, thing != 0);
+    if (lane == 0) {
+        sm.red[warp][0] = by0; sm.red[warp][1] = by1; sm.red[warp][2] = bx0; sm.red[warp][3] = bx1;
+        sm.redi[warp] = nonfinite;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) {
+        by0 = fminf(by0, sm.red[w8][0]); by1 = fmaxf(by1, sm.red[w8][1]);
+        bx0 = fminf(bx0, sm.red[w8][2]); bx1 = fmaxf(bx1, sm.red[w8][3]);
+        nonfinite |= sm.redi[w8];
+    }
+
+    // sweep 1: U2 = min_k maxdist^2(box, c_k)
+    float u2 = CUDART_INF_F;
+    for (int k = tid; k < K; k += kAssignThreads) {
+        const float2 c = __ldg(centers + k);
+        const float my = fmaxf(fabsf(c.x - by0), fabsf(c.x - by1));
+        const float mx = fmaxf(fabsf(c.y - bx0), fabsf(c.y - bx1));
+        u2 = fminf(u2, my * my + mx * mx);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) u2 = fminf(u2, __shfl_xor_sync(0xffffffffu, u2, d));
+    __syncthreads();                        // sm.red reads above are done
+    if (lane == 0) sm.red[warp][0] = u2;
+    __syncthreads();
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) u2 = fminf(u2, sm.red[w8][0]);
+    const float thr2 = nonfinite ? CUDART_INF_F : u2 * 1.001f + 1e-6f;
+
+    float best_s[kPx];
+    int best_k[kPx];
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) { best_s[p] = CUDART_INF_F; best_k[p] = -1; }
+
+    // sweep 2: ordered compaction of survivors, evaluated in batches of <= kCandCap
+    int n_list = 0;
+    for (int base = 0; base < K; base += kAssignThreads) {
+        const int k = base + tid;
+        bool keep = false;
+        float2 c = make_float2(0.f, 0.f);
+        if (k < K) {
+            c = __ldg(centers + k);                  // (cy, cx) = step * ctr (postprocess.py:152)
+            const float dy = fmaxf(fmaxf(by0 - c.x, c.x - by1), 0.f);
+            const float dx = fmaxf(fmaxf(bx0 - c.y, c.y - bx1), 0.f);
+            keep = nonfinite || !(dy * dy + dx * dx > thr2);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sm.wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) { const int cc = sm.wcnt[w8]; if (w8 < warp) woff += cc; tot += cc; }
+        if (keep) {
+            const int pos = n_list + woff + __popc(bal & lanemask_lt());
+            sm.cy[pos] = c.x; sm.cx[pos] = c.y; sm.ck[pos] = k;
+        }
+        n_list += tot;
+        __syncthreads();
+        if (n_list > kCandCap - kAssignThreads || base + kAssignThreads >= K) {
+            if (warp_has_thing) {                   // warp-uniform
+                // second, warp-level cull against this warp's own (much smaller) box: one
+                // lane per candidate, then only the survivors are evaluated per pixel
+                float wu2 = CUDART_INF_F;
+                for (int j0 = 0; j0 < n_list; j0 += 32) {
+                    const int j = j0 + lane;
+                    if (j < n_list) {
+                        const float ccy = sm.cy[j], ccx = sm.cx[j];
+                        const float my = fmaxf(fabsf(ccy - wy0), fabsf(ccy - wy1));
+                        const float mx = fmaxf(fabsf(ccx - wx0), fabsf(ccx - wx1));
+                        wu2 = fminf(wu2, my * my + mx * mx);
+                    }
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) wu2 = fminf(wu2, __shfl_xor_sync(0xffffffffu, wu2, d));
+                const float wthr2 = wnf ? CUDART_INF_F : wu2 * 1.001f + 1e-6f;
+                for (int j0 = 0; j0 < n_list; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool wkeep = false;
+                    if (j < n_list) {
+                        const float ccy = sm.cy[j], ccx = sm.cx[j];
+                        const float dy = fmaxf(fmaxf(wy0 - ccy, ccy - wy1), 0.f);
+                        const float dx = fmaxf(fmaxf(wx0 - ccx, ccx - wx1), 0.f);
+                        wkeep = wnf || !(dy * dy + dx * dx > wthr2);
+                    }
+                    unsigned m = __ballot_sync(0xffffffffu, wkeep);
+                    while (m) {                     // ascending j: ascending center index
+                        const int jj = j0 + __ffs(m) - 1;
+                        m &= m - 1;
+                        const float ccy = sm.cy[jj], ccx = sm.cx[jj];
+                        const int ck = sm.ck[jj];
+#pragma unroll
+                        for (int p = 0; p < kPx; ++p) {
+                            if (thing & (1u << p)) {
+                                const float dy = __fsub_rn(ccy, ly[p]);
+                                const float dx = __fsub_rn(ccx, lx[p]);
+                                const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+                                if (s2 < best_s[p]) {
+                                    if (__fsqrt_rn(s2) < __fsqrt_rn(best_s[p])) best_k[p] = ck;
+                                    best_s[p] = s2;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            n_list = 0;
+            __syncthreads();
+        }
+    }
+    const bool chunked = K > chunksize;
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) {
+        int id = 0;
+        if (thing & (1u << p)) {
+            if (chunked) id = (best_k[p] >= 0 && __fsqrt_rn(best_s[p]) < 1e5f) ? best_k[p] + 1 : 0;
+            else id = best_k[p] >= 0 ? best_k[p] + 1 : 1;
+        }
+        idv[p] = id;
+    }
 }
 
 template <int SEM, int IDM, int OUT>
@@ -547,7 +697,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
             for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
         } else {
 #pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a);
+            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
         }
 #pragma unroll
         for (int p = 0; p < kPx; ++p) {
@@ -568,8 +718,31 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 
     // ---- phase 2: nearest center over the culled candidate list ------------------------------
     if ((IDM == ID_ARGMIN || kCodes) && tid == 0) sm.kshared = Kld;
+    // Barrier 1 (also publishes the smem tables): is the whole CTA plain background?  Then its
+    // codes are a constant and it has nothing to vote, count or search: store and leave.  (The
+    // area of class 0 is derived in apply_lut from what the other CTAs count, see below.)
+    if (kCodes && SEM != SEM_NONE) {
+        if (!__syncthreads_or(!pure_bg)) {                  // block-uniform
+            {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const size_t o = (size_t)b * a.out_stride + (size_t)(row0 + i) * W + col0;
+                    if (OUT == OUT_CODE16) {
+                        unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
+                        if (a.vec) *reinterpret_cast<unsigned*>(op) = kClsBase | (kClsBase << 16);
+                        else { op[0] = (unsigned short)kClsBase; op[1] = (unsigned short)kClsBase; }
+                    } else {
+                        unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
+                        if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(kClsBase, kClsBase);
+                        else { op[0] = kClsBase; op[1] = kClsBase; }
+                    }
+                }
+                return;
+            }
+        }
+    }
     if (IDM == ID_ARGMIN) {
-        const int any = __syncthreads_or(thing != 0);       // also publishes the smem tables
+        const int any = __syncthreads_or(thing != 0);
         const int K = sm.kshared;
         if (any && K > 0) {                                 // block-uniform
             float ly[kPx], lx[kPx];
@@ -597,129 +770,18 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                     lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
                 }
             }
-            float by0 = CUDART_INF_F, by1 = -CUDART_INF_F, bx0 = CUDART_INF_F, bx1 = -CUDART_INF_F;
-            int nonfinite = 0;
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) {
-                if (thing & (1u << p)) {
-                    by0 = fminf(by0, ly[p]); by1 = fmaxf(by1, ly[p]);
-                    bx0 = fminf(bx0, lx[p]); bx1 = fmaxf(bx1, lx[p]);
-                    if (!isfinite(ly[p]) || !isfinite(lx[p])) nonfinite = 1;
-                }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
-                by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
-                bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
-                bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
-            }
-            nonfinite = __any_sync(0xffffffffu, nonfinite) ? 1 : 0;
-            if (lane == 0) {
-                sm.red[warp][0] = by0; sm.red[warp][1] = by1; sm.red[warp][2] = bx0; sm.red[warp][3] = bx1;
-                sm.redi[warp] = nonfinite;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) {
-                by0 = fminf(by0, sm.red[w8][0]); by1 = fmaxf(by1, sm.red[w8][1]);
-                bx0 = fminf(bx0, sm.red[w8][2]); bx1 = fmaxf(bx1, sm.red[w8][3]);
-                nonfinite |= sm.redi[w8];
-            }
-
-            // sweep 1: U2 = min_k maxdist^2(box, c_k)
-            float u2 = CUDART_INF_F;
-            for (int k = tid; k < K; k += kAssignThreads) {
-                const float2 c = __ldg(centers + k);
-                const float my = fmaxf(fabsf(c.x - by0), fabsf(c.x - by1));
-                const float mx = fmaxf(fabsf(c.y - bx0), fabsf(c.y - bx1));
-                u2 = fminf(u2, my * my + mx * mx);
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) u2 = fminf(u2, __shfl_xor_sync(0xffffffffu, u2, d));
-            __syncthreads();                        // sm.red reads above are done
-            if (lane == 0) sm.red[warp][0] = u2;
-            __syncthreads();
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) u2 = fminf(u2, sm.red[w8][0]);
-            const float thr2 = nonfinite ? CUDART_INF_F : u2 * 1.001f + 1e-6f;
-
-            float best_s[kPx];
-            int best_k[kPx];
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) { best_s[p] = CUDART_INF_F; best_k[p] = -1; }
-
-            // sweep 2: ordered compaction of survivors, evaluated in batches of <= kCandCap
-            int n_list = 0;
-            for (int base = 0; base < K; base += kAssignThreads) {
-                const int k = base + tid;
-                bool keep = false;
-                float2 c = make_float2(0.f, 0.f);
-                if (k < K) {
-                    c = __ldg(centers + k);                  // (cy, cx) = step * ctr (postprocess.py:152)
-                    const float dy = fmaxf(fmaxf(by0 - c.x, c.x - by1), 0.f);
-                    const float dx = fmaxf(fmaxf(bx0 - c.y, c.y - bx1), 0.f);
-                    keep = nonfinite || !(dy * dy + dx * dx > thr2);
-                }
-                const unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (lane == 0) sm.wcnt[warp] = __popc(bal);
-                __syncthreads();
-                int woff = 0, tot = 0;
-#pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) { const int cc = sm.wcnt[w8]; if (w8 < warp) woff += cc; tot += cc; }
-                if (keep) {
-                    const int pos = n_list + woff + __popc(bal & lanemask_lt());
-                    sm.cy[pos] = c.x; sm.cx[pos] = c.y; sm.ck[pos] = k;
-                }
-                n_list += tot;
-                __syncthreads();
-                if (n_list > kCandCap - kAssignThreads || base + kAssignThreads >= K) {
-                    if (thing != 0) {
-#pragma unroll 1
-                        for (int j = 0; j < n_list; ++j) {
-                            const float ccy = sm.cy[j], ccx = sm.cx[j];
-                            const int ck = sm.ck[j];
-#pragma unroll
-                            for (int p = 0; p < kPx; ++p) {
-                                if (thing & (1u << p)) {
-                                    const float dy = __fsub_rn(ccy, ly[p]);
-                                    const float dx = __fsub_rn(ccx, lx[p]);
-                                    const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-                                    if (s2 < best_s[p]) {
-                                        if (__fsqrt_rn(s2) < __fsqrt_rn(best_s[p])) best_k[p] = ck;
-                                        best_s[p] = s2;
-                                    }
-                                }
-                            }
-                        }
-                    }
-                    n_list = 0;
-                    __syncthreads();
-                }
-            }
-            const bool chunked = K > a.chunksize;
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) {
-                int id = 0;
-                if (thing & (1u << p)) {
-                    if (chunked) id = (best_k[p] >= 0 && __fsqrt_rn(best_s[p]) < 1e5f) ? best_k[p] + 1 : 0;
-                    else id = best_k[p] >= 0 ? best_k[p] + 1 : 1;
-                }
-                idv[p] = id;
-            }
+            nearest_center_8px(sm, centers, K, a.chunksize, thing, ly, lx, idv);
         }
-    } else if (kCodes) {
-        __syncthreads();                                    // publish the smem tables
     }
 
     // ---- phase 3: outputs, votes (postprocess.py:263-273), stuff areas (:284-291) ---------------
     unsigned code[kPx];
     unsigned vkey = kEmptyKey, akey = kEmptyKey;
     int vcnt = 0, acnt = 0;
+    int deficit = 0;            // in-image pixels that are NOT class-0 stuff (area[0] = H*W - sum)
     if (pure_bg) {
 #pragma unroll
         for (int p = 0; p < kPx; ++p) code[p] = kCodes ? kClsBase : 0u;
-        akey = 0u; acnt = kPx;
     } else {
         unsigned voted = 0, stuff = 0;      // bit p: pixel p votes for its instance / counts as stuff area
 #pragma unroll
@@ -729,10 +791,12 @@ assign_kernel(const __grid_constant__ AssignArgs a)
             const bool bd = (bad >> p) & 1u;
             const int id = idv[p];
             const bool v = th && id != 0;
-            const bool st = in && !th && !bd && !(IDM == ID_DENSE && id > 0);
+            const bool st0 = in && !th && !bd && !(IDM == ID_DENSE && id > 0);
+            const bool st = st0 && w[p] != 0u;              // class-0 stuff is counted by complement
+            deficit += (in && !(st0 && w[p] == 0u)) ? 1 : 0;
             voted |= (v ? 1u : 0u) << p;
             stuff |= (st ? 1u : 0u) << p;
-            if (kCodes) code[p] = v ? (unsigned)id : (st ? kClsBase + w[p] : 0u);
+            if (kCodes) code[p] = v ? (unsigned)id : (st0 ? kClsBase + w[p] : 0u);
             else code[p] = th ? (unsigned)id : 0u;
         }
         if (kCodes) {
@@ -757,7 +821,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 #pragma unroll
                 for (int p = 0; p < kPx; ++p) {
                     if ((vrest >> p) & 1u) vote_insert(sm, votes, (unsigned)idv[p] * (unsigned)T + (w[p] & 15u), 1);
-                    if ((arest >> p) & 1u) area_insert(sm, areas, w[p], 1);
+                    if ((arest >> p) & 1u) area_insert(sm.area, areas, w[p], 1);
                 }
             }
         }
@@ -799,31 +863,358 @@ assign_kernel(const __grid_constant__ AssignArgs a)
         {
             const unsigned peers = __match_any_sync(0xffffffffu, akey);
             const int sum = __reduce_add_sync(peers, acnt);
-            if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(sm, areas, akey, sum);
+            if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(sm.area, areas, akey, sum);
+        }
+        {
+            const int sum = __reduce_add_sync(0xffffffffu, deficit);
+            if (sum && lane == 0) atomicAdd(&sm.area[0], (unsigned)sum);    // bin 0 holds the deficit
         }
         __syncthreads();
-        if (tid < kAreaBins && sm.area[tid]) atomicAdd(areas + tid, sm.area[tid]);
+        if (tid < kAreaBins && sm.area[tid]) atomicAdd(areas + (tid == 0 ? kNumClasses : tid), sm.area[tid]);
         if (tid < kVoteSlots && sm.vkey[tid] != kEmptyKey && sm.vcnt[tid]) atomicAdd(votes + sm.vkey[tid], sm.vcnt[tid]);
 
-        // Label LUT.  Up to kSmemLut ids apply_lut rebuilds it in shared memory per CTA and nothing
-        // is left to do here.  Beyond that the last CTA of the tile builds it in global memory: the
-        // barrier orders every thread's atomics before thread 0's device-scope fence (fences are
-        // cumulative), which orders them before the ticket; votes are then read from L2 (__ldcg).
-        if (sm.kshared > kSmemLut) {                        // block-uniform
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                const int total = (int)(gridDim.x * gridDim.y);
-                sm.last = (atomicAdd(status + EMP_ST_TICKET, 1) == total - 1) ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused get_panoptic_segmentation path (emp_panoptic_batched) = three kernels per tile:
+//
+//   classify      every pixel: sem (8 B/px) -> code map (2 B/px).  Stuff pixels get their class
+//                 code, thing pixels a "pending" code (kPend + thing index).  Few registers, no
+//                 search: a pure streaming kernel at high occupancy.  CTAs holding thing pixels
+//                 append their tile to a worklist; stuff areas are counted here (class 0 by
+//                 complement, so plain-background CTAs count nothing and leave after one barrier).
+//   argmin_tiles  persistent CTAs over the worklist (thing tiles only, ~1/4 of an EM tile):
+//                 offsets (8 B/px, thing rows only) -> exact nearest center -> id codes + votes.
+//                 The last CTA to finish builds the label LUT.
+//   apply_lut     code map -> int64 labels.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPend16 = 0xEFF0u, kPend32 = 0xFFFFEFF0u;    // + thing index: thing pixel awaiting its id
+
+struct ClassifyArgs {
+    const void* sem;
+    void* codes;
+    char* ws;
+    size_t o_status, o_areas, o_worklist;
+    int H, W, vec;
+    unsigned long long thing_bits;
+    int things_small;
+    Things things;
+};
+
+template <int SEM, bool C16>
+__global__ void __launch_bounds__(256, 5)
+classify_kernel(const __grid_constant__ ClassifyArgs a)
+{
+    constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
+    constexpr uint32_t kPend = C16 ? kPend16 : kPend32;
+    __shared__ unsigned s_area[kAreaBins];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = a.H, W = a.W;
+    int32_t* status = reinterpret_cast<int32_t*>(a.ws + a.o_status);
+    uint32_t* areas = reinterpret_cast<uint32_t*>(a.ws + a.o_areas);
+    const bool multi = a.things.n > 1;
+
+    const int col0 = blockIdx.x * kTileW + 2 * lane;
+    const int row0 = blockIdx.y * kTileH + 4 * warp;
+    const bool cin = col0 < W, c1in = col0 + 1 < W;
+    if (tid < kAreaBins) s_area[tid] = 0;
+
+    long long sv[kPx];
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) sv[p] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool rin = row0 + i < H && cin;
+        const size_t e = (size_t)(row0 + i) * W + col0;
+        if (SEM == SEM_I64) {
+            const long long* sp = reinterpret_cast<const long long*>(a.sem) + e;
+            if (a.vec) {
+                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
+            } else {
+                if (rin) sv[2 * i] = __ldcs(sp);
+                if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
             }
-            __syncthreads();
-            if (sm.last) {
-                __threadfence();
-                build_label_lut((long long)sm.kshared, votes, a.things, a.label_divisor, a.void_label,
-                                reinterpret_cast<long long*>(ws + a.o_lut), sm.lut);
+        } else {
+            const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + e;
+            if (a.vec) {
+                if (rin) { const unsigned u = __ldcs(reinterpret_cast<const unsigned short*>(sp)); sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8; }
+            } else {
+                if (rin) sv[2 * i] = sp[0];
+                if (rin && c1in) sv[2 * i + 1] = sp[1];
             }
         }
     }
+    unsigned inb = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool rin = row0 + i < H && cin;
+        if (rin) inb |= 1u << (2 * i);
+        if (rin && c1in) inb |= 2u << (2 * i);
+    }
+    unsigned long long orall = 0ull;
+#pragma unroll
+    for (int p = 0; p < kPx; ++p) orall |= (unsigned long long)sv[p];
+    const bool pure_bg = inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull);
+
+    unsigned code[kPx];
+    unsigned thing = 0, akey = kEmptyKey;
+    int acnt = 0, deficit = 0, flags = 0;
+    if (pure_bg) {
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) code[p] = kClsBase;
+    } else {
+        unsigned w[kPx];
+        if (orall < 64ull) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
+        } else {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
+        }
+        unsigned stuff = 0;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) {
+            const bool in = (inb >> p) & 1u;
+            const bool th = in && (w[p] & kInfoThing);
+            const bool bd = in && (w[p] & kInfoBad);
+            const bool st0 = in && !th && !bd;
+            thing |= (th ? 1u : 0u) << p;
+            if (bd) flags |= EMP_FLAG_CLASS_RANGE;
+            code[p] = th ? kPend + (w[p] & 15u) : (st0 ? kClsBase + w[p] : 0u);
+            deficit += (in && !(st0 && w[p] == 0u)) ? 1 : 0;    // class-0 stuff is counted by complement
+            stuff |= ((st0 && w[p] != 0u) ? 1u : 0u) << p;
+        }
+#pragma unroll
+        for (int p = kPx - 1; p >= 0; --p) if ((stuff >> p) & 1u) akey = w[p];
+        unsigned arest = 0;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) {
+            const bool isa = (stuff >> p) & 1u;
+            acnt += (isa && w[p] == akey) ? 1 : 0;
+            arest |= ((isa && w[p] != akey) ? 1u : 0u) << p;
+        }
+        if (arest) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) if ((arest >> p) & 1u) area_insert(s_area, areas, w[p], 1);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (row0 + i < H && cin) {
+            const size_t o = (size_t)(row0 + i) * W + col0;
+            const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
+            if (C16) {
+                unsigned short* op = reinterpret_cast<unsigned short*>(a.codes) + o;
+                if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
+                else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
+            } else {
+                unsigned* op = reinterpret_cast<unsigned*>(a.codes) + o;
+                if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
+                else { op[0] = c0; if (c1in) op[1] = c1; }
+            }
+        }
+    }
+    // Barrier 1 (also publishes s_area): plain-background CTAs are done.
+    if (!__syncthreads_or(!pure_bg)) return;                        // block-uniform
+
+    if (flags) atomicOr(status + EMP_ST_FLAGS, flags);
+    {
+        const unsigned peers = __match_any_sync(0xffffffffu, akey);
+        const int sum = __reduce_add_sync(peers, acnt);
+        if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(s_area, areas, akey, sum);
+    }
+    {
+        const int sum = __reduce_add_sync(0xffffffffu, deficit);
+        if (sum && lane == 0) atomicAdd(&s_area[0], (unsigned)sum);             // bin 0 holds the deficit
+    }
+    const int any_thing = __syncthreads_or(thing != 0);
+    if (tid < kAreaBins && s_area[tid]) atomicAdd(areas + (tid == 0 ? kNumClasses : tid), s_area[tid]);
+    if (any_thing && tid == 0) {
+        const int idx = atomicAdd(status + EMP_ST_NTILES, 1);
+        reinterpret_cast<uint32_t*>(a.ws + a.o_worklist)[idx] = blockIdx.y * gridDim.x + blockIdx.x;
+    }
+}
+
+struct ArgminArgs {
+    const float* off;
+    void* codes;
+    char* ws;
+    size_t o_status, o_centers, o_votes, o_lut, o_worklist;
+    int H, W, tiles_x, vec, k_cap, chunksize;
+    float step;
+    long long label_divisor, void_label;
+    Things things;
+};
+
+template <bool C16>
+__global__ void __launch_bounds__(kAssignThreads, 3)
+argmin_tiles_kernel(const __grid_constant__ ArgminArgs a)
+{
+    constexpr uint32_t kPend = C16 ? kPend16 : kPend32;
+    __shared__ AssignSmem sm;
+    __shared__ int s_ntiles;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = a.H, W = a.W;
+    const size_t HW = (size_t)H * W;
+    int32_t* status = reinterpret_cast<int32_t*>(a.ws + a.o_status);
+    const float2* centers = reinterpret_cast<const float2*>(a.ws + a.o_centers);
+    uint32_t* votes = reinterpret_cast<uint32_t*>(a.ws + a.o_votes);
+    const uint32_t* worklist = reinterpret_cast<const uint32_t*>(a.ws + a.o_worklist);
+    const int T = a.things.n > 0 ? a.things.n : 1;
+
+    if (tid == 0) {
+        sm.kshared = min(__ldcg(status + EMP_ST_K), a.k_cap);
+        s_ntiles = __ldcg(status + EMP_ST_NTILES);
+    }
+    if (tid < kVoteSlots) { sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0; }
+    __syncthreads();
+    const int K = sm.kshared;
+    const int ntiles = s_ntiles;
+
+    for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {          // block-uniform
+        const unsigned tile = __ldcg(worklist + it);
+        const int col0 = (int)(tile % (unsigned)a.tiles_x) * kTileW + 2 * lane;
+        const int row0 = (int)(tile / (unsigned)a.tiles_x) * kTileH + 4 * warp;
+        const bool cin = col0 < W, c1in = col0 + 1 < W;
+
+        // codes written by classify (L2-resident): which of my pixels await an id?
+        unsigned code[kPx];
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) code[p] = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool rin = row0 + i < H && cin;
+            const size_t o = (size_t)(row0 + i) * W + col0;
+            if (C16) {
+                const unsigned short* cp = reinterpret_cast<const unsigned short*>(a.codes) + o;
+                if (a.vec) {
+                    if (rin) { const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(cp)); code[2 * i] = u & 0xFFFFu; code[2 * i + 1] = u >> 16; }
+                } else {
+                    if (rin) code[2 * i] = __ldcg(cp);
+                    if (rin && c1in) code[2 * i + 1] = __ldcg(cp + 1);
+                }
+            } else {
+                const unsigned* cp = reinterpret_cast<const unsigned*>(a.codes) + o;
+                if (a.vec) {
+                    if (rin) { const uint2 u = __ldcg(reinterpret_cast<const uint2*>(cp)); code[2 * i] = u.x; code[2 * i + 1] = u.y; }
+                } else {
+                    if (rin) code[2 * i] = __ldcg(cp);
+                    if (rin && c1in) code[2 * i + 1] = __ldcg(cp + 1);
+                }
+            }
+        }
+        unsigned thing = 0;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) thing |= ((code[p] - kPend < 16u) ? 1u : 0u) << p;
+
+        int idv[kPx];
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) idv[p] = 0;
+        if (K > 0) {                                                    // block-uniform
+            float ly[kPx], lx[kPx];
+            float2 fy[4], fx[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                fy[i] = make_float2(0.f, 0.f); fx[i] = make_float2(0.f, 0.f);
+                const float* oy = a.off + (size_t)(row0 + i) * W + col0;
+                const float* ox = oy + HW;
+                const unsigned t2 = (thing >> (2 * i)) & 3u;
+                if (a.vec) {
+                    if (t2) { fy[i] = __ldcs(reinterpret_cast<const float2*>(oy)); fx[i] = __ldcs(reinterpret_cast<const float2*>(ox)); }
+                } else {
+                    if (t2 & 1u) { fy[i].x = __ldcs(oy); fx[i].x = __ldcs(ox); }
+                    if (t2 & 2u) { fy[i].y = __ldcs(oy + 1); fx[i].y = __ldcs(ox + 1); }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float ycoord = __fmul_rn((float)(row0 + i), a.step);         // arange(0, H*step, step)
+                ly[2 * i] = __fadd_rn(ycoord, fy[i].x);
+                ly[2 * i + 1] = __fadd_rn(ycoord, fy[i].y);
+                lx[2 * i] = __fadd_rn(__fmul_rn((float)col0, a.step), fx[i].x);
+                lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
+            }
+            nearest_center_8px(sm, centers, K, a.chunksize, thing, ly, lx, idv);
+        }
+
+        // id codes back into the code map (only rows that held pending pixels), votes
+        unsigned vkey = kEmptyKey;
+        int vcnt = 0;
+        unsigned vrest = 0;
+#pragma unroll
+        for (int p = kPx - 1; p >= 0; --p)
+            if (((thing >> p) & 1u) && idv[p] != 0) vkey = (unsigned)idv[p] * (unsigned)T + (code[p] - kPend);
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) {
+            const bool isv = ((thing >> p) & 1u) && idv[p] != 0;
+            const unsigned kv = (unsigned)idv[p] * (unsigned)T + (code[p] - kPend);
+            vcnt += (isv && kv == vkey) ? 1 : 0;
+            vrest |= ((isv && kv != vkey) ? 1u : 0u) << p;
+        }
+        if (vrest) {
+#pragma unroll
+            for (int p = 0; p < kPx; ++p)
+                if ((vrest >> p) & 1u) vote_insert(sm, votes, (unsigned)idv[p] * (unsigned)T + (code[p] - kPend), 1);
+        }
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, vkey);
+            const int sum = __reduce_add_sync(peers, vcnt);
+            if (vkey != kEmptyKey && lane == __ffs(peers) - 1) vote_insert(sm, votes, vkey, sum);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned t2 = (thing >> (2 * i)) & 3u;
+            if (t2) {
+                const unsigned c0 = (t2 & 1u) ? (unsigned)idv[2 * i] : code[2 * i];
+                const unsigned c1 = (t2 & 2u) ? (unsigned)idv[2 * i + 1] : code[2 * i + 1];
+                const size_t o = (size_t)(row0 + i) * W + col0;
+                if (C16) {
+                    unsigned short* op = reinterpret_cast<unsigned short*>(a.codes) + o;
+                    if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
+                    else { if (t2 & 1u) op[0] = (unsigned short)c0; if (t2 & 2u) op[1] = (unsigned short)c1; }
+                } else {
+                    unsigned* op = reinterpret_cast<unsigned*>(a.codes) + o;
+                    if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
+                    else { if (t2 & 1u) op[0] = c0; if (t2 & 2u) op[1] = c1; }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < kVoteSlots) {
+            if (sm.vkey[tid] != kEmptyKey && sm.vcnt[tid]) atomicAdd(votes + sm.vkey[tid], sm.vcnt[tid]);
+            sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0;
+        }
+        __syncthreads();
+    }
+
+    // Last CTA builds the label LUT.  The barrier orders every thread's atomics before thread 0's
+    // device-scope fence (fences are cumulative), which orders them before the ticket; the last CTA
+    // reads the votes straight from L2 (__ldcg).
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        sm.last = (atomicAdd(status + EMP_ST_TICKET, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sm.last) {
+        __threadfence();
+        build_label_lut((long long)K, votes, a.things, a.label_divisor, a.void_label,
+                        reinterpret_cast<long long*>(a.ws + a.o_lut), sm.lut);
+    }
+}
+
+// label LUT for the merge entry points (emp_merge / emp_merge_coarse): one CTA
+__global__ void __launch_bounds__(256)
+build_lut_kernel(char* ws, size_t o_status, size_t o_votes, size_t o_lut, int k_cap, int k_fixed,
+                 const int32_t* k_dev, const __grid_constant__ Things things, long long label_divisor, long long void_label)
+{
+    __shared__ LutScratch sc;
+    __shared__ long long s_k;
+    if (threadIdx.x == 0) s_k = lut_extent(k_fixed, k_cap, reinterpret_cast<const int32_t*>(ws + o_status), k_dev);
+    __syncthreads();
+    build_label_lut(s_k, reinterpret_cast<const uint32_t*>(ws + o_votes), things, label_divisor, void_label,
+                    reinterpret_cast<long long*>(ws + o_lut), sc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -834,59 +1225,41 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 // ---------------------------------------------------------------------------------------------
 struct ApplyArgs {
     char* ws; size_t ws_stride;
-    size_t o_status, o_codes, o_lut, o_areas, o_votes;
-    const int32_t* k_dev;
-    int k_cap, k_fixed;
+    size_t o_codes, o_lut, o_areas;
     long long* pan; size_t n_px;
     long long label_divisor, stuff_area, void_label;
     int vec;
-    Things things;
 };
 
 template <bool C16>
-__device__ __forceinline__ long long decode(unsigned code, const long long* lut, const uint32_t* __restrict__ areas,
-                                            const ApplyArgs& a)
+__device__ __forceinline__ long long decode(unsigned code, const long long* __restrict__ lut,
+                                            const uint32_t* __restrict__ areas, const ApplyArgs& a)
 {
     constexpr uint32_t base = C16 ? kClsBase16 : kClsBase32;
     if (code >= base) {
         const unsigned c = code - base;
-        return ((long long)__ldg(areas + c) >= a.stuff_area) ? (long long)c * a.label_divisor : a.void_label;
+        const long long area = c ? (long long)__ldg(areas + c) : (long long)a.n_px - (long long)__ldg(areas + kNumClasses);
+        return (area >= a.stuff_area) ? (long long)c * a.label_divisor : a.void_label;
     }
-    return lut[code];
+    return __ldg(lut + code);
 }
 
-// Persistent CTAs (a few per SM).  Each first rebuilds the label LUT in shared memory from the
-// vote table (cheap: K is a few hundred) — or, beyond kSmemLut ids, uses the global LUT the assign
-// kernel's last CTA built — then streams: a warp handles 512 consecutive pixels per iteration, in
-// step q (0..7) lane l owns pixels 64q + 2l, 64q + 2l + 1, so each warp-wide load (128 B of uint16
-// codes) and store (512 B of int64 labels) is one contiguous run of full sectors.
+// A warp handles 512 consecutive pixels: in step q (0..7) lane l owns pixels 64q + 2l, 64q + 2l + 1,
+// so each warp-wide load (128 B of uint16 codes) and store (512 B of int64 labels) is one
+// contiguous run of full sectors.  One group per warp: short CTAs, cheap last wave.
 template <bool C16>
 __global__ void __launch_bounds__(256)
 apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
-    __shared__ long long s_lut[kSmemLut + 1];
-    __shared__ LutScratch s_sc;
-    __shared__ long long s_k;
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
-    const int32_t* status = reinterpret_cast<const int32_t*>(ws + a.o_status);
+    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
     const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
     const int lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) s_k = lut_extent(a.k_fixed, a.k_cap, status, a.k_dev);
-    __syncthreads();
-    const long long K = s_k;
-    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
-    if (K <= kSmemLut) {                                    // block-uniform
-        build_label_lut(K, reinterpret_cast<const uint32_t*>(ws + a.o_votes), a.things, a.label_divisor,
-                        a.void_label, s_lut, s_sc);
-        __syncthreads();
-        lut = s_lut;
-    }
-
     const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t n512 = a.vec ? a.n_px / 512 : 0;
+
     for (size_t g = warp_global; g < n512; g += n_warps) {
         const size_t base = g * 512;
         unsigned c0[8], c1[8];
@@ -1012,29 +1385,79 @@ void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th, long
     a.void_label = void_label;
 }
 
-int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, int k_cap, int k_fixed, const int32_t* k_dev,
-                 const Things& things, long long label_divisor, long long stuff_area, long long void_label,
-                 int64_t* pan_out, size_t n_px, cudaStream_t st)
+int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long label_divisor, long long stuff_area,
+                 long long void_label, int64_t* pan_out, size_t n_px, cudaStream_t st)
 {
     ApplyArgs a;
     memset(&a, 0, sizeof(a));
     a.ws = ws; a.ws_stride = ws_stride;
-    a.o_status = L.status; a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas; a.o_votes = L.votes;
-    a.k_dev = k_dev; a.k_cap = k_cap; a.k_fixed = k_fixed;
+    a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas;
     a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = n_px;
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
     a.vec = aligned16(pan_out);
-    a.things = things;
-    // persistent: up to 6 CTAs of 8 warps per SM, each warp striding over 512-pixel groups
     const size_t groups = a.vec ? n_px / 512 : 0;
     size_t blocks = groups ? (groups + 7) / 8 : (n_px + 255) / 256;
-    const size_t cap = (size_t)sm_count() * 6;
-    if (blocks > cap) blocks = cap;
+    if (blocks > (1u << 30)) blocks = 1u << 30;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
     if (L.code16) apply_lut_kernel<true><<<grid, 256, 0, st>>>(a);
     else apply_lut_kernel<false><<<grid, 256, 0, st>>>(a);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}
+
+int launch_build_lut(const WsLayout& L, char* ws, int k_cap, int k_fixed, const int32_t* k_dev, const Things& th,
+                     long long label_divisor, long long void_label, cudaStream_t st)
+{
+    ProfScope ps(ST_LUT, st);
+    build_lut_kernel<<<1, 256, 0, st>>>(ws, L.status, L.votes, L.lut, k_cap, k_fixed, k_dev, th, label_divisor, void_label);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}
+
+// classify -> argmin_tiles (+ LUT) for one tile of the fused path
+int launch_classify_argmin(const void* sem, int sem_u8, const float* off, int H, int W, const WsLayout& L, char* ws,
+                           int k_cap, const Things& th, long long label_divisor, long long void_label, cudaStream_t st)
+{
+    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
+    ClassifyArgs c;
+    memset(&c, 0, sizeof(c));
+    c.sem = sem; c.codes = ws + L.codes; c.ws = ws;
+    c.o_status = L.status; c.o_areas = L.areas; c.o_worklist = L.worklist;
+    c.H = H; c.W = W;
+    c.vec = (W % 4 == 0) && aligned16(sem);
+    c.things = th; c.thing_bits = 0ull; c.things_small = 1;
+    for (int i = 0; i < th.n; ++i) {
+        if (th.v[i] >= 0 && th.v[i] < 64) c.thing_bits |= 1ull << th.v[i];
+        else c.things_small = 0;
+    }
+    dim3 grid(tiles_x, tiles_y, 1);
+    {
+        ProfScope ps(ST_ASSIGN, st);
+        if (L.code16) {
+            if (sem_u8) classify_kernel<SEM_U8, true><<<grid, 256, 0, st>>>(c);
+            else classify_kernel<SEM_I64, true><<<grid, 256, 0, st>>>(c);
+        } else {
+            if (sem_u8) classify_kernel<SEM_U8, false><<<grid, 256, 0, st>>>(c);
+            else classify_kernel<SEM_I64, false><<<grid, 256, 0, st>>>(c);
+        }
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    ArgminArgs g;
+    memset(&g, 0, sizeof(g));
+    g.off = off; g.codes = ws + L.codes; g.ws = ws;
+    g.o_status = L.status; g.o_centers = L.centers; g.o_votes = L.votes; g.o_lut = L.lut; g.o_worklist = L.worklist;
+    g.H = H; g.W = W; g.tiles_x = tiles_x; g.k_cap = k_cap; g.chunksize = 20; g.step = 1.0f;
+    g.vec = (W % 4 == 0) && aligned16(off);
+    g.label_divisor = label_divisor; g.void_label = void_label; g.things = th;
+    int blocks = sm_count() * 3;
+    if (blocks > tiles_x * tiles_y) blocks = tiles_x * tiles_y;
+    {
+        ProfScope ps(ST_LUT, st);       // profiling slot 3: argmin over thing tiles + label LUT
+        if (L.code16) argmin_tiles_kernel<true><<<blocks, kAssignThreads, 0, st>>>(g);
+        else argmin_tiles_kernel<false><<<blocks, kAssignThreads, 0, st>>>(g);
+    }
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
@@ -1209,8 +1632,9 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.max_id = max_id; a.k_dev = k_dev;
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
     if ((rc = launch_assign(1, sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-    return launch_apply(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, stuff_area,
-                        void_label, pan_out, (size_t)H * W, st);
+    if ((rc = launch_build_lut(L, static_cast<char*>(ws), k_cap, k_cap, k_dev, th, label_divisor, void_label, st))) return rc;
+    return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out,
+                        (size_t)H * W, st);
 }
 
 EMP_API int emp_merge(const int64_t* sem, const int64_t* ins, int H, int W, int64_t label_divisor,
@@ -1258,22 +1682,15 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
     if ((rc = launch_centers(B, hm, H, W, threshold, nms_kernel, 1.0f, L, wsb, ws_bytes_per_tile, k_cap, ctr_out, cap, st))) return rc;
 
     const size_t sem_elt = sem_u8 ? 1 : 8;
-    // assign (+ label LUT in its last CTA) -> apply tile by tile so that a tile's code map (2 B/px) is still in L2
-    // when apply_lut reads it back.
+    // classify -> argmin over thing tiles (+ label LUT) -> apply, tile by tile, so that a tile's code
+    // map (2 B/px) is still in L2 when the next kernel reads it back.
     for (int b = 0; b < B; ++b) {
         char* wst = wsb + (size_t)b * ws_bytes_per_tile;
-        AssignArgs a;
-        memset(&a, 0, sizeof(a));
-        a.sem = static_cast<const char*>(sem) + (size_t)b * n_px * sem_elt; a.sem_stride = n_px;
-        a.off = off + (size_t)b * 2 * n_px; a.off_stride = 2 * n_px;
-        a.out = wst + L.codes; a.out_stride = 0;
-        a.ws = wst; a.ws_stride = ws_bytes_per_tile;
-        fill_assign_common(a, L, th, label_divisor, void_label);
-        a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
-        a.vec = (W % 4 == 0) && aligned16(a.sem) && aligned16(a.off);
-        if ((rc = launch_assign(1, sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-        if ((rc = launch_apply(1, L, wst, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, stuff_area,
-                               void_label, pan_out + (size_t)b * n_px, n_px, st))) return rc;
+        if ((rc = launch_classify_argmin(static_cast<const char*>(sem) + (size_t)b * n_px * sem_elt, sem_u8,
+                                         off + (size_t)b * 2 * n_px, H, W, L, wst, k_cap, th, label_divisor,
+                                         void_label, st))) return rc;
+        if ((rc = launch_apply(1, L, wst, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
+                               pan_out + (size_t)b * n_px, n_px, st))) return rc;
     }
     return EMP_OK;
 }
