@@ -35,7 +35,7 @@ THINGS = [1]
 LABEL_DIVISOR, STUFF_AREA, VOID, THR, NMS_K = 1000, 64, 0, 0.1, 7
 ALG_BYTES_PER_PX = 28          # sem i64 8 + heat-map f32 4 + offsets 2 x f32 8 in, pan i64 8 out
 # each kernel of the chain owns one of the four algorithmic streams
-STAGE_ALG_BYTES_PER_PX = {'nms_peaks': 4, 'classify': 8, 'argmin_tiles': 8, 'apply_lut': 8}
+STAGE_ALG_BYTES_PER_PX = {'nms_peaks': 4, 'assign': 16, 'apply_lut': 8}
 METRIC, UNIT = 'panoptic_postproc_throughput', 'Mpix/s'
 WORKLOAD = 'postproc_16x4096x4096_k500'
 

@@ -65,7 +65,8 @@ def lib():
     return _lib
 
 
-STAGES = ('nms_peaks', 'emit_centers', 'classify', 'argmin_tiles', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs')
+STAGES = ('nms_peaks', 'emit_centers', 'assign', 'build_lut', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs',
+          'bin_centers')
 
 
 def profile_enable(on):
@@ -74,8 +75,8 @@ def profile_enable(on):
 
 def profile_read():
     """{stage: (total ms, launches)} since the last read (waits for the recorded events)."""
-    ms = (ctypes.c_double * 8)()
-    n = (ctypes.c_int * 8)()
+    ms = (ctypes.c_double * len(STAGES))()
+    n = (ctypes.c_int * len(STAGES))()
     check(lib().emp_profile_read(ms, n))
     return {s: (ms[i], n[i]) for i, s in enumerate(STAGES)}
 

@@ -40,9 +40,13 @@ constexpr uint32_t kClsBase32 = 0xFFFFF000u;
 constexpr int kNumClasses = EMP_MAX_CLASSES;
 
 // Per-tile workspace layout.  Everything in [0, zero_bytes) is cleared by one memset per call.
+// Center index: centers binned into a uniform grid of 2^gshift-pixel cells (gshift chosen on the
+// device from K, so that a cell holds about one center and there are at most kMaxCells cells).
+constexpr int kMaxCells = 16384;
+
 struct WsLayout {
     size_t status, rowcnt, areas, votes, zero_bytes;
-    size_t mask, centers, lut, worklist, codes, total;
+    size_t mask, centers, ctr_i, cell_start, cell_fill, sorted, lut, codes, total;
     int wd;          // mask words per row
     bool code16;
 };
@@ -52,7 +56,7 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     WsLayout L;
     if (n_things < 1) n_things = 1;
     L.wd = (W + 31) / 32;
-    L.code16 = (uint32_t)k_cap < 0xEFF0u;     // ids must stay below the "pending" codes (kPend16)
+    L.code16 = (uint32_t)k_cap < kClsBase16;  // ids must stay below the class codes
     size_t o = 0;
     L.status = o; o = align_up(o + sizeof(int32_t) * EMP_ST_WORDS, 256);
     L.rowcnt = o; o = align_up(o + sizeof(uint32_t) * (size_t)H, 256);
@@ -60,9 +64,12 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     L.votes = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1) * n_things, 256);
     L.zero_bytes = o;
     L.mask = o;    o = align_up(o + sizeof(uint32_t) * (size_t)H * L.wd, 256);
-    L.centers = o; o = align_up(o + sizeof(float2) * ((size_t)k_cap + 1), 256);
+    L.centers = o; o = align_up(o + sizeof(float2) * ((size_t)k_cap + 1), 256);     // (cy, cx) = step * (y, x), row-major order
+    L.ctr_i = o;   o = align_up(o + sizeof(int2) * ((size_t)k_cap + 1), 256);       // (y, x) clamped to int32, for binning
+    L.cell_start = o; o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
+    L.cell_fill = o;  o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
+    L.sorted = o;  o = align_up(o + sizeof(float4) * ((size_t)k_cap + 1), 256);     // (cy, cx, bits of k, -) grouped by cell
     L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
-    L.worklist = o; o = align_up(o + sizeof(uint32_t) * (size_t)((W + 63) / 64) * (size_t)((H + 31) / 32), 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
     L.total = o;
     return L;
@@ -78,7 +85,7 @@ int make_things(const int64_t* list, int n, Things* out);
 // Optional per-stage device timing (emp_profile_enable / emp_profile_read): one CUDA event pair
 // around each kernel launch on the launching stream.  Off by default (no events recorded).
 enum { ST_NMS = 0, ST_EMIT = 1, ST_ASSIGN = 2, ST_LUT = 3, ST_APPLY = 4, ST_MEDIAN = 5, ST_RLE_MARK = 6,
-       ST_RLE_RUNS = 7, ST_COUNT = 8 };
+       ST_RLE_RUNS = 7, ST_BIN = 8, ST_COUNT = EMP_PROFILE_STAGES };
 struct ProfScope {
     ProfScope(int stage, cudaStream_t st);
     ~ProfScope();
@@ -113,6 +120,55 @@ __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total)
     }
     *total = __shfl_sync(0xffffffffu, x, 31);
     return x - v;
+}
+
+// ---- TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS) -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 1-D bulk copy global -> shared; src, dst 16-byte aligned, bytes a multiple of 16.  Completion is
+// signalled on `bar` (complete_tx).  L2 evict-first: the streamed planes are read exactly once.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 }  // namespace emp

@@ -4,12 +4,15 @@
 // Kernel chain for one tile (all HBM-bound integer / fp32-compare work, no tensor cores):
 //   nms_peaks      hm (4 B/px)                 -> peak bitmask (1 bit/px) + per-row counts
 //   emit_centers   bitmask                     -> centers in row-major order, K
-//   assign         sem (8 B/px) + off (8 B/px, thing sectors only)
+//   bin_centers    centers                     -> uniform-grid cell index (counting sort by cell)
+//   assign         sem (8 B/px, TMA-staged) + off (8 B/px, thing sectors only)
 //                                              -> code map (2 B/px) + votes + stuff areas
-//   build_lut      votes, areas                -> label LUT (K+1) + class LUT
+//   build_lut      votes                       -> label LUT (K+1)
 //   apply_lut      code map (2 B/px)           -> pan (8 B/px)
 // DESIGN.md has the data layout, the exactness argument for the culled argmin and the roofline.
+#include <limits.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -202,13 +205,14 @@ nms_peaks_kernel(const float* __restrict__ hm_base, size_t hm_stride, int H, int
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 emit_centers_kernel(char* __restrict__ ws_base, size_t ws_stride, size_t o_mask, size_t o_rowcnt,
-                    size_t o_centers, size_t o_status, int H, int wd, int k_cap, float step,
+                    size_t o_centers, size_t o_ctr_i, size_t o_status, int H, int wd, int k_cap, float step,
                     int64_t* __restrict__ ctr_out_base, size_t ctr_out_stride, int cap)
 {
     char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
     const uint32_t* mask = reinterpret_cast<const uint32_t*>(ws + o_mask);
     const uint32_t* rowcnt = reinterpret_cast<const uint32_t*>(ws + o_rowcnt);
     float2* centers = reinterpret_cast<float2*>(ws + o_centers);     // (cy, cx) = step * (y, x)
+    int2* ctr_i = reinterpret_cast<int2*>(ws + o_ctr_i);
     int32_t* status = reinterpret_cast<int32_t*>(ws + o_status);
     int64_t* ctr_out = ctr_out_base ? ctr_out_base + (size_t)blockIdx.z * ctr_out_stride : nullptr;
 
@@ -253,7 +257,10 @@ emit_centers_kernel(char* __restrict__ ws_base, size_t ws_stride, size_t o_mask,
                 const int b = __ffs(word) - 1;
                 word &= word - 1;
                 const int x = wi * 32 + b;
-                if (pos < k_cap) centers[pos] = make_float2(__fmul_rn(step, (float)y), __fmul_rn(step, (float)x));
+                if (pos < k_cap) {
+                    centers[pos] = make_float2(__fmul_rn(step, (float)y), __fmul_rn(step, (float)x));
+                    ctr_i[pos] = make_int2(y, x);
+                }
                 if (ctr_out && pos < cap) { ctr_out[2 * (size_t)pos] = y; ctr_out[2 * (size_t)pos + 1] = x; }
                 ++pos;
             }
@@ -268,34 +275,127 @@ emit_centers_kernel(char* __restrict__ ws_base, size_t ws_stride, size_t o_mask,
     }
 }
 
-// int64 (K,2) centers supplied by the caller (standalone group_pixels) -> int2 table
-__global__ void load_centers_kernel(const int64_t* __restrict__ ctr, int K, float step, float2* __restrict__ centers)
+// int64 (K,2) centers supplied by the caller (standalone group_pixels) -> center tables
+__global__ void load_centers_kernel(const int64_t* __restrict__ ctr, int K, float step, float2* __restrict__ centers,
+                                    int2* __restrict__ ctr_i)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < K)          // ctr = step * ctr: int64 -> float32, then one rounded product (postprocess.py:152)
-        centers[i] = make_float2(__fmul_rn(step, (float)ctr[2 * (size_t)i]), __fmul_rn(step, (float)ctr[2 * (size_t)i + 1]));
+    if (i < K) {        // ctr = step * ctr: int64 -> float32, then one rounded product (postprocess.py:152)
+        const long long y = ctr[2 * (size_t)i], x = ctr[2 * (size_t)i + 1];
+        centers[i] = make_float2(__fmul_rn(step, (float)y), __fmul_rn(step, (float)x));
+        ctr_i[i] = make_int2((int)max(min(y, (long long)INT_MAX), (long long)INT_MIN),
+                             (int)max(min(x, (long long)INT_MAX), (long long)INT_MIN));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b  bin_centers — a uniform-grid index over the centers of one tile, built once per tile by one
+// CTA: cell size 2^gshift pixels with gshift chosen from K (about one center per cell, at most
+// kMaxCells cells), counting sort of the centers by cell.  Within a cell the order is whatever the
+// atomics give; the search below compares (distance, index) lexicographically, so the result does
+// not depend on it.
+//   cell of a center = (clamp(y, 0, H-1) >> gshift, clamp(x, 0, W-1) >> gshift)   (integer pixels)
+//   sorted[j]        = (step*y, step*x, bits(k), -)    with the reference's rounding (postprocess.py:152)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_cells(int n, int gs) { return ((n - 1) >> gs) + 1; }
+
+__global__ void __launch_bounds__(1024)
+bin_centers_kernel(char* __restrict__ ws_base, size_t ws_stride, size_t o_status, size_t o_centers, size_t o_ctr_i,
+                   size_t o_cell_start, size_t o_cell_fill, size_t o_sorted, int H, int W, int k_cap, int k_fixed,
+                   float step)
+{
+    char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
+    int32_t* status = reinterpret_cast<int32_t*>(ws + o_status);
+    const float2* centers = reinterpret_cast<const float2*>(ws + o_centers);
+    const int2* ctr_i = reinterpret_cast<const int2*>(ws + o_ctr_i);
+    int* cell_start = reinterpret_cast<int*>(ws + o_cell_start);
+    int* cell_fill = reinterpret_cast<int*>(ws + o_cell_fill);
+    float4* sorted = reinterpret_cast<float4*>(ws + o_sorted);
+
+    __shared__ int s_warp[32];
+    __shared__ int s_k, s_gs;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const int K = k_fixed >= 0 ? k_fixed : min(__ldcg(status + EMP_ST_K), k_cap);
+        int gs = 30;                                        // one cell: the search degenerates to all K centers
+        if (K > 0 && step > 0.0f && step < CUDART_INF_F) {
+            const float target = (float)H * (float)W / (float)K;          // pixels per center
+            gs = max(3, (int)floorf(0.5f * log2f(target)));
+            if (gs > 30) gs = 30;
+            while (gs < 30 && (long long)grid_cells(H, gs) * grid_cells(W, gs) > kMaxCells) ++gs;
+        }
+        s_k = K; s_gs = gs;
+        status[EMP_ST_GSHIFT] = gs;
+    }
+    __syncthreads();
+    const int K = s_k, gs = s_gs;
+    const int ncy = grid_cells(H, gs), ncx = grid_cells(W, gs), n = ncy * ncx;
+
+    for (int i = tid; i <= n; i += 1024) cell_fill[i] = 0;
+    __syncthreads();
+    for (int k = tid; k < K; k += 1024) {
+        const int2 c = ctr_i[k];
+        const int cell = (min(max(c.x, 0), H - 1) >> gs) * ncx + (min(max(c.y, 0), W - 1) >> gs);
+        atomicAdd(cell_fill + cell, 1);
+    }
+    __syncthreads();
+    // exclusive scan of the n counts: each thread owns a contiguous chunk
+    const int per = (n + 1023) / 1024;
+    const int i0 = min(tid * per, n), i1 = min(i0 + per, n);
+    int sum = 0;
+    for (int i = i0; i < i1; ++i) sum += cell_fill[i];
+    int tot;
+    int ex = warp_excl_scan(sum, lane, &tot);
+    if (lane == 31) s_warp[warp] = tot;
+    __syncthreads();
+    if (warp == 0) {
+        int wt;
+        const int wex = warp_excl_scan(s_warp[lane], lane, &wt);
+        s_warp[lane] = wex;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + ex;
+    for (int i = i0; i < i1; ++i) {
+        const int c = cell_fill[i];
+        cell_start[i] = run;
+        cell_fill[i] = run;
+        run += c;
+    }
+    if (tid == 1023) cell_start[n] = run;                   // == K
+    __syncthreads();
+    for (int k = tid; k < K; k += 1024) {
+        const int2 c = ctr_i[k];
+        const int cell = (min(max(c.x, 0), H - 1) >> gs) * ncx + (min(max(c.y, 0), W - 1) >> gs);
+        const int pos = atomicAdd(cell_fill + cell, 1);
+        const float2 f = centers[k];
+        sorted[pos] = make_float4(f.x, f.y, __int_as_float(k), 0.f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3  assign — group_pixels (postprocess.py:146-167, :97-116) fused with the thing mask of
 // get_instance_segmentation (:207-221) and the vote / stuff-area pass of
-// merge_semantic_and_instance (:253-294); the last CTA to finish also builds the label LUT
-// (:263-281), so no separate single-CTA launch sits between assign and apply_lut.
+// merge_semantic_and_instance (:253-294).
 //
-// One CTA per 64x32 pixel tile, 8 pixels per thread (2 row groups x 4 consecutive columns, so
-// sem / offsets / codes move as 128-bit / 64-bit vectors and every warp touches whole lines).
-// Tiles without a thing pixel (most of an EM tile) leave after one barrier: classify, count
-// stuff area, write class codes.
+// Persistent kernel, warp-autonomous.  The work item is a strip of 4 rows x 64 columns; lane l
+// owns columns 2l, 2l+1 of each row, so every warp-wide access covers one whole 64-pixel row
+// segment: 512 B of int64 sem, 256 B of an offset plane (LDG.64), 128 B of uint16 codes (STG.32).
+// The sem plane — the only stream every pixel needs — is staged through a per-warp ring of
+// kStages shared-memory buffers filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx):
+// lane 0 issues the rows of the item kStages iterations ahead, so loads stay in flight while the warp
+// classifies, searches and stores.  There is no block-wide barrier anywhere in the loop.
 //
-// Exact culled argmin.  For each pixel the reference takes, over ALL K centers,
+// Exact nearest center.  For each pixel the reference takes, over ALL K centers,
 //       d_k = sqrt_rn(fma(dx, dx, rn(dy*dy))),  dy = cy_k - ly,  dx = cx_k - lx   (fp32)
-// and keeps the first minimum.  The CTA bounds the shifted locations (ly,lx) of its thing
-// pixels by a box, takes U2 = min_k maxdist^2(box, c_k) and keeps only centers with
-// mindist^2(box, c_k) <= U2 * 1.001 + 1e-6: a dropped center is farther from every point of the
-// box than some kept center by far more than the few-ulp rounding of d_k, so it can neither win
-// nor tie.  Survivors are compacted in ascending k (ballot + prefix), so "first minimum" is a
-// strict < on the rounded sqrt; sqrt is monotone, so it is only evaluated when s = d^2 improves.
-// A non-finite location disables the cull for the tile.
+// and keeps the first minimum.  The warp bounds the cells of its thing pixels' shifted locations
+// (ly,lx) by a box, widens it by r cells (r = 1, 2, 4, ...) and evaluates d_k — in exactly that
+// arithmetic — for the centers binned in the block, keeping the lexicographic minimum of (d_k, k).
+// A pixel is settled when its best d is below 0.9999 x its distance to the block's outer edge: every
+// center outside the block is farther than that edge in y or in x, far beyond the few-ulp rounding
+// of d_k, so it can neither win nor tie.  (Block edges are computed as step * (cell << gshift) with
+// the rounding the centers themselves got, which is monotone; a block side on the grid border is
+// +-inf because centers beyond the image are binned into border cells.)  If any pixel of the warp is
+// not settled the ring doubles; a block covering the whole grid is the reference's full search.
 // ---------------------------------------------------------------------------------------------
 enum { SEM_NONE = 0, SEM_I64 = 1, SEM_U8 = 2 };
 enum { ID_ARGMIN = 0, ID_DENSE = 1, ID_COARSE = 2 };
@@ -307,61 +407,28 @@ struct AssignArgs {
     const void* ids_in; size_t ids_stride;     // ID_DENSE: int64 H*W, ID_COARSE: int32 hc*wc
     void* out;          size_t out_stride;     // elements per tile
     char* ws;           size_t ws_stride;
-    size_t o_status, o_centers, o_votes, o_areas, o_lut;
-    const int32_t* k_dev;                      // optional device count bounding the LUT build
-    int H, W, wc, shift;
+    size_t o_status, o_votes, o_areas, o_cell_start, o_sorted;
+    int B, H, W, wc, shift;
+    int items_x, items_y;                      // strips per row / strip rows per tile
     float step;
     int chunksize, k_cap, k_fixed;             // k_fixed >= 0: K known on the host
     long long max_id;
-    long long label_divisor, void_label;
     int vec;                                   // 1: W % 4 == 0 and all planes 16-byte aligned
+    int tma;                                   // 1: the sem plane can be staged with bulk copies
     unsigned long long thing_bits;             // bit c set <=> class c (< 64) is a thing class
     int things_small;                          // every thing class is < 64 (bit test suffices)
     Things things;
 };
 
-constexpr int kTileW = 64, kTileH = 32, kAssignThreads = 256, kPx = 8;
-constexpr int kCandCap = 1024;
-constexpr int kAreaBins = 64, kVoteSlots = 64;
-constexpr unsigned kEmptyKey = 0xFFFFFFFFu;
+constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 256, kAssignWarps = 8, kPx = 8;
+constexpr int kStages = 3;
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
+constexpr unsigned kNoKey = 0xFFFFFFFFu;
 
 struct LutScratch {
     int run[EMP_MAX_THINGS];
     int wcnt[8];
 };
-
-struct AssignSmem {
-    float cy[kCandCap], cx[kCandCap];
-    int ck[kCandCap];
-    float red[8][4];
-    int redi[8];
-    int wcnt[8];
-    unsigned area[kAreaBins];
-    unsigned vkey[kVoteSlots], vcnt[kVoteSlots];
-    LutScratch lut;
-    int last;
-    int kshared;
-};
-
-// Rare paths are kept out of line so that the per-pixel code stays small and branch-light.
-__device__ __noinline__ void vote_insert(AssignSmem& sm, uint32_t* votes, unsigned key, int cnt)
-{
-    unsigned h = (key * 2654435761u) >> 26;
-#pragma unroll 1
-    for (int probe = 0; probe < kVoteSlots; ++probe) {
-        const unsigned slot = (h + probe) & (kVoteSlots - 1);
-        const unsigned prev = atomicCAS(&sm.vkey[slot], kEmptyKey, key);
-        if (prev == kEmptyKey || prev == key) { atomicAdd(&sm.vcnt[slot], (unsigned)cnt); return; }
-    }
-    atomicAdd(votes + key, (uint32_t)cnt);      // table full: straight to global
-}
-
-__device__ __forceinline__ void area_insert(unsigned* s_area, uint32_t* areas, unsigned cls, int cnt)
-{
-    if (cls < (unsigned)kAreaBins) atomicAdd(&s_area[cls], (unsigned)cnt);
-    else atomicAdd(areas + cls, (uint32_t)cnt);
-}
 
 // 16-bit info word of one pixel: thing -> kInfoThing | thing index, stuff -> class id,
 // class outside [0, 4096) -> kInfoBad (reported through EMP_FLAG_CLASS_RANGE).
@@ -392,7 +459,7 @@ __device__ __forceinline__ unsigned classify_small(unsigned c, unsigned long lon
 
 // merge_semantic_and_instance's bookkeeping (postprocess.py:263-281), by one 256-thread CTA:
 //   id -> majority thing class (ties -> smallest class, torch.mode) * L + 1-based rank among voted
-//   ids of that class in ascending id order.  `lut` may point to shared or global memory.
+//   ids of that class in ascending id order.
 __device__ void build_label_lut(long long K, const uint32_t* votes, const Things& things, long long label_divisor,
                                 long long void_label, long long* lut, LutScratch& sc)
 {
@@ -437,155 +504,73 @@ __device__ __forceinline__ long long lut_extent(int k_fixed, int k_cap, const in
     return K;
 }
 
-// Exact nearest center for the CTA's thing pixels (8 per thread): CTA-level cull of all K centers
-// against the box of shifted locations, ordered compaction of the survivors into shared memory,
-// warp-level cull against the warp's own box, then the reference's fp32 distance on what is left.
-// Must be called by all threads of the CTA (it synchronises).  idv[p] receives the 1-based id.
-__device__ __forceinline__ void nearest_center_8px(AssignSmem& sm, const float2* __restrict__ centers, int K,
-                                                   int chunksize, unsigned thing, const float (&ly)[kPx],
-                                                   const float (&lx)[kPx], int (&idv)[kPx])
+struct GridView {
+    const int* cell_start;
+    const float4* sorted;
+    int gs, ncy, ncx;
+    float inv_cell;         // 1 / (step * 2^gs)
+    float step;
+};
+
+// Exact nearest center for the warp's thing pixels (8 per lane), see the comment above.  Called by
+// all 32 lanes (converged).  bd / bk come back as the lexicographic minimum of (d_k, k); bk stays
+// INT_MAX when no distance compared below +inf (non-finite locations).
+__device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thing, const float (&ly)[kPx],
+                                                 const float (&lx)[kPx], float (&bd)[kPx], int (&bk)[kPx])
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    float by0 = CUDART_INF_F, by1 = -CUDART_INF_F, bx0 = CUDART_INF_F, bx1 = -CUDART_INF_F;
-    int nonfinite = 0;
+    int y0 = INT_MAX, y1 = -1, x0 = INT_MAX, x1 = -1;
+    unsigned fin = 0;                                   // thing pixels with a finite location
 #pragma unroll
     for (int p = 0; p < kPx; ++p) {
-        if (thing & (1u << p)) {
-            by0 = fminf(by0, ly[p]); by1 = fmaxf(by1, ly[p]);
-            bx0 = fminf(bx0, lx[p]); bx1 = fmaxf(bx1, lx[p]);
-            if (!isfinite(ly[p]) || !isfinite(lx[p])) nonfinite = 1;
+        bd[p] = CUDART_INF_F; bk[p] = INT_MAX;
+        if (((thing >> p) & 1u) && isfinite(ly[p]) && isfinite(lx[p])) {
+            fin |= 1u << p;
+            const int gy = min(max(__float2int_rd(ly[p] * g.inv_cell), 0), g.ncy - 1);
+            const int gx = min(max(__float2int_rd(lx[p] * g.inv_cell), 0), g.ncx - 1);
+            y0 = min(y0, gy); y1 = max(y1, gy); x0 = min(x0, gx); x1 = max(x1, gx);
         }
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
-        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
-        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
-        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
-    }
-    nonfinite = __any_sync(0xffffffffu, nonfinite) ? 1 : 0;
-    const float wy0 = by0, wy1 = by1, wx0 = bx0, wx1 = bx1;    // this warp's own box (4 x 64 px)
-    const bool wnf = nonfinite != 0;
-    const bool warp_has_thing = __any_sync(0xffffffffu, thing != 0);
-    if (lane == 0) {
-        sm.red[warp][0] = by0; sm.red[warp][1] = by1; sm.red[warp][2] = bx0; sm.red[warp][3] = bx1;
-        sm.redi[warp] = nonfinite;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) {
-        by0 = fminf(by0, sm.red[w8][0]); by1 = fmaxf(by1, sm.red[w8][1]);
-        bx0 = fminf(bx0, sm.red[w8][2]); bx1 = fmaxf(bx1, sm.red[w8][3]);
-        nonfinite |= sm.redi[w8];
-    }
+    y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
+    x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+    if (y1 < 0) return;                                 // warp-uniform: nothing finite to search for
 
-    // sweep 1: U2 = min_k maxdist^2(box, c_k)
-    float u2 = CUDART_INF_F;
-    for (int k = tid; k < K; k += kAssignThreads) {
-        const float2 c = __ldg(centers + k);
-        const float my = fmaxf(fabsf(c.x - by0), fabsf(c.x - by1));
-        const float mx = fmaxf(fabsf(c.y - bx0), fabsf(c.y - bx1));
-        u2 = fminf(u2, my * my + mx * mx);
-    }
+    for (int r = 1;; r <<= 1) {
+        const int ya = max(y0 - r, 0), yb = min(y1 + r, g.ncy - 1);
+        const int xa = max(x0 - r, 0), xb = min(x1 + r, g.ncx - 1);
+        for (int row = ya; row <= yb; ++row) {
+            const int s = __ldg(g.cell_start + row * g.ncx + xa);
+            const int e = __ldg(g.cell_start + row * g.ncx + xb + 1);
+            for (int j = s; j < e; ++j) {
+                const float4 c = __ldg(g.sorted + j);
+                const int ck = __float_as_int(c.z);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) u2 = fminf(u2, __shfl_xor_sync(0xffffffffu, u2, d));
-    __syncthreads();                        // sm.red reads above are done
-    if (lane == 0) sm.red[warp][0] = u2;
-    __syncthreads();
-#pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) u2 = fminf(u2, sm.red[w8][0]);
-    const float thr2 = nonfinite ? CUDART_INF_F : u2 * 1.001f + 1e-6f;
-
-    float best_s[kPx];
-    int best_k[kPx];
-#pragma unroll
-    for (int p = 0; p < kPx; ++p) { best_s[p] = CUDART_INF_F; best_k[p] = -1; }
-
-    // sweep 2: ordered compaction of survivors, evaluated in batches of <= kCandCap
-    int n_list = 0;
-    for (int base = 0; base < K; base += kAssignThreads) {
-        const int k = base + tid;
-        bool keep = false;
-        float2 c = make_float2(0.f, 0.f);
-        if (k < K) {
-            c = __ldg(centers + k);                  // (cy, cx) = step * ctr (postprocess.py:152)
-            const float dy = fmaxf(fmaxf(by0 - c.x, c.x - by1), 0.f);
-            const float dx = fmaxf(fmaxf(bx0 - c.y, c.y - bx1), 0.f);
-            keep = nonfinite || !(dy * dy + dx * dx > thr2);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) sm.wcnt[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int w8 = 0; w8 < 8; ++w8) { const int cc = sm.wcnt[w8]; if (w8 < warp) woff += cc; tot += cc; }
-        if (keep) {
-            const int pos = n_list + woff + __popc(bal & lanemask_lt());
-            sm.cy[pos] = c.x; sm.cx[pos] = c.y; sm.ck[pos] = k;
-        }
-        n_list += tot;
-        __syncthreads();
-        if (n_list > kCandCap - kAssignThreads || base + kAssignThreads >= K) {
-            if (warp_has_thing) {                   // warp-uniform
-                // second, warp-level cull against this warp's own (much smaller) box: one
-                // lane per candidate, then only the survivors are evaluated per pixel
-                float wu2 = CUDART_INF_F;
-                for (int j0 = 0; j0 < n_list; j0 += 32) {
-                    const int j = j0 + lane;
-                    if (j < n_list) {
-                        const float ccy = sm.cy[j], ccx = sm.cx[j];
-                        const float my = fmaxf(fabsf(ccy - wy0), fabsf(ccy - wy1));
-                        const float mx = fmaxf(fabsf(ccx - wx0), fabsf(ccx - wx1));
-                        wu2 = fminf(wu2, my * my + mx * mx);
-                    }
-                }
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) wu2 = fminf(wu2, __shfl_xor_sync(0xffffffffu, wu2, d));
-                const float wthr2 = wnf ? CUDART_INF_F : wu2 * 1.001f + 1e-6f;
-                for (int j0 = 0; j0 < n_list; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool wkeep = false;
-                    if (j < n_list) {
-                        const float ccy = sm.cy[j], ccx = sm.cx[j];
-                        const float dy = fmaxf(fmaxf(wy0 - ccy, ccy - wy1), 0.f);
-                        const float dx = fmaxf(fmaxf(wx0 - ccx, ccx - wx1), 0.f);
-                        wkeep = wnf || !(dy * dy + dx * dx > wthr2);
-                    }
-                    unsigned m = __ballot_sync(0xffffffffu, wkeep);
-                    while (m) {                     // ascending j: ascending center index
-                        const int jj = j0 + __ffs(m) - 1;
-                        m &= m - 1;
-                        const float ccy = sm.cy[jj], ccx = sm.cx[jj];
-                        const int ck = sm.ck[jj];
-#pragma unroll
-                        for (int p = 0; p < kPx; ++p) {
-                            if (thing & (1u << p)) {
-                                const float dy = __fsub_rn(ccy, ly[p]);
-                                const float dx = __fsub_rn(ccx, lx[p]);
-                                const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-                                if (s2 < best_s[p]) {
-                                    if (__fsqrt_rn(s2) < __fsqrt_rn(best_s[p])) best_k[p] = ck;
-                                    best_s[p] = s2;
-                                }
-                            }
-                        }
-                    }
+                for (int p = 0; p < kPx; ++p) {
+                    const float dy = __fsub_rn(c.x, ly[p]);
+                    const float dx = __fsub_rn(c.y, lx[p]);
+                    const float d = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                    const bool better = d < bd[p] || (d == bd[p] && ck < bk[p]);
+                    bd[p] = better ? d : bd[p];
+                    bk[p] = better ? ck : bk[p];
                 }
             }
-            n_list = 0;
-            __syncthreads();
         }
-    }
-    const bool chunked = K > chunksize;
+        if (ya == 0 && yb == g.ncy - 1 && xa == 0 && xb == g.ncx - 1) break;     // every center seen
+        const float Ylo = ya == 0 ? -CUDART_INF_F : __fmul_rn(g.step, (float)(ya << g.gs));
+        const float Yhi = yb == g.ncy - 1 ? CUDART_INF_F : __fmul_rn(g.step, (float)((yb + 1) << g.gs));
+        const float Xlo = xa == 0 ? -CUDART_INF_F : __fmul_rn(g.step, (float)(xa << g.gs));
+        const float Xhi = xb == g.ncx - 1 ? CUDART_INF_F : __fmul_rn(g.step, (float)((xb + 1) << g.gs));
+        bool ok = true;
 #pragma unroll
-    for (int p = 0; p < kPx; ++p) {
-        int id = 0;
-        if (thing & (1u << p)) {
-            if (chunked) id = (best_k[p] >= 0 && __fsqrt_rn(best_s[p]) < 1e5f) ? best_k[p] + 1 : 0;
-            else id = best_k[p] >= 0 ? best_k[p] + 1 : 1;
+        for (int p = 0; p < kPx; ++p) {
+            const float m = fminf(fminf(ly[p] - Ylo, Yhi - ly[p]), fminf(lx[p] - Xlo, Xhi - lx[p]));
+            if (((fin >> p) & 1u) && !(bd[p] < 0.9999f * m)) ok = false;
         }
-        idv[p] = id;
+        if (__all_sync(0xffffffffu, ok)) break;
     }
+    // non-finite locations: every d_k is +inf or NaN; the caller maps "no index" to the reference's answer
+#pragma unroll
+    for (int p = 0; p < kPx; ++p)
+        if (!((fin >> p) & 1u)) { bd[p] = CUDART_INF_F; bk[p] = INT_MAX; }
 }
 
 template <int SEM, int IDM, int OUT>
@@ -594,162 +579,239 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 {
     constexpr bool kCodes = (OUT == OUT_CODE16 || OUT == OUT_CODE32);
     constexpr uint32_t kClsBase = (OUT == OUT_CODE16) ? kClsBase16 : kClsBase32;
-    __shared__ AssignSmem sm;
+    constexpr int kRowBytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;       // one staged row of sem
+    constexpr int kSemElt = (SEM == SEM_I64) ? 8 : 1;
+    extern __shared__ __align__(128) unsigned char dsm[];                   // [warp][stage][row][kRowBytes]
+    __shared__ uint64_t s_bar[kAssignWarps][kStages];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.z;
     const int H = a.H, W = a.W;
     const size_t HW = (size_t)H * W;
-    char* ws = a.ws + (size_t)b * a.ws_stride;
-    int32_t* status = reinterpret_cast<int32_t*>(ws + a.o_status);
-    const float2* centers = reinterpret_cast<const float2*>(ws + a.o_centers);
-    uint32_t* votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
-    uint32_t* areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
     const int T = a.things.n > 0 ? a.things.n : 1;
     const bool multi = a.things.n > 1;
+    const int per_img = a.items_x * a.items_y;             // host guarantees per_img * B < 2^31
+    const int n_items = per_img * a.B;
+    const int total_warps = (int)gridDim.x * kAssignWarps;
+    const int gw = (int)blockIdx.x * kAssignWarps + warp;
+    const bool tma = (SEM != SEM_NONE) && a.tma;
 
-    // Thread <-> pixel map: warp w owns tile rows 4w..4w+3, lane l owns columns 2l, 2l+1 of each,
-    // so one warp-wide access covers one whole 64-pixel tile row: 512 B of int64 sem (LDG.128),
-    // 256 B of an offset plane (LDG.64), 128 B of uint16 codes (STG.32) — always full sectors.
-    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
-    const int col0 = tx0 + 2 * lane;
-    const int row0 = ty0 + 4 * warp;
-    const bool cin = col0 < W;
-    const bool c1in = col0 + 1 < W;
-
-    // ---- phase 1a: issue every load of the tile before anything depends on one --------------
-    int Kld = 0;                // thread 0 resolves the device-side id count for the whole CTA
-    if ((IDM == ID_ARGMIN || kCodes) && tid == 0) Kld = (int)lut_extent(a.k_fixed, a.k_cap, status, a.k_dev);
-    if (kCodes) {
-        if (tid < kAreaBins) sm.area[tid] = 0;
-        if (tid < kVoteSlots) { sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0; }
+    unsigned char* ring = dsm + (size_t)warp * kStages * kItemH * kRowBytes;
+    uint64_t policy = 0;
+    // lane 0 arms the stage's barrier with the byte count and issues one bulk copy per row of the item
+    auto issue = [&](int stage, int item) {
+        const int b = item / per_img;
+        const int r = item - b * per_img;
+        const int iy = r / a.items_x, ix = r - iy * a.items_x;
+        const int colb = ix * kItemW, rowb = iy * kItemH;
+        const unsigned bytes = (unsigned)min(kItemW, W - colb) * kSemElt;
+        const int nrows = min(kItemH, H - rowb);
+        if (lane == 0) {
+            mbar_expect_tx(&s_bar[warp][stage], bytes * nrows);
+            const unsigned char* src = static_cast<const unsigned char*>(a.sem) +
+                                       ((size_t)b * a.sem_stride + (size_t)rowb * W + colb) * kSemElt;
+            unsigned char* dst = ring + (size_t)stage * kItemH * kRowBytes;
+#pragma unroll
+            for (int rr = 0; rr < kItemH; ++rr)
+                if (rr < nrows) bulk_g2s(dst + rr * kRowBytes, src + (size_t)rr * W * kSemElt, bytes, &s_bar[warp][stage], policy);
+        }
+    };
+    if (tma) {
+        policy = l2_policy_evict_first();
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) mbar_init(&s_bar[warp][s], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            const long long item = (long long)gw + (long long)s * total_warps;
+            if (item < n_items) issue(s, (int)item);
+        }
     }
-    long long sv[kPx];
-    long long iv[kPx];
-#pragma unroll
-    for (int p = 0; p < kPx; ++p) { sv[p] = 0; iv[p] = 0; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = row0 + i;
-        const bool rin = row < H && cin;
-        const size_t e = (size_t)row * W + col0;
-        if (SEM == SEM_I64) {
-            const long long* sp = reinterpret_cast<const long long*>(a.sem) + (size_t)b * a.sem_stride + e;
-            if (a.vec) {
-                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
-            } else {
-                if (rin) sv[2 * i] = __ldcs(sp);
-                if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
+
+    // per-image state
+    int cur_b = -1;
+    int K = 0;
+    bool chunked = false;
+    GridView g;
+    g.cell_start = nullptr; g.sorted = nullptr; g.gs = 30; g.ncy = 1; g.ncx = 1; g.inv_cell = 0.f; g.step = a.step;
+    int32_t* status = nullptr;
+    uint32_t* votes = nullptr;
+    uint32_t* areas = nullptr;
+    unsigned deficit_acc = 0;       // in-image pixels of the current image that are NOT class-0 stuff
+    unsigned akey_acc = kNoKey, acnt_acc = 0;    // pending stuff-area count of one non-zero class
+    int flags = 0;
+
+    auto flush_image = [&]() {      // warp-uniform call sites only
+        if (cur_b < 0) return;
+        if (kCodes) {
+            const unsigned dsum = __reduce_add_sync(0xffffffffu, deficit_acc);
+            if (dsum && lane == 0) atomicAdd(areas + kNumClasses, dsum);
+            const unsigned peers = __match_any_sync(0xffffffffu, akey_acc);
+            const unsigned asum = __reduce_add_sync(peers, acnt_acc);
+            if (akey_acc != kNoKey && asum && lane == __ffs(peers) - 1) atomicAdd(areas + akey_acc, asum);
+        }
+        const int f = __reduce_or_sync(0xffffffffu, flags);
+        if (f && lane == 0) atomicOr(status + EMP_ST_FLAGS, f);
+        deficit_acc = 0; akey_acc = kNoKey; acnt_acc = 0; flags = 0;
+    };
+
+    int n = 0;
+    for (long long item = gw; item < n_items; item += total_warps, ++n) {
+        const int b = (int)item / per_img;
+        const int r = (int)item - b * per_img;
+        const int iy = r / a.items_x, ix = r - iy * a.items_x;
+        const int col0 = ix * kItemW + 2 * lane;
+        const int row0 = iy * kItemH;
+        const bool cin = col0 < W, c1in = col0 + 1 < W;
+
+        if (b != cur_b) {                                   // warp-uniform
+            flush_image();
+            cur_b = b;
+            char* ws = a.ws + (size_t)b * a.ws_stride;
+            status = reinterpret_cast<int32_t*>(ws + a.o_status);
+            votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
+            areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
+            if (IDM == ID_ARGMIN) {
+                K = a.k_fixed >= 0 ? a.k_fixed : min(__ldcg(status + EMP_ST_K), a.k_cap);
+                chunked = K > a.chunksize;
+                g.gs = __ldcg(status + EMP_ST_GSHIFT);
+                g.ncy = grid_cells(H, g.gs); g.ncx = grid_cells(W, g.gs);
+                g.inv_cell = __frcp_rn(__fmul_rn(a.step, (float)(1 << g.gs)));
+                g.cell_start = reinterpret_cast<const int*>(ws + a.o_cell_start);
+                g.sorted = reinterpret_cast<const float4*>(ws + a.o_sorted);
             }
-        } else if (SEM == SEM_U8) {
-            const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + (size_t)b * a.sem_stride + e;
-            if (a.vec) {
-                if (rin) { const unsigned u = __ldcs(reinterpret_cast<const unsigned short*>(sp)); sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8; }
+        }
+
+        // ---- sem (staged by TMA, or loaded directly) and instance ids -----------------------------
+        long long sv[kPx];
+        long long iv[kPx];
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) { sv[p] = 0; iv[p] = 0; }
+        unsigned inb = 0;           // bit p: pixel p = 2*i + j is inside the image
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i) {
+            const bool rin = (row0 + i) < H && cin;
+            if (rin) inb |= 1u << (2 * i);
+            if (rin && c1in) inb |= 2u << (2 * i);
+        }
+        if (SEM != SEM_NONE) {
+            if (tma) {
+                const int stage = n % kStages;
+                mbar_wait(&s_bar[warp][stage], (unsigned)(n / kStages) & 1u);
+                const unsigned char* sp = ring + (size_t)stage * kItemH * kRowBytes;
+#pragma unroll
+                for (int i = 0; i < kItemH; ++i) {
+                    if (SEM == SEM_I64) {
+                        const longlong2 u = *reinterpret_cast<const longlong2*>(sp + i * kRowBytes + lane * 16);
+                        sv[2 * i] = u.x; sv[2 * i + 1] = u.y;
+                    } else {
+                        const unsigned u = *reinterpret_cast<const unsigned short*>(sp + i * kRowBytes + lane * 2);
+                        sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8;
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < kPx; ++p) sv[p] = ((inb >> p) & 1u) ? sv[p] : 0;    // rows / columns never copied
+                __syncwarp();                               // every lane has its values: the slot is free
+                const long long nxt = item + (long long)kStages * total_warps;
+                if (nxt < n_items) issue(stage, (int)nxt);
             } else {
-                if (rin) sv[2 * i] = sp[0];
-                if (rin && c1in) sv[2 * i + 1] = sp[1];
+#pragma unroll
+                for (int i = 0; i < kItemH; ++i) {
+                    const bool rin = (inb >> (2 * i)) & 1u;
+                    const size_t e = (size_t)b * a.sem_stride + (size_t)(row0 + i) * W + col0;
+                    if (SEM == SEM_I64) {
+                        const long long* sp = reinterpret_cast<const long long*>(a.sem) + e;
+                        if (a.vec) {
+                            if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
+                        } else {
+                            if (rin) sv[2 * i] = __ldcs(sp);
+                            if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
+                        }
+                    } else {
+                        const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + e;
+                        if (rin) sv[2 * i] = sp[0];
+                        if (rin && c1in) sv[2 * i + 1] = sp[1];
+                    }
+                }
             }
         }
         if (IDM == ID_DENSE) {
-            const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride + e;
-            if (a.vec) {
-                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(ip)); iv[2 * i] = u.x; iv[2 * i + 1] = u.y; }
-            } else {
-                if (rin) iv[2 * i] = __ldcs(ip);
-                if (rin && c1in) iv[2 * i + 1] = __ldcs(ip + 1);
+#pragma unroll
+            for (int i = 0; i < kItemH; ++i) {
+                const bool rin = (inb >> (2 * i)) & 1u;
+                const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride +
+                                      (size_t)(row0 + i) * W + col0;
+                if (a.vec) {
+                    if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(ip)); iv[2 * i] = u.x; iv[2 * i + 1] = u.y; }
+                } else {
+                    if (rin) iv[2 * i] = __ldcs(ip);
+                    if (rin && c1in) iv[2 * i + 1] = __ldcs(ip + 1);
+                }
             }
         } else if (IDM == ID_COARSE) {
-            const int* ip = reinterpret_cast<const int*>(a.ids_in) + (size_t)b * a.ids_stride;
-            const size_t crow = (size_t)(row >> a.shift) * a.wc;
-            if (rin) iv[2 * i] = __ldg(ip + crow + (col0 >> a.shift));
-            if (rin && c1in) iv[2 * i + 1] = __ldg(ip + crow + ((col0 + 1) >> a.shift));
+#pragma unroll
+            for (int i = 0; i < kItemH; ++i) {
+                const bool rin = (inb >> (2 * i)) & 1u;
+                const int* ip = reinterpret_cast<const int*>(a.ids_in) + (size_t)b * a.ids_stride;
+                const size_t crow = (size_t)((row0 + i) >> a.shift) * a.wc;
+                if (rin) iv[2 * i] = __ldg(ip + crow + (col0 >> a.shift));
+                if (rin && c1in) iv[2 * i + 1] = __ldg(ip + crow + ((col0 + 1) >> a.shift));
+            }
         }
-    }
 
-    // ---- phase 1b: classify ------------------------------------------------------------------
-    unsigned inb = 0;           // bit p: pixel p = 2*i + j is inside the image
+        // ---- classify ------------------------------------------------------------------------------
+        unsigned long long orall = 0ull, orid = 0ull;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool rin = (row0 + i) < H && cin;
-        if (rin) inb |= 1u << (2 * i);
-        if (rin && c1in) inb |= 2u << (2 * i);
-    }
-    unsigned long long orall = 0ull, orid = 0ull;
+        for (int p = 0; p < kPx; ++p) { orall |= (unsigned long long)sv[p]; orid |= (unsigned long long)iv[p]; }
+        // Fast path: the lane's 8 pixels are all in the image, all background class 0 (not a thing
+        // class) and carry no instance id that could void them — the bulk of an EM tile.
+        const bool pure_bg = SEM != SEM_NONE && inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull) &&
+                             (IDM != ID_DENSE || orid == 0ull);
+        unsigned code[kPx];
+        if (__all_sync(0xffffffffu, pure_bg)) {             // warp-uniform: constant output, nothing to count
 #pragma unroll
-    for (int p = 0; p < kPx; ++p) { orall |= (unsigned long long)sv[p]; orid |= (unsigned long long)iv[p]; }
-    // Fast path: the thread's 8 pixels are all in the image, all background class 0 (not a thing
-    // class) and carry no instance id that could void them — the bulk of an EM tile.
-    const bool pure_bg = SEM != SEM_NONE && inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull) &&
-                         (IDM != ID_DENSE || orid == 0ull);
-    unsigned w[kPx];            // 16-bit info word per pixel
-    unsigned thing = 0;         // bit p: pixel p takes an instance id
-    unsigned bad = 0;
-    int flags = 0;
-    int idv[kPx];               // instance id (ID_DENSE / ID_COARSE) or argmin result
-#pragma unroll
-    for (int p = 0; p < kPx; ++p) { w[p] = 0; idv[p] = 0; }
-    if (!pure_bg) {
-        if (SEM == SEM_NONE) {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = kInfoThing;
-        } else if (orall < 64ull) {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
+            for (int p = 0; p < kPx; ++p) code[p] = kCodes ? kClsBase : 0u;
         } else {
+            unsigned w[kPx];        // 16-bit info word per pixel
+            unsigned thing = 0;     // bit p: pixel p takes an instance id
+            unsigned bad = 0;
+            int idv[kPx];           // instance id (ID_DENSE / ID_COARSE) or argmin result
 #pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
-        }
+            for (int p = 0; p < kPx; ++p) { w[p] = 0; idv[p] = 0; }
+            if (SEM == SEM_NONE) {
 #pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            w[p] = ((inb >> p) & 1u) ? w[p] : 0u;
-            thing |= ((w[p] >> 15) & 1u) << p;
-            bad |= ((w[p] >> 14) & 1u) << p;
-        }
-        if (bad) flags |= EMP_FLAG_CLASS_RANGE;
-        if (IDM != ID_ARGMIN) {
+                for (int p = 0; p < kPx; ++p) w[p] = kInfoThing;
+            } else if (orall < 64ull) {
+#pragma unroll
+                for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
+            } else {
+#pragma unroll
+                for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
+            }
 #pragma unroll
             for (int p = 0; p < kPx; ++p) {
-                long long v = iv[p];
-                if (v < 0 || v > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v = 0; }
-                idv[p] = (int)v;
+                w[p] = ((inb >> p) & 1u) ? w[p] : 0u;
+                thing |= ((w[p] >> 15) & 1u) << p;
+                bad |= ((w[p] >> 14) & 1u) << p;
             }
-        }
-    }
-
-    // ---- phase 2: nearest center over the culled candidate list ------------------------------
-    if ((IDM == ID_ARGMIN || kCodes) && tid == 0) sm.kshared = Kld;
-    // Barrier 1 (also publishes the smem tables): is the whole CTA plain background?  Then its
-    // codes are a constant and it has nothing to vote, count or search: store and leave.  (The
-    // area of class 0 is derived in apply_lut from what the other CTAs count, see below.)
-    if (kCodes && SEM != SEM_NONE) {
-        if (!__syncthreads_or(!pure_bg)) {                  // block-uniform
-            {
+            if (bad) flags |= EMP_FLAG_CLASS_RANGE;
+            if (IDM != ID_ARGMIN) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const size_t o = (size_t)b * a.out_stride + (size_t)(row0 + i) * W + col0;
-                    if (OUT == OUT_CODE16) {
-                        unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
-                        if (a.vec) *reinterpret_cast<unsigned*>(op) = kClsBase | (kClsBase << 16);
-                        else { op[0] = (unsigned short)kClsBase; op[1] = (unsigned short)kClsBase; }
-                    } else {
-                        unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
-                        if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(kClsBase, kClsBase);
-                        else { op[0] = kClsBase; op[1] = kClsBase; }
-                    }
+                for (int p = 0; p < kPx; ++p) {
+                    long long v = iv[p];
+                    if (v < 0 || v > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v = 0; }
+                    idv[p] = (int)v;
                 }
-                return;
             }
-        }
-    }
-    if (IDM == ID_ARGMIN) {
-        const int any = __syncthreads_or(thing != 0);
-        const int K = sm.kshared;
-        if (any && K > 0) {                                 // block-uniform
-            float ly[kPx], lx[kPx];
-            {
-                float2 fy[4], fx[4];
+
+            // ---- nearest center over the cell index ------------------------------------------------
+            if (IDM == ID_ARGMIN && K > 0 && __any_sync(0xffffffffu, thing != 0)) {       // warp-uniform
+                float ly[kPx], lx[kPx];
+                float2 fy[kItemH], fx[kItemH];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < kItemH; ++i) {
                     fy[i] = make_float2(0.f, 0.f); fx[i] = make_float2(0.f, 0.f);
                     const float* oy = a.off + (size_t)b * a.off_stride + (size_t)(row0 + i) * W + col0;
                     const float* ox = oy + HW;
@@ -762,453 +824,115 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float ycoord = __fmul_rn((float)(row0 + i), a.step);     // arange(0, H*step, step)
+                for (int i = 0; i < kItemH; ++i) {
+                    const float ycoord = __fmul_rn((float)(row0 + i), a.step);         // arange(0, H*step, step)
                     ly[2 * i] = __fadd_rn(ycoord, fy[i].x);
                     ly[2 * i + 1] = __fadd_rn(ycoord, fy[i].y);
                     lx[2 * i] = __fadd_rn(__fmul_rn((float)col0, a.step), fx[i].x);
                     lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
                 }
-            }
-            nearest_center_8px(sm, centers, K, a.chunksize, thing, ly, lx, idv);
-        }
-    }
-
-    // ---- phase 3: outputs, votes (postprocess.py:263-273), stuff areas (:284-291) ---------------
-    unsigned code[kPx];
-    unsigned vkey = kEmptyKey, akey = kEmptyKey;
-    int vcnt = 0, acnt = 0;
-    int deficit = 0;            // in-image pixels that are NOT class-0 stuff (area[0] = H*W - sum)
-    if (pure_bg) {
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) code[p] = kCodes ? kClsBase : 0u;
-    } else {
-        unsigned voted = 0, stuff = 0;      // bit p: pixel p votes for its instance / counts as stuff area
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            const bool in = (inb >> p) & 1u;
-            const bool th = (thing >> p) & 1u;
-            const bool bd = (bad >> p) & 1u;
-            const int id = idv[p];
-            const bool v = th && id != 0;
-            const bool st0 = in && !th && !bd && !(IDM == ID_DENSE && id > 0);
-            const bool st = st0 && w[p] != 0u;              // class-0 stuff is counted by complement
-            deficit += (in && !(st0 && w[p] == 0u)) ? 1 : 0;
-            voted |= (v ? 1u : 0u) << p;
-            stuff |= (st ? 1u : 0u) << p;
-            if (kCodes) code[p] = v ? (unsigned)id : (st0 ? kClsBase + w[p] : 0u);
-            else code[p] = th ? (unsigned)id : 0u;
-        }
-        if (kCodes) {
-            // key of the thread's first voting / stuff pixel and how many of its pixels share it;
-            // stragglers with another key take the out-of-line insert
-#pragma unroll
-            for (int p = kPx - 1; p >= 0; --p) {
-                if ((voted >> p) & 1u) vkey = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
-                if ((stuff >> p) & 1u) akey = w[p];
-            }
-            unsigned vrest = 0, arest = 0;
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) {
-                const unsigned kv = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
-                const bool isv = (voted >> p) & 1u, isa = (stuff >> p) & 1u;
-                vcnt += (isv && kv == vkey) ? 1 : 0;
-                vrest |= ((isv && kv != vkey) ? 1u : 0u) << p;
-                acnt += (isa && w[p] == akey) ? 1 : 0;
-                arest |= ((isa && w[p] != akey) ? 1u : 0u) << p;
-            }
-            if (vrest | arest) {
+                float bd[kPx];
+                int bk[kPx];
+                grid_nearest_8px(g, thing, ly, lx, bd, bk);
 #pragma unroll
                 for (int p = 0; p < kPx; ++p) {
-                    if ((vrest >> p) & 1u) vote_insert(sm, votes, (unsigned)idv[p] * (unsigned)T + (w[p] & 15u), 1);
-                    if ((arest >> p) & 1u) area_insert(sm.area, areas, w[p], 1);
+                    int id = 0;
+                    if ((thing >> p) & 1u) {
+                        if (chunked) id = (bk[p] != INT_MAX && bd[p] < 1e5f) ? bk[p] + 1 : 0;     // sentinel, postprocess.py:98,:110
+                        else id = bk[p] != INT_MAX ? bk[p] + 1 : 1;
+                    }
+                    idv[p] = id;
+                }
+            }
+
+            // ---- codes, votes (postprocess.py:263-273), stuff areas (:284-291) -----------------------
+            unsigned voted = 0, stuff = 0;      // bit p: pixel p votes for its instance / counts as stuff area
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) {
+                const bool in = (inb >> p) & 1u;
+                const bool th = (thing >> p) & 1u;
+                const bool bd2 = (bad >> p) & 1u;
+                const int id = idv[p];
+                const bool v = th && id != 0;
+                const bool st0 = in && !th && !bd2 && !(IDM == ID_DENSE && id > 0);
+                const bool st = st0 && w[p] != 0u;              // class-0 stuff is counted by complement
+                if (kCodes) deficit_acc += (in && !(st0 && w[p] == 0u)) ? 1u : 0u;
+                voted |= (v ? 1u : 0u) << p;
+                stuff |= (st ? 1u : 0u) << p;
+                if (kCodes) code[p] = v ? (unsigned)id : (st0 ? kClsBase + w[p] : 0u);
+                else code[p] = th ? (unsigned)id : 0u;
+            }
+            if (kCodes) {
+                // votes: one warp-aggregated atomic per distinct (id, class) key among the lanes' first
+                // keys; a lane's pixels with another key (instance borders) go one by one
+                unsigned vkey = kNoKey;
+                int vcnt = 0;
+#pragma unroll
+                for (int p = kPx - 1; p >= 0; --p)
+                    if ((voted >> p) & 1u) vkey = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
+#pragma unroll
+                for (int p = 0; p < kPx; ++p) {
+                    const unsigned kv = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
+                    const bool isv = (voted >> p) & 1u;
+                    if (isv && kv == vkey) ++vcnt;
+                    else if (isv) atomicAdd(votes + kv, 1u);
+                }
+                if (__any_sync(0xffffffffu, vkey != kNoKey)) {
+                    const unsigned peers = __match_any_sync(0xffffffffu, vkey);
+                    const int sum = __reduce_add_sync(peers, vcnt);
+                    if (vkey != kNoKey && lane == __ffs(peers) - 1) atomicAdd(votes + vkey, (uint32_t)sum);
+                }
+                // stuff areas of non-zero classes: accumulated per lane while the class stays the same
+                if (stuff) {
+#pragma unroll
+                    for (int p = 0; p < kPx; ++p) {
+                        if ((stuff >> p) & 1u) {
+                            if (w[p] != akey_acc) {
+                                if (akey_acc != kNoKey && acnt_acc) atomicAdd(areas + akey_acc, acnt_acc);
+                                akey_acc = w[p]; acnt_acc = 0;
+                            }
+                            ++acnt_acc;
+                        }
+                    }
                 }
             }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = row0 + i;
-        if (row < H && cin) {
-            const size_t o = (size_t)b * a.out_stride + (size_t)row * W + col0;
-            const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
-            if (OUT == OUT_CODE16) {
-                unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
-                if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
-                else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
-            } else if (OUT == OUT_CODE32) {
-                unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
-                if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
-                else { op[0] = c0; if (c1in) op[1] = c1; }
-            } else if (OUT == OUT_IDS64) {
-                long long* op = reinterpret_cast<long long*>(a.out) + o;
-                if (a.vec) __stcs(reinterpret_cast<longlong2*>(op), make_longlong2((long long)c0, (long long)c1));
-                else { op[0] = (long long)c0; if (c1in) op[1] = (long long)c1; }
-            } else {
-                int* op = reinterpret_cast<int*>(a.out) + o;
-                if (a.vec) *reinterpret_cast<int2*>(op) = make_int2((int)c0, (int)c1);
-                else { op[0] = (int)c0; if (c1in) op[1] = (int)c1; }
-            }
-        }
-    }
-    if (flags) atomicOr(status + EMP_ST_FLAGS, flags);
 
-    if (kCodes) {
-        // one warp-aggregated insert per distinct key, then one global atomic per live bin per CTA
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, vkey);
-            const int sum = __reduce_add_sync(peers, vcnt);
-            if (vkey != kEmptyKey && lane == __ffs(peers) - 1) vote_insert(sm, votes, vkey, sum);
-        }
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, akey);
-            const int sum = __reduce_add_sync(peers, acnt);
-            if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(sm.area, areas, akey, sum);
-        }
-        {
-            const int sum = __reduce_add_sync(0xffffffffu, deficit);
-            if (sum && lane == 0) atomicAdd(&sm.area[0], (unsigned)sum);    // bin 0 holds the deficit
-        }
-        __syncthreads();
-        if (tid < kAreaBins && sm.area[tid]) atomicAdd(areas + (tid == 0 ? kNumClasses : tid), sm.area[tid]);
-        if (tid < kVoteSlots && sm.vkey[tid] != kEmptyKey && sm.vcnt[tid]) atomicAdd(votes + sm.vkey[tid], sm.vcnt[tid]);
-
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Fused get_panoptic_segmentation path (emp_panoptic_batched) = three kernels per tile:
-//
-//   classify      every pixel: sem (8 B/px) -> code map (2 B/px).  Stuff pixels get their class
-//                 code, thing pixels a "pending" code (kPend + thing index).  Few registers, no
-//                 search: a pure streaming kernel at high occupancy.  CTAs holding thing pixels
-//                 append their tile to a worklist; stuff areas are counted here (class 0 by
-//                 complement, so plain-background CTAs count nothing and leave after one barrier).
-//   argmin_tiles  persistent CTAs over the worklist (thing tiles only, ~1/4 of an EM tile):
-//                 offsets (8 B/px, thing rows only) -> exact nearest center -> id codes + votes.
-//                 The last CTA to finish builds the label LUT.
-//   apply_lut     code map -> int64 labels.
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t kPend16 = 0xEFF0u, kPend32 = 0xFFFFEFF0u;    // + thing index: thing pixel awaiting its id
-
-struct ClassifyArgs {
-    const void* sem;
-    void* codes;
-    char* ws;
-    size_t o_status, o_areas, o_worklist;
-    int H, W, vec;
-    unsigned long long thing_bits;
-    int things_small;
-    Things things;
-};
-
-template <int SEM, bool C16>
-__global__ void __launch_bounds__(256, 5)
-classify_kernel(const __grid_constant__ ClassifyArgs a)
-{
-    constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
-    constexpr uint32_t kPend = C16 ? kPend16 : kPend32;
-    __shared__ unsigned s_area[kAreaBins];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H = a.H, W = a.W;
-    int32_t* status = reinterpret_cast<int32_t*>(a.ws + a.o_status);
-    uint32_t* areas = reinterpret_cast<uint32_t*>(a.ws + a.o_areas);
-    const bool multi = a.things.n > 1;
-
-    const int col0 = blockIdx.x * kTileW + 2 * lane;
-    const int row0 = blockIdx.y * kTileH + 4 * warp;
-    const bool cin = col0 < W, c1in = col0 + 1 < W;
-    if (tid < kAreaBins) s_area[tid] = 0;
-
-    long long sv[kPx];
+        // ---- store ------------------------------------------------------------------------------------
 #pragma unroll
-    for (int p = 0; p < kPx; ++p) sv[p] = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool rin = row0 + i < H && cin;
-        const size_t e = (size_t)(row0 + i) * W + col0;
-        if (SEM == SEM_I64) {
-            const long long* sp = reinterpret_cast<const long long*>(a.sem) + e;
-            if (a.vec) {
-                if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
-            } else {
-                if (rin) sv[2 * i] = __ldcs(sp);
-                if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
-            }
-        } else {
-            const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + e;
-            if (a.vec) {
-                if (rin) { const unsigned u = __ldcs(reinterpret_cast<const unsigned short*>(sp)); sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8; }
-            } else {
-                if (rin) sv[2 * i] = sp[0];
-                if (rin && c1in) sv[2 * i + 1] = sp[1];
-            }
-        }
-    }
-    unsigned inb = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool rin = row0 + i < H && cin;
-        if (rin) inb |= 1u << (2 * i);
-        if (rin && c1in) inb |= 2u << (2 * i);
-    }
-    unsigned long long orall = 0ull;
-#pragma unroll
-    for (int p = 0; p < kPx; ++p) orall |= (unsigned long long)sv[p];
-    const bool pure_bg = inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull);
-
-    unsigned code[kPx];
-    unsigned thing = 0, akey = kEmptyKey;
-    int acnt = 0, deficit = 0, flags = 0;
-    if (pure_bg) {
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) code[p] = kClsBase;
-    } else {
-        unsigned w[kPx];
-        if (orall < 64ull) {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
-        } else {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
-        }
-        unsigned stuff = 0;
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            const bool in = (inb >> p) & 1u;
-            const bool th = in && (w[p] & kInfoThing);
-            const bool bd = in && (w[p] & kInfoBad);
-            const bool st0 = in && !th && !bd;
-            thing |= (th ? 1u : 0u) << p;
-            if (bd) flags |= EMP_FLAG_CLASS_RANGE;
-            code[p] = th ? kPend + (w[p] & 15u) : (st0 ? kClsBase + w[p] : 0u);
-            deficit += (in && !(st0 && w[p] == 0u)) ? 1 : 0;    // class-0 stuff is counted by complement
-            stuff |= ((st0 && w[p] != 0u) ? 1u : 0u) << p;
-        }
-#pragma unroll
-        for (int p = kPx - 1; p >= 0; --p) if ((stuff >> p) & 1u) akey = w[p];
-        unsigned arest = 0;
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            const bool isa = (stuff >> p) & 1u;
-            acnt += (isa && w[p] == akey) ? 1 : 0;
-            arest |= ((isa && w[p] != akey) ? 1u : 0u) << p;
-        }
-        if (arest) {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) if ((arest >> p) & 1u) area_insert(s_area, areas, w[p], 1);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (row0 + i < H && cin) {
-            const size_t o = (size_t)(row0 + i) * W + col0;
-            const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
-            if (C16) {
-                unsigned short* op = reinterpret_cast<unsigned short*>(a.codes) + o;
-                if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
-                else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
-            } else {
-                unsigned* op = reinterpret_cast<unsigned*>(a.codes) + o;
-                if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
-                else { op[0] = c0; if (c1in) op[1] = c1; }
-            }
-        }
-    }
-    // Barrier 1 (also publishes s_area): plain-background CTAs are done.
-    if (!__syncthreads_or(!pure_bg)) return;                        // block-uniform
-
-    if (flags) atomicOr(status + EMP_ST_FLAGS, flags);
-    {
-        const unsigned peers = __match_any_sync(0xffffffffu, akey);
-        const int sum = __reduce_add_sync(peers, acnt);
-        if (akey != kEmptyKey && lane == __ffs(peers) - 1) area_insert(s_area, areas, akey, sum);
-    }
-    {
-        const int sum = __reduce_add_sync(0xffffffffu, deficit);
-        if (sum && lane == 0) atomicAdd(&s_area[0], (unsigned)sum);             // bin 0 holds the deficit
-    }
-    const int any_thing = __syncthreads_or(thing != 0);
-    if (tid < kAreaBins && s_area[tid]) atomicAdd(areas + (tid == 0 ? kNumClasses : tid), s_area[tid]);
-    if (any_thing && tid == 0) {
-        const int idx = atomicAdd(status + EMP_ST_NTILES, 1);
-        reinterpret_cast<uint32_t*>(a.ws + a.o_worklist)[idx] = blockIdx.y * gridDim.x + blockIdx.x;
-    }
-}
-
-struct ArgminArgs {
-    const float* off;
-    void* codes;
-    char* ws;
-    size_t o_status, o_centers, o_votes, o_lut, o_worklist;
-    int H, W, tiles_x, vec, k_cap, chunksize;
-    float step;
-    long long label_divisor, void_label;
-    Things things;
-};
-
-template <bool C16>
-__global__ void __launch_bounds__(kAssignThreads, 3)
-argmin_tiles_kernel(const __grid_constant__ ArgminArgs a)
-{
-    constexpr uint32_t kPend = C16 ? kPend16 : kPend32;
-    __shared__ AssignSmem sm;
-    __shared__ int s_ntiles;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int H = a.H, W = a.W;
-    const size_t HW = (size_t)H * W;
-    int32_t* status = reinterpret_cast<int32_t*>(a.ws + a.o_status);
-    const float2* centers = reinterpret_cast<const float2*>(a.ws + a.o_centers);
-    uint32_t* votes = reinterpret_cast<uint32_t*>(a.ws + a.o_votes);
-    const uint32_t* worklist = reinterpret_cast<const uint32_t*>(a.ws + a.o_worklist);
-    const int T = a.things.n > 0 ? a.things.n : 1;
-
-    if (tid == 0) {
-        sm.kshared = min(__ldcg(status + EMP_ST_K), a.k_cap);
-        s_ntiles = __ldcg(status + EMP_ST_NTILES);
-    }
-    if (tid < kVoteSlots) { sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0; }
-    __syncthreads();
-    const int K = sm.kshared;
-    const int ntiles = s_ntiles;
-
-    for (int it = blockIdx.x; it < ntiles; it += gridDim.x) {          // block-uniform
-        const unsigned tile = __ldcg(worklist + it);
-        const int col0 = (int)(tile % (unsigned)a.tiles_x) * kTileW + 2 * lane;
-        const int row0 = (int)(tile / (unsigned)a.tiles_x) * kTileH + 4 * warp;
-        const bool cin = col0 < W, c1in = col0 + 1 < W;
-
-        // codes written by classify (L2-resident): which of my pixels await an id?
-        unsigned code[kPx];
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) code[p] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool rin = row0 + i < H && cin;
-            const size_t o = (size_t)(row0 + i) * W + col0;
-            if (C16) {
-                const unsigned short* cp = reinterpret_cast<const unsigned short*>(a.codes) + o;
-                if (a.vec) {
-                    if (rin) { const unsigned u = __ldcg(reinterpret_cast<const unsigned*>(cp)); code[2 * i] = u & 0xFFFFu; code[2 * i + 1] = u >> 16; }
-                } else {
-                    if (rin) code[2 * i] = __ldcg(cp);
-                    if (rin && c1in) code[2 * i + 1] = __ldcg(cp + 1);
-                }
-            } else {
-                const unsigned* cp = reinterpret_cast<const unsigned*>(a.codes) + o;
-                if (a.vec) {
-                    if (rin) { const uint2 u = __ldcg(reinterpret_cast<const uint2*>(cp)); code[2 * i] = u.x; code[2 * i + 1] = u.y; }
-                } else {
-                    if (rin) code[2 * i] = __ldcg(cp);
-                    if (rin && c1in) code[2 * i + 1] = __ldcg(cp + 1);
-                }
-            }
-        }
-        unsigned thing = 0;
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) thing |= ((code[p] - kPend < 16u) ? 1u : 0u) << p;
-
-        int idv[kPx];
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) idv[p] = 0;
-        if (K > 0) {                                                    // block-uniform
-            float ly[kPx], lx[kPx];
-            float2 fy[4], fx[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                fy[i] = make_float2(0.f, 0.f); fx[i] = make_float2(0.f, 0.f);
-                const float* oy = a.off + (size_t)(row0 + i) * W + col0;
-                const float* ox = oy + HW;
-                const unsigned t2 = (thing >> (2 * i)) & 3u;
-                if (a.vec) {
-                    if (t2) { fy[i] = __ldcs(reinterpret_cast<const float2*>(oy)); fx[i] = __ldcs(reinterpret_cast<const float2*>(ox)); }
-                } else {
-                    if (t2 & 1u) { fy[i].x = __ldcs(oy); fx[i].x = __ldcs(ox); }
-                    if (t2 & 2u) { fy[i].y = __ldcs(oy + 1); fx[i].y = __ldcs(ox + 1); }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float ycoord = __fmul_rn((float)(row0 + i), a.step);         // arange(0, H*step, step)
-                ly[2 * i] = __fadd_rn(ycoord, fy[i].x);
-                ly[2 * i + 1] = __fadd_rn(ycoord, fy[i].y);
-                lx[2 * i] = __fadd_rn(__fmul_rn((float)col0, a.step), fx[i].x);
-                lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
-            }
-            nearest_center_8px(sm, centers, K, a.chunksize, thing, ly, lx, idv);
-        }
-
-        // id codes back into the code map (only rows that held pending pixels), votes
-        unsigned vkey = kEmptyKey;
-        int vcnt = 0;
-        unsigned vrest = 0;
-#pragma unroll
-        for (int p = kPx - 1; p >= 0; --p)
-            if (((thing >> p) & 1u) && idv[p] != 0) vkey = (unsigned)idv[p] * (unsigned)T + (code[p] - kPend);
-#pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            const bool isv = ((thing >> p) & 1u) && idv[p] != 0;
-            const unsigned kv = (unsigned)idv[p] * (unsigned)T + (code[p] - kPend);
-            vcnt += (isv && kv == vkey) ? 1 : 0;
-            vrest |= ((isv && kv != vkey) ? 1u : 0u) << p;
-        }
-        if (vrest) {
-#pragma unroll
-            for (int p = 0; p < kPx; ++p)
-                if ((vrest >> p) & 1u) vote_insert(sm, votes, (unsigned)idv[p] * (unsigned)T + (code[p] - kPend), 1);
-        }
-        {
-            const unsigned peers = __match_any_sync(0xffffffffu, vkey);
-            const int sum = __reduce_add_sync(peers, vcnt);
-            if (vkey != kEmptyKey && lane == __ffs(peers) - 1) vote_insert(sm, votes, vkey, sum);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const unsigned t2 = (thing >> (2 * i)) & 3u;
-            if (t2) {
-                const unsigned c0 = (t2 & 1u) ? (unsigned)idv[2 * i] : code[2 * i];
-                const unsigned c1 = (t2 & 2u) ? (unsigned)idv[2 * i + 1] : code[2 * i + 1];
-                const size_t o = (size_t)(row0 + i) * W + col0;
-                if (C16) {
-                    unsigned short* op = reinterpret_cast<unsigned short*>(a.codes) + o;
+        for (int i = 0; i < kItemH; ++i) {
+            if ((inb >> (2 * i)) & 1u) {
+                const size_t o = (size_t)b * a.out_stride + (size_t)(row0 + i) * W + col0;
+                const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
+                if (OUT == OUT_CODE16) {
+                    unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
                     if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
-                    else { if (t2 & 1u) op[0] = (unsigned short)c0; if (t2 & 2u) op[1] = (unsigned short)c1; }
-                } else {
-                    unsigned* op = reinterpret_cast<unsigned*>(a.codes) + o;
+                    else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
+                } else if (OUT == OUT_CODE32) {
+                    unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
                     if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
-                    else { if (t2 & 1u) op[0] = c0; if (t2 & 2u) op[1] = c1; }
+                    else { op[0] = c0; if (c1in) op[1] = c1; }
+                } else if (OUT == OUT_IDS64) {
+                    long long* op = reinterpret_cast<long long*>(a.out) + o;
+                    if (a.vec) __stcs(reinterpret_cast<longlong2*>(op), make_longlong2((long long)c0, (long long)c1));
+                    else { op[0] = (long long)c0; if (c1in) op[1] = (long long)c1; }
+                } else {
+                    int* op = reinterpret_cast<int*>(a.out) + o;
+                    if (a.vec) *reinterpret_cast<int2*>(op) = make_int2((int)c0, (int)c1);
+                    else { op[0] = (int)c0; if (c1in) op[1] = (int)c1; }
                 }
             }
         }
-        __syncthreads();
-        if (tid < kVoteSlots) {
-            if (sm.vkey[tid] != kEmptyKey && sm.vcnt[tid]) atomicAdd(votes + sm.vkey[tid], sm.vcnt[tid]);
-            sm.vkey[tid] = kEmptyKey; sm.vcnt[tid] = 0;
-        }
-        __syncthreads();
     }
-
-    // Last CTA builds the label LUT.  The barrier orders every thread's atomics before thread 0's
-    // device-scope fence (fences are cumulative), which orders them before the ticket; the last CTA
-    // reads the votes straight from L2 (__ldcg).
-    __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        sm.last = (atomicAdd(status + EMP_ST_TICKET, 1) == (int)gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (sm.last) {
-        __threadfence();
-        build_label_lut((long long)K, votes, a.things, a.label_divisor, a.void_label,
-                        reinterpret_cast<long long*>(a.ws + a.o_lut), sm.lut);
-    }
+    flush_image();
 }
 
-// label LUT for the merge entry points (emp_merge / emp_merge_coarse): one CTA
+// label LUT: one CTA per tile
 __global__ void __launch_bounds__(256)
-build_lut_kernel(char* ws, size_t o_status, size_t o_votes, size_t o_lut, int k_cap, int k_fixed,
+build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_votes, size_t o_lut, int k_cap, int k_fixed,
                  const int32_t* k_dev, const __grid_constant__ Things things, long long label_divisor, long long void_label)
 {
+    char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
     __shared__ LutScratch sc;
     __shared__ long long s_k;
     if (threadIdx.x == 0) s_k = lut_extent(k_fixed, k_cap, reinterpret_cast<const int32_t*>(ws + o_status), k_dev);
@@ -1333,47 +1057,70 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
     dim3 g2((H + 31) / 32, 1, B);
     {
         ProfScope ps(ST_EMIT, st);
-        emit_centers_kernel<<<g2, 256, 0, st>>>(ws, ws_stride, L.mask, L.rowcnt, L.centers, L.status, H, L.wd, k_cap,
+        emit_centers_kernel<<<g2, 256, 0, st>>>(ws, ws_stride, L.mask, L.rowcnt, L.centers, L.ctr_i, L.status, H, L.wd, k_cap,
                                                 step, ctr_out, (size_t)cap * 2, cap);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
 
-template <int SEM, int IDM>
-static int launch_assign_out(int out_mode, const AssignArgs& a, dim3 grid, cudaStream_t st)
+template <int SEM, int IDM, int OUT>
+static int launch_assign_t(const AssignArgs& a, cudaStream_t st)
 {
+    constexpr int row_bytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;
+    constexpr int ring_bytes = kAssignWarps * kStages * kItemH * row_bytes;
+    const size_t smem = a.tma ? ring_bytes : 0;
+    EMP_CUDA_CHECK(cudaFuncSetAttribute(assign_kernel<SEM, IDM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+    const long long n_items = (long long)a.items_x * a.items_y * a.B;
+    long long blocks = (n_items + kAssignWarps - 1) / kAssignWarps;
+    const long long resident = (long long)sm_count() * 3;          // __launch_bounds__(256, 3)
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
     ProfScope ps(ST_ASSIGN, st);
-    switch (out_mode) {
-        case OUT_CODE16: assign_kernel<SEM, IDM, OUT_CODE16><<<grid, kAssignThreads, 0, st>>>(a); break;
-        case OUT_CODE32: assign_kernel<SEM, IDM, OUT_CODE32><<<grid, kAssignThreads, 0, st>>>(a); break;
-        case OUT_IDS64:  assign_kernel<SEM, IDM, OUT_IDS64><<<grid, kAssignThreads, 0, st>>>(a); break;
-        default:         assign_kernel<SEM, IDM, OUT_IDS32><<<grid, kAssignThreads, 0, st>>>(a); break;
-    }
+    assign_kernel<SEM, IDM, OUT><<<(unsigned)blocks, kAssignThreads, smem, st>>>(a);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
 
-int launch_assign(int B, int sem_mode, int id_mode, int out_mode, const AssignArgs& a, cudaStream_t st)
+template <int SEM, int IDM>
+static int launch_assign_out(int out_mode, const AssignArgs& a, cudaStream_t st)
 {
-    dim3 grid((a.W + kTileW - 1) / kTileW, (a.H + kTileH - 1) / kTileH, B);
+    switch (out_mode) {
+        case OUT_CODE16: return launch_assign_t<SEM, IDM, OUT_CODE16>(a, st);
+        case OUT_CODE32: return launch_assign_t<SEM, IDM, OUT_CODE32>(a, st);
+        case OUT_IDS64:  return launch_assign_t<SEM, IDM, OUT_IDS64>(a, st);
+        default:         return launch_assign_t<SEM, IDM, OUT_IDS32>(a, st);
+    }
+}
+
+// a.B tiles in one launch; a.sem / a.off / a.ids_in / a.out / a.ws point at the first of them
+int launch_assign(int sem_mode, int id_mode, int out_mode, AssignArgs& a, cudaStream_t st)
+{
+    a.items_x = (a.W + kItemW - 1) / kItemW;
+    a.items_y = (a.H + kItemH - 1) / kItemH;
+    EMP_REQUIRE((long long)a.items_x * a.items_y * a.B < (1ll << 31), EMP_ERR_INVALID, "batch too large for one launch");
+    // TMA staging of the sem plane: 16-byte aligned row segments of a multiple of 16 bytes
+    a.tma = 0;
+    if (sem_mode == SEM_I64) a.tma = a.vec && aligned16(a.sem) && (a.sem_stride % 2 == 0);
+    else if (sem_mode == SEM_U8) a.tma = (a.W % 16 == 0) && aligned16(a.sem) && (a.sem_stride % 16 == 0);
     if (id_mode == ID_ARGMIN) {
-        if (sem_mode == SEM_NONE) return launch_assign_out<SEM_NONE, ID_ARGMIN>(out_mode, a, grid, st);
-        if (sem_mode == SEM_I64) return launch_assign_out<SEM_I64, ID_ARGMIN>(out_mode, a, grid, st);
-        return launch_assign_out<SEM_U8, ID_ARGMIN>(out_mode, a, grid, st);
+        if (sem_mode == SEM_NONE) return launch_assign_out<SEM_NONE, ID_ARGMIN>(out_mode, a, st);
+        if (sem_mode == SEM_I64) return launch_assign_out<SEM_I64, ID_ARGMIN>(out_mode, a, st);
+        return launch_assign_out<SEM_U8, ID_ARGMIN>(out_mode, a, st);
     }
     if (id_mode == ID_DENSE) {
         EMP_REQUIRE(sem_mode == SEM_I64, EMP_ERR_INVALID, "dense-id merge needs int64 sem");
-        return launch_assign_out<SEM_I64, ID_DENSE>(out_mode, a, grid, st);
+        return launch_assign_out<SEM_I64, ID_DENSE>(out_mode, a, st);
     }
-    if (sem_mode == SEM_I64) return launch_assign_out<SEM_I64, ID_COARSE>(out_mode, a, grid, st);
+    if (sem_mode == SEM_I64) return launch_assign_out<SEM_I64, ID_COARSE>(out_mode, a, st);
     EMP_REQUIRE(sem_mode == SEM_U8, EMP_ERR_INVALID, "coarse-id merge needs int64 or uint8 sem");
-    return launch_assign_out<SEM_U8, ID_COARSE>(out_mode, a, grid, st);
+    return launch_assign_out<SEM_U8, ID_COARSE>(out_mode, a, st);
 }
 
-void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th, long long label_divisor, long long void_label)
+void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th)
 {
-    a.o_status = L.status; a.o_centers = L.centers; a.o_votes = L.votes; a.o_areas = L.areas; a.o_lut = L.lut;
+    a.o_status = L.status; a.o_votes = L.votes; a.o_areas = L.areas;
+    a.o_cell_start = L.cell_start; a.o_sorted = L.sorted;
     a.things = th;
     a.thing_bits = 0ull;
     a.things_small = 1;
@@ -1381,8 +1128,6 @@ void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th, long
         if (th.v[i] >= 0 && th.v[i] < 64) a.thing_bits |= 1ull << th.v[i];
         else a.things_small = 0;
     }
-    a.label_divisor = label_divisor;
-    a.void_label = void_label;
 }
 
 int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long label_divisor, long long stuff_area,
@@ -1394,7 +1139,7 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas;
     a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = n_px;
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
-    a.vec = aligned16(pan_out);
+    a.vec = aligned16(pan_out) && (n_px % 2 == 0 || B == 1);
     const size_t groups = a.vec ? n_px / 512 : 0;
     size_t blocks = groups ? (groups + 7) / 8 : (n_px + 255) / 256;
     if (blocks > (1u << 30)) blocks = 1u << 30;
@@ -1407,57 +1152,23 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     return EMP_OK;
 }
 
-int launch_build_lut(const WsLayout& L, char* ws, int k_cap, int k_fixed, const int32_t* k_dev, const Things& th,
-                     long long label_divisor, long long void_label, cudaStream_t st)
+int launch_build_lut(int B, const WsLayout& L, char* ws, size_t ws_stride, int k_cap, int k_fixed, const int32_t* k_dev,
+                     const Things& th, long long label_divisor, long long void_label, cudaStream_t st)
 {
     ProfScope ps(ST_LUT, st);
-    build_lut_kernel<<<1, 256, 0, st>>>(ws, L.status, L.votes, L.lut, k_cap, k_fixed, k_dev, th, label_divisor, void_label);
+    build_lut_kernel<<<dim3(1, 1, B), 256, 0, st>>>(ws, ws_stride, L.status, L.votes, L.lut, k_cap, k_fixed, k_dev, th,
+                                                    label_divisor, void_label);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
 
-// classify -> argmin_tiles (+ LUT) for one tile of the fused path
-int launch_classify_argmin(const void* sem, int sem_u8, const float* off, int H, int W, const WsLayout& L, char* ws,
-                           int k_cap, const Things& th, long long label_divisor, long long void_label, cudaStream_t st)
+// cell index over the centers of B tiles (k_fixed < 0: K comes from the status block)
+int launch_bin(int B, const WsLayout& L, char* ws, size_t ws_stride, int H, int W, int k_cap, int k_fixed, float step,
+               cudaStream_t st)
 {
-    const int tiles_x = (W + kTileW - 1) / kTileW, tiles_y = (H + kTileH - 1) / kTileH;
-    ClassifyArgs c;
-    memset(&c, 0, sizeof(c));
-    c.sem = sem; c.codes = ws + L.codes; c.ws = ws;
-    c.o_status = L.status; c.o_areas = L.areas; c.o_worklist = L.worklist;
-    c.H = H; c.W = W;
-    c.vec = (W % 4 == 0) && aligned16(sem);
-    c.things = th; c.thing_bits = 0ull; c.things_small = 1;
-    for (int i = 0; i < th.n; ++i) {
-        if (th.v[i] >= 0 && th.v[i] < 64) c.thing_bits |= 1ull << th.v[i];
-        else c.things_small = 0;
-    }
-    dim3 grid(tiles_x, tiles_y, 1);
-    {
-        ProfScope ps(ST_ASSIGN, st);
-        if (L.code16) {
-            if (sem_u8) classify_kernel<SEM_U8, true><<<grid, 256, 0, st>>>(c);
-            else classify_kernel<SEM_I64, true><<<grid, 256, 0, st>>>(c);
-        } else {
-            if (sem_u8) classify_kernel<SEM_U8, false><<<grid, 256, 0, st>>>(c);
-            else classify_kernel<SEM_I64, false><<<grid, 256, 0, st>>>(c);
-        }
-    }
-    EMP_CUDA_CHECK(cudaGetLastError());
-    ArgminArgs g;
-    memset(&g, 0, sizeof(g));
-    g.off = off; g.codes = ws + L.codes; g.ws = ws;
-    g.o_status = L.status; g.o_centers = L.centers; g.o_votes = L.votes; g.o_lut = L.lut; g.o_worklist = L.worklist;
-    g.H = H; g.W = W; g.tiles_x = tiles_x; g.k_cap = k_cap; g.chunksize = 20; g.step = 1.0f;
-    g.vec = (W % 4 == 0) && aligned16(off);
-    g.label_divisor = label_divisor; g.void_label = void_label; g.things = th;
-    int blocks = sm_count() * 3;
-    if (blocks > tiles_x * tiles_y) blocks = tiles_x * tiles_y;
-    {
-        ProfScope ps(ST_LUT, st);       // profiling slot 3: argmin over thing tiles + label LUT
-        if (L.code16) argmin_tiles_kernel<true><<<blocks, kAssignThreads, 0, st>>>(g);
-        else argmin_tiles_kernel<false><<<blocks, kAssignThreads, 0, st>>>(g);
-    }
+    ProfScope ps(ST_BIN, st);
+    bin_centers_kernel<<<dim3(1, 1, B), 1024, 0, st>>>(ws, ws_stride, L.status, L.centers, L.ctr_i, L.cell_start,
+                                                       L.cell_fill, L.sorted, H, W, k_cap, k_fixed, step);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
@@ -1465,10 +1176,26 @@ int launch_classify_argmin(const void* sem, int sem_u8, const float* off, int H,
 int load_centers(const int64_t* ctr, int K, float step, const WsLayout& L, char* ws, cudaStream_t st)
 {
     if (K > 0) {
-        load_centers_kernel<<<(K + 255) / 256, 256, 0, st>>>(ctr, K, step, reinterpret_cast<float2*>(ws + L.centers));
+        load_centers_kernel<<<(K + 255) / 256, 256, 0, st>>>(ctr, K, step, reinterpret_cast<float2*>(ws + L.centers),
+                                                             reinterpret_cast<int2*>(ws + L.ctr_i));
         EMP_CUDA_CHECK(cudaGetLastError());
     }
     return EMP_OK;
+}
+
+// tiles per assign -> build_lut -> apply launch group of the fused path: a group's code maps
+// (2 B/px each) should still be in L2 when apply_lut reads them back (126 MB L2).
+static int tile_group(size_t code_bytes_per_tile)
+{
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("EMP_TILE_GROUP");
+        env = e ? atoi(e) : 0;
+    }
+    if (env > 0) return env;
+    const size_t budget = 40u << 20;
+    const size_t g = budget / (code_bytes_per_tile ? code_bytes_per_tile : 1);
+    return g < 1 ? 1 : (int)g;
 }
 
 }  // namespace emp
@@ -1489,7 +1216,7 @@ EMP_API int emp_profile_enable(int on)
 
 EMP_API int emp_profile_read(double* ms_per_stage, int* launches_per_stage)
 {
-    for (int i = 0; i < ST_COUNT; ++i) { ms_per_stage[i] = 0.0; launches_per_stage[i] = 0; }
+    for (int i = 0; i < ST_COUNT; ++i) { ms_per_stage[i] = 0.0; launches_per_stage[i] = 0; }   // ST_COUNT == EMP_PROFILE_STAGES
     for (size_t i = 0; i < g_prof_used; ++i) {
         EMP_CUDA_CHECK(cudaEventSynchronize(g_prof[i].b));
         float ms = 0.f;
@@ -1543,15 +1270,16 @@ EMP_API int emp_group_pixels(const int64_t* ctr, int K, const float* off, int H,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EMP_CUDA_CHECK(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
     if ((rc = load_centers(ctr, K, step, L, static_cast<char*>(ws), st))) return rc;
+    if ((rc = launch_bin(1, L, static_cast<char*>(ws), L.total, H, W, K, K, step, st))) return rc;
     AssignArgs a;
     memset(&a, 0, sizeof(a));
     a.off = off; a.off_stride = (size_t)2 * H * W;
     a.out = ids_out; a.out_stride = (size_t)H * W;
     a.ws = static_cast<char*>(ws); a.ws_stride = L.total;
-    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none, 0, 0); }
-    a.H = H; a.W = W; a.step = step; a.chunksize = chunksize; a.k_cap = K; a.k_fixed = K;
+    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none); }
+    a.B = 1; a.H = H; a.W = W; a.step = step; a.chunksize = chunksize; a.k_cap = K; a.k_fixed = K;
     a.vec = (W % 4 == 0) && aligned16(off) && aligned16(ids_out);
-    return launch_assign(1, SEM_NONE, ID_ARGMIN, ids_i32 ? OUT_IDS32 : OUT_IDS64, a, st);
+    return launch_assign(SEM_NONE, ID_ARGMIN, ids_i32 ? OUT_IDS32 : OUT_IDS64, a, st);
 }
 
 EMP_API int emp_coarse_ids(const float* hm, const float* off, int h, int w, float threshold, int nms_kernel,
@@ -1566,15 +1294,16 @@ EMP_API int emp_coarse_ids(const float* hm, const float* off, int h, int w, floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EMP_CUDA_CHECK(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
     if ((rc = launch_centers(1, hm, h, w, threshold, nms_kernel, step, L, static_cast<char*>(ws), L.total, k_cap, nullptr, 0, st))) return rc;
+    if ((rc = launch_bin(1, L, static_cast<char*>(ws), L.total, h, w, k_cap, -1, step, st))) return rc;
     AssignArgs a;
     memset(&a, 0, sizeof(a));
     a.off = off; a.off_stride = (size_t)2 * h * w;
     a.out = ids_out; a.out_stride = (size_t)h * w;
     a.ws = static_cast<char*>(ws); a.ws_stride = L.total;
-    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none, 0, 0); }
-    a.H = h; a.W = w; a.step = step; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
+    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none); }
+    a.B = 1; a.H = h; a.W = w; a.step = step; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
     a.vec = (w % 4 == 0) && aligned16(off) && aligned16(ids_out);
-    return launch_assign(1, SEM_NONE, ID_ARGMIN, OUT_IDS32, a, st);
+    return launch_assign(SEM_NONE, ID_ARGMIN, OUT_IDS32, a, st);
 }
 
 EMP_API int emp_instance_segmentation(const int64_t* sem, const float* hm, const float* off, int H, int W,
@@ -1593,16 +1322,17 @@ EMP_API int emp_instance_segmentation(const int64_t* sem, const float* hm, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     EMP_CUDA_CHECK(cudaMemsetAsync(ws, 0, L.zero_bytes, st));
     if ((rc = launch_centers(1, hm, H, W, threshold, nms_kernel, 1.0f, L, static_cast<char*>(ws), L.total, k_cap, ctr_out, cap, st))) return rc;
+    if ((rc = launch_bin(1, L, static_cast<char*>(ws), L.total, H, W, k_cap, -1, 1.0f, st))) return rc;
     AssignArgs a;
     memset(&a, 0, sizeof(a));
     a.sem = sem; a.sem_stride = (size_t)H * W;
     a.off = off; a.off_stride = (size_t)2 * H * W;
     a.out = ins_out; a.out_stride = (size_t)H * W;
     a.ws = static_cast<char*>(ws); a.ws_stride = L.total;
-    fill_assign_common(a, L, th, 0, 0);
-    a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
+    fill_assign_common(a, L, th);
+    a.B = 1; a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
     a.vec = (W % 4 == 0) && aligned16(sem) && aligned16(off) && aligned16(ins_out);
-    return launch_assign(1, SEM_I64, ID_ARGMIN, OUT_IDS64, a, st);
+    return launch_assign(SEM_I64, ID_ARGMIN, OUT_IDS64, a, st);
 }
 
 static int merge_common(const void* sem, int sem_mode, int id_mode, const void* ids_in, int wc, int shift,
@@ -1627,12 +1357,12 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.ids_in = ids_in; a.ids_stride = 0; a.wc = wc; a.shift = shift;
     a.out = static_cast<char*>(ws) + L.codes; a.out_stride = 0;
     a.ws = static_cast<char*>(ws); a.ws_stride = L.total;
-    fill_assign_common(a, L, th, label_divisor, void_label);
-    a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = k_cap;
-    a.max_id = max_id; a.k_dev = k_dev;
+    fill_assign_common(a, L, th);
+    a.B = 1; a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = k_cap;
+    a.max_id = max_id;
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
-    if ((rc = launch_assign(1, sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-    if ((rc = launch_build_lut(L, static_cast<char*>(ws), k_cap, k_cap, k_dev, th, label_divisor, void_label, st))) return rc;
+    if ((rc = launch_assign(sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
+    if ((rc = launch_build_lut(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, void_label, st))) return rc;
     return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out,
                         (size_t)H * W, st);
 }
@@ -1677,20 +1407,30 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
     char* wsb = static_cast<char*>(ws);
     const size_t n_px = (size_t)H * W;
 
-    for (int b = 0; b < B; ++b)
-        EMP_CUDA_CHECK(cudaMemsetAsync(wsb + (size_t)b * ws_bytes_per_tile, 0, L.zero_bytes, st));
+    EMP_CUDA_CHECK(cudaMemset2DAsync(wsb, ws_bytes_per_tile, 0, L.zero_bytes, (size_t)B, st));
     if ((rc = launch_centers(B, hm, H, W, threshold, nms_kernel, 1.0f, L, wsb, ws_bytes_per_tile, k_cap, ctr_out, cap, st))) return rc;
+    if ((rc = launch_bin(B, L, wsb, ws_bytes_per_tile, H, W, k_cap, -1, 1.0f, st))) return rc;
 
     const size_t sem_elt = sem_u8 ? 1 : 8;
-    // classify -> argmin over thing tiles (+ label LUT) -> apply, tile by tile, so that a tile's code
-    // map (2 B/px) is still in L2 when the next kernel reads it back.
-    for (int b = 0; b < B; ++b) {
-        char* wst = wsb + (size_t)b * ws_bytes_per_tile;
-        if ((rc = launch_classify_argmin(static_cast<const char*>(sem) + (size_t)b * n_px * sem_elt, sem_u8,
-                                         off + (size_t)b * 2 * n_px, H, W, L, wst, k_cap, th, label_divisor,
-                                         void_label, st))) return rc;
-        if ((rc = launch_apply(1, L, wst, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
-                               pan_out + (size_t)b * n_px, n_px, st))) return rc;
+    // assign -> label LUT -> apply in groups of tiles small enough that a group's code maps
+    // (2 B/px) are still in L2 when apply_lut reads them back.
+    const int G = tile_group((L.code16 ? 2 : 4) * n_px);
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int nb = std::min(G, B - b0);
+        char* wsg = wsb + (size_t)b0 * ws_bytes_per_tile;
+        AssignArgs a;
+        memset(&a, 0, sizeof(a));
+        a.sem = static_cast<const char*>(sem) + (size_t)b0 * n_px * sem_elt; a.sem_stride = n_px;
+        a.off = off + (size_t)b0 * 2 * n_px; a.off_stride = 2 * n_px;
+        a.out = wsg + L.codes; a.out_stride = ws_bytes_per_tile / (L.code16 ? 2 : 4);
+        a.ws = wsg; a.ws_stride = ws_bytes_per_tile;
+        fill_assign_common(a, L, th);
+        a.B = nb; a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
+        a.vec = (W % 4 == 0) && aligned16(a.sem) && aligned16(a.off) && (n_px % 4 == 0 || nb == 1);
+        if ((rc = launch_assign(sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
+        if ((rc = launch_build_lut(nb, L, wsg, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, void_label, st))) return rc;
+        if ((rc = launch_apply(nb, L, wsg, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
+                               pan_out + (size_t)b0 * n_px, n_px, st))) return rc;
     }
     return EMP_OK;
 }

@@ -47,9 +47,9 @@ extern "C" {
 #define EMP_ST_NROWRUNS 2   /* rle: row-runs found */
 #define EMP_ST_NRUNS 3      /* rle: final runs */
 #define EMP_ST_NINST 4      /* rle: instances (distinct output labels) */
-#define EMP_ST_TICKET 5     /* internal: CTA completion counter of the argmin kernel */
-#define EMP_ST_NTILES 6     /* internal: tiles holding thing pixels (worklist length) */
+#define EMP_ST_GSHIFT 5     /* internal: log2 of the center-index cell size in pixels */
 #define EMP_ST_WORDS 16
+#define EMP_PROFILE_STAGES 9
 
 #define EMP_FLAG_K_OVERFLOW 1     /* more centers than k_cap: result invalid, retry with larger cap */
 #define EMP_FLAG_CLASS_RANGE 2    /* a semantic class id outside [0, EMP_MAX_CLASSES) was seen */
@@ -61,10 +61,9 @@ const char* emp_last_error(void);
 
 /* Optional per-stage device timing for benchmarks: while enabled, every kernel launch is
  * bracketed by a CUDA event pair on its stream.  emp_profile_read() waits for the recorded events
- * and returns, per stage (0 nms_peaks, 1 emit_centers, 2 classify [assign in the merge entry points],
- * 3 argmin_tiles + label LUT [build_lut in the merge entry points], 4 apply_lut,
- * 5 median_harden, 6 rle_mark, 7 rle run kernels), the summed milliseconds and the number of
- * launches since the last read.  Both arrays have 8 entries (host). */
+ * and returns, per stage (0 nms_peaks, 1 emit_centers, 2 assign, 3 build_lut, 4 apply_lut,
+ * 5 median_harden, 6 rle_mark, 7 rle run kernels, 8 bin_centers), the summed milliseconds and the
+ * number of launches since the last read.  Both arrays have EMP_PROFILE_STAGES entries (host). */
 int emp_profile_enable(int on);
 int emp_profile_read(double* ms_per_stage, int* launches_per_stage);
 
