@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libempanada_b200.so')
+LIB_PATH = os.environ.get('EMP_B200_LIB') or os.path.join(_HERE, 'lib', 'libempanada_b200.so')
 
 EMP_OK = 0
 ST_K, ST_FLAGS, ST_NROWRUNS, ST_NRUNS, ST_NINST, ST_WORDS = 0, 1, 2, 3, 4, 16

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_DIR = os.path.join(HERE, 'lib')
-LIB = os.path.join(LIB_DIR, 'libempanada_b200.so')
+LIB = os.environ.get('EMP_B200_LIB') or os.path.join(LIB_DIR, 'libempanada_b200.so')   # override: tuning experiments only
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',
@@ -42,12 +42,13 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', 'nvcc')
     objs = []
     procs = []
-    obj_dir = os.path.join(HERE, 'build')
+    extra = os.environ.get('EMP_NVCC_EXTRA', '').split()      # e.g. -DEMP_ASSIGN_CTAS_PER_SM=4 (tuning experiments)
+    obj_dir = os.path.join(HERE, 'build' + ('_' + str(abs(hash(tuple(extra))) % 10000) if extra else ''))
     os.makedirs(obj_dir, exist_ok=True)
     for src in sources():
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for cmd, p in procs:

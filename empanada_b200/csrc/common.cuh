@@ -164,6 +164,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+// One box of a tiled tensor map (cuTensorMapEncodeTiled) global -> shared, rank 3; elements outside
+// the tensor are zero-filled and still count towards the barrier's byte total.  SASS: UTMALDG.
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;

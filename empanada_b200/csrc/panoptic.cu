@@ -10,6 +10,7 @@
 //   build_lut      votes                       -> label LUT (K+1)
 //   apply_lut      code map (2 B/px)           -> pan (8 B/px)
 // DESIGN.md has the data layout, the exactness argument for the culled argmin and the roofline.
+#include <cuda.h>       // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved through the runtime
 #include <limits.h>
 #include <math_constants.h>
 #include <stdlib.h>
@@ -377,13 +378,16 @@ bin_centers_kernel(char* __restrict__ ws_base, size_t ws_stride, size_t o_status
 // get_instance_segmentation (:207-221) and the vote / stuff-area pass of
 // merge_semantic_and_instance (:253-294).
 //
-// Persistent kernel, warp-autonomous.  The work item is a strip of 4 rows x 64 columns; lane l
-// owns columns 2l, 2l+1 of each row, so every warp-wide access covers one whole 64-pixel row
-// segment: 512 B of int64 sem, 256 B of an offset plane (LDG.64), 128 B of uint16 codes (STG.32).
-// The sem plane — the only stream every pixel needs — is staged through a per-warp ring of
-// kStages shared-memory buffers filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx):
-// lane 0 issues the rows of the item kStages iterations ahead, so loads stay in flight while the warp
-// classifies, searches and stores.  There is no block-wide barrier anywhere in the loop.
+// Persistent kernel, warp-autonomous.  Warps draw 64 x 64-pixel blocks (the first statically, the
+// rest from a device-wide counter, so instance-heavy blocks balance out) and walk each block as 16
+// strips of 4 rows x 64 columns; lane l owns columns 2l, 2l+1 of each row, so every warp-wide access
+// covers one whole 64-pixel row segment: 512 B of int64 sem, 256 B of an offset plane (LDG.64),
+// 128 B of uint16 codes (STG.32).  The sem plane — the only stream every pixel needs — is staged
+// through a per-warp ring of kStages shared-memory buffers, each filled by ONE TMA tensor copy
+// (cp.async.bulk.tensor.3d, box 1 x 4 x 64 of the (B,H,W) view, out-of-image elements zero-filled by
+// the hardware, completion on an mbarrier): lane 0 issues the strip kStages iterations ahead — across
+// block boundaries — so loads stay in flight while the warp classifies, searches and stores.  There
+// is no block-wide barrier anywhere in the loop.
 //
 // Exact nearest center.  For each pixel the reference takes, over ALL K centers,
 //       d_k = sqrt_rn(fma(dx, dx, rn(dy*dy))),  dy = cy_k - ly,  dx = cx_k - lx   (fp32)
@@ -402,26 +406,32 @@ enum { ID_ARGMIN = 0, ID_DENSE = 1, ID_COARSE = 2 };
 enum { OUT_CODE16 = 0, OUT_CODE32 = 1, OUT_IDS64 = 2, OUT_IDS32 = 3 };
 
 struct AssignArgs {
+    CUtensorMap tmap;                          // FAST: (B, H, W) view of the sem planes, box 1 x 4 x 64
     const void* sem;    size_t sem_stride;     // elements per tile
     const float* off;   size_t off_stride;     // floats per tile (2*H*W)
     const void* ids_in; size_t ids_stride;     // ID_DENSE: int64 H*W, ID_COARSE: int32 hc*wc
     void* out;          size_t out_stride;     // elements per tile
     char* ws;           size_t ws_stride;
     size_t o_status, o_votes, o_areas, o_cell_start, o_sorted;
+    int32_t* counter;                          // zeroed device word: dynamic block hand-out
     int B, H, W, wc, shift;
-    int items_x, items_y;                      // strips per row / strip rows per tile
+    int blocks_x, blocks_y;                    // 64 x 64 blocks per tile row / column
     float step;
     int chunksize, k_cap, k_fixed;             // k_fixed >= 0: K known on the host
     long long max_id;
-    int vec;                                   // 1: W % 4 == 0 and all planes 16-byte aligned
-    int tma;                                   // 1: the sem plane can be staged with bulk copies
+    int vec;                                   // host: W % 4 == 0 and all planes 16-byte aligned
+    int fast;                                  // host: launch the FAST instantiation (vector accesses + TMA staging)
     unsigned long long thing_bits;             // bit c set <=> class c (< 64) is a thing class
     int things_small;                          // every thing class is < 64 (bit test suffices)
     Things things;
 };
 
-constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 256, kAssignWarps = 8, kPx = 8;
+#ifndef EMP_ASSIGN_CTAS_PER_SM
+#define EMP_ASSIGN_CTAS_PER_SM 4
+#endif
+constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 128, kAssignWarps = 4, kAssignCtasPerSm = EMP_ASSIGN_CTAS_PER_SM, kPx = 8;
 constexpr int kStages = 3;
+constexpr int kBlkItems = 16;                  // strips per block: 64 rows
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
 constexpr unsigned kNoKey = 0xFFFFFFFFu;
 
@@ -455,6 +465,16 @@ __device__ __forceinline__ unsigned classify_small(unsigned c, unsigned long lon
     const unsigned th = (unsigned)(tbits >> c) & 1u;
     const unsigned t = multi ? (unsigned)__popcll(tbits & ((1ull << c) - 1ull)) : 0u;
     return th ? (kInfoThing | t) : c;
+}
+
+// rare paths are kept out of line so that the per-pixel code stays small
+__device__ __noinline__ void count_slow(uint32_t* p, unsigned v) { atomicAdd(p, v); }
+
+__device__ __forceinline__ unsigned classify(long long v, unsigned long long tbits, bool multi, int things_small,
+                                             const Things& things)
+{
+    if ((unsigned long long)v < 64ull) return classify_small((unsigned)v, tbits, multi);
+    return classify_slow(v, tbits, things_small, things);
 }
 
 // merge_semantic_and_instance's bookkeeping (postprocess.py:263-281), by one 256-thread CTA:
@@ -512,34 +532,80 @@ struct GridView {
     float step;
 };
 
-// Exact nearest center for the warp's thing pixels (8 per lane), see the comment above.  Called by
-// all 32 lanes (converged).  bd / bk come back as the lexicographic minimum of (d_k, k); bk stays
-// INT_MAX when no distance compared below +inf (non-finite locations).
-__device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thing, const float (&ly)[kPx],
-                                                 const float (&lx)[kPx], float (&bd)[kPx], int (&bk)[kPx])
+// The reference's own comparison for ONE pixel over the centers binned in cell rows ya..yb, columns
+// xa..xb: minimum of the rounded distances sqrt_rn(s), ties to the lower index.  Out of line and
+// scalar: it only runs for pixels that met a near-tie in the sqrt-free pass below (exact ties need
+// integer-like offsets).  Returns (bits of s of the winner) << 32 | index.
+__device__ __noinline__ unsigned long long precise_pixel(const int* __restrict__ cell_start, const float4* __restrict__ sorted,
+                                                         int ncx, int ya, int yb, int xa, int xb, float ly, float lx)
 {
-    int y0 = INT_MAX, y1 = -1, x0 = INT_MAX, x1 = -1;
+    float bd = CUDART_INF_F, bs = CUDART_INF_F;
+    int bk = INT_MAX;
+    for (int row = ya; row <= yb; ++row) {
+        const int s = __ldg(cell_start + row * ncx + xa);
+        const int e = __ldg(cell_start + row * ncx + xb + 1);
+        for (int j = s; j < e; ++j) {
+            const float4 c = __ldg(sorted + j);
+            const int ck = __float_as_int(c.z);
+            const float dy = __fsub_rn(c.x, ly);
+            const float dx = __fsub_rn(c.y, lx);
+            const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            const float d = __fsqrt_rn(s2);
+            if (d < bd || (d == bd && ck < bk)) { bd = d; bs = s2; bk = ck; }
+        }
+    }
+    return ((unsigned long long)__float_as_uint(bs) << 32) | (unsigned)bk;
+}
+
+// Exact nearest center for the warp's thing pixels (8 per lane), see the comment above.  Called by
+// all 32 lanes (converged).  bs / bk come back as (d_k^2, k) of the lexicographic minimum of
+// (d_k, k) over all centers; bk stays INT_MAX when no distance compared below +inf (non-finite
+// locations).
+//
+// The pass over a block keeps s = d^2 and evaluates no sqrt: sqrt_rn is monotone, and two s that
+// differ by more than 1e-6 relative have sqrt_rn values several ulps apart, so
+// "s2 < bs * (1 - 1e-6)" is a strict win and "s2 > bs * (1 + 1e-6)" a strict loss.  A pixel that
+// meets a candidate inside that sliver is redone by precise_pixel().
+__device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thing, const float (&ly)[kPx],
+                                                 const float (&lx)[kPx], float (&bs)[kPx], int (&bk)[kPx])
+{
+    // box of the shifted locations (fminf / fmaxf skip NaNs), then its cell range over the warp
+    float fy0 = CUDART_INF_F, fy1 = -CUDART_INF_F, fx0 = CUDART_INF_F, fx1 = -CUDART_INF_F;
     unsigned fin = 0;                                   // thing pixels with a finite location
 #pragma unroll
     for (int p = 0; p < kPx; ++p) {
-        bd[p] = CUDART_INF_F; bk[p] = INT_MAX;
-        if (((thing >> p) & 1u) && isfinite(ly[p]) && isfinite(lx[p])) {
-            fin |= 1u << p;
-            const int gy = min(max(__float2int_rd(ly[p] * g.inv_cell), 0), g.ncy - 1);
-            const int gx = min(max(__float2int_rd(lx[p] * g.inv_cell), 0), g.ncx - 1);
-            y0 = min(y0, gy); y1 = max(y1, gy); x0 = min(x0, gx); x1 = max(x1, gx);
+        bs[p] = CUDART_INF_F; bk[p] = INT_MAX;
+        if ((thing >> p) & 1u) {
+            fy0 = fminf(fy0, ly[p]); fy1 = fmaxf(fy1, ly[p]);
+            fx0 = fminf(fx0, lx[p]); fx1 = fmaxf(fx1, lx[p]);
+            if (fabsf(ly[p]) < CUDART_INF_F && fabsf(lx[p]) < CUDART_INF_F) fin |= 1u << p;
         }
+    }
+    int y0 = INT_MAX, y1 = -1, x0 = INT_MAX, x1 = -1;
+    if (fin) {
+        y0 = min(max(__float2int_rd(fy0 * g.inv_cell), 0), g.ncy - 1);
+        y1 = min(max(__float2int_rd(fy1 * g.inv_cell), 0), g.ncy - 1);
+        x0 = min(max(__float2int_rd(fx0 * g.inv_cell), 0), g.ncx - 1);
+        x1 = min(max(__float2int_rd(fx1 * g.inv_cell), 0), g.ncx - 1);
     }
     y0 = __reduce_min_sync(0xffffffffu, y0); y1 = __reduce_max_sync(0xffffffffu, y1);
     x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
     if (y1 < 0) return;                                 // warp-uniform: nothing finite to search for
 
-    for (int r = 1;; r <<= 1) {
+    // ring 0 is the box's own cells: a location within a pixel or two of its center settles there
+    // unless it sits right at a cell border
+#pragma unroll 1
+    for (int r = 0;; r = r ? 2 * r : 1) {
         const int ya = max(y0 - r, 0), yb = min(y1 + r, g.ncy - 1);
         const int xa = max(x0 - r, 0), xb = min(x1 + r, g.ncx - 1);
+        unsigned near = 0;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) { bs[p] = CUDART_INF_F; bk[p] = INT_MAX; }
+#pragma unroll 1
         for (int row = ya; row <= yb; ++row) {
             const int s = __ldg(g.cell_start + row * g.ncx + xa);
             const int e = __ldg(g.cell_start + row * g.ncx + xb + 1);
+#pragma unroll 1
             for (int j = s; j < e; ++j) {
                 const float4 c = __ldg(g.sorted + j);
                 const int ck = __float_as_int(c.z);
@@ -547,13 +613,26 @@ __device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thi
                 for (int p = 0; p < kPx; ++p) {
                     const float dy = __fsub_rn(c.x, ly[p]);
                     const float dx = __fsub_rn(c.y, lx[p]);
-                    const float d = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                    const bool better = d < bd[p] || (d == bd[p] && ck < bk[p]);
-                    bd[p] = better ? d : bd[p];
+                    const float s2 = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+                    const bool better = s2 < __fmul_rn(bs[p], 0.999999f);
+                    near |= ((!better && s2 <= __fmul_rn(bs[p], 1.000001f)) ? 1u : 0u) << p;
+                    bs[p] = better ? s2 : bs[p];
                     bk[p] = better ? ck : bk[p];
                 }
             }
         }
+        near &= fin;
+        if (near) {                                     // rare, divergent
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) {
+                if ((near >> p) & 1u) {
+                    const unsigned long long v = precise_pixel(g.cell_start, g.sorted, g.ncx, ya, yb, xa, xb, ly[p], lx[p]);
+                    bs[p] = __uint_as_float((unsigned)(v >> 32));
+                    bk[p] = (int)(unsigned)v;
+                }
+            }
+        }
+        __syncwarp();
         if (ya == 0 && yb == g.ncy - 1 && xa == 0 && xb == g.ncx - 1) break;     // every center seen
         const float Ylo = ya == 0 ? -CUDART_INF_F : __fmul_rn(g.step, (float)(ya << g.gs));
         const float Yhi = yb == g.ncy - 1 ? CUDART_INF_F : __fmul_rn(g.step, (float)((yb + 1) << g.gs));
@@ -562,25 +641,32 @@ __device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thi
         bool ok = true;
 #pragma unroll
         for (int p = 0; p < kPx; ++p) {
+            // settled iff d < 0.9999 * m; tested on squares with the slack rounded in our favour
             const float m = fminf(fminf(ly[p] - Ylo, Yhi - ly[p]), fminf(lx[p] - Xlo, Xhi - lx[p]));
-            if (((fin >> p) & 1u) && !(bd[p] < 0.9999f * m)) ok = false;
+            if (((fin >> p) & 1u) && !(m > 0.f && bs[p] < 0.9997f * (m * m))) ok = false;
         }
         if (__all_sync(0xffffffffu, ok)) break;
     }
     // non-finite locations: every d_k is +inf or NaN; the caller maps "no index" to the reference's answer
 #pragma unroll
     for (int p = 0; p < kPx; ++p)
-        if (!((fin >> p) & 1u)) { bd[p] = CUDART_INF_F; bk[p] = INT_MAX; }
+        if (!((fin >> p) & 1u)) { bs[p] = CUDART_INF_F; bk[p] = INT_MAX; }
 }
 
-template <int SEM, int IDM, int OUT>
-__global__ void __launch_bounds__(kAssignThreads, 3)
+// a block of kBlkItems strips (64 rows x 64 columns) of one tile: the unit handed out to warps
+struct Blk {
+    int b, row0, colb, nitems;      // nitems == 0: no such block (past the end)
+};
+
+template <int SEM, int IDM, int OUT, bool FAST>
+__global__ void __launch_bounds__(kAssignThreads, kAssignCtasPerSm)
 assign_kernel(const __grid_constant__ AssignArgs a)
 {
     constexpr bool kCodes = (OUT == OUT_CODE16 || OUT == OUT_CODE32);
+    constexpr bool kTma = FAST && SEM != SEM_NONE;
     constexpr uint32_t kClsBase = (OUT == OUT_CODE16) ? kClsBase16 : kClsBase32;
     constexpr int kRowBytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;       // one staged row of sem
-    constexpr int kSemElt = (SEM == SEM_I64) ? 8 : 1;
+    constexpr unsigned kStageBytes = kItemH * kRowBytes;
     extern __shared__ __align__(128) unsigned char dsm[];                   // [warp][stage][row][kRowBytes]
     __shared__ uint64_t s_bar[kAssignWarps][kStages];
 
@@ -589,33 +675,60 @@ assign_kernel(const __grid_constant__ AssignArgs a)
     const size_t HW = (size_t)H * W;
     const int T = a.things.n > 0 ? a.things.n : 1;
     const bool multi = a.things.n > 1;
-    const int per_img = a.items_x * a.items_y;             // host guarantees per_img * B < 2^31
-    const int n_items = per_img * a.B;
+    const bool class0_stuff = !(a.thing_bits & 1ull);
+    const int per_img = a.blocks_x * a.blocks_y;           // host guarantees per_img * B + warps < 2^31
+    const int n_blocks = per_img * a.B;
     const int total_warps = (int)gridDim.x * kAssignWarps;
-    const int gw = (int)blockIdx.x * kAssignWarps + warp;
-    const bool tma = (SEM != SEM_NONE) && a.tma;
 
-    unsigned char* ring = dsm + (size_t)warp * kStages * kItemH * kRowBytes;
+    auto decode = [&](int blk) {
+        Blk k;
+        k.b = a.B; k.row0 = 0; k.colb = 0; k.nitems = 0;
+        if (blk < n_blocks) {
+            k.b = blk / per_img;
+            const int r = blk - k.b * per_img;
+            const int by = r / a.blocks_x;
+            k.colb = (r - by * a.blocks_x) * kItemW;
+            k.row0 = by * (kBlkItems * kItemH);
+            k.nitems = min(kBlkItems, (H - k.row0 + kItemH - 1) / kItemH);
+        }
+        return k;
+    };
+    // the first block of every warp is static; the rest come from a device-wide counter, so warps
+    // that drew instance-heavy blocks simply take fewer of them
+    auto grab = [&]() {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(a.counter, 1);
+        return total_warps + __shfl_sync(0xffffffffu, v, 0);
+    };
+    int cur = (int)blockIdx.x * kAssignWarps + warp;
+    int nxt = cur < n_blocks ? grab() : n_blocks;
+    Blk kc = decode(cur), kn = decode(nxt);
+
+    // ---- TMA ring: one 64 x 4 box of the sem plane per strip, kStages strips ahead ------------------
+    unsigned char* ring = dsm + (size_t)warp * kStages * kStageBytes;
     uint64_t policy = 0;
-    // lane 0 arms the stage's barrier with the byte count and issues one bulk copy per row of the item
-    auto issue = [&](int stage, int item) {
-        const int b = item / per_img;
-        const int r = item - b * per_img;
-        const int iy = r / a.items_x, ix = r - iy * a.items_x;
-        const int colb = ix * kItemW, rowb = iy * kItemH;
-        const unsigned bytes = (unsigned)min(kItemW, W - colb) * kSemElt;
-        const int nrows = min(kItemH, H - rowb);
-        if (lane == 0) {
-            mbar_expect_tx(&s_bar[warp][stage], bytes * nrows);
-            const unsigned char* src = static_cast<const unsigned char*>(a.sem) +
-                                       ((size_t)b * a.sem_stride + (size_t)rowb * W + colb) * kSemElt;
-            unsigned char* dst = ring + (size_t)stage * kItemH * kRowBytes;
-#pragma unroll
-            for (int rr = 0; rr < kItemH; ++rr)
-                if (rr < nrows) bulk_g2s(dst + rr * kRowBytes, src + (size_t)rr * W * kSemElt, bytes, &s_bar[warp][stage], policy);
+    int p_which = 0, p_i = 0, inflight = 0, st_issue = 0;   // prefetch position: block (0 cur, 1 nxt, 2 beyond), strip
+    auto pump = [&]() {
+        while (inflight < kStages && p_which < 2) {
+            const int nit = p_which == 0 ? kc.nitems : kn.nitems;
+            if (p_i < nit) {
+                if (lane == 0) {
+                    const int pb = p_which == 0 ? kc.b : kn.b;
+                    const int prow = (p_which == 0 ? kc.row0 : kn.row0) + p_i * kItemH;
+                    const int pcol = p_which == 0 ? kc.colb : kn.colb;
+                    mbar_expect_tx(&s_bar[warp][st_issue], kStageBytes);
+                    tma_load_3d(ring + (size_t)st_issue * kStageBytes, &a.tmap, pcol, prow, pb, &s_bar[warp][st_issue], policy);
+                }
+                ++p_i; ++inflight;
+                st_issue = st_issue + 1 == kStages ? 0 : st_issue + 1;
+            } else if (nit == 0) {
+                break;                                      // no such block: nothing further is known yet
+            } else {
+                ++p_which; p_i = 0;
+            }
         }
     };
-    if (tma) {
+    if (kTma) {
         policy = l2_policy_evict_first();
         if (lane == 0) {
 #pragma unroll
@@ -623,11 +736,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
             mbar_fence_init();
         }
         __syncwarp();
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) {
-            const long long item = (long long)gw + (long long)s * total_warps;
-            if (item < n_items) issue(s, (int)item);
-        }
+        pump();
     }
 
     // per-image state
@@ -657,16 +766,11 @@ assign_kernel(const __grid_constant__ AssignArgs a)
         deficit_acc = 0; akey_acc = kNoKey; acnt_acc = 0; flags = 0;
     };
 
-    int n = 0;
-    for (long long item = gw; item < n_items; item += total_warps, ++n) {
-        const int b = (int)item / per_img;
-        const int r = (int)item - b * per_img;
-        const int iy = r / a.items_x, ix = r - iy * a.items_x;
-        const int col0 = ix * kItemW + 2 * lane;
-        const int row0 = iy * kItemH;
-        const bool cin = col0 < W, c1in = col0 + 1 < W;
-
-        if (b != cur_b) {                                   // warp-uniform
+    int st_cons = 0;
+    unsigned parity = 0;
+    while (kc.nitems > 0) {                                 // warp-uniform
+        const int b = kc.b;
+        if (b != cur_b) {
             flush_image();
             cur_b = b;
             char* ws = a.ws + (size_t)b * a.ws_stride;
@@ -683,24 +787,22 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                 g.sorted = reinterpret_cast<const float4*>(ws + a.o_sorted);
             }
         }
+        const int col0 = kc.colb + 2 * lane;
+        const bool cols_full = kc.colb + kItemW <= W;
+        const float xc0 = __fmul_rn((float)col0, a.step), xc1 = __fmul_rn((float)(col0 + 1), a.step);
 
-        // ---- sem (staged by TMA, or loaded directly) and instance ids -----------------------------
-        long long sv[kPx];
-        long long iv[kPx];
+        for (int it = 0; it < kc.nitems; ++it) {
+            const int row0 = kc.row0 + it * kItemH;
+            const bool full = cols_full && row0 + kItemH <= H;              // warp-uniform: no edge masking needed
+            const size_t px0 = (size_t)row0 * W + col0;                     // this lane's first pixel within the tile
+
+            // ---- sem: staged by TMA (FAST) or loaded directly -----------------------------------------
+            long long sv[kPx];
 #pragma unroll
-        for (int p = 0; p < kPx; ++p) { sv[p] = 0; iv[p] = 0; }
-        unsigned inb = 0;           // bit p: pixel p = 2*i + j is inside the image
-#pragma unroll
-        for (int i = 0; i < kItemH; ++i) {
-            const bool rin = (row0 + i) < H && cin;
-            if (rin) inb |= 1u << (2 * i);
-            if (rin && c1in) inb |= 2u << (2 * i);
-        }
-        if (SEM != SEM_NONE) {
-            if (tma) {
-                const int stage = n % kStages;
-                mbar_wait(&s_bar[warp][stage], (unsigned)(n / kStages) & 1u);
-                const unsigned char* sp = ring + (size_t)stage * kItemH * kRowBytes;
+            for (int p = 0; p < kPx; ++p) sv[p] = 0;
+            if (kTma) {
+                mbar_wait(&s_bar[warp][st_cons], parity);
+                const unsigned char* sp = ring + (size_t)st_cons * kStageBytes;
 #pragma unroll
                 for (int i = 0; i < kItemH; ++i) {
                     if (SEM == SEM_I64) {
@@ -711,217 +813,250 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                         sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8;
                     }
                 }
-#pragma unroll
-                for (int p = 0; p < kPx; ++p) sv[p] = ((inb >> p) & 1u) ? sv[p] : 0;    // rows / columns never copied
                 __syncwarp();                               // every lane has its values: the slot is free
-                const long long nxt = item + (long long)kStages * total_warps;
-                if (nxt < n_items) issue(stage, (int)nxt);
-            } else {
+                --inflight;
+                if (++st_cons == kStages) { st_cons = 0; parity ^= 1u; }
+                pump();
+            } else if (SEM != SEM_NONE) {
 #pragma unroll
                 for (int i = 0; i < kItemH; ++i) {
-                    const bool rin = (inb >> (2 * i)) & 1u;
-                    const size_t e = (size_t)b * a.sem_stride + (size_t)(row0 + i) * W + col0;
+                    const bool rin = row0 + i < H && col0 < W;
+                    const bool c1in = col0 + 1 < W;
                     if (SEM == SEM_I64) {
-                        const long long* sp = reinterpret_cast<const long long*>(a.sem) + e;
-                        if (a.vec) {
-                            if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(sp)); sv[2 * i] = u.x; sv[2 * i + 1] = u.y; }
-                        } else {
-                            if (rin) sv[2 * i] = __ldcs(sp);
-                            if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
-                        }
+                        const long long* sp = reinterpret_cast<const long long*>(a.sem) + (size_t)b * a.sem_stride + px0 + (size_t)i * W;
+                        if (rin) sv[2 * i] = __ldcs(sp);
+                        if (rin && c1in) sv[2 * i + 1] = __ldcs(sp + 1);
                     } else {
-                        const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + e;
+                        const unsigned char* sp = reinterpret_cast<const unsigned char*>(a.sem) + (size_t)b * a.sem_stride + px0 + (size_t)i * W;
                         if (rin) sv[2 * i] = sp[0];
                         if (rin && c1in) sv[2 * i + 1] = sp[1];
                     }
                 }
             }
-        }
-        if (IDM == ID_DENSE) {
+
+            // ---- fast path: a full strip of class-0 background (the bulk of an EM tile) ----------------
+            if (SEM != SEM_NONE && IDM != ID_DENSE && kCodes) {
+                unsigned long long orall = 0ull;
 #pragma unroll
-            for (int i = 0; i < kItemH; ++i) {
-                const bool rin = (inb >> (2 * i)) & 1u;
-                const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride +
-                                      (size_t)(row0 + i) * W + col0;
-                if (a.vec) {
-                    if (rin) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(ip)); iv[2 * i] = u.x; iv[2 * i + 1] = u.y; }
-                } else {
-                    if (rin) iv[2 * i] = __ldcs(ip);
-                    if (rin && c1in) iv[2 * i + 1] = __ldcs(ip + 1);
+                for (int p = 0; p < kPx; ++p) orall |= (unsigned long long)sv[p];
+                if (full && class0_stuff && __all_sync(0xffffffffu, orall == 0ull)) {      // warp-uniform
+                    // constant codes, nothing to vote or count (class 0's area is taken by complement)
+#pragma unroll
+                    for (int i = 0; i < kItemH; ++i) {
+                        const size_t o = (size_t)b * a.out_stride + px0 + (size_t)i * W;
+                        if (OUT == OUT_CODE16) {
+                            unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
+                            if (FAST) *reinterpret_cast<unsigned*>(op) = kClsBase | (kClsBase << 16);
+                            else { op[0] = (unsigned short)kClsBase; op[1] = (unsigned short)kClsBase; }
+                        } else {
+                            unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
+                            if (FAST) *reinterpret_cast<uint2*>(op) = make_uint2(kClsBase, kClsBase);
+                            else { op[0] = kClsBase; op[1] = kClsBase; }
+                        }
+                    }
+                    continue;
                 }
             }
-        } else if (IDM == ID_COARSE) {
-#pragma unroll
-            for (int i = 0; i < kItemH; ++i) {
-                const bool rin = (inb >> (2 * i)) & 1u;
-                const int* ip = reinterpret_cast<const int*>(a.ids_in) + (size_t)b * a.ids_stride;
-                const size_t crow = (size_t)((row0 + i) >> a.shift) * a.wc;
-                if (rin) iv[2 * i] = __ldg(ip + crow + (col0 >> a.shift));
-                if (rin && c1in) iv[2 * i + 1] = __ldg(ip + crow + ((col0 + 1) >> a.shift));
-            }
-        }
 
-        // ---- classify ------------------------------------------------------------------------------
-        unsigned long long orall = 0ull, orid = 0ull;
+            // ---- general path ---------------------------------------------------------------------------
+            unsigned inb = 0xFFu;       // bit p: pixel p = 2*i + j is inside the image
+            if (!full) {
+                inb = 0;
 #pragma unroll
-        for (int p = 0; p < kPx; ++p) { orall |= (unsigned long long)sv[p]; orid |= (unsigned long long)iv[p]; }
-        // Fast path: the lane's 8 pixels are all in the image, all background class 0 (not a thing
-        // class) and carry no instance id that could void them — the bulk of an EM tile.
-        const bool pure_bg = SEM != SEM_NONE && inb == 0xFFu && orall == 0ull && !(a.thing_bits & 1ull) &&
-                             (IDM != ID_DENSE || orid == 0ull);
-        unsigned code[kPx];
-        if (__all_sync(0xffffffffu, pure_bg)) {             // warp-uniform: constant output, nothing to count
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) code[p] = kCodes ? kClsBase : 0u;
-        } else {
-            unsigned w[kPx];        // 16-bit info word per pixel
-            unsigned thing = 0;     // bit p: pixel p takes an instance id
-            unsigned bad = 0;
-            int idv[kPx];           // instance id (ID_DENSE / ID_COARSE) or argmin result
-#pragma unroll
-            for (int p = 0; p < kPx; ++p) { w[p] = 0; idv[p] = 0; }
-            if (SEM == SEM_NONE) {
-#pragma unroll
-                for (int p = 0; p < kPx; ++p) w[p] = kInfoThing;
-            } else if (orall < 64ull) {
-#pragma unroll
-                for (int p = 0; p < kPx; ++p) w[p] = classify_small((unsigned)sv[p], a.thing_bits, multi);
-            } else {
-#pragma unroll
-                for (int p = 0; p < kPx; ++p) w[p] = classify_slow(sv[p], a.thing_bits, a.things_small, a.things);
+                for (int i = 0; i < kItemH; ++i) {
+                    if (row0 + i < H && col0 < W) inb |= 1u << (2 * i);
+                    if (row0 + i < H && col0 + 1 < W) inb |= 2u << (2 * i);
+                }
             }
+            unsigned w[kPx];            // info word: thing -> kInfoThing | thing index, stuff -> class, kInfoBad
+            int idv[kPx];               // instance id (ID_DENSE / ID_COARSE) or argmin result
+            unsigned thing = 0;         // bit p: pixel p takes an instance id
+            unsigned bad = 0;           // bit p: class out of range
+            unsigned cls0 = 0;          // bit p: class 0 and not a thing
 #pragma unroll
             for (int p = 0; p < kPx; ++p) {
-                w[p] = ((inb >> p) & 1u) ? w[p] : 0u;
+                w[p] = (SEM == SEM_NONE) ? kInfoThing : classify(sv[p], a.thing_bits, multi, a.things_small, a.things);
                 thing |= ((w[p] >> 15) & 1u) << p;
                 bad |= ((w[p] >> 14) & 1u) << p;
+                cls0 |= (w[p] == 0u ? 1u : 0u) << p;
+                idv[p] = 0;
             }
+            thing &= inb; bad &= inb; cls0 &= inb;          // rows / columns outside the image count for nothing
             if (bad) flags |= EMP_FLAG_CLASS_RANGE;
-            if (IDM != ID_ARGMIN) {
+
+            // instance ids supplied by the caller (merge entry points)
+            unsigned idpos = 0;         // ID_DENSE: bit p: the pixel carries an instance id > 0
+            if (IDM == ID_DENSE) {
 #pragma unroll
-                for (int p = 0; p < kPx; ++p) {
-                    long long v = iv[p];
-                    if (v < 0 || v > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v = 0; }
-                    idv[p] = (int)v;
+                for (int i = 0; i < kItemH; ++i) {
+                    const long long* ip = reinterpret_cast<const long long*>(a.ids_in) + (size_t)b * a.ids_stride + px0 + (size_t)i * W;
+                    long long v0 = 0, v1 = 0;
+                    if (FAST) {
+                        if ((inb >> (2 * i)) & 1u) { const longlong2 u = __ldcs(reinterpret_cast<const longlong2*>(ip)); v0 = u.x; v1 = u.y; }
+                    } else {
+                        if ((inb >> (2 * i)) & 1u) v0 = __ldcs(ip);
+                        if ((inb >> (2 * i)) & 2u) v1 = __ldcs(ip + 1);
+                    }
+                    if (v0 < 0 || v0 > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v0 = 0; }
+                    if (v1 < 0 || v1 > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v1 = 0; }
+                    idv[2 * i] = (int)v0; idv[2 * i + 1] = (int)v1;
+                    idpos |= (v0 > 0 ? 1u : 0u) << (2 * i);
+                    idpos |= (v1 > 0 ? 2u : 0u) << (2 * i);
+                }
+            } else if (IDM == ID_COARSE) {
+#pragma unroll
+                for (int i = 0; i < kItemH; ++i) {
+                    const int* ip = reinterpret_cast<const int*>(a.ids_in) + (size_t)b * a.ids_stride;
+                    const size_t crow = (size_t)((row0 + i) >> a.shift) * a.wc;
+                    int v0 = 0, v1 = 0;
+                    if ((inb >> (2 * i)) & 1u) v0 = __ldg(ip + crow + (col0 >> a.shift));
+                    if ((inb >> (2 * i)) & 2u) v1 = __ldg(ip + crow + ((col0 + 1) >> a.shift));
+                    if (v0 < 0 || v0 > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v0 = 0; }
+                    if (v1 < 0 || v1 > a.max_id) { flags |= EMP_FLAG_ID_RANGE; v1 = 0; }
+                    idv[2 * i] = v0; idv[2 * i + 1] = v1;
                 }
             }
 
-            // ---- nearest center over the cell index ------------------------------------------------
+            // nearest center over the cell index
             if (IDM == ID_ARGMIN && K > 0 && __any_sync(0xffffffffu, thing != 0)) {       // warp-uniform
                 float ly[kPx], lx[kPx];
-                float2 fy[kItemH], fx[kItemH];
 #pragma unroll
                 for (int i = 0; i < kItemH; ++i) {
-                    fy[i] = make_float2(0.f, 0.f); fx[i] = make_float2(0.f, 0.f);
-                    const float* oy = a.off + (size_t)b * a.off_stride + (size_t)(row0 + i) * W + col0;
+                    float2 fy = make_float2(0.f, 0.f), fx = make_float2(0.f, 0.f);
+                    const float* oy = a.off + (size_t)b * a.off_stride + px0 + (size_t)i * W;
                     const float* ox = oy + HW;
                     const unsigned t2 = (thing >> (2 * i)) & 3u;
-                    if (a.vec) {
-                        if (t2) { fy[i] = __ldcs(reinterpret_cast<const float2*>(oy)); fx[i] = __ldcs(reinterpret_cast<const float2*>(ox)); }
+                    if (FAST) {
+                        if (t2) { fy = __ldcs(reinterpret_cast<const float2*>(oy)); fx = __ldcs(reinterpret_cast<const float2*>(ox)); }
                     } else {
-                        if (t2 & 1u) { fy[i].x = __ldcs(oy); fx[i].x = __ldcs(ox); }
-                        if (t2 & 2u) { fy[i].y = __ldcs(oy + 1); fx[i].y = __ldcs(ox + 1); }
+                        if (t2 & 1u) { fy.x = __ldcs(oy); fx.x = __ldcs(ox); }
+                        if (t2 & 2u) { fy.y = __ldcs(oy + 1); fx.y = __ldcs(ox + 1); }
                     }
-                }
-#pragma unroll
-                for (int i = 0; i < kItemH; ++i) {
                     const float ycoord = __fmul_rn((float)(row0 + i), a.step);         // arange(0, H*step, step)
-                    ly[2 * i] = __fadd_rn(ycoord, fy[i].x);
-                    ly[2 * i + 1] = __fadd_rn(ycoord, fy[i].y);
-                    lx[2 * i] = __fadd_rn(__fmul_rn((float)col0, a.step), fx[i].x);
-                    lx[2 * i + 1] = __fadd_rn(__fmul_rn((float)(col0 + 1), a.step), fx[i].y);
+                    ly[2 * i] = __fadd_rn(ycoord, fy.x);
+                    ly[2 * i + 1] = __fadd_rn(ycoord, fy.y);
+                    lx[2 * i] = __fadd_rn(xc0, fx.x);
+                    lx[2 * i + 1] = __fadd_rn(xc1, fx.y);
                 }
-                float bd[kPx];
-                int bk[kPx];
-                grid_nearest_8px(g, thing, ly, lx, bd, bk);
+                float bs[kPx];
+                grid_nearest_8px(g, thing, ly, lx, bs, idv);
 #pragma unroll
                 for (int p = 0; p < kPx; ++p) {
+                    const int bk = idv[p];
                     int id = 0;
                     if ((thing >> p) & 1u) {
-                        if (chunked) id = (bk[p] != INT_MAX && bd[p] < 1e5f) ? bk[p] + 1 : 0;     // sentinel, postprocess.py:98,:110
-                        else id = bk[p] != INT_MAX ? bk[p] + 1 : 1;
+                        if (chunked) {      // sentinel (postprocess.py:98,:110): d < 1e5 on the rounded sqrt
+                            const bool lt = bs[p] < 9.99e9f || (bs[p] < 1.001e10f && __fsqrt_rn(bs[p]) < 1e5f);
+                            id = (bk != INT_MAX && lt) ? bk + 1 : 0;
+                        } else {
+                            id = bk != INT_MAX ? bk + 1 : 1;
+                        }
                     }
                     idv[p] = id;
                 }
             }
 
-            // ---- codes, votes (postprocess.py:263-273), stuff areas (:284-291) -----------------------
-            unsigned voted = 0, stuff = 0;      // bit p: pixel p votes for its instance / counts as stuff area
+            unsigned voted = 0;         // bit p: a thing pixel with an instance id
 #pragma unroll
-            for (int p = 0; p < kPx; ++p) {
-                const bool in = (inb >> p) & 1u;
-                const bool th = (thing >> p) & 1u;
-                const bool bd2 = (bad >> p) & 1u;
-                const int id = idv[p];
-                const bool v = th && id != 0;
-                const bool st0 = in && !th && !bd2 && !(IDM == ID_DENSE && id > 0);
-                const bool st = st0 && w[p] != 0u;              // class-0 stuff is counted by complement
-                if (kCodes) deficit_acc += (in && !(st0 && w[p] == 0u)) ? 1u : 0u;
-                voted |= (v ? 1u : 0u) << p;
-                stuff |= (st ? 1u : 0u) << p;
-                if (kCodes) code[p] = v ? (unsigned)id : (st0 ? kClsBase + w[p] : 0u);
-                else code[p] = th ? (unsigned)id : 0u;
-            }
+            for (int p = 0; p < kPx; ++p) voted |= (idv[p] != 0 ? 1u : 0u) << p;
+            voted &= thing;
+            // stuff pixels (pasted by class if the class is large enough): in the image, not a thing,
+            // class in range, and — with caller-supplied ids — not covered by an instance
+            const unsigned st0 = inb & ~thing & ~bad & ~idpos;
+
+            // votes (postprocess.py:263-273), stuff areas (:284-291)
             if (kCodes) {
-                // votes: one warp-aggregated atomic per distinct (id, class) key among the lanes' first
-                // keys; a lane's pixels with another key (instance borders) go one by one
-                unsigned vkey = kNoKey;
-                int vcnt = 0;
+                deficit_acc += (unsigned)__popc(inb & ~(st0 & cls0));       // class-0 stuff is counted by complement
+                // votes: one warp-aggregated atomic per distinct (id, class) key
+                unsigned vk[kPx];
 #pragma unroll
-                for (int p = kPx - 1; p >= 0; --p)
-                    if ((voted >> p) & 1u) vkey = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
+                for (int p = 0; p < kPx; ++p)
+                    vk[p] = ((voted >> p) & 1u) ? (unsigned)idv[p] * (unsigned)T + (w[p] & 15u) : kNoKey;
+                for (;;) {
+                    unsigned mine = kNoKey;
 #pragma unroll
-                for (int p = 0; p < kPx; ++p) {
-                    const unsigned kv = (unsigned)idv[p] * (unsigned)T + (w[p] & 15u);
-                    const bool isv = (voted >> p) & 1u;
-                    if (isv && kv == vkey) ++vcnt;
-                    else if (isv) atomicAdd(votes + kv, 1u);
-                }
-                if (__any_sync(0xffffffffu, vkey != kNoKey)) {
-                    const unsigned peers = __match_any_sync(0xffffffffu, vkey);
-                    const int sum = __reduce_add_sync(peers, vcnt);
-                    if (vkey != kNoKey && lane == __ffs(peers) - 1) atomicAdd(votes + vkey, (uint32_t)sum);
-                }
-                // stuff areas of non-zero classes: accumulated per lane while the class stays the same
-                if (stuff) {
+                    for (int p = kPx - 1; p >= 0; --p) mine = vk[p] != kNoKey ? vk[p] : mine;
+                    const unsigned bal = __ballot_sync(0xffffffffu, mine != kNoKey);
+                    if (!bal) break;                        // warp-uniform
+                    const int leader = __ffs(bal) - 1;
+                    const unsigned key = __shfl_sync(0xffffffffu, mine, leader);
+                    int cnt = 0;
 #pragma unroll
                     for (int p = 0; p < kPx; ++p) {
-                        if ((stuff >> p) & 1u) {
-                            if (w[p] != akey_acc) {
-                                if (akey_acc != kNoKey && acnt_acc) atomicAdd(areas + akey_acc, acnt_acc);
-                                akey_acc = w[p]; acnt_acc = 0;
-                            }
-                            ++acnt_acc;
-                        }
+                        const bool m = vk[p] == key;
+                        cnt += m ? 1 : 0;
+                        vk[p] = m ? kNoKey : vk[p];
+                    }
+                    const int sum = __reduce_add_sync(0xffffffffu, cnt);
+                    if (lane == leader) atomicAdd(votes + key, (uint32_t)sum);
+                }
+                // stuff areas of non-zero classes: accumulated per lane while the class stays the same
+                const unsigned stuff = st0 & ~cls0;
+                if (stuff) {
+                    unsigned key = kNoKey, cnt = 0, rest = 0;
+#pragma unroll
+                    for (int p = kPx - 1; p >= 0; --p)
+                        if ((stuff >> p) & 1u) key = w[p];
+#pragma unroll
+                    for (int p = 0; p < kPx; ++p) {
+                        const bool isa = (stuff >> p) & 1u;
+                        cnt += (isa && w[p] == key) ? 1u : 0u;
+                        rest |= ((isa && w[p] != key) ? 1u : 0u) << p;
+                    }
+                    if (key != akey_acc) {
+                        if (akey_acc != kNoKey && acnt_acc) count_slow(areas + akey_acc, acnt_acc);
+                        akey_acc = key; acnt_acc = 0;
+                    }
+                    acnt_acc += cnt;
+                    if (rest) {
+#pragma unroll
+                        for (int p = 0; p < kPx; ++p)
+                            if ((rest >> p) & 1u) count_slow(areas + w[p], 1u);
+                    }
+                }
+            }
+
+            // codes / ids out
+#pragma unroll
+            for (int i = 0; i < kItemH; ++i) {
+                if ((inb >> (2 * i)) & 1u) {
+                    unsigned c[2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int p = 2 * i + j;
+                        if (kCodes) c[j] = ((voted >> p) & 1u) ? (unsigned)idv[p] : (((st0 >> p) & 1u) ? kClsBase + w[p] : 0u);
+                        else c[j] = ((thing >> p) & 1u) ? (unsigned)idv[p] : 0u;
+                    }
+                    const bool c1in = (inb >> (2 * i)) & 2u;
+                    const size_t o = (size_t)b * a.out_stride + px0 + (size_t)i * W;
+                    if (OUT == OUT_CODE16) {
+                        unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
+                        if (FAST) *reinterpret_cast<unsigned*>(op) = c[0] | (c[1] << 16);
+                        else { op[0] = (unsigned short)c[0]; if (c1in) op[1] = (unsigned short)c[1]; }
+                    } else if (OUT == OUT_CODE32) {
+                        unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
+                        if (FAST) *reinterpret_cast<uint2*>(op) = make_uint2(c[0], c[1]);
+                        else { op[0] = c[0]; if (c1in) op[1] = c[1]; }
+                    } else if (OUT == OUT_IDS64) {
+                        long long* op = reinterpret_cast<long long*>(a.out) + o;
+                        if (FAST) __stcs(reinterpret_cast<longlong2*>(op), make_longlong2((long long)c[0], (long long)c[1]));
+                        else { op[0] = (long long)c[0]; if (c1in) op[1] = (long long)c[1]; }
+                    } else {
+                        int* op = reinterpret_cast<int*>(a.out) + o;
+                        if (FAST) *reinterpret_cast<int2*>(op) = make_int2((int)c[0], (int)c[1]);
+                        else { op[0] = (int)c[0]; if (c1in) op[1] = (int)c[1]; }
                     }
                 }
             }
         }
 
-        // ---- store ------------------------------------------------------------------------------------
-#pragma unroll
-        for (int i = 0; i < kItemH; ++i) {
-            if ((inb >> (2 * i)) & 1u) {
-                const size_t o = (size_t)b * a.out_stride + (size_t)(row0 + i) * W + col0;
-                const unsigned c0 = code[2 * i], c1 = code[2 * i + 1];
-                if (OUT == OUT_CODE16) {
-                    unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
-                    if (a.vec) *reinterpret_cast<unsigned*>(op) = c0 | (c1 << 16);
-                    else { op[0] = (unsigned short)c0; if (c1in) op[1] = (unsigned short)c1; }
-                } else if (OUT == OUT_CODE32) {
-                    unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
-                    if (a.vec) *reinterpret_cast<uint2*>(op) = make_uint2(c0, c1);
-                    else { op[0] = c0; if (c1in) op[1] = c1; }
-                } else if (OUT == OUT_IDS64) {
-                    long long* op = reinterpret_cast<long long*>(a.out) + o;
-                    if (a.vec) __stcs(reinterpret_cast<longlong2*>(op), make_longlong2((long long)c0, (long long)c1));
-                    else { op[0] = (long long)c0; if (c1in) op[1] = (long long)c1; }
-                } else {
-                    int* op = reinterpret_cast<int*>(a.out) + o;
-                    if (a.vec) *reinterpret_cast<int2*>(op) = make_int2((int)c0, (int)c1);
-                    else { op[0] = (int)c0; if (c1in) op[1] = (int)c1; }
-                }
-            }
+        // next block; the prefetcher is already inside it (or beyond it)
+        kc = kn;
+        nxt = kc.nitems > 0 ? grab() : n_blocks;
+        kn = decode(nxt);
+        if (kTma) {
+            if (p_which == 0) p_i = 0; else --p_which;
+            pump();
         }
     }
     flush_image();
@@ -1064,22 +1199,55 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
     return EMP_OK;
 }
 
-template <int SEM, int IDM, int OUT>
-static int launch_assign_t(const AssignArgs& a, cudaStream_t st)
+template <int SEM, int IDM, int OUT, bool FAST>
+static int launch_assign_f(const AssignArgs& a, cudaStream_t st)
 {
     constexpr int row_bytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;
     constexpr int ring_bytes = kAssignWarps * kStages * kItemH * row_bytes;
-    const size_t smem = a.tma ? ring_bytes : 0;
-    EMP_CUDA_CHECK(cudaFuncSetAttribute(assign_kernel<SEM, IDM, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
-    const long long n_items = (long long)a.items_x * a.items_y * a.B;
-    long long blocks = (n_items + kAssignWarps - 1) / kAssignWarps;
-    const long long resident = (long long)sm_count() * 3;          // __launch_bounds__(256, 3)
+    const size_t smem = (FAST && SEM != SEM_NONE) ? ring_bytes : 0;
+    EMP_CUDA_CHECK(cudaFuncSetAttribute(assign_kernel<SEM, IDM, OUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+    const long long n_blocks = (long long)a.blocks_x * a.blocks_y * a.B;
+    long long blocks = (n_blocks + kAssignWarps - 1) / kAssignWarps;
+    const long long resident = (long long)sm_count() * kAssignCtasPerSm;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     ProfScope ps(ST_ASSIGN, st);
-    assign_kernel<SEM, IDM, OUT><<<(unsigned)blocks, kAssignThreads, smem, st>>>(a);
+    assign_kernel<SEM, IDM, OUT, FAST><<<(unsigned)blocks, kAssignThreads, smem, st>>>(a);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
+}
+
+// (B, H, W) tensor map over the sem planes for the assign kernel's TMA ring: box 1 x 4 x 64
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_sem_tensor_map(AssignArgs& a, int sem_mode)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        EMP_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        EMP_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, EMP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t elt = sem_mode == SEM_I64 ? 8 : 1;
+    const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    const cuuint64_t strides[2] = {(cuuint64_t)a.W * elt, (cuuint64_t)a.sem_stride * elt};
+    const cuuint32_t box[3] = {(cuuint32_t)kItemW, (cuuint32_t)kItemH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(&a.tmap, sem_mode == SEM_I64 ? CU_TENSOR_MAP_DATA_TYPE_INT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                              const_cast<void*>(a.sem), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EMP_REQUIRE(r == CUDA_SUCCESS, EMP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EMP_OK;
+}
+
+template <int SEM, int IDM, int OUT>
+static int launch_assign_t(const AssignArgs& a, cudaStream_t st)
+{
+    return a.fast ? launch_assign_f<SEM, IDM, OUT, true>(a, st) : launch_assign_f<SEM, IDM, OUT, false>(a, st);
 }
 
 template <int SEM, int IDM>
@@ -1096,13 +1264,20 @@ static int launch_assign_out(int out_mode, const AssignArgs& a, cudaStream_t st)
 // a.B tiles in one launch; a.sem / a.off / a.ids_in / a.out / a.ws point at the first of them
 int launch_assign(int sem_mode, int id_mode, int out_mode, AssignArgs& a, cudaStream_t st)
 {
-    a.items_x = (a.W + kItemW - 1) / kItemW;
-    a.items_y = (a.H + kItemH - 1) / kItemH;
-    EMP_REQUIRE((long long)a.items_x * a.items_y * a.B < (1ll << 31), EMP_ERR_INVALID, "batch too large for one launch");
-    // TMA staging of the sem plane: 16-byte aligned row segments of a multiple of 16 bytes
-    a.tma = 0;
-    if (sem_mode == SEM_I64) a.tma = a.vec && aligned16(a.sem) && (a.sem_stride % 2 == 0);
-    else if (sem_mode == SEM_U8) a.tma = (a.W % 16 == 0) && aligned16(a.sem) && (a.sem_stride % 16 == 0);
+    a.blocks_x = (a.W + kItemW - 1) / kItemW;
+    a.blocks_y = (a.H + kBlkItems * kItemH - 1) / (kBlkItems * kItemH);
+    EMP_REQUIRE((long long)a.blocks_x * a.blocks_y * a.B < (1ll << 30), EMP_ERR_INVALID, "batch too large for one launch");
+    a.counter = reinterpret_cast<int32_t*>(a.ws + a.o_status) + EMP_ST_TICKET;      // zeroed with the status block
+    // FAST: every plane moves as 8/16-byte vectors and the sem plane is staged by TMA tensor copies
+    // (16-byte aligned base and row pitch); otherwise scalar accesses throughout.
+    a.fast = a.vec;
+    if (sem_mode == SEM_I64) a.fast = a.vec && aligned16(a.sem) && (a.sem_stride % 2 == 0);
+    else if (sem_mode == SEM_U8) a.fast = a.vec && (a.W % 16 == 0) && aligned16(a.sem) && (a.sem_stride % 16 == 0);
+    if (sem_mode != SEM_NONE && (a.W < kItemW || a.H < kItemH)) a.fast = 0;       // the TMA box must fit the tensor
+    if (a.fast && sem_mode != SEM_NONE) {
+        const int rc = make_sem_tensor_map(a, sem_mode);
+        if (rc) return rc;
+    }
     if (id_mode == ID_ARGMIN) {
         if (sem_mode == SEM_NONE) return launch_assign_out<SEM_NONE, ID_ARGMIN>(out_mode, a, st);
         if (sem_mode == SEM_I64) return launch_assign_out<SEM_I64, ID_ARGMIN>(out_mode, a, st);

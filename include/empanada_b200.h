@@ -48,6 +48,7 @@ extern "C" {
 #define EMP_ST_NRUNS 3      /* rle: final runs */
 #define EMP_ST_NINST 4      /* rle: instances (distinct output labels) */
 #define EMP_ST_GSHIFT 5     /* internal: log2 of the center-index cell size in pixels */
+#define EMP_ST_TICKET 6     /* internal: block hand-out counter of the assign kernel */
 #define EMP_ST_WORDS 16
 #define EMP_PROFILE_STAGES 9
 
