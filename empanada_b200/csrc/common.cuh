@@ -46,7 +46,7 @@ constexpr int kMaxCells = 16384;
 
 struct WsLayout {
     size_t status, rowcnt, areas, votes, zero_bytes;
-    size_t mask, centers, ctr_i, cell_start, cell_fill, sorted, lut, codes, total;
+    size_t mask, centers, ctr_i, cell_start, cell_fill, sorted, lut, sflags, codes, total;
     int wd;          // mask words per row
     bool code16;
 };
@@ -70,6 +70,8 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     L.cell_fill = o;  o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
     L.sorted = o;  o = align_up(o + sizeof(float4) * ((size_t)k_cap + 1), 256);     // (cy, cx, bits of k, -) grouped by cell
     L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
+    // one flag byte per 4 x 64 strip, 16 per 64 x 64 block (blocks row-major)
+    L.sflags = o;  o = align_up(o + (size_t)16 * ((W + 63) / 64) * ((H + 63) / 64), 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
     L.total = o;
     return L;
@@ -176,6 +178,13 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
 

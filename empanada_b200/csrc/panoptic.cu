@@ -91,110 +91,226 @@ int make_things(const int64_t* list, int n, Things* out)
 // heat-map), the full k x k window only for 3x3 maxima.  Output: one ballot word per 32 pixels
 // and a per-row popcount.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool window_is_peak(const float* __restrict__ hm, int H, int W, int y,
-                                               int x, float v, int lo, int hi)
+// Full k x k window test of ONE 3x3 maximum at (y, x) with value v, by the whole (converged) warp:
+// one neighbour per lane through L1/L2, so a peak costs a couple of load round trips instead of a
+// 48-load chain.  Only reached for k >= 4 and only by 3x3 maxima (about one pixel per instance).
+__device__ __noinline__ bool nms_window_has_bigger(const float* __restrict__ hm, int H, int W, int y, int x, float v,
+                                                   int lo, int hi)
 {
-    const int span = 2 * lo;            // lo >= hi always
-    for (int i = 0; i <= span; ++i) {
-        const int dy = (i & 1) ? -((i + 1) >> 1) : (i >> 1);      // 0,-1,+1,-2,+2,...
-        if (dy < -lo || dy > hi) continue;
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
-        const float* row = hm + (size_t)yy * W;
-        for (int j = 0; j <= span; ++j) {
-            const int dx = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
-            if (dx < -lo || dx > hi) continue;
-            const int xx = x + dx;
-            if (xx < 0 || xx >= W) continue;
-            if (__ldg(row + xx) > v) return false;
-        }
+    const int side = lo + hi + 1, n = side * side;
+    bool bigger = false;
+    for (int idx = threadIdx.x & 31; idx < n; idx += 32) {
+        const int yy = y + idx / side - lo, xx = x + idx % side - lo;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W && __ldg(hm + (size_t)yy * W + xx) > v) bigger = true;
     }
-    return true;
+    return __any_sync(0xffffffffu, bigger);
 }
 
-// Called by a whole (converged) warp for one 32-pixel word of one row in which some lane is above
-// threshold (a few % of all words).  Neighbour values come through L1 here (the streaming loop does
-// not keep them): 3x3 neighbourhood first, the rest of the k x k window only for 3x3 maxima.
-__device__ __noinline__ unsigned nms_word_check(const float* __restrict__ hm, int H, int W, int y, int x,
-                                                bool cand, float thr, int lo, int hi)
+// Persistent, warp-autonomous.  The work item is 4 rows x 256 pixels = 4 full 32-byte sectors of the
+// peak mask; lane l takes pixels 32j + l (j = 0..7) of each row, so a ballot over the warp IS the mask
+// word.  Items are walked in column strips of kNmsBlkItems items (64 rows), strips dealt round-robin to
+// the warps of the grid.
+// FAST: each item is one TMA tensor copy — box 1 x 6 x 256 floats of the (B,H,W) view: the 4 rows plus
+// one halo row above and below; rows outside the image arrive as zeros, which can neither be a
+// candidate nor beat one — into a per-warp ring of kNmsStages shared-memory buffers, issued
+// kNmsStages items ahead.  Pixels above threshold (a few %) take the 3x3 test straight from shared
+// memory (the two halo columns of a strip come through L1/L2); that alone rejects every slope pixel of
+// a smooth heat-map, and only 3x3 maxima go on to the full k x k window.  Without FAST (unaligned or
+// tiny planes) the same code reads global memory.
+constexpr int kNmsRows = 4, kNmsWords = 8, kNmsStages = 2, kNmsWarps = 4, kNmsBlkItems = 16;
+constexpr int kNmsItemW = kNmsWords * 32, kNmsBoxRows = kNmsRows + 2;
+constexpr unsigned kNmsStageFloats = kNmsBoxRows * kNmsItemW;
+constexpr unsigned kNmsStageBytes = kNmsStageFloats * sizeof(float);
+
+struct NmsArgs {
+    CUtensorMap tmap;                           // FAST: (B, H, W) fp32 view of the heat-maps, box 1 x 6 x 256
+    const float* hm; size_t hm_stride;
+    char* ws; size_t ws_stride;
+    size_t o_mask, o_rowcnt;
+    int B, H, W, wd, lo, hi;
+    int blocks_x, blocks_y;                     // column strips per tile row / strips per tile column
+    float thr;
+};
+
+template <bool FAST>
+__global__ void __launch_bounds__(kNmsWarps * 32, 4)
+nms_peaks_kernel(const __grid_constant__ NmsArgs a)
 {
-    bool peak = false;
-    if (cand) {
-        const float c = __ldg(hm + (size_t)y * W + x);
-        const bool before = lo >= 1, after = hi >= 1;   // window reaches to -1 / +1 at all?
-        float m = -CUDART_INF_F;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dy == 0 && dx == 0) continue;
-                if ((dy < 0 || dx < 0) && !before) continue;
-                if ((dy > 0 || dx > 0) && !after) continue;
-                const int yy = y + dy, xx = x + dx;
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) m = fmaxf(m, __ldg(hm + (size_t)yy * W + xx));
+    extern __shared__ __align__(128) unsigned char dsm[];            // [warp][stage][6 rows][256] fp32
+    __shared__ uint64_t s_bar[kNmsWarps][kNmsStages];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, W = a.W, wd = a.wd, lo = a.lo, hi = a.hi;
+    const int per_img = a.blocks_x * a.blocks_y;
+    const int n_blocks = per_img * a.B;
+    const int total_warps = (int)gridDim.x * kNmsWarps;
+    const int gw = (int)blockIdx.x * kNmsWarps + warp;
+    const float t0 = fmaxf(a.thr, 0.0f);                            // v > thr and v > 0  <=>  v > max(thr, 0)
+    const bool before = lo >= 1, after = hi >= 1;                   // does the window reach to -1 / +1 at all?
+
+    struct Strip { int b, row0, colb, nitems; };
+    auto decode = [&](int blk) {
+        Strip k;
+        k.b = 0; k.row0 = 0; k.colb = 0; k.nitems = 0;
+        if (blk < n_blocks) {
+            k.b = blk / per_img;
+            const int r = blk - k.b * per_img;
+            const int by = r / a.blocks_x;
+            k.colb = (r - by * a.blocks_x) * kNmsItemW;
+            k.row0 = by * (kNmsBlkItems * kNmsRows);
+            k.nitems = min(kNmsBlkItems, (H - k.row0 + kNmsRows - 1) / kNmsRows);
+        }
+        return k;
+    };
+
+    float* ring = reinterpret_cast<float*>(dsm) + (size_t)warp * kNmsStages * kNmsStageFloats;
+    uint64_t policy = 0;
+    int p_blk = gw, p_i = 0, inflight = 0, st_issue = 0;
+    Strip kp = decode(p_blk);
+    auto pump = [&]() {
+        while (inflight < kNmsStages && kp.nitems > 0) {
+            if (p_i < kp.nitems) {
+                if (lane == 0) {
+                    mbar_expect_tx(&s_bar[warp][st_issue], kNmsStageBytes);
+                    tma_load_3d(ring + (size_t)st_issue * kNmsStageFloats, &a.tmap, kp.colb, kp.row0 + p_i * kNmsRows - 1,
+                                kp.b, &s_bar[warp][st_issue], policy);
+                }
+                ++p_i; ++inflight;
+                st_issue = st_issue + 1 == kNmsStages ? 0 : st_issue + 1;
+            } else {
+                p_blk += total_warps; p_i = 0;
+                kp = decode(p_blk);
             }
         }
-        peak = !(m > c);
-        if (peak && lo >= 2) peak = window_is_peak(hm, H, W, y, x, c, lo, hi);
-    }
-    return __ballot_sync(0xffffffffu, peak);
-}
-
-// One warp owns 4 rows x 256 pixels = 4 full 32-byte sectors of the peak mask, so it needs no
-// shared memory and no barrier: lane l streams pixels 32j + l (j = 0..7) of each row (128-byte
-// coalesced loads), keeps one "above threshold" flag per pixel, and only words with a flagged
-// lane take the neighbourhood check.
-constexpr int kNmsRows = 4, kNmsWords = 8;
-
-__global__ void __launch_bounds__(256)
-nms_peaks_kernel(const float* __restrict__ hm_base, size_t hm_stride, int H, int W, float thr,
-                 int lo, int hi, char* __restrict__ ws_base, size_t ws_stride, size_t o_mask,
-                 size_t o_rowcnt, int wd)
-{
-    const float* hm = hm_base + (size_t)blockIdx.z * hm_stride;
-    char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
-    uint32_t* mask = reinterpret_cast<uint32_t*>(ws + o_mask);
-    uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + o_rowcnt);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w0 = blockIdx.x * kNmsWords;                          // first mask word of this warp
-    const int y0 = (blockIdx.y * 8 + warp) * kNmsRows;
-    if (y0 >= H) return;                                            // warp-uniform
-    const int x0 = w0 * 32 + lane;
-
-    unsigned cm = 0;                                                // bit 8*r + j: pixel (y0+r, x0+32j) is a candidate
-    const long long Wl = W;
-    const float* p = hm + (long long)y0 * Wl + x0;
+    };
+    if (FAST) {
+        policy = l2_policy_evict_normal();              // halo rows are read again by the next item
+        if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < kNmsRows; ++r) {
-        const bool rin = y0 + r < H;
-#pragma unroll
-        for (int j = 0; j < kNmsWords; ++j) {
-            float v = -CUDART_INF_F;
-            if (rin && x0 + 32 * j < W) v = __ldcs(p + 32 * j);
-            cm |= ((v > thr && v > 0.0f) ? 1u : 0u) << (8 * r + j);
+            for (int s = 0; s < kNmsStages; ++s) mbar_init(&s_bar[warp][s], 1);
+            mbar_fence_init();
         }
-        p += Wl;
+        __syncwarp();
+        pump();
     }
-    unsigned mine[kNmsRows] = {0, 0, 0, 0};                         // lane j (< 8) ends up with word j of each row
-    unsigned todo = __reduce_or_sync(0xffffffffu, cm);              // (row, word) pairs with any candidate
-    while (todo) {                                                  // warp-uniform
-        const int bit = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int r = bit >> 3, j = bit & 7;
-        const unsigned word = nms_word_check(hm, H, W, y0 + r, x0 + 32 * j, (cm >> bit) & 1u, thr, lo, hi);
-        if (lane == j) {
-            if (r == 0) mine[0] = word; else if (r == 1) mine[1] = word; else if (r == 2) mine[2] = word; else mine[3] = word;
-        }
-    }
+
+    int st_cons = 0;
+    unsigned parity = 0;
+    for (int blk = gw; blk < n_blocks; blk += total_warps) {
+        const Strip kc = decode(blk);
+        const float* hm = a.hm + (size_t)kc.b * a.hm_stride;
+        char* ws = a.ws + (size_t)kc.b * a.ws_stride;
+        uint32_t* mask = reinterpret_cast<uint32_t*>(ws + a.o_mask);
+        uint32_t* rowcnt = reinterpret_cast<uint32_t*>(ws + a.o_rowcnt);
+        const int w0 = kc.colb >> 5;                                    // first mask word of the strip
+        const int x0 = kc.colb + lane;
+
+        for (int it = 0; it < kc.nitems; ++it) {
+            const int y0 = kc.row0 + it * kNmsRows;
+            // FAST: (row 0 of the item, this lane) inside the stage; row -1 / row 4 are the halo rows
+            const float* sp = ring + (size_t)st_cons * kNmsStageFloats + kNmsItemW + lane;
+            unsigned cm = 0;                                            // bit 8*r + j: pixel (y0+r, x0+32j) is a candidate
+            if (FAST) {
+                mbar_wait(&s_bar[warp][st_cons], parity);
 #pragma unroll
-    for (int r = 0; r < kNmsRows; ++r) {
-        const int y = y0 + r;
-        if (y < H) {                                                // warp-uniform
-            const bool wl = lane < kNmsWords && w0 + lane < wd;
-            if (wl) mask[(size_t)y * wd + w0 + lane] = mine[r];
-            const unsigned cnt = __reduce_add_sync(0xffffffffu, wl ? (unsigned)__popc(mine[r]) : 0u);
-            if (cnt && lane == 0) atomicAdd(rowcnt + y, cnt);
+                for (int r = 0; r < kNmsRows; ++r) {
+#pragma unroll
+                    for (int j = 0; j < kNmsWords; ++j) cm |= (sp[r * kNmsItemW + 32 * j] > t0 ? 1u : 0u) << (8 * r + j);
+                }
+            } else {
+                const float* p = hm + (size_t)y0 * W + x0;
+#pragma unroll
+                for (int r = 0; r < kNmsRows; ++r) {
+                    const bool rin = y0 + r < H;
+#pragma unroll
+                    for (int j = 0; j < kNmsWords; ++j) {
+                        float v = -CUDART_INF_F;
+                        if (rin && x0 + 32 * j < W) v = __ldg(p + 32 * j);
+                        cm |= (v > t0 ? 1u : 0u) << (8 * r + j);
+                    }
+                    p += W;
+                }
+            }
+
+            // 3x3 test of this lane's candidates (lanes proceed independently)
+            unsigned pk = 0;                                            // bit 8*r + j: 3x3 maximum
+            for (unsigned rest = cm; rest; rest &= rest - 1) {
+                const int bit = __ffs(rest) - 1;
+                const int r = bit >> 3, j = bit & 7;
+                const int y = y0 + r, x = x0 + 32 * j, cs = 32 * j + lane;      // cs: column within the item
+                const float* q = sp + r * kNmsItemW + 32 * j;
+                const float c = FAST ? q[0] : __ldg(hm + (size_t)y * W + x);
+                float m = -CUDART_INF_F;
+#pragma unroll
+                for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        if (dy == 0 && dx == 0) continue;
+                        if ((dy < 0 || dx < 0) && !before) continue;
+                        if ((dy > 0 || dx > 0) && !after) continue;
+                        float nb;
+                        if (FAST && cs + dx >= 0 && cs + dx < kNmsItemW) {
+                            nb = q[dy * kNmsItemW + dx];
+                        } else {                                        // no staging, or a halo column of the strip
+                            const int yy = y + dy, xx = x + dx;
+                            nb = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(hm + (size_t)yy * W + xx) : -CUDART_INF_F;
+                        }
+                        m = fmaxf(m, nb);
+                    }
+                }
+                if (!(m > c)) pk |= 1u << bit;
+            }
+            __syncwarp();
+
+            // k x k window of the 3x3 maxima, one at a time, by the whole warp (k >= 4 only)
+            unsigned fin = pk;                                          // verified peaks
+            if (lo >= 2) {
+                unsigned pend = pk;
+                fin = 0;
+                for (;;) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, pend != 0u);
+                    if (!bal) break;                                    // warp-uniform
+                    const int src = __ffs(bal) - 1;
+                    const int bit = __ffs(__shfl_sync(0xffffffffu, pend, src)) - 1;
+                    const int r = bit >> 3, j = bit & 7;
+                    const int y = y0 + r, x = kc.colb + src + 32 * j;
+                    float v = 0.f;
+                    if (lane == src) v = FAST ? sp[r * kNmsItemW + 32 * j] : __ldg(hm + (size_t)y * W + x);
+                    v = __shfl_sync(0xffffffffu, v, src);
+                    const bool bigger = nms_window_has_bigger(hm, H, W, y, x, v, lo, hi);
+                    if (lane == src) {
+                        pend &= pend - 1;
+                        if (!bigger) fin |= 1u << bit;
+                    }
+                }
+            }
+            if (FAST) {
+                __syncwarp();                                           // every lane is done with the stage: the slot is free
+                --inflight;
+                if (++st_cons == kNmsStages) { st_cons = 0; parity ^= 1u; }
+                pump();
+            }
+
+            unsigned mine[kNmsRows] = {0, 0, 0, 0};                     // lane j (< 8) ends up with word j of each row
+            unsigned todo = __reduce_or_sync(0xffffffffu, fin);         // (row, word) pairs holding a peak
+            while (todo) {                                              // warp-uniform
+                const int bit = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int r = bit >> 3, j = bit & 7;
+                const unsigned word = __ballot_sync(0xffffffffu, (fin >> bit) & 1u);
+                if (lane == j) {
+                    if (r == 0) mine[0] = word; else if (r == 1) mine[1] = word; else if (r == 2) mine[2] = word; else mine[3] = word;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < kNmsRows; ++r) {
+                const int y = y0 + r;
+                if (y < H) {                                            // warp-uniform
+                    const bool wl = lane < kNmsWords && w0 + lane < wd;
+                    if (wl) mask[(size_t)y * wd + w0 + lane] = mine[r];
+                    const unsigned cnt = __reduce_add_sync(0xffffffffu, wl ? (unsigned)__popc(mine[r]) : 0u);
+                    if (cnt && lane == 0) atomicAdd(rowcnt + y, cnt);
+                }
+            }
         }
     }
 }
@@ -412,7 +528,7 @@ struct AssignArgs {
     const void* ids_in; size_t ids_stride;     // ID_DENSE: int64 H*W, ID_COARSE: int32 hc*wc
     void* out;          size_t out_stride;     // elements per tile
     char* ws;           size_t ws_stride;
-    size_t o_status, o_votes, o_areas, o_cell_start, o_sorted;
+    size_t o_status, o_votes, o_areas, o_cell_start, o_sorted, o_sflags;
     int32_t* counter;                          // zeroed device word: dynamic block hand-out
     int B, H, W, wc, shift;
     int blocks_x, blocks_y;                    // 64 x 64 blocks per tile row / column
@@ -748,6 +864,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
     int32_t* status = nullptr;
     uint32_t* votes = nullptr;
     uint32_t* areas = nullptr;
+    unsigned char* sflags = nullptr;    // one byte per strip: 1 = all class-0 stuff (no codes stored), 0 = see the code map
     unsigned deficit_acc = 0;       // in-image pixels of the current image that are NOT class-0 stuff
     unsigned akey_acc = kNoKey, acnt_acc = 0;    // pending stuff-area count of one non-zero class
     int flags = 0;
@@ -777,6 +894,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
             status = reinterpret_cast<int32_t*>(ws + a.o_status);
             votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
             areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
+            sflags = reinterpret_cast<unsigned char*>(ws + a.o_sflags);
             if (IDM == ID_ARGMIN) {
                 K = a.k_fixed >= 0 ? a.k_fixed : min(__ldcg(status + EMP_ST_K), a.k_cap);
                 chunked = K > a.chunksize;
@@ -789,6 +907,8 @@ assign_kernel(const __grid_constant__ AssignArgs a)
         }
         const int col0 = kc.colb + 2 * lane;
         const bool cols_full = kc.colb + kItemW <= W;
+        // strip flags of a block are contiguous: [(block row * blocks_x + block column) * kBlkItems + strip]
+        unsigned char* bflags = sflags + ((size_t)(kc.row0 / (kBlkItems * kItemH)) * a.blocks_x + kc.colb / kItemW) * kBlkItems;
         const float xc0 = __fmul_rn((float)col0, a.step), xc1 = __fmul_rn((float)(col0 + 1), a.step);
 
         for (int it = 0; it < kc.nitems; ++it) {
@@ -840,23 +960,13 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 #pragma unroll
                 for (int p = 0; p < kPx; ++p) orall |= (unsigned long long)sv[p];
                 if (full && class0_stuff && __all_sync(0xffffffffu, orall == 0ull)) {      // warp-uniform
-                    // constant codes, nothing to vote or count (class 0's area is taken by complement)
-#pragma unroll
-                    for (int i = 0; i < kItemH; ++i) {
-                        const size_t o = (size_t)b * a.out_stride + px0 + (size_t)i * W;
-                        if (OUT == OUT_CODE16) {
-                            unsigned short* op = reinterpret_cast<unsigned short*>(a.out) + o;
-                            if (FAST) *reinterpret_cast<unsigned*>(op) = kClsBase | (kClsBase << 16);
-                            else { op[0] = (unsigned short)kClsBase; op[1] = (unsigned short)kClsBase; }
-                        } else {
-                            unsigned* op = reinterpret_cast<unsigned*>(a.out) + o;
-                            if (FAST) *reinterpret_cast<uint2*>(op) = make_uint2(kClsBase, kClsBase);
-                            else { op[0] = kClsBase; op[1] = kClsBase; }
-                        }
-                    }
+                    // nothing to vote or count (class 0's area is taken by complement), and no codes:
+                    // the strip flag tells apply_lut that every pixel is class-0 stuff
+                    if (lane == 0) bflags[it] = 1;
                     continue;
                 }
             }
+            if (kCodes && lane == 0) bflags[it] = 0;
 
             // ---- general path ---------------------------------------------------------------------------
             unsigned inb = 0xFFu;       // bit p: pixel p = 2*i + j is inside the image
@@ -1080,14 +1190,17 @@ build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_vote
 // K5  apply_lut — code map -> int64 panoptic labels (postprocess.py:281, :287-294).
 //   code 0 -> void; 1..CLS_BASE-1 -> lut[id]; CLS_BASE + c -> c*L if area[c] >= stuff_area else void
 // (a thing-class pixel never carries a class code, so no thing test is needed here).
-// 16 codes per thread per iteration; a thread whose codes are all equal (background) decodes once.
+// Same geometry as assign: a warp takes a 64 x 64 block and walks its 16 strips of 4 rows x 64
+// columns, lane l owning columns 2l, 2l+1 (128 B of codes in, 512 B of labels out per row).  The
+// block's 16 strip flags arrive in one 16-byte load; a flagged strip (all class-0 stuff, the bulk of
+// an EM tile) has no codes to read: the warp streams out the one label.
 // ---------------------------------------------------------------------------------------------
 struct ApplyArgs {
     char* ws; size_t ws_stride;
-    size_t o_codes, o_lut, o_areas;
+    size_t o_codes, o_lut, o_areas, o_sflags;
     long long* pan; size_t n_px;
+    int H, W, blocks_x, blocks_y;
     long long label_divisor, stuff_area, void_label;
-    int vec;
 };
 
 template <bool C16>
@@ -1103,55 +1216,70 @@ __device__ __forceinline__ long long decode(unsigned code, const long long* __re
     return __ldg(lut + code);
 }
 
-// A warp handles 512 consecutive pixels: in step q (0..7) lane l owns pixels 64q + 2l, 64q + 2l + 1,
-// so each warp-wide load (128 B of uint16 codes) and store (512 B of int64 labels) is one
-// contiguous run of full sectors.  One group per warp: short CTAs, cheap last wave.
-template <bool C16>
+template <bool C16, bool FAST>
 __global__ void __launch_bounds__(256)
 apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
+    constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
     const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
     const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
-    const int lane = threadIdx.x & 31;
-    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const size_t n512 = a.vec ? a.n_px / 512 : 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, W = a.W;
+    const int blk = (int)blockIdx.x * 8 + warp;
+    if (blk >= a.blocks_x * a.blocks_y) return;                     // warp-uniform
+    const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
+    const int colb = bx * kItemW, rowb = by * (kBlkItems * kItemH);
+    const int col0 = colb + 2 * lane;
+    const int nitems = min(kBlkItems, (H - rowb + kItemH - 1) / kItemH);
+    const bool cols_full = colb + kItemW <= W;
 
-    for (size_t g = warp_global; g < n512; g += n_warps) {
-        const size_t base = g * 512;
-        unsigned c0[8], c1[8];
-        if (C16) {
-            const unsigned* cp = reinterpret_cast<const unsigned*>(ws + a.o_codes) + base / 2 + lane;
+    const uint4 fl = *reinterpret_cast<const uint4*>(ws + a.o_sflags + (size_t)blk * kBlkItems);
+    const long long bg = decode<C16>(kClsBase, lut, areas, a);      // label of class-0 stuff
+
+    for (int it = 0; it < nitems; ++it) {
+        const int row0 = rowb + it * kItemH;
+        const unsigned fw = it < 4 ? fl.x : it < 8 ? fl.y : it < 12 ? fl.z : fl.w;
+        const bool flagged = ((fw >> (8 * (it & 3))) & 0xFFu) != 0u;
+        const size_t px0 = (size_t)row0 * W + col0;
+        if (FAST && flagged) {                                      // flagged strips are always full strips
 #pragma unroll
-            for (int q = 0; q < 8; ++q) { const unsigned u = __ldcs(cp + q * 32); c0[q] = u & 0xFFFFu; c1[q] = u >> 16; }
-        } else {
-            const uint2* cp = reinterpret_cast<const uint2*>(ws + a.o_codes) + base / 2 + lane;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { const uint2 u = __ldcs(cp + q * 32); c0[q] = u.x; c1[q] = u.y; }
+            for (int i = 0; i < kItemH; ++i) __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W), make_longlong2(bg, bg));
+            continue;
         }
-        longlong2* op = reinterpret_cast<longlong2*>(pan + base) + lane;
-        bool same = true;
+        const bool full = cols_full && row0 + kItemH <= H;
+        if (FAST && full) {
+            unsigned c0[kItemH], c1[kItemH];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) same = same && (c0[q] == c0[0]) && (c1[q] == c0[0]);
-        if (same) {
-            const long long v = decode<C16>(c0[0], lut, areas, a);
+            for (int i = 0; i < kItemH; ++i) {
+                if (C16) {
+                    const unsigned u = __ldcs(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(ws + a.o_codes) + px0 + (size_t)i * W));
+                    c0[i] = u & 0xFFFFu; c1[i] = u >> 16;
+                } else {
+                    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + px0 + (size_t)i * W));
+                    c0[i] = u.x; c1[i] = u.y;
+                }
+            }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) __stcs(op + q * 32, make_longlong2(v, v));
+            for (int i = 0; i < kItemH; ++i)
+                __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W),
+                       make_longlong2(decode<C16>(c0[i], lut, areas, a), decode<C16>(c1[i], lut, areas, a)));
         } else {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                __stcs(op + q * 32, make_longlong2(decode<C16>(c0[q], lut, areas, a), decode<C16>(c1[q], lut, areas, a)));
+            for (int i = 0; i < kItemH; ++i) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (row0 + i < H && col0 + j < W) {
+                        const size_t e = px0 + (size_t)i * W + j;
+                        const unsigned code = flagged ? kClsBase
+                                            : C16 ? (unsigned)reinterpret_cast<const unsigned short*>(ws + a.o_codes)[e]
+                                                  : reinterpret_cast<const unsigned*>(ws + a.o_codes)[e];
+                        pan[e] = decode<C16>(code, lut, areas, a);
+                    }
+                }
+            }
         }
-    }
-    // tail (and the whole image when it is not 512-divisible / aligned): one pixel per thread
-    const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = n512 * 512 + t0; i < a.n_px; i += stride) {
-        const unsigned code = C16 ? (unsigned)reinterpret_cast<const unsigned short*>(ws + a.o_codes)[i]
-                                  : reinterpret_cast<const unsigned*>(ws + a.o_codes)[i];
-        pan[i] = decode<C16>(code, lut, areas, a);
     }
 }
 
@@ -1179,14 +1307,64 @@ int check_ws(const void* ws, size_t ws_bytes, size_t need)
     return EMP_OK;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// (B, H, W) tiled tensor map over B planes `plane_stride` elements apart, box 1 x box_h x box_w
+static int make_plane_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, size_t elt, const void* base, int B, int H, int W,
+                                 size_t plane_stride, int box_h, int box_w)
+{
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        EMP_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        EMP_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, EMP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * elt, (cuuint64_t)plane_stride * elt};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(out, dtype, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EMP_REQUIRE(r == CUDA_SUCCESS, EMP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return EMP_OK;
+}
+
 int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float step, const WsLayout& L,
                    char* ws, size_t ws_stride, int k_cap, int64_t* ctr_out, int cap, cudaStream_t st)
 {
-    const int lo = k / 2, hi = k - 1 - lo;
-    dim3 g1((L.wd + kNmsWords - 1) / kNmsWords, (H + 8 * kNmsRows - 1) / (8 * kNmsRows), B);
+    NmsArgs n;
+    memset(&n, 0, sizeof(n));
+    n.hm = hm; n.hm_stride = (size_t)H * W;
+    n.ws = ws; n.ws_stride = ws_stride; n.o_mask = L.mask; n.o_rowcnt = L.rowcnt;
+    n.B = B; n.H = H; n.W = W; n.wd = L.wd; n.lo = k / 2; n.hi = k - 1 - n.lo; n.thr = thr;
+    n.blocks_x = (W + kNmsItemW - 1) / kNmsItemW;
+    n.blocks_y = (H + kNmsBlkItems * kNmsRows - 1) / (kNmsBlkItems * kNmsRows);
+    const long long n_blocks = (long long)n.blocks_x * n.blocks_y * B;
+    EMP_REQUIRE(n_blocks < (1ll << 30), EMP_ERR_INVALID, "batch too large for one launch");
+    // TMA staging needs a 16-byte aligned base and row pitch, and the box must fit the tensor
+    const bool fast = aligned16(hm) && W % 4 == 0 && W >= kNmsItemW && H >= kNmsBoxRows && (n.hm_stride % 4 == 0);
+    if (fast) {
+        const int rc = make_plane_tensor_map(&n.tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hm, B, H, W, n.hm_stride, kNmsBoxRows, kNmsItemW);
+        if (rc) return rc;
+    }
+    long long blocks = (n_blocks + kNmsWarps - 1) / kNmsWarps;
+    const long long resident = (long long)sm_count() * 4;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
     {
         ProfScope ps(ST_NMS, st);
-        nms_peaks_kernel<<<g1, 256, 0, st>>>(hm, (size_t)H * W, H, W, thr, lo, hi, ws, ws_stride, L.mask, L.rowcnt, L.wd);
+        if (fast) {
+            const int ring_bytes = kNmsWarps * kNmsStages * (int)kNmsStageBytes;
+            EMP_CUDA_CHECK(cudaFuncSetAttribute(nms_peaks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+            EMP_CUDA_CHECK(cudaFuncSetAttribute(nms_peaks_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            nms_peaks_kernel<true><<<(unsigned)blocks, kNmsWarps * 32, ring_bytes, st>>>(n);
+        } else {
+            nms_peaks_kernel<false><<<(unsigned)blocks, kNmsWarps * 32, 0, st>>>(n);
+        }
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     dim3 g2((H + 31) / 32, 1, B);
@@ -1218,30 +1396,10 @@ static int launch_assign_f(const AssignArgs& a, cudaStream_t st)
 }
 
 // (B, H, W) tensor map over the sem planes for the assign kernel's TMA ring: box 1 x 4 x 64
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int make_sem_tensor_map(AssignArgs& a, int sem_mode)
 {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        EMP_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        EMP_REQUIRE(fn != nullptr && q == cudaDriverEntryPointSuccess, EMP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
-    const cuuint64_t elt = sem_mode == SEM_I64 ? 8 : 1;
-    const cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-    const cuuint64_t strides[2] = {(cuuint64_t)a.W * elt, (cuuint64_t)a.sem_stride * elt};
-    const cuuint32_t box[3] = {(cuuint32_t)kItemW, (cuuint32_t)kItemH, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(&a.tmap, sem_mode == SEM_I64 ? CU_TENSOR_MAP_DATA_TYPE_INT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                              const_cast<void*>(a.sem), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    EMP_REQUIRE(r == CUDA_SUCCESS, EMP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return EMP_OK;
+    return make_plane_tensor_map(&a.tmap, sem_mode == SEM_I64 ? CU_TENSOR_MAP_DATA_TYPE_INT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                                 sem_mode == SEM_I64 ? 8 : 1, a.sem, a.B, a.H, a.W, a.sem_stride, kItemH, kItemW);
 }
 
 template <int SEM, int IDM, int OUT>
@@ -1295,7 +1453,7 @@ int launch_assign(int sem_mode, int id_mode, int out_mode, AssignArgs& a, cudaSt
 void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th)
 {
     a.o_status = L.status; a.o_votes = L.votes; a.o_areas = L.areas;
-    a.o_cell_start = L.cell_start; a.o_sorted = L.sorted;
+    a.o_cell_start = L.cell_start; a.o_sorted = L.sorted; a.o_sflags = L.sflags;
     a.things = th;
     a.thing_bits = 0ull;
     a.things_small = 1;
@@ -1306,23 +1464,28 @@ void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th)
 }
 
 int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long label_divisor, long long stuff_area,
-                 long long void_label, int64_t* pan_out, size_t n_px, cudaStream_t st)
+                 long long void_label, int64_t* pan_out, int H, int W, cudaStream_t st)
 {
     ApplyArgs a;
     memset(&a, 0, sizeof(a));
     a.ws = ws; a.ws_stride = ws_stride;
-    a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas;
-    a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = n_px;
+    a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas; a.o_sflags = L.sflags;
+    a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = (size_t)H * W;
+    a.H = H; a.W = W;
+    a.blocks_x = (W + kItemW - 1) / kItemW;
+    a.blocks_y = (H + kBlkItems * kItemH - 1) / (kBlkItems * kItemH);
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
-    a.vec = aligned16(pan_out) && (n_px % 2 == 0 || B == 1);
-    const size_t groups = a.vec ? n_px / 512 : 0;
-    size_t blocks = groups ? (groups + 7) / 8 : (n_px + 255) / 256;
-    if (blocks > (1u << 30)) blocks = 1u << 30;
-    if (blocks < 1) blocks = 1;
+    const bool fast = aligned16(pan_out) && W % 4 == 0;             // 16-byte label stores, 4-byte code loads
+    const long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
-    if (L.code16) apply_lut_kernel<true><<<grid, 256, 0, st>>>(a);
-    else apply_lut_kernel<false><<<grid, 256, 0, st>>>(a);
+    if (L.code16) {
+        if (fast) apply_lut_kernel<true, true><<<grid, 256, 0, st>>>(a);
+        else apply_lut_kernel<true, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (fast) apply_lut_kernel<false, true><<<grid, 256, 0, st>>>(a);
+        else apply_lut_kernel<false, false><<<grid, 256, 0, st>>>(a);
+    }
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
@@ -1538,8 +1701,7 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
     if ((rc = launch_assign(sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
     if ((rc = launch_build_lut(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, void_label, st))) return rc;
-    return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out,
-                        (size_t)H * W, st);
+    return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out, H, W, st);
 }
 
 EMP_API int emp_merge(const int64_t* sem, const int64_t* ins, int H, int W, int64_t label_divisor,
@@ -1605,7 +1767,7 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
         if ((rc = launch_assign(sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
         if ((rc = launch_build_lut(nb, L, wsg, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, void_label, st))) return rc;
         if ((rc = launch_apply(nb, L, wsg, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
-                               pan_out + (size_t)b0 * n_px, n_px, st))) return rc;
+                               pan_out + (size_t)b0 * n_px, H, W, st))) return rc;
     }
     return EMP_OK;
 }
