@@ -117,7 +117,13 @@ __device__ __noinline__ bool nms_window_has_bigger(const float* __restrict__ hm,
 // memory (the two halo columns of a strip come through L1/L2); that alone rejects every slope pixel of
 // a smooth heat-map, and only 3x3 maxima go on to the full k x k window.  Without FAST (unaligned or
 // tiny planes) the same code reads global memory.
-constexpr int kNmsRows = 4, kNmsWords = 8, kNmsStages = 2, kNmsWarps = 4, kNmsBlkItems = 16;
+#ifndef EMP_NMS_STAGES
+#define EMP_NMS_STAGES 3
+#endif
+#ifndef EMP_NMS_CTAS_PER_SM
+#define EMP_NMS_CTAS_PER_SM 3
+#endif
+constexpr int kNmsRows = 4, kNmsWords = 8, kNmsStages = EMP_NMS_STAGES, kNmsWarps = 4, kNmsBlkItems = 16, kNmsCtasPerSm = EMP_NMS_CTAS_PER_SM;
 constexpr int kNmsItemW = kNmsWords * 32, kNmsBoxRows = kNmsRows + 2;
 constexpr unsigned kNmsStageFloats = kNmsBoxRows * kNmsItemW;
 constexpr unsigned kNmsStageBytes = kNmsStageFloats * sizeof(float);
@@ -133,7 +139,7 @@ struct NmsArgs {
 };
 
 template <bool FAST>
-__global__ void __launch_bounds__(kNmsWarps * 32, 4)
+__global__ void __launch_bounds__(kNmsWarps * 32, kNmsCtasPerSm)
 nms_peaks_kernel(const __grid_constant__ NmsArgs a)
 {
     extern __shared__ __align__(128) unsigned char dsm[];            // [warp][stage][6 rows][256] fp32
@@ -211,6 +217,27 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
             unsigned cm = 0;                                            // bit 8*r + j: pixel (y0+r, x0+32j) is a candidate
             if (FAST) {
                 mbar_wait(&s_bar[warp][st_cons], parity);
+                // most items hold no pixel above threshold: 8 x LDS.128 and a max tree decide that
+                const float4* vp = reinterpret_cast<const float4*>(ring + (size_t)st_cons * kNmsStageFloats + kNmsItemW) + lane;
+                float mx = -CUDART_INF_F;
+#pragma unroll
+                for (int r = 0; r < kNmsRows; ++r) {
+#pragma unroll
+                    for (int h = 0; h < kNmsItemW / 128; ++h) {
+                        const float4 v = vp[r * (kNmsItemW / 4) + h * 32];
+                        mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));       // fmaxf skips NaNs, like "v > t0" does
+                    }
+                }
+                if (!__any_sync(0xffffffffu, mx > t0)) {                // warp-uniform
+                    __syncwarp();
+                    --inflight;
+                    if (++st_cons == kNmsStages) { st_cons = 0; parity ^= 1u; }
+                    pump();
+#pragma unroll
+                    for (int r = 0; r < kNmsRows; ++r)
+                        if (y0 + r < H && lane < kNmsWords && w0 + lane < wd) mask[(size_t)(y0 + r) * wd + w0 + lane] = 0u;
+                    continue;
+                }
 #pragma unroll
                 for (int r = 0; r < kNmsRows; ++r) {
 #pragma unroll
@@ -1352,7 +1379,7 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
         if (rc) return rc;
     }
     long long blocks = (n_blocks + kNmsWarps - 1) / kNmsWarps;
-    const long long resident = (long long)sm_count() * 4;
+    const long long resident = (long long)sm_count() * kNmsCtasPerSm;
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     {
@@ -1521,19 +1548,18 @@ int load_centers(const int64_t* ctr, int K, float step, const WsLayout& L, char*
     return EMP_OK;
 }
 
-// tiles per assign -> build_lut -> apply launch group of the fused path: a group's code maps
-// (2 B/px each) should still be in L2 when apply_lut reads them back (126 MB L2).
-static int tile_group(size_t code_bytes_per_tile)
+// Tiles per assign -> build_lut -> apply launch group of the fused path.  Measured on B200
+// (profiles/): one group holding the whole batch is fastest — the persistent assign kernel wants
+// many blocks per warp to balance, and strip flags already keep most of the code map out of DRAM.
+// EMP_TILE_GROUP=g (tuning knob) forces groups of g tiles.
+static int tile_group(int B)
 {
     static int env = -1;
     if (env < 0) {
         const char* e = getenv("EMP_TILE_GROUP");
         env = e ? atoi(e) : 0;
     }
-    if (env > 0) return env;
-    const size_t budget = 40u << 20;
-    const size_t g = budget / (code_bytes_per_tile ? code_bytes_per_tile : 1);
-    return g < 1 ? 1 : (int)g;
+    return env > 0 ? env : B;
 }
 
 }  // namespace emp
@@ -1751,7 +1777,7 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
     const size_t sem_elt = sem_u8 ? 1 : 8;
     // assign -> label LUT -> apply in groups of tiles small enough that a group's code maps
     // (2 B/px) are still in L2 when apply_lut reads them back.
-    const int G = tile_group((L.code16 ? 2 : 4) * n_px);
+    const int G = tile_group(B);
     for (int b0 = 0; b0 < B; b0 += G) {
         const int nb = std::min(G, B - b0);
         char* wsg = wsb + (size_t)b0 * ws_bytes_per_tile;
