@@ -8,7 +8,8 @@ synthetic 4096x4096 tiles (~500 centers per tile) per GPU.
   value     Mpix/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
   e2e       the same metric through the host-buffer C-ABI entry (emp_panoptic_batched_host): pinned
             host tensors in, H2D + kernels + D2H of the int64 panoptic maps inside the timed region
-  roofline  the dominant kernel (assign) against the measured HBM copy peak (MEASURED_PEAKS.json)
+  roofline  the dominant kernel (assign: sem + offsets -> code map) against the measured HBM copy peak
+            (MEASURED_PEAKS.json); traffic = ncu DRAM bytes per launch from profiles/traffic.json
   cpu_baseline  the reference's CPU op sequence (oracle/torch_port.py) on a bounded crop, rank 0, N=1
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
@@ -42,6 +43,16 @@ WORKLOAD = 'postproc_16x4096x4096_k500'
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per pixel of `kernel` from the committed ncu capture of this command
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch / pixels per launch)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            return float(json.load(f)['dram_bytes_per_px'][kernel])
+    except Exception:
+        return None
 
 
 def measured_peak():
@@ -272,6 +283,8 @@ def main():
         stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
         launches = sum(v[1] for v in prof.values())
         pipeline_gbs = ALG_BYTES_PER_PX * B * n_px / (ms_step * 1e-3) / 1e9
+        tpp = ncu_traffic(dom)
+        traffic = tpp * px_per_launch if tpp is not None else None
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
@@ -285,7 +298,7 @@ def main():
                     'api': 'emp_panoptic_batched_host (pinned host tensors, 3-slot H2D/compute/D2H pipeline)'},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'alg_bytes_per_px': STAGE_ALG_BYTES_PER_PX[dom], 'avg_launch_ms': dom_ms,
                          'pipeline': {'alg_bytes_per_px': ALG_BYTES_PER_PX, 'achieved': pipeline_gbs,
                                       'frac': pipeline_gbs / peak, 'frac_of_8TBs_spec': pipeline_gbs / 8000.0},
