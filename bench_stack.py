@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""
+bench_stack.py — BASELINE.json configs[2]: the 3D stack post-processing path on a synthetic
+512 x 2048 x 2048 anisotropic volume, z-sharded over N GPUs of one node, RLE out.
+
+What is timed (per rank, max over ranks): everything between "the CNN heads of my z-block are in HBM"
+and "every slice's RLE dict is on the host with globally unique labels" — the recursive median
+chain + harden (engines.py:47-90,114-121), coarse center search + group_pixels(step=4) on the
+512 x 512 maps (:257-272), the upsample-fused merge (:274-292), pan_seg -> RLE (rle.py:26-86),
+the D2H of the run tables, the carry-plane exchange between neighbouring ranks and the all-gather of
+instance counts (inference/stack.py).  The CNN forward is the unchanged PyTorch/cuDNN model and is
+not part of this path (its heads are synthetic here, cycled from a few distinct slices per rank).
+
+    python bench_stack.py [--depth 512] [--hw 2048] [--ks 3]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_stack.py --gpus N
+
+Prints one JSON line (rank 0): voxels/s over all ranks, ms per slice, scaling "strong" (the volume is
+fixed, ranks split it).  This is a secondary figure; the driver's bench is bench.py (configs[1]).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--depth', type=int, default=512)
+    ap.add_argument('--hw', type=int, default=2048)
+    ap.add_argument('--ks', type=int, default=3)
+    ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices per rank (cycled)')
+    ap.add_argument('--blobs', type=int, default=400)
+    ap.add_argument('--repeat', type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+
+    import torch
+    import torch.distributed as dist
+    from empanada_b200.inference import engines, stack
+    from empanada_b200.synth import synth_stack_slices
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    D, H = args.depth, args.hw
+
+    # a few distinct slices of a blob volume (slices 40.. of a 64-slice volume so blobs are live)
+    t0 = time.time()
+    slices = []
+    for i, s in enumerate(synth_stack_slices(40 + args.distinct, H, H, args.blobs, seed=100 + rank, coarse=4)):
+        if i >= 40:
+            slices.append({k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')})
+    if rank == 0:
+        print(f'[rank 0] {len(slices)} distinct slices ready in {time.time() - t0:.1f} s', file=sys.stderr, flush=True)
+
+    # pdl_inference3d.py defaults (:28-37): nms kernel 3, threshold 0.1, confidence 0.3, label divisor 20000
+    eng = engines.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0,
+                                              nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3, coarse_boundaries=True)
+
+    def run_once():
+        shard = stack.StackShard(eng, labels=[1], depth=D, rank=rank, world_size=world, median_kernel_size=args.ks,
+                                 upsampling=1, force_connected=True)
+        for z in shard.slices():
+            s = slices[z % len(slices)]
+            shard.add(z, s['sem_prob'], s['ctr_hmp'], s['offsets'], size=(H, H))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t = time.perf_counter()
+        out = shard.finish()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t
+        n_inst = sum(len(v[1]) for v in out.values())
+        n_runs = sum(len(a['starts']) for v in out.values() for a in v[1].values())
+        return dt, len(out), n_inst, n_runs
+
+    run_once()                                          # warm-up (workspaces, module load)
+    best = None
+    for _ in range(args.repeat):
+        r = run_once()
+        best = r if best is None or r[0] < best[0] else best
+    dt, n_slices, n_inst, n_runs = best
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        c = torch.tensor([n_inst, n_runs], device=dev, dtype=torch.int64)
+        dist.all_reduce(c)
+        n_inst, n_runs = int(c[0]), int(c[1])
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
+            'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
+            'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
+                       'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
+        }), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
