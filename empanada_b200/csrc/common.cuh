@@ -70,8 +70,8 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     L.cell_fill = o;  o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
     L.sorted = o;  o = align_up(o + sizeof(float4) * ((size_t)k_cap + 1), 256);     // (cy, cx, bits of k, -) grouped by cell
     L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
-    // one flag byte per 4 x 64 strip, 16 per 64 x 64 block (blocks row-major)
-    L.sflags = o;  o = align_up(o + (size_t)16 * ((W + 63) / 64) * ((H + 63) / 64), 256);
+    // one flag byte per 4 x 64 strip in slots of 16 per block (blocks row-major; a block is 1..16 strips tall)
+    L.sflags = o;  o = align_up(o + (size_t)16 * ((W + 63) / 64) * ((H + 3) / 4), 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);
     L.total = o;
     return L;

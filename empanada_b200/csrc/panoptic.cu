@@ -134,7 +134,7 @@ struct NmsArgs {
     char* ws; size_t ws_stride;
     size_t o_mask, o_rowcnt;
     int B, H, W, wd, lo, hi;
-    int blocks_x, blocks_y;                     // column strips per tile row / strips per tile column
+    int blocks_x, blocks_y, blk_items;          // column strips per tile row / per tile column, items per strip
     float thr;
 };
 
@@ -162,8 +162,8 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
             const int r = blk - k.b * per_img;
             const int by = r / a.blocks_x;
             k.colb = (r - by * a.blocks_x) * kNmsItemW;
-            k.row0 = by * (kNmsBlkItems * kNmsRows);
-            k.nitems = min(kNmsBlkItems, (H - k.row0 + kNmsRows - 1) / kNmsRows);
+            k.row0 = by * (a.blk_items * kNmsRows);
+            k.nitems = min(a.blk_items, (H - k.row0 + kNmsRows - 1) / kNmsRows);
         }
         return k;
     };
@@ -558,7 +558,7 @@ struct AssignArgs {
     size_t o_status, o_votes, o_areas, o_cell_start, o_sorted, o_sflags;
     int32_t* counter;                          // zeroed device word: dynamic block hand-out
     int B, H, W, wc, shift;
-    int blocks_x, blocks_y;                    // 64 x 64 blocks per tile row / column
+    int blocks_x, blocks_y, blk_items;         // blocks (blk_items strips of 4 x 64) per tile row / column
     float step;
     int chunksize, k_cap, k_fixed;             // k_fixed >= 0: K known on the host
     long long max_id;
@@ -574,7 +574,7 @@ struct AssignArgs {
 #endif
 constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 128, kAssignWarps = 4, kAssignCtasPerSm = EMP_ASSIGN_CTAS_PER_SM, kPx = 8;
 constexpr int kStages = 3;
-constexpr int kBlkItems = 16;                  // strips per block: 64 rows
+constexpr int kBlkItems = 16;                  // most strips per block (64 rows); small images use shorter blocks
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
 constexpr unsigned kNoKey = 0xFFFFFFFFu;
 
@@ -831,8 +831,8 @@ assign_kernel(const __grid_constant__ AssignArgs a)
             const int r = blk - k.b * per_img;
             const int by = r / a.blocks_x;
             k.colb = (r - by * a.blocks_x) * kItemW;
-            k.row0 = by * (kBlkItems * kItemH);
-            k.nitems = min(kBlkItems, (H - k.row0 + kItemH - 1) / kItemH);
+            k.row0 = by * (a.blk_items * kItemH);
+            k.nitems = min(a.blk_items, (H - k.row0 + kItemH - 1) / kItemH);
         }
         return k;
     };
@@ -935,7 +935,7 @@ assign_kernel(const __grid_constant__ AssignArgs a)
         const int col0 = kc.colb + 2 * lane;
         const bool cols_full = kc.colb + kItemW <= W;
         // strip flags of a block are contiguous: [(block row * blocks_x + block column) * kBlkItems + strip]
-        unsigned char* bflags = sflags + ((size_t)(kc.row0 / (kBlkItems * kItemH)) * a.blocks_x + kc.colb / kItemW) * kBlkItems;
+        unsigned char* bflags = sflags + ((size_t)(kc.row0 / (a.blk_items * kItemH)) * a.blocks_x + kc.colb / kItemW) * kBlkItems;
         const float xc0 = __fmul_rn((float)col0, a.step), xc1 = __fmul_rn((float)(col0 + 1), a.step);
 
         for (int it = 0; it < kc.nitems; ++it) {
@@ -1226,7 +1226,7 @@ struct ApplyArgs {
     char* ws; size_t ws_stride;
     size_t o_codes, o_lut, o_areas, o_sflags;
     long long* pan; size_t n_px;
-    int H, W, blocks_x, blocks_y;
+    int H, W, blocks_x, blocks_y, blk_items;
     long long label_divisor, stuff_area, void_label;
 };
 
@@ -1257,9 +1257,9 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
     const int blk = (int)blockIdx.x * 8 + warp;
     if (blk >= a.blocks_x * a.blocks_y) return;                     // warp-uniform
     const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
-    const int colb = bx * kItemW, rowb = by * (kBlkItems * kItemH);
+    const int colb = bx * kItemW, rowb = by * (a.blk_items * kItemH);
     const int col0 = colb + 2 * lane;
-    const int nitems = min(kBlkItems, (H - rowb + kItemH - 1) / kItemH);
+    const int nitems = min(a.blk_items, (H - rowb + kItemH - 1) / kItemH);
     const bool cols_full = colb + kItemW <= W;
 
     const uint4 fl = *reinterpret_cast<const uint4*>(ws + a.o_sflags + (size_t)blk * kBlkItems);
@@ -1369,7 +1369,9 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
     n.ws = ws; n.ws_stride = ws_stride; n.o_mask = L.mask; n.o_rowcnt = L.rowcnt;
     n.B = B; n.H = H; n.W = W; n.wd = L.wd; n.lo = k / 2; n.hi = k - 1 - n.lo; n.thr = thr;
     n.blocks_x = (W + kNmsItemW - 1) / kNmsItemW;
-    n.blocks_y = (H + kNmsBlkItems * kNmsRows - 1) / (kNmsBlkItems * kNmsRows);
+    n.blk_items = kNmsBlkItems;                 // shorter strips for small planes, so that every warp has work
+    while (n.blk_items > 1 && (long long)((H + n.blk_items * kNmsRows - 1) / (n.blk_items * kNmsRows)) * n.blocks_x * B < 2048) n.blk_items >>= 1;
+    n.blocks_y = (H + n.blk_items * kNmsRows - 1) / (n.blk_items * kNmsRows);
     const long long n_blocks = (long long)n.blocks_x * n.blocks_y * B;
     EMP_REQUIRE(n_blocks < (1ll << 30), EMP_ERR_INVALID, "batch too large for one launch");
     // TMA staging needs a 16-byte aligned base and row pitch, and the box must fit the tensor
@@ -1402,6 +1404,17 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
+}
+
+// Strips per block for an H x W tile: as tall as possible (fewer hand-outs, longer prefetch runs)
+// while a tile still yields a few thousand blocks, so that small images (the 512 x 512 coarse maps of
+// the stack path) keep every warp of the persistent grid busy.  assign and apply_lut must agree.
+static int block_items(int H, int W)
+{
+    const long long strips_x = (W + kItemW - 1) / kItemW, strips_y = (H + kItemH - 1) / kItemH;
+    int b = kBlkItems;
+    while (b > 1 && ((strips_y + b - 1) / b) * strips_x < 4096) b >>= 1;
+    return b;
 }
 
 template <int SEM, int IDM, int OUT, bool FAST>
@@ -1449,8 +1462,9 @@ static int launch_assign_out(int out_mode, const AssignArgs& a, cudaStream_t st)
 // a.B tiles in one launch; a.sem / a.off / a.ids_in / a.out / a.ws point at the first of them
 int launch_assign(int sem_mode, int id_mode, int out_mode, AssignArgs& a, cudaStream_t st)
 {
+    a.blk_items = block_items(a.H, a.W);
     a.blocks_x = (a.W + kItemW - 1) / kItemW;
-    a.blocks_y = (a.H + kBlkItems * kItemH - 1) / (kBlkItems * kItemH);
+    a.blocks_y = (a.H + a.blk_items * kItemH - 1) / (a.blk_items * kItemH);
     EMP_REQUIRE((long long)a.blocks_x * a.blocks_y * a.B < (1ll << 30), EMP_ERR_INVALID, "batch too large for one launch");
     a.counter = reinterpret_cast<int32_t*>(a.ws + a.o_status) + EMP_ST_TICKET;      // zeroed with the status block
     // FAST: every plane moves as 8/16-byte vectors and the sem plane is staged by TMA tensor copies
@@ -1499,8 +1513,9 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas; a.o_sflags = L.sflags;
     a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = (size_t)H * W;
     a.H = H; a.W = W;
+    a.blk_items = block_items(H, W);
     a.blocks_x = (W + kItemW - 1) / kItemW;
-    a.blocks_y = (H + kBlkItems * kItemH - 1) / (kBlkItems * kItemH);
+    a.blocks_y = (H + a.blk_items * kItemH - 1) / (a.blk_items * kItemH);
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
     const bool fast = aligned16(pan_out) && W % 4 == 0;             // 16-byte label stores, 4-byte code loads
     const long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;

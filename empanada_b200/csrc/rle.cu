@@ -80,6 +80,20 @@ __device__ __forceinline__ long long key_offset(int ci, int n, const RleClasses&
 }
 
 // ---------------------------------------------------------------------------------------------
+// rle_mark — the one pass over the pixels.  A warp takes 256 consecutive pixels of a row (8 mask
+// words); lane l loads pixels 32j + l (j = 0..7: eight independent 8-byte loads in flight per lane,
+// 256 B per warp-wide access) and reduces each to a 32-bit run key — 0 if the value belongs to no
+// selected class, else (class index + 1) << 22 | (value - class base), injective because
+// label_divisor <= 2^22 — so that neighbours compare with one shuffle.  An item with no selected pixel
+// (the bulk of an EM slice) stores zeros and moves on.
+constexpr int kMarkWords = 8;
+
+__device__ __forceinline__ unsigned run_key(long long v, const RleClasses& rc)
+{
+    const int c = class_of(v, rc);
+    return c >= 0 ? ((unsigned)(c + 1) << 22) | (unsigned)(v - rc.lo[c]) : 0u;
+}
+
 __global__ void __launch_bounds__(256)
 rle_mark_kernel(const long long* __restrict__ pan, int H, int W, int wd, RleClasses rc,
                 uint32_t* __restrict__ smask, uint32_t* __restrict__ emask, uint32_t* __restrict__ rowcnt)
@@ -87,26 +101,60 @@ rle_mark_kernel(const long long* __restrict__ pan, int H, int W, int wd, RleClas
     const int lane = threadIdx.x & 31;
     const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const size_t chunks = (size_t)H * wd;
-    for (size_t ch = warp_global; ch < chunks; ch += n_warps) {
-        const int y = (int)(ch / wd), wi = (int)(ch % wd);
-        const int x = wi * 32 + lane;
+    const int groups = (wd + kMarkWords - 1) / kMarkWords;             // items per row
+    const size_t items = (size_t)H * groups;
+    for (size_t it = warp_global; it < items; it += n_warps) {
+        const int y = (int)(it / groups), wg = (int)(it % groups);
+        const int w0 = wg * kMarkWords;
+        const int xb = w0 * 32;                                         // first pixel of the item
         const long long* row = pan + (size_t)y * W;
-        const long long v = x < W ? __ldcs(row + x) : 0;
-        long long left = __shfl_up_sync(0xffffffffu, v, 1);
-        long long right = __shfl_down_sync(0xffffffffu, v, 1);
-        if (lane == 0) left = x > 0 ? __ldg(row + x - 1) : 0;
-        if (lane == 31) right = (x + 1 < W) ? __ldg(row + x + 1) : 0;
-        const bool sel = x < W && class_of(v, rc) >= 0;
-        const bool start = sel && (x == 0 || left != v);
-        const bool end = sel && (x == W - 1 || right != v);
-        const unsigned sw = __ballot_sync(0xffffffffu, start);
-        const unsigned ew = __ballot_sync(0xffffffffu, end);
-        if (lane == 0) {
-            smask[ch] = sw;
-            emask[ch] = ew;
-            if (sw) atomicAdd(rowcnt + y, (uint32_t)__popc(sw));
+        long long v[kMarkWords];
+#pragma unroll
+        for (int j = 0; j < kMarkWords; ++j) {
+            const int x = xb + 32 * j + lane;
+            v[j] = x < W ? __ldcs(row + x) : 0;
         }
+        unsigned key[kMarkWords];
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < kMarkWords; ++j) {
+            key[j] = (v[j] != 0) ? run_key(v[j], rc) : 0u;
+            any |= key[j];
+        }
+        if (!__any_sync(0xffffffffu, any != 0u)) {                      // warp-uniform: nothing selected here
+            if (lane < kMarkWords && w0 + lane < wd) {
+                smask[(size_t)y * wd + w0 + lane] = 0u;
+                emask[(size_t)y * wd + w0 + lane] = 0u;
+            }
+            continue;
+        }
+        // keys of the pixels just outside the item (0 at the image border: the row starts / ends a run)
+        unsigned edge = 0;
+        if (lane == 0 && xb > 0) edge = run_key(__ldg(row + xb - 1), rc);
+        if (lane == 31 && xb + 32 * kMarkWords < W) edge = run_key(__ldg(row + xb + 32 * kMarkWords), rc);
+        unsigned mys = 0, mye = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < kMarkWords; ++j) {
+            unsigned left = __shfl_up_sync(0xffffffffu, key[j], 1);
+            unsigned right = __shfl_down_sync(0xffffffffu, key[j], 1);
+            const unsigned prev_last = __shfl_sync(0xffffffffu, j > 0 ? key[j > 0 ? j - 1 : 0] : edge, j > 0 ? 31 : 0);
+            const unsigned next_first = __shfl_sync(0xffffffffu, j + 1 < kMarkWords ? key[j + 1 < kMarkWords ? j + 1 : j] : edge,
+                                                    j + 1 < kMarkWords ? 0 : 31);
+            if (lane == 0) left = prev_last;
+            if (lane == 31) right = next_first;
+            const int x = xb + 32 * j + lane;
+            if (x == W - 1) right = 0;                                  // the last pixel of the row always ends its run
+            const bool sel = key[j] != 0u;
+            const unsigned sw = __ballot_sync(0xffffffffu, sel && left != key[j]);
+            const unsigned ew = __ballot_sync(0xffffffffu, sel && right != key[j]);
+            if (lane == j) { mys = sw; mye = ew; }
+            cnt += (unsigned)__popc(sw);
+        }
+        if (lane < kMarkWords && w0 + lane < wd) {
+            smask[(size_t)y * wd + w0 + lane] = mys;
+            emask[(size_t)y * wd + w0 + lane] = mye;
+        }
+        if (lane == 0 && cnt) atomicAdd(rowcnt + y, cnt);
     }
 }
 
@@ -460,8 +508,8 @@ EMP_API int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels, int
     EMP_CUDA_CHECK(cudaMemsetAsync(w, 0, R.zero_bytes, st));
     EMP_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * R.flags_len, st));
 
-    const size_t chunks = (size_t)H * R.wd;
-    unsigned g_mark = (unsigned)std::min<size_t>((chunks + 7) / 8, (size_t)148 * 32);
+    const size_t chunks = (size_t)H * ((R.wd + kMarkWords - 1) / kMarkWords);      // 256-pixel items, one per warp
+    unsigned g_mark = (unsigned)std::min<size_t>((chunks + 7) / 8, (size_t)148 * 16);
     if (g_mark < 1) g_mark = 1;
     {
         ProfScope ps(ST_RLE_MARK, st);
