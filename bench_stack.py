@@ -82,14 +82,14 @@ def main():
         dt = time.perf_counter() - t
         n_inst = sum(len(v[1]) for v in out.values())
         n_runs = sum(len(a['starts']) for v in out.values() for a in v[1].values())
-        return dt, len(out), n_inst, n_runs
+        return dt, len(out), n_inst, n_runs, dict(getattr(shard, 'timing_', {}))
 
     run_once()                                          # warm-up (workspaces, module load)
     best = None
     for _ in range(args.repeat):
         r = run_once()
         best = r if best is None or r[0] < best[0] else best
-    dt, n_slices, n_inst, n_runs = best
+    dt, n_slices, n_inst, n_runs, timing = best
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -101,6 +101,7 @@ def main():
         print(json.dumps({
             'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
             'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
+            'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
             'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
                        'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
         }), flush=True)

@@ -256,8 +256,12 @@ class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
         return ids, ws, k_cap
 
     @torch.no_grad()
-    def _fused_postprocess(self, sem_prob, ctr_hmp, offsets, upsampling):
-        """median-queue output -> pan (1,H,W) int64 with no dense intermediate besides uint8 sem."""
+    def _fused_enqueue(self, sem_prob, ctr_hmp, offsets, upsampling, k_cap=None):
+        """Enqueue median-queue output -> pan (1,H,W) int64 on the current stream, with no dense
+        intermediate besides uint8 sem and NO host synchronisation.  Returns (pan, coarse workspace,
+        merge workspace, k_cap); the status blocks at the start of the two workspaces (K / overflow
+        flag, class-range flags) are valid once the stream has run — and only until the next call
+        reuses the cached workspaces, so callers that defer the check copy them out first."""
         dev = sem_prob.device
         step = 4 if self.coarse_boundaries else 1
         _, sem = median_harden([sem_prob], self.confidence_thr, want_median=False, want_sem='u8')
@@ -267,17 +271,24 @@ class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
         shift = int(math.log2(s))
         assert (1 << shift) == s
         L = C.lib()
+        ids, cws, k_cap = self._coarse_ids(ctr_hmp, offsets, step, k_cap)
+        things, nt = C.i64_array(self.thing_list)
+        nbytes = L.emp_workspace_bytes(H, W, k_cap, max(nt, 1))
+        ws = C.workspace(dev, nbytes, 'merge')
+        pan = torch.empty((1, H, W), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            C.check(L.emp_merge_coarse(_ptr(sem), 1, _ptr(ids), h, w, shift, H, W, int(self.label_divisor),
+                                       things, nt, int(self.stuff_area), int(self.void_label), k_cap,
+                                       _ptr(cws), _ptr(pan), _ptr(ws), ws.numel(), C.stream_ptr(dev)))
+        return pan, cws, ws, k_cap
+
+    @torch.no_grad()
+    def _fused_postprocess(self, sem_prob, ctr_hmp, offsets, upsampling):
+        """median-queue output -> pan (1,H,W) int64; reads the status blocks back (one sync) and
+        retries with a larger center table in the (rare) overflow case."""
         k_cap = None
         while True:
-            ids, cws, k_cap = self._coarse_ids(ctr_hmp, offsets, step, k_cap)
-            things, nt = C.i64_array(self.thing_list)
-            nbytes = L.emp_workspace_bytes(H, W, k_cap, max(nt, 1))
-            ws = C.workspace(dev, nbytes, 'merge')
-            pan = torch.empty((1, H, W), dtype=torch.int64, device=dev)
-            with torch.cuda.device(dev):
-                C.check(L.emp_merge_coarse(_ptr(sem), 1, _ptr(ids), h, w, shift, H, W, int(self.label_divisor),
-                                           things, nt, int(self.stuff_area), int(self.void_label), k_cap,
-                                           _ptr(cws), _ptr(pan), _ptr(ws), ws.numel(), C.stream_ptr(dev)))
+            pan, cws, ws, k_cap = self._fused_enqueue(sem_prob, ctr_hmp, offsets, upsampling, k_cap)
             st = C.read_status(cws)
             if not (int(st[C.ST_FLAGS]) & C.FLAG_K_OVERFLOW):
                 break

@@ -33,6 +33,29 @@ def _as_cuda_i64(pan_seg, device=None):
     return t.contiguous()
 
 
+def rle_enqueue(pan, labels, label_divisor, thing_list, force_connected, runs_out, inst_out):
+    """Enqueue emp_rle for a contiguous (H,W) int64 CUDA tensor on the current stream, writing into
+    the caller's runs_out (run_cap,3) / inst_out (inst_cap,8) int64 CUDA tensors.  No host
+    synchronisation.  Returns the workspace tensor whose first 64 bytes are the status block
+    (row-runs / runs / instances found, overflow flag) once the stream has run."""
+    dev = pan.device
+    H, W = pan.shape
+    L = C.lib()
+    labels_a, nl = C.i64_array(labels)
+    things_a, nt = C.i64_array(thing_list)
+    run_cap, inst_cap = runs_out.shape[0], inst_out.shape[0]
+    nbytes = L.emp_rle_workspace_bytes(H, W, run_cap, nl, int(label_divisor))
+    if nbytes == 0:
+        raise ValueError('bad arguments to pan_seg_to_rle_seg')
+    ws = C.workspace(dev, nbytes, 'rle')
+    with torch.cuda.device(dev):
+        C.check(L.emp_rle(ctypes.c_void_p(pan.data_ptr()), H, W, labels_a, nl, int(label_divisor), things_a, nt,
+                          int(bool(force_connected)), ctypes.c_void_p(runs_out.data_ptr()), run_cap,
+                          ctypes.c_void_p(inst_out.data_ptr()), inst_cap, ctypes.c_void_p(ws.data_ptr()),
+                          ws.numel(), C.stream_ptr(dev)))
+    return ws
+
+
 def rle_tables(pan_seg, labels, label_divisor, thing_list, force_connected=True, run_cap=None,
                device=None):
     """GPU part: returns host numpy tables (inst (n_inst, 8) int64, runs (n_runs, 3) int64) as
@@ -40,24 +63,13 @@ def rle_tables(pan_seg, labels, label_divisor, thing_list, force_connected=True,
     pan = _as_cuda_i64(pan_seg, device)
     dev = pan.device
     H, W = pan.shape
-    L = C.lib()
-    labels_a, nl = C.i64_array(labels)
-    things_a, nt = C.i64_array(thing_list)
     if run_cap is None:
         run_cap = max(1 << 16, (H * W) // 64)
     inst_cap = run_cap
     while True:
-        nbytes = L.emp_rle_workspace_bytes(H, W, run_cap, nl, int(label_divisor))
-        if nbytes == 0:
-            raise ValueError('bad arguments to pan_seg_to_rle_seg')
-        ws = C.workspace(dev, nbytes, 'rle')
         runs = torch.empty((run_cap, 3), dtype=torch.int64, device=dev)
         inst = torch.empty((inst_cap, 8), dtype=torch.int64, device=dev)
-        with torch.cuda.device(dev):
-            C.check(L.emp_rle(ctypes.c_void_p(pan.data_ptr()), H, W, labels_a, nl, int(label_divisor), things_a, nt,
-                              int(bool(force_connected)), ctypes.c_void_p(runs.data_ptr()), run_cap,
-                              ctypes.c_void_p(inst.data_ptr()), inst_cap, ctypes.c_void_p(ws.data_ptr()),
-                              ws.numel(), C.stream_ptr(dev)))
+        ws = rle_enqueue(pan, labels, label_divisor, thing_list, force_connected, runs, inst)
         st = C.read_status(ws)
         n_rowruns, n_runs, n_inst = int(st[C.ST_NROWRUNS]), int(st[C.ST_NRUNS]), int(st[C.ST_NINST])
         if not (int(st[C.ST_FLAGS]) & C.FLAG_RLE_OVERFLOW):
@@ -67,24 +79,29 @@ def rle_tables(pan_seg, labels, label_divisor, thing_list, force_connected=True,
     return inst[:n_inst].cpu().numpy(), runs[:n_runs].cpu().numpy()
 
 
-def tables_to_rle_seg(inst, runs, labels):
-    """Host part: group the start-ordered runs by instance slot (stable) into the reference's
-    nested dict {class: {label: {'box', 'starts', 'runs'}}}."""
+def grouped_to_rle_seg(inst, starts, lens, labels):
+    """Assemble the reference's nested dict {class: {label: {'box', 'starts', 'runs'}}} from the
+    instance table and the runs already grouped by instance slot (ascending start inside a slot).
+    The per-instance arrays are views into `starts` / `lens` (no per-instance copies)."""
     rle_seg = {int(l): {} for l in labels}
-    if inst.shape[0] == 0:
+    n = inst.shape[0]
+    if n == 0:
         return rle_seg
-    order = np.argsort(runs[:, 2], kind='stable')
-    starts = runs[order, 0]
-    lens = runs[order, 1]
-    bounds = np.concatenate(([0], np.cumsum(inst[:, 6])))
-    for i, row in enumerate(inst):
-        a, b = int(bounds[i]), int(bounds[i + 1])
-        rle_seg[int(row[0])][int(row[1])] = {
-            'box': (int(row[2]), int(row[3]), int(row[4]), int(row[5])),
-            'starts': starts[a:b].copy(),
-            'runs': lens[a:b].copy(),
-        }
+    b = np.concatenate(([0], np.cumsum(inst[:, 6]))).tolist()
+    boxes = inst[:, 2:6].tolist()
+    cls, labs = inst[:, 0].tolist(), inst[:, 1].tolist()
+    for i in range(n):
+        rle_seg[cls[i]][labs[i]] = {'box': tuple(boxes[i]), 'starts': starts[b[i]:b[i + 1]], 'runs': lens[b[i]:b[i + 1]]}
     return rle_seg
+
+
+def tables_to_rle_seg(inst, runs, labels):
+    """Host part: group the start-ordered runs by instance slot (stable) and assemble the dict."""
+    if inst.shape[0] == 0:
+        return {int(l): {} for l in labels}
+    # runs are in ascending start order, so a plain sort of (slot, position) is the stable grouping
+    order = np.argsort(runs[:, 2] * (1 << 32) + np.arange(runs.shape[0], dtype=np.int64))
+    return grouped_to_rle_seg(inst, runs[order, 0], runs[order, 1], labels)
 
 
 def pan_seg_to_rle_seg(pan_seg, labels, label_divisor, thing_list, force_connected=True):

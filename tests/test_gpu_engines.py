@@ -101,3 +101,60 @@ def test_render_engine3d(name, cuda_device):
         assert len(outs) == sum(p['emitted']) + p['n_tail']
         for i, o in enumerate(outs):
             assert _mismatch(o, g[f'out_{i}']) == 0, f'{mode} slice {i}'
+
+
+def _rle_equal(a, b):
+    assert list(a.keys()) == list(b.keys())
+    for c in a:
+        assert list(a[c].keys()) == list(b[c].keys()), f'class {c}'
+        for lab in a[c]:
+            assert a[c][lab]['box'] == b[c][lab]['box']
+            np.testing.assert_array_equal(a[c][lab]['starts'], b[c][lab]['starts'])
+            np.testing.assert_array_equal(a[c][lab]['runs'], b[c][lab]['runs'])
+
+
+@pytest.mark.parametrize('ks', [1, 3, 5])
+def test_stack_shard_matches_sequential_engine(ks, cuda_device):
+    """The z-sharded driver (deferred-sync block processing, inference/stack.py) must give, slice for
+    slice, the RLE dicts of the sequential Render engine (median queue -> fused post-process -> RLE)."""
+    from empanada_b200.inference import rle, stack
+    from empanada_b200.synth import synth_stack_slices
+    D, H, W = 11, 192, 256
+    sl = list(synth_stack_slices(D, H, W, 40, seed=21, coarse=4, sigma=4.0, z_extent=(4, 12), semi_axes=(6, 20)))
+    heads = [{k: torch.from_numpy(s[k]).to(cuda_device) for k in ('sem_prob', 'ctr_hmp', 'offsets')} for s in sl]
+
+    class Probs(torch.nn.Module):                    # a "model" whose sem_logits are logit(prob)
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1, device=cuda_device))
+            self.i = 0
+
+        def forward(self, image, render_steps=None, interpolate_ins=None):
+            h = heads[self.i]
+            self.i += 1
+            return {'sem_logits': torch.logit(h['sem_prob'].double()).float(), 'ctr_hmp': h['ctr_hmp'].clone(),
+                    'offsets': h['offsets'].clone()}
+
+    kw = dict(thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3,
+              confidence_thr=0.3, coarse_boundaries=True)
+    seq = eng.PanopticDeepLabRenderEngine3d(Probs(), median_kernel_size=ks, **kw)
+    pans = []
+    for z in range(D):
+        o = seq(torch.zeros(1, 1, H, W), (H, W), 1)
+        if o is not None:
+            pans.append(o)
+    pans += seq.end(1)
+    assert len(pans) == D
+    want = [rle.pan_seg_to_rle_seg(p, [1], 20000, [1], True) for p in pans]
+
+    # the shard must see exactly the probabilities the engine saw: sigmoid(logit(p)) in fp32
+    probs = [eng.logits_to_prob(torch.logit(h['sem_prob'].double()).float()) for h in heads]
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), **kw)
+    shard = stack.StackShard(e, labels=[1], depth=D, rank=0, world_size=1, median_kernel_size=ks)
+    for z in shard.slices():
+        shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=(H, W))
+    got = shard.finish()
+    assert sorted(got.keys()) == list(range(D))
+    assert sum(len(v[1]) for v in got.values()) > 20
+    for z in range(D):
+        _rle_equal(got[z], want[z])
