@@ -714,14 +714,29 @@ __device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thi
 {
     // box of the shifted locations (fminf / fmaxf skip NaNs), then its cell range over the warp
     float fy0 = CUDART_INF_F, fy1 = -CUDART_INF_F, fx0 = CUDART_INF_F, fx1 = -CUDART_INF_F;
-    unsigned fin = 0;                                   // thing pixels with a finite location
+    float nanacc = 0.f;                                 // stays 0 unless a thing pixel's location is NaN / inf
 #pragma unroll
     for (int p = 0; p < kPx; ++p) {
         bs[p] = CUDART_INF_F; bk[p] = INT_MAX;
         if ((thing >> p) & 1u) {
             fy0 = fminf(fy0, ly[p]); fy1 = fmaxf(fy1, ly[p]);
             fx0 = fminf(fx0, lx[p]); fx1 = fmaxf(fx1, lx[p]);
-            if (fabsf(ly[p]) < CUDART_INF_F && fabsf(lx[p]) < CUDART_INF_F) fin |= 1u << p;
+            nanacc = __fmaf_rn(ly[p], 0.f, __fmaf_rn(lx[p], 0.f, nanacc));
+        }
+    }
+    unsigned fin = thing;                               // thing pixels with a finite location
+    if (__any_sync(0xffffffffu, !(nanacc == 0.f))) {    // warp-uniform, rare: sort out which ones
+        fin = 0;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p)
+            if (((thing >> p) & 1u) && fabsf(ly[p]) < CUDART_INF_F && fabsf(lx[p]) < CUDART_INF_F) fin |= 1u << p;
+        fy0 = fx0 = CUDART_INF_F; fy1 = fx1 = -CUDART_INF_F;
+#pragma unroll
+        for (int p = 0; p < kPx; ++p) {
+            if ((fin >> p) & 1u) {
+                fy0 = fminf(fy0, ly[p]); fy1 = fmaxf(fy1, ly[p]);
+                fx0 = fminf(fx0, lx[p]); fx1 = fmaxf(fx1, lx[p]);
+            }
         }
     }
     int y0 = INT_MAX, y1 = -1, x0 = INT_MAX, x1 = -1;
@@ -781,14 +796,24 @@ __device__ __forceinline__ void grid_nearest_8px(const GridView& g, unsigned thi
         const float Yhi = yb == g.ncy - 1 ? CUDART_INF_F : __fmul_rn(g.step, (float)((yb + 1) << g.gs));
         const float Xlo = xa == 0 ? -CUDART_INF_F : __fmul_rn(g.step, (float)(xa << g.gs));
         const float Xhi = xb == g.ncx - 1 ? CUDART_INF_F : __fmul_rn(g.step, (float)((xb + 1) << g.gs));
-        bool ok = true;
+        // settled iff d < 0.9999 * m, m = distance to the block's outer edge; tested on squares with the
+        // slack rounded in our favour.  First per lane — its pixels' box against its largest s — which
+        // almost always decides; pixel by pixel only if some lane fails that.
+        float smax = 0.f;
 #pragma unroll
-        for (int p = 0; p < kPx; ++p) {
-            // settled iff d < 0.9999 * m; tested on squares with the slack rounded in our favour
-            const float m = fminf(fminf(ly[p] - Ylo, Yhi - ly[p]), fminf(lx[p] - Xlo, Xhi - lx[p]));
-            if (((fin >> p) & 1u) && !(m > 0.f && bs[p] < 0.9997f * (m * m))) ok = false;
+        for (int p = 0; p < kPx; ++p) smax = ((fin >> p) & 1u) ? fmaxf(smax, bs[p]) : smax;
+        const float ml = fminf(fminf(fy0 - Ylo, Yhi - fy1), fminf(fx0 - Xlo, Xhi - fx1));
+        bool ok = fin == 0u || (ml > 0.f && smax < 0.9997f * (ml * ml));
+        if (!__all_sync(0xffffffffu, ok)) {             // warp-uniform
+            ok = true;
+#pragma unroll
+            for (int p = 0; p < kPx; ++p) {
+                const float m = fminf(fminf(ly[p] - Ylo, Yhi - ly[p]), fminf(lx[p] - Xlo, Xhi - lx[p]));
+                if (((fin >> p) & 1u) && !(m > 0.f && bs[p] < 0.9997f * (m * m))) ok = false;
+            }
+            if (!__all_sync(0xffffffffu, ok)) continue;
         }
-        if (__all_sync(0xffffffffu, ok)) break;
+        break;
     }
     // non-finite locations: every d_k is +inf or NaN; the caller maps "no index" to the reference's answer
 #pragma unroll
@@ -1077,19 +1102,18 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                 }
                 float bs[kPx];
                 grid_nearest_8px(g, thing, ly, lx, bs, idv);
+                // index -> 1-based id; "no index" (non-finite location) is id 1 without the sentinel, 0 with it
+                // (values of non-thing pixels are never used)
+                unsigned far = 0;
 #pragma unroll
                 for (int p = 0; p < kPx; ++p) {
-                    const int bk = idv[p];
-                    int id = 0;
-                    if ((thing >> p) & 1u) {
-                        if (chunked) {      // sentinel (postprocess.py:98,:110): d < 1e5 on the rounded sqrt
-                            const bool lt = bs[p] < 9.99e9f || (bs[p] < 1.001e10f && __fsqrt_rn(bs[p]) < 1e5f);
-                            id = (bk != INT_MAX && lt) ? bk + 1 : 0;
-                        } else {
-                            id = bk != INT_MAX ? bk + 1 : 1;
-                        }
-                    }
-                    idv[p] = id;
+                    idv[p] = idv[p] == INT_MAX ? (chunked ? 0 : 1) : idv[p] + 1;
+                    far |= (bs[p] >= 9.99e9f ? 1u : 0u) << p;
+                }
+                if (chunked && (far & thing)) {         // sentinel (postprocess.py:98,:110): d < 1e5 on the rounded sqrt
+#pragma unroll
+                    for (int p = 0; p < kPx; ++p)
+                        if (((far >> p) & 1u) && !(bs[p] < 1.001e10f && __fsqrt_rn(bs[p]) < 1e5f)) idv[p] = 0;
                 }
             }
 
