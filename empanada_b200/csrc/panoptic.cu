@@ -573,7 +573,10 @@ struct AssignArgs {
 #define EMP_ASSIGN_CTAS_PER_SM 4
 #endif
 constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 128, kAssignWarps = 4, kAssignCtasPerSm = EMP_ASSIGN_CTAS_PER_SM, kPx = 8;
-constexpr int kStages = 3;
+#ifndef EMP_ASSIGN_STAGES
+#define EMP_ASSIGN_STAGES 3
+#endif
+constexpr int kStages = EMP_ASSIGN_STAGES;
 constexpr int kBlkItems = 16;                  // most strips per block (64 rows); small images use shorter blocks
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
 constexpr unsigned kNoKey = 0xFFFFFFFFu;
@@ -988,7 +991,17 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                 __syncwarp();                               // every lane has its values: the slot is free
                 --inflight;
                 if (++st_cons == kStages) { st_cons = 0; parity ^= 1u; }
-                pump();
+                if (p_which == 0 && p_i < kc.nitems) {      // common case: the next strip of this block
+                    if (lane == 0) {
+                        mbar_expect_tx(&s_bar[warp][st_issue], kStageBytes);
+                        tma_load_3d(ring + (size_t)st_issue * kStageBytes, &a.tmap, kc.colb, kc.row0 + p_i * kItemH, kc.b,
+                                    &s_bar[warp][st_issue], policy);
+                    }
+                    ++p_i; ++inflight;
+                    st_issue = st_issue + 1 == kStages ? 0 : st_issue + 1;
+                } else {
+                    pump();                                 // block boundary: the general state machine
+                }
             } else if (SEM != SEM_NONE) {
 #pragma unroll
                 for (int i = 0; i < kItemH; ++i) {
