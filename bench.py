@@ -158,6 +158,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tiles', type=int, default=TILES)
     ap.add_argument('--instances', type=int, default=N_INST)
+    ap.add_argument('--dense', action='store_true', help='BASELINE configs[4]: ~5000 instances of semi-axes 4..12 px per tile')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -191,7 +192,10 @@ def main():
     off_h = torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory()
     pan_h = torch.empty((B, H, W), dtype=torch.int64).pin_memory()
     for b in range(B):
-        d = synth_tile(H, W, args.instances, seed=rank * 1000 + b)
+        if args.dense:
+            d = synth_tile(H, W, 5000, seed=rank * 1000 + b, semi_axes=(4.0, 12.0), sigma=2.0)
+        else:
+            d = synth_tile(H, W, args.instances, seed=rank * 1000 + b)
         sem_h[b] = torch.from_numpy(d['sem'][0, 0])
         hm_h[b] = torch.from_numpy(d['ctr_hmp'][0, 0])
         off_h[b] = torch.from_numpy(d['offsets'][0])
@@ -289,7 +293,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'int64/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'tiles_per_gpu': B, 'tile': [H, W], 'centers_per_tile': [min(Ks), max(Ks)],
+            'config': {'workload': WORKLOAD if not args.dense else 'postproc_16x4096x4096_dense_k5000', 'tiles_per_gpu': B, 'tile': [H, W], 'centers_per_tile': [min(Ks), max(Ks)],
                        'thing_list': THINGS, 'label_divisor': LABEL_DIVISOR, 'nms_kernel': NMS_K,
                        'l2': f'inputs {B * n_px * 20 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed',
                        'parallelism': f'dp{world} (independent tiles per rank, no collective on the data path)'},

@@ -43,6 +43,7 @@ _SIGNATURES = {
     'emp_rle_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32, _i64]),
     'emp_rle': (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                        _vp, _sz, _vp]),
+    'emp_rle_pair_overlaps': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)

@@ -1,0 +1,304 @@
+"""
+Drop-in for the RLE part of ``empanada.inference.matcher`` (reference empanada/inference/matcher.py):
+``rle_matcher`` and ``RLEMatcher`` with the reference's signatures, return values and label
+bookkeeping.  The pixel intersections behind every IoU / IoA — the reference's per-pair sort-and-sweep
+on the host (array_utils.rle_intersection) — come from one CUDA launch over the run tables
+(libempanada_b200 ``emp_rle_pair_overlaps``); the Hungarian assignment
+(scipy.optimize.linear_sum_assignment, as in the reference) and the n x m matrix logic stay on the host.
+
+Two ways in:
+  * the reference's dict API — ``rle_matcher(target_rles, match_rles, ...)`` / ``RLEMatcher`` — uploads
+    the two run lists, one launch per call;
+  * ``block_overlaps`` + ``StackMatcher`` for the z-sharded stack driver: the run tables of a whole
+    z-block are already in HBM (inference/stack.py), so ONE launch yields the overlaps of every
+    consecutive slice pair, and the forward / backward matching chains (patterns.py:68-112) then run on
+    the host without touching run lists at all — merged instances are handled as groups of the
+    original per-slice instances, whose intersections add up because instances of a slice are disjoint.
+
+``fast_matcher`` (dense label maps + skimage regionprops) is not part of the RLE path and is not provided.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from scipy.optimize import linear_sum_assignment
+
+from empanada_b200 import _cabi as C
+from empanada_b200.inference.rle import unpack_rle_attrs
+
+__all__ = ['rle_matcher', 'RLEMatcher', 'merge_attrs', 'merge_rles', 'merge_boxes', 'pair_overlaps', 'block_overlaps',
+           'StackMatcher']
+
+
+# ---- host helpers with the reference's semantics (array_utils.py:101-125, :634-718) ---------------
+def merge_boxes(box1, box2):
+    n = len(box1)
+    ndim = n // 2
+    return tuple(min(box1[i], box2[i]) if i < ndim else max(box1[i], box2[i]) for i in range(n))
+
+
+def merge_rles(starts_a, runs_a, starts_b=None, runs_b=None):
+    """Union of possibly overlapping run lists as sorted, non-overlapping runs; ranges that overlap or
+    touch are joined (array_utils.py:690-718, _join_ranges :634-663)."""
+    s = np.asarray(starts_a, dtype=np.int64)
+    e = s + np.asarray(runs_a, dtype=np.int64)
+    if starts_b is not None and runs_b is not None:
+        sb = np.asarray(starts_b, dtype=np.int64)
+        s = np.concatenate([s, sb])
+        e = np.concatenate([e, sb + np.asarray(runs_b, dtype=np.int64)])
+    order = np.argsort(s, kind='stable')
+    s, e = s[order], e[order]
+    reach = np.maximum.accumulate(e)
+    head = np.ones(s.shape[0], dtype=bool)
+    head[1:] = s[1:] > reach[:-1]                       # a new range starts where nothing before reaches it
+    idx = np.flatnonzero(head)
+    ends = np.maximum.reduceat(e, idx)
+    return s[idx], ends - s[idx]
+
+
+def merge_attrs(rle_attr1, rle_attr2):
+    """matcher.py:14-29."""
+    starts, runs = merge_rles(rle_attr1['starts'], rle_attr1['runs'], rle_attr2['starts'], rle_attr2['runs'])
+    return {'box': merge_boxes(rle_attr1['box'], rle_attr2['box']), 'starts': starts, 'runs': runs}
+
+
+# ---- overlaps on the GPU ----------------------------------------------------------------------------
+def _overlap_rows(runs, n_runs_dev, max_runs, device):
+    """emp_rle_pair_overlaps on a (n_slices, run_stride, 3) int64 CUDA tensor -> summed rows
+    (pair, slot_a, slot_b, inter) as int64 numpy arrays."""
+    n_slices, run_stride = int(runs.shape[0]), int(runs.shape[1])
+    L = C.lib()
+    cap = max(1024, 2 * max_runs * max(n_slices - 1, 1))
+    while True:
+        out = torch.empty((cap, 4), dtype=torch.int32, device=device)
+        count = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            C.check(L.emp_rle_pair_overlaps(ctypes.c_void_p(runs.data_ptr()), run_stride, ctypes.c_void_p(n_runs_dev.data_ptr()),
+                                            n_slices, int(max_runs), ctypes.c_void_p(out.data_ptr()), cap,
+                                            ctypes.c_void_p(count.data_ptr()), C.stream_ptr(device)))
+        n = int(count.item())
+        if n <= cap:
+            break
+        cap = n
+    rows = out[:n].to(torch.int64)
+    if n == 0:
+        z = np.zeros(0, np.int64)
+        return z, z, z, z
+    key = (rows[:, 0] << 42) | (rows[:, 1] << 21) | rows[:, 2]          # slots < 2^21
+    uniq, inv = torch.unique(key, return_inverse=True)
+    inter = torch.zeros(uniq.shape[0], dtype=torch.int64, device=device).index_add_(0, inv, rows[:, 3])
+    uniq, inter = uniq.cpu().numpy(), inter.cpu().numpy()
+    return uniq >> 42, (uniq >> 21) & ((1 << 21) - 1), uniq & ((1 << 21) - 1), inter
+
+
+def _flat_runs(starts_list, runs_list):
+    """All runs of one side as (start, length, slot) rows in ascending start order."""
+    if len(starts_list) == 0:
+        return np.zeros((0, 3), np.int64)
+    slot = np.repeat(np.arange(len(starts_list), dtype=np.int64), [len(s) for s in starts_list])
+    st = np.concatenate([np.asarray(s, np.int64) for s in starts_list]) if slot.size else np.zeros(0, np.int64)
+    ru = np.concatenate([np.asarray(r, np.int64) for r in runs_list]) if slot.size else np.zeros(0, np.int64)
+    order = np.argsort(st, kind='stable')
+    return np.stack([st[order], ru[order], slot[order]], 1)
+
+
+def pair_overlaps(target_starts, target_runs, match_starts, match_runs, device=None):
+    """(n, m) int64 matrix of pixel intersections between two lists of run-length encoded instances
+    (each list's instances mutually disjoint, as instances of one slice are)."""
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    n, m = len(target_starts), len(match_starts)
+    inter = np.zeros((n, m), np.int64)
+    if n == 0 or m == 0:
+        return inter
+    a, b = _flat_runs(target_starts, target_runs), _flat_runs(match_starts, match_runs)
+    stride = max(a.shape[0], b.shape[0], 1)
+    both = np.zeros((2, stride, 3), np.int64)
+    both[0, :a.shape[0]] = a
+    both[1, :b.shape[0]] = b
+    runs = torch.from_numpy(both).to(device)
+    n_runs = torch.tensor([a.shape[0], b.shape[0]], dtype=torch.int32, device=device)
+    _, sa, sb, ov = _overlap_rows(runs, n_runs, stride, device)
+    inter[sa, sb] = ov
+    return inter
+
+
+def block_overlaps(runs_all, n_runs, device=None):
+    """Overlaps of every consecutive slice pair of a z-block whose run tables are in HBM.
+    runs_all (n_slices, run_stride, 3) int64 CUDA tensor (emp_rle's runs_out per slice, rows in
+    ascending start order), n_runs host array of valid rows per slice.  Returns a list of n_slices-1
+    tuples (slot_a, slot_b, inter) of int64 numpy arrays."""
+    device = runs_all.device if device is None else device
+    n_runs = np.asarray(n_runs, np.int64)
+    n = int(runs_all.shape[0])
+    nr = torch.from_numpy(n_runs.astype(np.int32)).to(device)
+    pair, sa, sb, ov = _overlap_rows(runs_all, nr, int(n_runs.max()) if n else 0, device)
+    cuts = np.searchsorted(pair, np.arange(1, max(n - 1, 1)))
+    return [tuple(x) for x in zip(np.split(sa, cuts), np.split(sb, cuts), np.split(ov, cuts))][:max(n - 1, 0)]
+
+
+# ---- the reference's matcher ------------------------------------------------------------------------
+def _match_from_inter(target_labels, match_labels, inter, area_t, area_m, iou_thr, return_iou, return_ioa):
+    """matcher.py:196-232 given the intersection matrix: IoU in float64 ('float' in the reference), IoA in
+    float32, Hungarian on the IoU matrix, threshold on the assigned pairs."""
+    with np.errstate(divide='ignore', invalid='ignore'):
+        union = area_t[:, None] + area_m[None, :] - inter
+        iou_matrix = np.where(inter > 0, inter / union, 0.0).astype('float')
+        ioa_matrix = np.where(inter > 0, inter / area_m[None, :], 0.0).astype(np.float32)
+    match_rows, match_cols = linear_sum_assignment(iou_matrix, maximize=True)
+    if iou_thr is not None:
+        iou_mask = iou_matrix[match_rows, match_cols] >= iou_thr
+        match_rows, match_cols = match_rows[iou_mask], match_cols[iou_mask]
+    matched_labels = (target_labels[match_rows], match_labels[match_cols])
+    output = (matched_labels, [target_labels, match_labels], iou_matrix[(match_rows, match_cols)])
+    if return_iou:
+        output = output + (iou_matrix,)
+    if return_ioa:
+        output = output + (ioa_matrix,)
+    return output
+
+
+def rle_matcher(target_instance_rles, match_instance_rles, iou_thr=0.5, return_iou=False, return_ioa=False, inter=None):
+    r"""Performs Hungarian matching on run length encodings (matcher.py:136-232).
+
+    Same arguments and return values as the reference; ``inter`` (optional, an (n, m) int64 matrix of
+    pixel intersections in the dicts' key order) skips the GPU launch when the caller already has it."""
+    target_labels, target_boxes, target_starts, target_runs = unpack_rle_attrs(target_instance_rles)
+    match_labels, match_boxes, match_starts, match_runs = unpack_rle_attrs(match_instance_rles)
+    if len(target_labels) == 0 or len(match_labels) == 0:
+        empty = np.array([])
+        if return_ioa:
+            return (empty, empty), (target_labels, match_labels), empty, empty
+        return (empty, empty), (target_labels, match_labels), empty
+    if inter is None:
+        inter = pair_overlaps(target_starts, target_runs, match_starts, match_runs)
+    area_t = np.array([int(np.sum(r)) for r in target_runs], dtype=np.int64)
+    area_m = np.array([int(np.sum(r)) for r in match_runs], dtype=np.int64)
+    return _match_from_inter(target_labels, match_labels, inter, area_t, area_m, iou_thr, return_iou, return_ioa)
+
+
+class RLEMatcher:
+    r"""Tracks and matches instances across consecutive run length encodings in a stack
+    (matcher.py:234-326; same constructor arguments, attributes and call semantics)."""
+
+    def __init__(self, class_id, label_divisor, merge_iou_thr=0.25, merge_ioa_thr=0.25, assign_new=True, **kwargs):
+        self.class_id = class_id
+        self.label_divisor = label_divisor
+        self.merge_iou_thr = merge_iou_thr
+        self.merge_ioa_thr = merge_ioa_thr
+        self.assign_new = assign_new
+        self.next_label = (class_id * label_divisor) + 1
+        self.target_rle = None
+        self.last_assignment = None         # [(match label, new label)] of the last call, in match order
+
+    def initialize_target(self, target_instance_rles):
+        self.target_rle = target_instance_rles
+        objs = list(target_instance_rles.keys())
+        if len(objs) > 0:
+            self.next_label = max(objs) + 1
+
+    def update_target(self, instance_rles):
+        self.target_rle = instance_rles
+
+    def __call__(self, match_instance_rle, update_target=True, inter=None):
+        """Matches the given instance segmentation to target"""
+        assert self.target_rle is not None, "Initialize target rle before running!"
+        matched_labels, all_labels, matched_ious, ioa_matrix = rle_matcher(
+            self.target_rle, match_instance_rle, self.merge_iou_thr, return_ioa=True, inter=inter)
+        target_labels, match_labels = all_labels
+        label_matches = {ml: tl for tl, ml in zip(matched_labels[0], matched_labels[1])}
+        matched_rles = {}
+        assignment = []
+        for i, (ml, mattrs) in enumerate(match_instance_rle.items()):
+            if ml in label_matches:
+                new_label = label_matches[ml]
+            else:
+                assert ml == match_labels[i]
+                ioa_max = ioa_matrix[:, i].max() if len(ioa_matrix) > 0 else 0
+                if ioa_max >= self.merge_ioa_thr:
+                    new_label = target_labels[ioa_matrix[:, i].argmax()]
+                elif self.assign_new:
+                    new_label = self.next_label
+                    self.next_label += 1
+                else:
+                    new_label = ml
+            assignment.append((ml, new_label))
+            if new_label not in matched_rles:
+                matched_rles[new_label] = mattrs
+            else:
+                matched_rles[new_label] = merge_attrs(matched_rles[new_label], mattrs)
+        self.last_assignment = assignment
+        if update_target:
+            self.update_target(matched_rles)
+        return matched_rles
+
+
+class StackMatcher:
+    """Forward and backward matching of one class through a z-block (the loop of
+    patterns.forward_matching / backward_matching, patterns.py:68-112) driven by precomputed overlaps
+    of the ORIGINAL per-slice instances (``block_overlaps``): no run list is touched while matching.
+
+    rles       list over slices of {label: attrs} for this class (dict order = instance slot order)
+    overlaps   list over consecutive pairs of (slot_a, slot_b, inter) arrays
+    """
+
+    def __init__(self, class_id, label_divisor, merge_iou_thr=0.25, merge_ioa_thr=0.25):
+        self.matcher = RLEMatcher(class_id, label_divisor, merge_iou_thr, merge_ioa_thr, True)
+
+    @staticmethod
+    def _group_inter(t_groups, m_groups, n_t_slots, n_m_slots, slot_t, slot_m, ov):
+        """(labels of t_groups) x (labels of m_groups) intersections from slot-level overlaps."""
+        row = np.full(n_t_slots, -1, np.int64)
+        col = np.full(n_m_slots, -1, np.int64)
+        for i, slots in enumerate(t_groups.values()):
+            row[slots] = i
+        for j, slots in enumerate(m_groups.values()):
+            col[slots] = j
+        inter = np.zeros((len(t_groups), len(m_groups)), np.int64)
+        r, c = row[slot_t], col[slot_m]
+        ok = (r >= 0) & (c >= 0)
+        np.add.at(inter, (r[ok], c[ok]), ov[ok])
+        return inter
+
+    def forward(self, rles, overlaps):
+        """Returns (matched rles per slice, groups per slice: {label: [original slots]})."""
+        m = self.matcher
+        out, groups = [], []
+        for z, seg in enumerate(rles):
+            own = {lab: [i] for i, lab in enumerate(seg.keys())}
+            if m.target_rle is None:
+                m.initialize_target(seg)
+                out.append(seg)
+                groups.append(own)
+                continue
+            sa, sb, ov = overlaps[z - 1]
+            inter = self._group_inter(groups[-1], own, len(rles[z - 1]), len(seg), sa, sb, ov)
+            matched = m(seg, inter=inter)
+            g = {}
+            for old, new in m.last_assignment:
+                g.setdefault(new, []).extend(own[old])
+            out.append(matched)
+            groups.append(g)
+        return out, groups
+
+    def backward(self, fwd, groups, rles, overlaps):
+        """patterns.backward_matching: targets reset, assign_new off, slices in reverse."""
+        m = self.matcher
+        m.target_rle = None
+        m.assign_new = False
+        out = [None] * len(fwd)
+        g_next = None
+        for z in range(len(fwd) - 1, -1, -1):
+            seg = fwd[z]
+            if m.target_rle is None:
+                m.initialize_target(seg)
+                out[z], g_next = seg, groups[z]
+                continue
+            sa, sb, ov = overlaps[z]                    # pair (z, z+1): a = slots of z, b = slots of z+1
+            inter = self._group_inter(g_next, groups[z], len(rles[z + 1]), len(rles[z]), sb, sa, ov)
+            matched = m(seg, inter=inter)
+            g = {}
+            for old, new in m.last_assignment:
+                g.setdefault(new, []).extend(groups[z][old])
+            out[z], g_next = matched, g
+        return out

@@ -226,7 +226,55 @@ class StackShard:
                 at += k
         # host seconds: enqueueing, waiting for the device, read-back + dict assembly
         self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'assemble_s': time.perf_counter() - t_c}
+        # kept for match(): the run tables stay in HBM, slots index each slice's instances in dict order
+        self.tables_ = {'runs_all': runs_all, 'n_runs': np.where(ok, n_runs, 0), 'bad': bad,
+                        'inst': [inst_h[i, :n_inst[i]] if ok[i] else None for i in range(n)], 'zs': list(zs)}
         return segs
+
+    def match(self, segs, merge_iou_thr=0.25, merge_ioa_thr=0.25):
+        """Forward + backward cross-slice matching of this rank's block (the host loop of
+        patterns.forward_matching / backward_matching, patterns.py:68-112, per thing class), with every
+        IoU / IoA taken from ONE overlap launch over the block's run tables (inference/matcher.py).
+        segs: what finish() returned.  Returns {z: matched rle_seg}.  A single-rank block only: chaining
+        blocks of several ranks needs the last slice's matched labels of rank r-1 and is the caller's job."""
+        from empanada_b200.inference import matcher as mt
+        e = self.engine
+        t = self.tables_
+        zs = t['zs']
+        assert zs == sorted(segs.keys())
+        if t['bad'].any():                              # a slice was redone synchronously: use the dict API
+            pair_rows = None
+        else:
+            pair_rows = mt.block_overlaps(t['runs_all'], t['n_runs'])
+        out = {z: dict(segs[z]) for z in zs}
+        for c in self.labels:
+            if c not in e.thing_list:
+                continue
+            rles = [segs[z][c] for z in zs]
+            if pair_rows is None:
+                overlaps = []
+                for a, b in zip(rles[:-1], rles[1:]):
+                    la, _, sa, ra = mt.unpack_rle_attrs(a)
+                    lb, _, sb, rb = mt.unpack_rle_attrs(b)
+                    m = mt.pair_overlaps(sa, ra, sb, rb)
+                    i, j = np.nonzero(m)
+                    overlaps.append((i, j, m[i, j]))
+            else:
+                # slots count every class of the slice; keep this class's and renumber from 0
+                overlaps = []
+                for p, (sa, sb, ov) in enumerate(pair_rows):
+                    ia, ib = t['inst'][p], t['inst'][p + 1]
+                    ca, cb = ia[sa, 0] == c, ib[sb, 0] == c
+                    fa = int(np.argmax(ia[:, 0] == c)) if (ia[:, 0] == c).any() else 0
+                    fb = int(np.argmax(ib[:, 0] == c)) if (ib[:, 0] == c).any() else 0
+                    k = ca & cb
+                    overlaps.append((sa[k] - fa, sb[k] - fb, ov[k]))
+            sm = mt.StackMatcher(c, e.label_divisor, merge_iou_thr, merge_ioa_thr)
+            fwd, groups = sm.forward(rles, overlaps)
+            bwd = sm.backward(fwd, groups, rles, overlaps)
+            for z, seg in zip(zs, bwd):
+                out[z][c] = seg
+        return out
 
     def finish(self):
         from empanada_b200.inference import engines as eng

@@ -176,6 +176,20 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
             int force_connected, int64_t* runs_out, int run_cap, int64_t* inst_out, int inst_cap,
             void* ws, size_t ws_bytes, void* stream);
 
+/* Cross-slice matcher support — empanada/inference/matcher.py:136-232 (rle_matcher) with
+ * array_utils.rle_intersection :371-403 / rle_iou :405-429 / rle_ioa :431-449: pixel overlaps between
+ * the instances of consecutive slices, from the run tables emp_rle wrote.  For pair p = (slice p,
+ * slice p+1) every overlapping pair of runs contributes one row (p, slot in slice p, slot in slice
+ * p+1, overlap in pixels); summing rows with equal (p, slot, slot) gives the intersection the
+ * reference computes per instance pair (IoU = inter / (area_a + area_b - inter), IoA = inter / area_b).
+ *   runs    (n_slices, run_stride, 3) int64 rows (start, length, slot); the first n_runs[s] rows of
+ *           slice s in ascending start order and disjoint (emp_rle's runs_out)
+ *   n_runs  device int32[n_slices];  max_runs >= every n_runs[s] (sizes the grid)
+ *   out     (cap, 4) int32 rows, unordered, 16-byte aligned;  count: device int32, rows found — if it
+ *           exceeds cap the surplus rows were dropped: retry with cap >= count. */
+int emp_rle_pair_overlaps(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices,
+                          int max_runs, int32_t* out, int cap, int32_t* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

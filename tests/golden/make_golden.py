@@ -401,8 +401,96 @@ def rle_cases():
     rle_case('rle_empty', np.zeros((16, 16), np.int64), [1, 2], 1000, [1], True)
 
 
+# ---------------------------------------------------------------------------------------------
+# cross-slice matcher: the reference's rle_matcher / RLEMatcher, forward + backward
+# ---------------------------------------------------------------------------------------------
+def blob_stack(D, H, W, n_blobs, seed, L=1000):
+    """(D,H,W) int64 panoptic-style label maps: ellipsoidal blobs drifting in z, labelled per slice
+    1..n by raster order (as the post-processing would), so labels do NOT agree across slices."""
+    rng = np.random.default_rng(seed)
+    zc, zr = rng.uniform(0, D, n_blobs), rng.uniform(1.5, D / 2, n_blobs)
+    cy, cx = rng.uniform(0, H, n_blobs), rng.uniform(0, W, n_blobs)
+    vy, vx = rng.normal(0, 1.5, n_blobs), rng.normal(0, 1.5, n_blobs)
+    a, b = rng.uniform(4, 14, n_blobs), rng.uniform(4, 14, n_blobs)
+    yy, xx = np.mgrid[0:H, 0:W]
+    out = np.zeros((D, H, W), np.int64)
+    for z in range(D):
+        ins = np.zeros((H, W), np.int64)
+        for i in np.flatnonzero(np.abs(z - zc) < zr):
+            f = np.sqrt(max(0.05, 1 - ((z - zc[i]) / zr[i]) ** 2))
+            m = ((yy - cy[i] - vy[i] * (z - zc[i])) / (a[i] * f)) ** 2 + ((xx - cx[i] - vx[i] * (z - zc[i])) / (b[i] * f)) ** 2 <= 1
+            ins[m] = i + 1
+        out[z] = np.where(ins > 0, L + ins, 0)
+    return out
+
+
+def matcher_cases():
+    from empanada.inference import matcher as rmatch  # reference, via shim
+
+    # 1. the reference's own known-answer test (tests/test_matcher.py:6-66)
+    target = matcher_target()
+    match = np.zeros((200, 200), dtype=np.uint32)
+    match[:16, :16] = 1009; match[30:50, 30:50] = 1008; match[:10, -10:] = 1007; match[-50:, :50] = 1006
+    match[-30:, 45:80] = 1005; match[-20:, -20:] = 1004; match[100:115, 90:110] = 1003
+    match[115:130, 90:110] = 1002; match[50:75, 125:160] = 1001
+    out = np.zeros((200, 200), dtype=np.uint32)
+    out[:16, :16] = 1001; out[30:50, 30:50] = 1002; out[:10, -10:] = 1003; out[-50:, :50] = 1004
+    out[-30:, 45:80] = 1008; out[-20:, -20:] = 1005; out[100:115, 90:110] = 1006
+    out[115:130, 90:110] = 1006; out[50:75, 125:160] = 1007
+    m = rmatch.RLEMatcher(1, 1000, 0.25, 0.25, True)
+    trle = rrle.pan_seg_to_rle_seg(target, [1], 1000, [1], False)
+    mrle = rrle.pan_seg_to_rle_seg(match, [1], 1000, [1], False)
+    m.initialize_target(trle[1])
+    mrle[1] = m(mrle[1], update_target=False)
+    assert np.array_equal(rrle.rle_seg_to_pan_seg(mrle, target.shape), out)       # the reference's own assertion
+    (ml, al, mi, iou, ioa) = rmatch.rle_matcher(trle[1], rrle.pan_seg_to_rle_seg(match, [1], 1000, [1], False)[1], 0.25,
+                                                return_iou=True, return_ioa=True)
+    save('matcher_known_answer', target=target.astype(np.int64), match=match.astype(np.int64), out=out.astype(np.int64),
+         matched_t=np.asarray(ml[0], np.int64), matched_m=np.asarray(ml[1], np.int64), matched_ious=np.asarray(mi, np.float64),
+         iou=np.asarray(iou, np.float64), ioa=np.asarray(ioa, np.float32))
+
+    # 2. forward + backward matching over drifting blob stacks (patterns.py:68-112 recipe)
+    for name, (D, H, W, n, seed, fc) in {'matcher_stack_a': (9, 96, 128, 40, 7, True),
+                                           'matcher_stack_b': (7, 64, 200, 70, 8, True),
+                                           'matcher_stack_nofc': (6, 80, 80, 25, 9, False)}.items():
+        vol = blob_stack(D, H, W, n, seed)
+        rles = [rrle.pan_seg_to_rle_seg(vol[z], [1], 1000, [1], fc) for z in range(D)]
+        res = {'in_vol': vol}
+        mt = rmatch.RLEMatcher(1, 1000, 0.25, 0.25, True)
+        fwd = []
+        for z in range(D):
+            seg = {1: rles[z][1]}
+            if mt.target_rle is None:
+                mt.initialize_target(seg[1])
+            else:
+                seg[1] = mt(seg[1])
+            fwd.append(seg)
+            res[f'fwd_{z}'] = rrle.rle_seg_to_pan_seg(seg, (H, W)).astype(np.int64)
+            inst, st, ru = flatten_rle(seg)
+            res[f'fwd_inst_{z}'], res[f'fwd_starts_{z}'], res[f'fwd_runs_{z}'] = inst, st, ru
+        res['fwd_next_label'] = np.int64(mt.next_label)
+        mt.target_rle = None
+        mt.assign_new = False
+        for z in range(D - 1, -1, -1):
+            seg = {1: fwd[z][1]}
+            if mt.target_rle is None:
+                mt.initialize_target(seg[1])
+            else:
+                seg[1] = mt(seg[1])
+            res[f'bwd_{z}'] = rrle.rle_seg_to_pan_seg(seg, (H, W)).astype(np.int64)
+            inst, st, ru = flatten_rle(seg)
+            res[f'bwd_inst_{z}'], res[f'bwd_starts_{z}'], res[f'bwd_runs_{z}'] = inst, st, ru
+        # pairwise matrices of the first two slices, straight from rle_matcher
+        (ml, al, mi, iou, ioa) = rmatch.rle_matcher(rles[0][1], rles[1][1], 0.25, return_iou=True, return_ioa=True)
+        res.update(pair_matched_t=np.asarray(ml[0], np.int64), pair_matched_m=np.asarray(ml[1], np.int64),
+                   pair_ious=np.asarray(mi, np.float64), pair_iou=np.asarray(iou, np.float64), pair_ioa=np.asarray(ioa, np.float32))
+        save(name, params=json.dumps(dict(D=D, H=H, W=W, force_connected=fc, label_divisor=1000, class_id=1,
+                                          merge_iou_thr=0.25, merge_ioa_thr=0.25)), **res)
+        print(f'  {name}: {sum(len(r[1]) for r in rles)} instances in, final labels {len(np.unique(res["bwd_0"])) - 1} in slice 0')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle']
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher']
     if 'pp' in which:
         pp_cases()
     if 'merge' in which:
@@ -411,3 +499,5 @@ if __name__ == '__main__':
         engine_cases()
     if 'rle' in which:
         rle_cases()
+    if 'matcher' in which:
+        matcher_cases()

@@ -158,3 +158,27 @@ def test_stack_shard_matches_sequential_engine(ks, cuda_device):
     assert sum(len(v[1]) for v in got.values()) > 20
     for z in range(D):
         _rle_equal(got[z], want[z])
+
+    # cross-slice matching of the block: one overlap launch + host chain == the dict-API chain slice by slice
+    if ks == 3:
+        from empanada_b200.inference import matcher as mt
+        matched = shard.match(got)
+        mat = mt.RLEMatcher(1, 20000, 0.25, 0.25, True)
+        fwd = []
+        for z in range(D):
+            seg = got[z][1]
+            if mat.target_rle is None:
+                mat.initialize_target(seg)
+            else:
+                seg = mat(seg)
+            fwd.append(seg)
+        mat.target_rle, mat.assign_new = None, False
+        for z in range(D - 1, -1, -1):
+            seg = fwd[z]
+            if mat.target_rle is None:
+                mat.initialize_target(seg)
+            else:
+                seg = mat(seg)
+            _rle_equal({1: matched[z][1]}, {1: seg})
+        labels0 = set(matched[0][1].keys())
+        assert any(set(matched[z][1].keys()) & labels0 for z in range(1, D))      # objects are tracked across slices

@@ -157,3 +157,67 @@ def test_torch_port_matches_reference(name):
                                    p['stuff_area'], p['void_label'], p['threshold'], p['nms_kernel'])
     np.testing.assert_array_equal(ctr[0].numpy(), g['out_centers'])
     np.testing.assert_array_equal(pan.numpy(), g['out_pan'])
+
+
+# ---- cross-slice matcher -----------------------------------------------------------
+def _unflatten(inst, starts, runs):
+    seg, at = {}, 0
+    for cls, lab, y0, x0, y1, x1, n in inst.tolist():
+        seg.setdefault(int(cls), {})[int(lab)] = {'box': (y0, x0, y1, x1), 'starts': starts[at:at + n], 'runs': runs[at:at + n]}
+        at += n
+    return seg
+
+
+def _same_rles(got, inst, starts, runs):
+    want = _unflatten(inst, starts, runs).get(1, {})
+    assert [int(k) for k in got.keys()] == list(want.keys())
+    for k, a in want.items():
+        g = got[k]
+        assert tuple(int(v) for v in g['box']) == a['box']
+        np.testing.assert_array_equal(np.asarray(g['starts']), a['starts'])
+        np.testing.assert_array_equal(np.asarray(g['runs']), a['runs'])
+
+
+def test_matcher_oracle_known_answer():
+    from oracle import matcher as om
+    g = load_golden('matcher_known_answer')
+    t = oracle.pan_seg_to_rle_seg(g['target'], [1], 1000, [1], False)[1]
+    m = oracle.pan_seg_to_rle_seg(g['match'], [1], 1000, [1], False)[1]
+    (mt, mm), _, ious, iou, ioa = om.rle_matcher(t, m, 0.25, return_iou=True, return_ioa=True)
+    np.testing.assert_array_equal(mt, g['matched_t'])
+    np.testing.assert_array_equal(mm, g['matched_m'])
+    np.testing.assert_array_equal(ious, g['matched_ious'])
+    np.testing.assert_array_equal(iou, g['iou'])
+    np.testing.assert_array_equal(ioa, g['ioa'])
+    mat = om.RLEMatcher(1, 1000, 0.25, 0.25, True)
+    mat.initialize_target(t)
+    out = mat(m, update_target=False)
+    np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg({1: out}, (200, 200)), g['out'])
+
+
+@pytest.mark.parametrize('name', golden_names('matcher_stack_'))
+def test_matcher_oracle_stack(name):
+    from oracle import matcher as om
+    g = load_golden(name)
+    p = g['params']
+    D = p['D']
+    rles = [oracle.pan_seg_to_rle_seg(g['in_vol'][z], [1], 1000, [1], p['force_connected'])[1] for z in range(D)]
+    mat = om.RLEMatcher(1, 1000, 0.25, 0.25, True)
+    fwd = []
+    for z in range(D):
+        seg = rles[z]
+        if mat.target_rle is None:
+            mat.initialize_target(seg)
+        else:
+            seg = mat(seg)
+        fwd.append(seg)
+        _same_rles(seg, g[f'fwd_inst_{z}'], g[f'fwd_starts_{z}'], g[f'fwd_runs_{z}'])
+    assert mat.next_label == int(g['fwd_next_label'])
+    mat.target_rle, mat.assign_new = None, False
+    for z in range(D - 1, -1, -1):
+        seg = fwd[z]
+        if mat.target_rle is None:
+            mat.initialize_target(seg)
+        else:
+            seg = mat(seg)
+        _same_rles(seg, g[f'bwd_inst_{z}'], g[f'bwd_starts_{z}'], g[f'bwd_runs_{z}'])
