@@ -38,6 +38,8 @@ def main():
     ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices per rank (cycled)')
     ap.add_argument('--blobs', type=int, default=400)
     ap.add_argument('--repeat', type=int, default=2)
+    ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
+    ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -82,7 +84,15 @@ def main():
         dt = time.perf_counter() - t
         n_inst = sum(len(v[1]) for v in out.values())
         n_runs = sum(len(a['starts']) for v in out.values() for a in v[1].values())
-        return dt, len(out), n_inst, n_runs, dict(getattr(shard, 'timing_', {}))
+        timing = dict(getattr(shard, 'timing_', {}))
+        if args.match:
+            t = time.perf_counter()
+            matched = shard.match(out)
+            torch.cuda.synchronize(dev)
+            timing['match_s'] = time.perf_counter() - t
+            timing['match_objects_in_first_slice'] = len(matched[min(matched)][1])
+            run_once.last = (out, matched)
+        return dt, len(out), n_inst, n_runs, timing
 
     run_once()                                          # warm-up (workspaces, module load)
     best = None
@@ -97,11 +107,28 @@ def main():
         c = torch.tensor([n_inst, n_runs], device=dev, dtype=torch.int64)
         dist.all_reduce(c)
         n_inst, n_runs = int(c[0]), int(c[1])
+    match_cpu = None
+    if args.match and rank == 0:
+        # the reference's matcher on the host (oracle port, numpy): forward chain over the first slices
+        from oracle import matcher as om
+        out, _ = run_once.last
+        zs = sorted(out)[:args.match_cpu_slices]
+        t = time.perf_counter()
+        m = om.RLEMatcher(1, 20000, 0.25, 0.25, True)
+        for z in zs:
+            seg = out[z][1]
+            if m.target_rle is None:
+                m.initialize_target(seg)
+            else:
+                m(seg)
+        match_cpu = {'ms_per_slice_forward_only': 1e3 * (time.perf_counter() - t) / max(len(zs) - 1, 1), 'slices': len(zs),
+                     'kind': 'port', 'cores': 1}
     if rank == 0:
         print(json.dumps({
             'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
             'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
             'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
+            'matcher_cpu_baseline': match_cpu,
             'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
                        'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
         }), flush=True)

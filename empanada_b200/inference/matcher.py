@@ -139,12 +139,20 @@ def block_overlaps(runs_all, n_runs, device=None):
 
 # ---- the reference's matcher ------------------------------------------------------------------------
 def _match_from_inter(target_labels, match_labels, inter, area_t, area_m, iou_thr, return_iou, return_ioa):
-    """matcher.py:196-232 given the intersection matrix: IoU in float64 ('float' in the reference), IoA in
-    float32, Hungarian on the IoU matrix, threshold on the assigned pairs."""
-    with np.errstate(divide='ignore', invalid='ignore'):
-        union = area_t[:, None] + area_m[None, :] - inter
-        iou_matrix = np.where(inter > 0, inter / union, 0.0).astype('float')
-        ioa_matrix = np.where(inter > 0, inter / area_m[None, :], 0.0).astype(np.float32)
+    """matcher.py:196-232 given the intersections: IoU in float64 ('float' in the reference), IoA in
+    float32, Hungarian on the IoU matrix, threshold on the assigned pairs.  `inter` is a dense (n, m)
+    int64 matrix or its non-zero entries as (rows, cols, values)."""
+    n, m = len(target_labels), len(match_labels)
+    if isinstance(inter, tuple):
+        r, c, v = inter
+    else:
+        r, c = np.nonzero(inter)
+        v = inter[r, c]
+    v = np.asarray(v, dtype=np.int64)
+    iou_matrix = np.zeros((n, m), dtype='float')
+    ioa_matrix = np.zeros((n, m), dtype=np.float32)
+    iou_matrix[r, c] = v / (area_t[r] + area_m[c] - v)
+    ioa_matrix[r, c] = v / area_m[c]
     match_rows, match_cols = linear_sum_assignment(iou_matrix, maximize=True)
     if iou_thr is not None:
         iou_mask = iou_matrix[match_rows, match_cols] >= iou_thr
@@ -158,23 +166,32 @@ def _match_from_inter(target_labels, match_labels, inter, area_t, area_m, iou_th
     return output
 
 
-def rle_matcher(target_instance_rles, match_instance_rles, iou_thr=0.5, return_iou=False, return_ioa=False, inter=None):
+def rle_matcher(target_instance_rles, match_instance_rles, iou_thr=0.5, return_iou=False, return_ioa=False,
+                inter=None, areas=None):
     r"""Performs Hungarian matching on run length encodings (matcher.py:136-232).
 
-    Same arguments and return values as the reference; ``inter`` (optional, an (n, m) int64 matrix of
-    pixel intersections in the dicts' key order) skips the GPU launch when the caller already has it."""
-    target_labels, target_boxes, target_starts, target_runs = unpack_rle_attrs(target_instance_rles)
-    match_labels, match_boxes, match_starts, match_runs = unpack_rle_attrs(match_instance_rles)
+    Same arguments and return values as the reference.  Optional, for callers that already hold them
+    (StackMatcher): ``inter`` — the pixel intersections in the dicts' key order, an (n, m) int64 matrix
+    or (rows, cols, values) — skips the GPU launch; ``areas`` — (target areas, match areas) int64."""
+    target_labels = np.array([int(k) for k in target_instance_rles.keys()])
+    match_labels = np.array([int(k) for k in match_instance_rles.keys()])
     if len(target_labels) == 0 or len(match_labels) == 0:
         empty = np.array([])
         if return_ioa:
             return (empty, empty), (target_labels, match_labels), empty, empty
         return (empty, empty), (target_labels, match_labels), empty
     if inter is None:
+        _, _, target_starts, target_runs = unpack_rle_attrs(target_instance_rles)
+        _, _, match_starts, match_runs = unpack_rle_attrs(match_instance_rles)
         inter = pair_overlaps(target_starts, target_runs, match_starts, match_runs)
-    area_t = np.array([int(np.sum(r)) for r in target_runs], dtype=np.int64)
-    area_m = np.array([int(np.sum(r)) for r in match_runs], dtype=np.int64)
-    return _match_from_inter(target_labels, match_labels, inter, area_t, area_m, iou_thr, return_iou, return_ioa)
+    if areas is None:
+        areas = (instance_areas(target_instance_rles), instance_areas(match_instance_rles))
+    return _match_from_inter(target_labels, match_labels, inter, areas[0], areas[1], iou_thr, return_iou, return_ioa)
+
+
+def instance_areas(instance_rles):
+    """Pixels per instance, in dict order."""
+    return np.array([int(np.sum(a['runs'])) for a in instance_rles.values()], dtype=np.int64)
 
 
 class RLEMatcher:
@@ -200,23 +217,27 @@ class RLEMatcher:
     def update_target(self, instance_rles):
         self.target_rle = instance_rles
 
-    def __call__(self, match_instance_rle, update_target=True, inter=None):
+    def __call__(self, match_instance_rle, update_target=True, inter=None, areas=None):
         """Matches the given instance segmentation to target"""
         assert self.target_rle is not None, "Initialize target rle before running!"
         matched_labels, all_labels, matched_ious, ioa_matrix = rle_matcher(
-            self.target_rle, match_instance_rle, self.merge_iou_thr, return_ioa=True, inter=inter)
+            self.target_rle, match_instance_rle, self.merge_iou_thr, return_ioa=True, inter=inter, areas=areas)
         target_labels, match_labels = all_labels
         label_matches = {ml: tl for tl, ml in zip(matched_labels[0], matched_labels[1])}
         matched_rles = {}
         assignment = []
+        has_ioa = len(ioa_matrix) > 0
+        if has_ioa:                                     # per match instance: best IoA and the target holding it
+            ioa_best = ioa_matrix.max(axis=0)
+            ioa_arg = ioa_matrix.argmax(axis=0)
         for i, (ml, mattrs) in enumerate(match_instance_rle.items()):
             if ml in label_matches:
                 new_label = label_matches[ml]
             else:
                 assert ml == match_labels[i]
-                ioa_max = ioa_matrix[:, i].max() if len(ioa_matrix) > 0 else 0
+                ioa_max = ioa_best[i] if has_ioa else 0
                 if ioa_max >= self.merge_ioa_thr:
-                    new_label = target_labels[ioa_matrix[:, i].argmax()]
+                    new_label = target_labels[ioa_arg[i]]
                 elif self.assign_new:
                     new_label = self.next_label
                     self.next_label += 1
@@ -245,40 +266,54 @@ class StackMatcher:
     def __init__(self, class_id, label_divisor, merge_iou_thr=0.25, merge_ioa_thr=0.25):
         self.matcher = RLEMatcher(class_id, label_divisor, merge_iou_thr, merge_ioa_thr, True)
 
+    # A slice's (possibly merged) instances are kept as `(labels, group_of_slot)`: the labels in dict
+    # order and, for every ORIGINAL instance slot of the slice, the index of the label it now belongs to.
     @staticmethod
-    def _group_inter(t_groups, m_groups, n_t_slots, n_m_slots, slot_t, slot_m, ov):
-        """(labels of t_groups) x (labels of m_groups) intersections from slot-level overlaps."""
-        row = np.full(n_t_slots, -1, np.int64)
-        col = np.full(n_m_slots, -1, np.int64)
-        for i, slots in enumerate(t_groups.values()):
-            row[slots] = i
-        for j, slots in enumerate(m_groups.values()):
-            col[slots] = j
-        inter = np.zeros((len(t_groups), len(m_groups)), np.int64)
-        r, c = row[slot_t], col[slot_m]
-        ok = (r >= 0) & (c >= 0)
-        np.add.at(inter, (r[ok], c[ok]), ov[ok])
-        return inter
+    def _group_inter(g_t, g_m, slot_t, slot_m, ov):
+        """Non-zero (target label index, match label index, intersection) entries from slot-level overlaps:
+        instances of a slice are disjoint, so a group's intersection is the sum over its slots."""
+        n_m = max(len(g_m[0]), 1)
+        key = g_t[1][slot_t] * n_m + g_m[1][slot_m]
+        if key.size == 0:
+            return key, key, ov
+        uniq, inv = np.unique(key, return_inverse=True)
+        return uniq // n_m, uniq % n_m, np.bincount(inv, weights=ov, minlength=uniq.size).astype(np.int64)
 
-    def forward(self, rles, overlaps):
-        """Returns (matched rles per slice, groups per slice: {label: [original slots]})."""
+    @staticmethod
+    def _group_areas(g, slot_areas):
+        return np.bincount(g[1], weights=slot_areas, minlength=len(g[0])).astype(np.int64)
+
+    @staticmethod
+    def _regroup(g_old, assignment):
+        """Groups after a matching step: `assignment` lists (old label, new label) in the old dict order."""
+        new_labels, index = [], {}
+        of_old = np.empty(len(assignment), np.int64)
+        for i, (_, new) in enumerate(assignment):
+            j = index.get(new)
+            if j is None:
+                j = index[new] = len(new_labels)
+                new_labels.append(new)
+            of_old[i] = j
+        return new_labels, of_old[g_old[1]]
+
+    def forward(self, rles, overlaps, slot_areas=None):
+        """Returns (matched rles per slice, groups per slice).
+        slot_areas: optional list over slices of per-instance pixel counts (dict order)."""
         m = self.matcher
+        self.slot_areas = slot_areas if slot_areas is not None else [instance_areas(seg) for seg in rles]
         out, groups = [], []
         for z, seg in enumerate(rles):
-            own = {lab: [i] for i, lab in enumerate(seg.keys())}
+            own = (list(seg.keys()), np.arange(len(seg), dtype=np.int64))
             if m.target_rle is None:
                 m.initialize_target(seg)
                 out.append(seg)
                 groups.append(own)
                 continue
             sa, sb, ov = overlaps[z - 1]
-            inter = self._group_inter(groups[-1], own, len(rles[z - 1]), len(seg), sa, sb, ov)
-            matched = m(seg, inter=inter)
-            g = {}
-            for old, new in m.last_assignment:
-                g.setdefault(new, []).extend(own[old])
-            out.append(matched)
-            groups.append(g)
+            inter = self._group_inter(groups[-1], own, sa, sb, ov)
+            areas = (self._group_areas(groups[-1], self.slot_areas[z - 1]), self.slot_areas[z])
+            out.append(m(seg, inter=inter, areas=areas))
+            groups.append(self._regroup(own, m.last_assignment))
         return out, groups
 
     def backward(self, fwd, groups, rles, overlaps):
@@ -295,10 +330,8 @@ class StackMatcher:
                 out[z], g_next = seg, groups[z]
                 continue
             sa, sb, ov = overlaps[z]                    # pair (z, z+1): a = slots of z, b = slots of z+1
-            inter = self._group_inter(g_next, groups[z], len(rles[z + 1]), len(rles[z]), sb, sa, ov)
-            matched = m(seg, inter=inter)
-            g = {}
-            for old, new in m.last_assignment:
-                g.setdefault(new, []).extend(groups[z][old])
-            out[z], g_next = matched, g
+            inter = self._group_inter(g_next, groups[z], sb, sa, ov)
+            areas = (self._group_areas(g_next, self.slot_areas[z + 1]), self._group_areas(groups[z], self.slot_areas[z]))
+            out[z] = m(seg, inter=inter, areas=areas)
+            g_next = self._regroup(groups[z], m.last_assignment)
         return out

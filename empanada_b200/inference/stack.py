@@ -216,19 +216,26 @@ class StackShard:
         starts_h = rv[:, :, 0].reshape(-1)[perm].cpu().numpy()
         lens_h = rv[:, :, 1].reshape(-1)[perm].cpu().numpy()
         inst_h = inst_all[:, :max(mi, 1)].cpu().numpy()
-        segs, at = {}, 0
+        segs, slot_areas, at = {}, [None] * n, 0
         for i, z in enumerate(zs):
             if bad[i]:
                 segs[z] = _slice_sync(e, self.heads[z], filtered[z], self.labels, self.upsampling, self.force_connected)
             else:
                 k = int(n_runs[i])
-                segs[z] = rle.grouped_to_rle_seg(inst_h[i, :n_inst[i]], starts_h[at:at + k], lens_h[at:at + k], self.labels)
+                ins = inst_h[i, :n_inst[i]]
+                segs[z] = rle.grouped_to_rle_seg(ins, starts_h[at:at + k], lens_h[at:at + k], self.labels)
+                if ins.shape[0]:                        # pixels per instance slot (runs are grouped by slot)
+                    first = np.concatenate(([0], np.cumsum(ins[:-1, 6])))
+                    slot_areas[i] = np.add.reduceat(lens_h[at:at + k], first) if k else np.zeros(0, np.int64)
+                else:
+                    slot_areas[i] = np.zeros(0, np.int64)
                 at += k
         # host seconds: enqueueing, waiting for the device, read-back + dict assembly
         self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'assemble_s': time.perf_counter() - t_c}
         # kept for match(): the run tables stay in HBM, slots index each slice's instances in dict order
         self.tables_ = {'runs_all': runs_all, 'n_runs': np.where(ok, n_runs, 0), 'bad': bad,
-                        'inst': [inst_h[i, :n_inst[i]] if ok[i] else None for i in range(n)], 'zs': list(zs)}
+                        'inst': [inst_h[i, :n_inst[i]] if ok[i] else None for i in range(n)], 'zs': list(zs),
+                        'slot_areas': slot_areas}
         return segs
 
     def match(self, segs, merge_iou_thr=0.25, merge_ioa_thr=0.25):
@@ -251,6 +258,7 @@ class StackShard:
             if c not in e.thing_list:
                 continue
             rles = [segs[z][c] for z in zs]
+            areas = None
             if pair_rows is None:
                 overlaps = []
                 for a, b in zip(rles[:-1], rles[1:]):
@@ -262,6 +270,7 @@ class StackShard:
             else:
                 # slots count every class of the slice; keep this class's and renumber from 0
                 overlaps = []
+                areas = [t['slot_areas'][i][t['inst'][i][:, 0] == c] for i in range(len(zs))]
                 for p, (sa, sb, ov) in enumerate(pair_rows):
                     ia, ib = t['inst'][p], t['inst'][p + 1]
                     ca, cb = ia[sa, 0] == c, ib[sb, 0] == c
@@ -270,7 +279,7 @@ class StackShard:
                     k = ca & cb
                     overlaps.append((sa[k] - fa, sb[k] - fb, ov[k]))
             sm = mt.StackMatcher(c, e.label_divisor, merge_iou_thr, merge_ioa_thr)
-            fwd, groups = sm.forward(rles, overlaps)
+            fwd, groups = sm.forward(rles, overlaps, areas)
             bwd = sm.backward(fwd, groups, rles, overlaps)
             for z, seg in zip(zs, bwd):
                 out[z][c] = seg
