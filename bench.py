@@ -158,6 +158,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tiles', type=int, default=TILES)
     ap.add_argument('--instances', type=int, default=N_INST)
+    ap.add_argument('--thr', type=float, default=THR, help='center threshold (experiments; the workload uses 0.1)')
     ap.add_argument('--dense', action='store_true', help='BASELINE configs[4]: ~5000 instances of semi-axes 4..12 px per tile')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -212,7 +213,7 @@ def main():
 
     def step():
         C.check(L.emp_panoptic_batched(B, sem.data_ptr(), 0, hm.data_ptr(), off.data_ptr(), H, W, things, nt,
-                                       LABEL_DIVISOR, STUFF_AREA, VOID, THR, NMS_K, pan.data_ptr(), None, 0, k_cap,
+                                       LABEL_DIVISOR, STUFF_AREA, VOID, args.thr, NMS_K, pan.data_ptr(), None, 0, k_cap,
                                        ws.data_ptr(), per_tile, ctypes.c_void_p(stream.cuda_stream)))
 
     def barrier():
@@ -257,7 +258,7 @@ def main():
 
     def e2e_step():
         C.check(L.emp_panoptic_batched_host(B, sem_h.data_ptr(), hm_h.data_ptr(), off_h.data_ptr(), H, W, things, nt,
-                                            LABEL_DIVISOR, STUFF_AREA, VOID, THR, NMS_K, pan_h.data_ptr(), k_out, f_out,
+                                            LABEL_DIVISOR, STUFF_AREA, VOID, args.thr, NMS_K, pan_h.data_ptr(), k_out, f_out,
                                             k_cap, scratch.data_ptr(), scratch_bytes))
 
     e2e_step()

@@ -124,7 +124,11 @@ __device__ __noinline__ bool nms_window_has_bigger(const float* __restrict__ hm,
 #define EMP_NMS_CTAS_PER_SM 3
 #endif
 constexpr int kNmsRows = 4, kNmsWords = 8, kNmsStages = EMP_NMS_STAGES, kNmsWarps = 4, kNmsBlkItems = 16, kNmsCtasPerSm = EMP_NMS_CTAS_PER_SM;
-constexpr int kNmsItemW = kNmsWords * 32, kNmsBoxRows = kNmsRows + 2;
+#ifndef EMP_NMS_HALO
+#define EMP_NMS_HALO 1
+#endif
+constexpr int kNmsHalo = EMP_NMS_HALO;          // 1: stage one halo row above and below each item
+constexpr int kNmsItemW = kNmsWords * 32, kNmsBoxRows = kNmsRows + 2 * kNmsHalo;
 constexpr unsigned kNmsStageFloats = kNmsBoxRows * kNmsItemW;
 constexpr unsigned kNmsStageBytes = kNmsStageFloats * sizeof(float);
 
@@ -177,7 +181,7 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
             if (p_i < kp.nitems) {
                 if (lane == 0) {
                     mbar_expect_tx(&s_bar[warp][st_issue], kNmsStageBytes);
-                    tma_load_3d(ring + (size_t)st_issue * kNmsStageFloats, &a.tmap, kp.colb, kp.row0 + p_i * kNmsRows - 1,
+                    tma_load_3d(ring + (size_t)st_issue * kNmsStageFloats, &a.tmap, kp.colb, kp.row0 + p_i * kNmsRows - kNmsHalo,
                                 kp.b, &s_bar[warp][st_issue], policy);
                 }
                 ++p_i; ++inflight;
@@ -213,12 +217,12 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
         for (int it = 0; it < kc.nitems; ++it) {
             const int y0 = kc.row0 + it * kNmsRows;
             // FAST: (row 0 of the item, this lane) inside the stage; row -1 / row 4 are the halo rows
-            const float* sp = ring + (size_t)st_cons * kNmsStageFloats + kNmsItemW + lane;
+            const float* sp = ring + (size_t)st_cons * kNmsStageFloats + kNmsHalo * kNmsItemW + lane;
             unsigned cm = 0;                                            // bit 8*r + j: pixel (y0+r, x0+32j) is a candidate
             if (FAST) {
                 mbar_wait(&s_bar[warp][st_cons], parity);
                 // most items hold no pixel above threshold: 8 x LDS.128 and a max tree decide that
-                const float4* vp = reinterpret_cast<const float4*>(ring + (size_t)st_cons * kNmsStageFloats + kNmsItemW) + lane;
+                const float4* vp = reinterpret_cast<const float4*>(ring + (size_t)st_cons * kNmsStageFloats + kNmsHalo * kNmsItemW) + lane;
                 float mx = -CUDART_INF_F;
 #pragma unroll
                 for (int r = 0; r < kNmsRows; ++r) {
@@ -275,7 +279,7 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
                         if ((dy < 0 || dx < 0) && !before) continue;
                         if ((dy > 0 || dx > 0) && !after) continue;
                         float nb;
-                        if (FAST && cs + dx >= 0 && cs + dx < kNmsItemW) {
+                        if (FAST && cs + dx >= 0 && cs + dx < kNmsItemW && (kNmsHalo || (r + dy >= 0 && r + dy < kNmsRows))) {
                             nb = q[dy * kNmsItemW + dx];
                         } else {                                        // no staging, or a halo column of the strip
                             const int yy = y + dy, xx = x + dx;
@@ -1347,6 +1351,66 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
     }
 }
 
+// Row-linear variant of apply_lut for aligned planes: a CTA owns one strip row (4 image rows) of a tile
+// and writes each of its rows left to right — warp w takes the 64-column segments w, w+8, ... — so the
+// label stream leaves the SM as whole rows (32 KB each at W = 4096) like a fill kernel, instead of
+// 512-byte pieces of 64 different rows.  Flags and codes are fetched per segment before the stores.
+template <bool C16, int POLICY>
+__global__ void __launch_bounds__(256)
+apply_rows_kernel(const __grid_constant__ ApplyArgs a)
+{
+    constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
+    constexpr int kSegs = 8;                                        // segments per warp handled at once
+    char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
+    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
+    const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
+    const unsigned char* sflags = reinterpret_cast<const unsigned char*>(ws + a.o_sflags);
+    long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, W = a.W;
+    const int sr = blockIdx.x;                                      // strip row
+    const int row0 = sr * kItemH;
+    const int by = sr / a.blk_items, it = sr - by * a.blk_items;
+    const long long bg = decode<C16>(kClsBase, lut, areas, a);
+    const int nrows = min(kItemH, H - row0);
+
+    for (int seg0 = warp; seg0 < a.blocks_x; seg0 += 8 * kSegs) {
+        // this warp's segments: seg0, seg0 + 8, ... (kSegs of them)
+        unsigned flagged = 0;
+#pragma unroll
+        for (int k = 0; k < kSegs; ++k) {
+            const int seg = seg0 + 8 * k;
+            if (seg < a.blocks_x && __ldg(sflags + ((size_t)by * a.blocks_x + seg) * kBlkItems + it)) flagged |= 1u << k;
+        }
+        for (int r = 0; r < nrows; ++r) {
+            const size_t rowpx = (size_t)(row0 + r) * W;
+#pragma unroll
+            for (int k = 0; k < kSegs; ++k) {
+                const int seg = seg0 + 8 * k;
+                const int col0 = seg * kItemW + 2 * lane;
+                if (seg >= a.blocks_x || col0 >= W) continue;
+                long long v0 = bg, v1 = bg;
+                if (!((flagged >> k) & 1u)) {
+                    unsigned c0, c1;
+                    if (C16) {
+                        const unsigned u = __ldcs(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(ws + a.o_codes) + rowpx + col0));
+                        c0 = u & 0xFFFFu; c1 = u >> 16;
+                    } else {
+                        const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + rowpx + col0));
+                        c0 = u.x; c1 = u.y;
+                    }
+                    v0 = decode<C16>(c0, lut, areas, a);
+                    v1 = decode<C16>(c1, lut, areas, a);
+                }
+                longlong2* op = reinterpret_cast<longlong2*>(pan + rowpx + col0);
+                if (POLICY == 0) __stcs(op, make_longlong2(v0, v1));
+                else if (POLICY == 1) *op = make_longlong2(v0, v1);
+                else __stcg(op, make_longlong2(v0, v1));
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side launch helpers
 // ---------------------------------------------------------------------------------------------
@@ -1558,6 +1622,24 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     const long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
+    // aligned planes take the row-linear kernel (measured 3 % faster than the block walk; the store
+    // policy — .cs / default / .cg — makes no difference); EMP_APPLY_VARIANT=0 forces the block walk
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("EMP_APPLY_VARIANT"); variant = e ? atoi(e) : 1; }
+    if (fast && variant > 0 && W % 2 == 0) {
+        dim3 g2((unsigned)((H + kItemH - 1) / kItemH), 1, B);
+        if (L.code16) {
+            if (variant == 1) apply_rows_kernel<true, 0><<<g2, 256, 0, st>>>(a);
+            else if (variant == 2) apply_rows_kernel<true, 1><<<g2, 256, 0, st>>>(a);
+            else apply_rows_kernel<true, 2><<<g2, 256, 0, st>>>(a);
+        } else {
+            if (variant == 1) apply_rows_kernel<false, 0><<<g2, 256, 0, st>>>(a);
+            else if (variant == 2) apply_rows_kernel<false, 1><<<g2, 256, 0, st>>>(a);
+            else apply_rows_kernel<false, 2><<<g2, 256, 0, st>>>(a);
+        }
+        EMP_CUDA_CHECK(cudaGetLastError());
+        return EMP_OK;
+    }
     if (L.code16) {
         if (fast) apply_lut_kernel<true, true><<<grid, 256, 0, st>>>(a);
         else apply_lut_kernel<true, false><<<grid, 256, 0, st>>>(a);
