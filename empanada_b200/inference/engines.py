@@ -82,54 +82,62 @@ class _Engine:
 
 
 class _MedianQueue:
-    """deque(maxlen=ks) of model outputs; ``get_next`` replaces the middle entry's tensors by the
-    median over the queue and stores them back, so the filter is recursive (engines.py:47-90)."""
+    """A sliding window of the last ``median_kernel_size`` model outputs (reference engines.py:47-90).
+
+    While the window is still shorter than half the kernel the newest entry passes through raw; until
+    it is full nothing is emitted; once full, the middle entry is emitted with the requested tensors
+    replaced by the per-element median over the window — and the replacement is stored back into the
+    window, which is what makes the reference's filter recursive (later windows see filtered planes)."""
 
     def __init__(self, median_kernel_size, **kwargs):
         super().__init__(**kwargs)
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         self.ks = median_kernel_size
-        self.mid_idx = (median_kernel_size - 1) // 2
-        self.median_queue = deque(maxlen=median_kernel_size)
+        self.mid_idx = median_kernel_size // 2
+        self.reset()
 
     def reset(self):
         self.median_queue = deque(maxlen=self.ks)
 
-    @torch.no_grad()
-    def get_median(self, key):
-        median, _ = median_harden([output[key] for output in self.median_queue], 0.0)
-        return median
-
-    def get_next(self, keys):
-        nq = len(self.median_queue)
-        if nq <= self.mid_idx:
-            output = self.median_queue[-1]
-        elif nq > self.mid_idx and nq < self.ks:
-            return None
-        elif nq == self.ks:
-            output = self.median_queue[self.mid_idx]
-            for key in keys:
-                output[key] = self.get_median(key)
-        return output
-
     def enqueue(self, item):
         self.median_queue.append(item)
 
+    @torch.no_grad()
+    def get_median(self, key):
+        window = [entry[key] for entry in self.median_queue]
+        return median_harden(window, 0.0)[0]
+
+    def get_next(self, keys):
+        filled = len(self.median_queue)
+        if filled <= self.mid_idx:
+            return self.median_queue[-1]                # start of the stack: raw
+        if filled < self.ks:
+            return None                                 # still filling
+        centre = self.median_queue[self.mid_idx]
+        centre.update({key: self.get_median(key) for key in keys})
+        return centre
+
     def end(self):
-        return list(self.median_queue)[self.mid_idx + 1:]
+        return [self.median_queue[i] for i in range(self.mid_idx + 1, len(self.median_queue))]
+
+
+def _single_image(image):
+    assert image.ndim == 4 and image.size(0) == 1
+
+
+def _log2_factor(upsampling):
+    assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
+    return int(2 + math.log(upsampling, 2))
 
 
 class PanopticDeepLabEngine(_Engine):
     def __init__(self, model, thing_list, label_divisor=1000, stuff_area=64, void_label=0,
                  nms_threshold=0.1, nms_kernel=7, confidence_thr=0.5, **kwargs):
         super().__init__(model=model)
-        self.thing_list = thing_list
-        self.label_divisor = label_divisor
-        self.stuff_area = stuff_area
-        self.void_label = void_label
-        self.nms_threshold = nms_threshold
-        self.nms_kernel = nms_kernel
-        self.confidence_thr = confidence_thr
+        for name, value in (('thing_list', thing_list), ('label_divisor', label_divisor), ('stuff_area', stuff_area),
+                            ('void_label', void_label), ('nms_threshold', nms_threshold), ('nms_kernel', nms_kernel),
+                            ('confidence_thr', confidence_thr)):
+            setattr(self, name, value)
 
     @torch.no_grad()
     def _harden_seg(self, sem):
@@ -153,12 +161,12 @@ class PanopticDeepLabEngine(_Engine):
         )
         return pan_seg
 
+    def _pan_from(self, heads):
+        return self.postprocess(self._harden_seg(heads['sem']), heads['ctr_hmp'], heads['offsets'])
+
     def __call__(self, image):
-        assert image.ndim == 4 and image.size(0) == 1
-        image = self.to_model_device(image)
-        model_out = self.infer(image)
-        model_out['sem'] = self._harden_seg(model_out['sem'])
-        return self.postprocess(model_out['sem'], model_out['ctr_hmp'], model_out['offsets'])
+        _single_image(image)
+        return self._pan_from(self.infer(self.to_model_device(image)))
 
 
 class PanopticDeepLabEngine3d(_MedianQueue, PanopticDeepLabEngine):
@@ -173,22 +181,14 @@ class PanopticDeepLabEngine3d(_MedianQueue, PanopticDeepLabEngine):
         )
 
     def end(self):
-        """Post-process whatever is left in the queue past the middle (engines.py:183-198)."""
-        final_segs = []
-        for model_out in list(self.median_queue)[self.mid_idx + 1:]:
-            model_out['sem'] = self._harden_seg(model_out['sem'])
-            final_segs.append(self.postprocess(model_out['sem'], model_out['ctr_hmp'], model_out['offsets']))
-        return final_segs
+        """The slices still waiting behind the window's centre, post-processed raw (engines.py:183-198)."""
+        return [self._pan_from(heads) for heads in _MedianQueue.end(self)]
 
     def __call__(self, image):
-        assert image.ndim == 4 and image.size(0) == 1
-        image = self.to_model_device(image)
-        model_out = self.infer(image)
-        self.enqueue(model_out)
-        median_out = self.get_next(keys=['sem'])
-        if median_out is None:
-            return None
-        return self.postprocess(self._harden_seg(median_out['sem']), median_out['ctr_hmp'], median_out['offsets'])
+        _single_image(image)
+        self.enqueue(self.infer(self.to_model_device(image)))
+        heads = self.get_next(keys=['sem'])
+        return None if heads is None else self._pan_from(heads)
 
 
 class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
@@ -296,18 +296,18 @@ class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
         pp._check_flags(int(C.read_status(ws)[C.ST_FLAGS]))
         return pan
 
-    def _check_call(self, image, upsampling):
-        assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
-        assert image.ndim == 4 and image.size(0) == 1
+    def _heads(self, image, upsampling):
+        """Checks, pads to the model's stride, runs the CNN with the render steps the upsampling needs."""
+        steps = _log2_factor(upsampling)
+        _single_image(image)
+        return self.infer(self.to_model_device(factor_pad(image, self.padding_factor)), steps)
+
+    def _pan_cropped(self, heads, size, upsampling):
+        pan = self._fused_postprocess(heads['sem'], heads['ctr_hmp'], heads['offsets'], upsampling)
+        return pan[..., :size[0], :size[1]]
 
     def __call__(self, image, size, upsampling=1):
-        self._check_call(image, upsampling)
-        h, w = size
-        image = factor_pad(image, self.padding_factor)
-        image = self.to_model_device(image)
-        model_out = self.infer(image, int(2 + math.log(upsampling, 2)))
-        pan_seg = self._fused_postprocess(model_out['sem'], model_out['ctr_hmp'], model_out['offsets'], upsampling)
-        return pan_seg[..., :h, :w]
+        return self._pan_cropped(self._heads(image, upsampling), size, upsampling)
 
 
 class PanopticDeepLabRenderEngine3d(_MedianQueue, PanopticDeepLabRenderEngine):
@@ -323,26 +323,21 @@ class PanopticDeepLabRenderEngine3d(_MedianQueue, PanopticDeepLabRenderEngine):
         )
 
     def end(self, upsampling=1):
-        final_segs = []
-        for model_out in list(self.median_queue)[self.mid_idx + 1:]:
-            h, w = model_out['size']
-            pan_seg = self._fused_postprocess(model_out['sem'], model_out['ctr_hmp'], model_out['offsets'], upsampling)
-            final_segs.append(pan_seg[..., :h, :w])
-        return final_segs
+        return [self._pan_cropped(heads, heads['size'], upsampling) for heads in _MedianQueue.end(self)]
 
     def __call__(self, image, size, upsampling=1):
-        self._check_call(image, upsampling)
-        h, w = size
-        image = factor_pad(image, self.padding_factor)
-        image = self.to_model_device(image)
-        model_out = self.infer(image, int(2 + math.log(upsampling, 2)))
-        model_out['size'] = size
-        self.enqueue(model_out)
-        median_out = self.get_next(keys=['sem'])
-        if median_out is None:
-            return None
-        pan_seg = self._fused_postprocess(median_out['sem'], median_out['ctr_hmp'], median_out['offsets'], upsampling)
-        return pan_seg[..., :h, :w]
+        heads = self._heads(image, upsampling)
+        heads['size'] = size
+        self.enqueue(heads)
+        heads = self.get_next(keys=['sem'])
+        return None if heads is None else self._pan_cropped(heads, size, upsampling)
+
+
+def _boundary_contour(model_out):
+    """sigmoid of the (binary) semantic and contour logits, stacked: (N, 2, H, W)."""
+    sem_logits, cnt_logits = model_out['sem_logits'], model_out['cnt_logits']
+    assert sem_logits.size(1) == 1
+    return {'bc': torch.sigmoid(torch.cat([sem_logits, cnt_logits], dim=1))}
 
 
 class BCEngine(_Engine):
@@ -353,13 +348,10 @@ class BCEngine(_Engine):
 
     @torch.no_grad()
     def infer(self, image):
-        model_out = self.model(image)
-        sem_logits, cnt_logits = model_out['sem_logits'], model_out['cnt_logits']
-        assert sem_logits.size(1) == 1
-        return {'bc': torch.cat([torch.sigmoid(sem_logits), torch.sigmoid(cnt_logits)], dim=1)}
+        return _boundary_contour(self.model(image))
 
     def __call__(self, image):
-        assert image.ndim == 4 and image.size(0) == 1
+        _single_image(image)
         return self.infer(self.to_model_device(image))['bc']
 
 
@@ -370,28 +362,20 @@ class BCEngine3d(_MedianQueue, BCEngine):
 
     @torch.no_grad()
     def infer(self, image, render_steps=2):
-        model_out = self.model(image, render_steps)
-        sem_logits, cnt_logits = model_out['sem_logits'], model_out['cnt_logits']
-        assert sem_logits.size(1) == 1
-        return {'bc': torch.cat([torch.sigmoid(sem_logits), torch.sigmoid(cnt_logits)], dim=1)}
+        return _boundary_contour(self.model(image, render_steps))
+
+    @staticmethod
+    def _cropped(out):
+        return out['bc'][..., :out['size'][0], :out['size'][1]]
 
     def end(self, upsampling=1):
-        final_segs = []
-        for model_out in list(self.median_queue)[self.mid_idx + 1:]:
-            h, w = model_out['size']
-            final_segs.append(model_out['bc'][..., :h, :w])
-        return final_segs
+        return [self._cropped(out) for out in _MedianQueue.end(self)]
 
     def __call__(self, image, size, upsampling=1):
-        assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
-        assert image.ndim == 4 and image.size(0) == 1
-        h, w = size
-        image = factor_pad(image, self.padding_factor)
-        image = self.to_model_device(image)
-        model_out = self.infer(image, int(2 + math.log(upsampling, 2)))
-        model_out['size'] = size
-        self.enqueue(model_out)
-        median_out = self.get_next(keys=['bc'])
-        if median_out is None:
-            return None
-        return median_out['bc'][..., :h, :w]
+        steps = _log2_factor(upsampling)
+        _single_image(image)
+        out = self.infer(self.to_model_device(factor_pad(image, self.padding_factor)), steps)
+        out['size'] = size
+        self.enqueue(out)
+        out = self.get_next(keys=['bc'])
+        return None if out is None else self._cropped(out)

@@ -195,8 +195,15 @@ def instance_areas(instance_rles):
 
 
 class RLEMatcher:
-    r"""Tracks and matches instances across consecutive run length encodings in a stack
-    (matcher.py:234-326; same constructor arguments, attributes and call semantics)."""
+    r"""Carries instance labels from slice to slice of a stack (reference matcher.py:234-326; same
+    constructor arguments, attributes ``next_label`` / ``target_rle`` / ``assign_new`` and call semantics).
+
+    For every instance of the incoming slice, in dict order:
+      1. Hungarian-matched to a target instance with IoU >= ``merge_iou_thr``  -> that target's label;
+      2. else, if its best IoA over the targets is >= ``merge_ioa_thr`` (a false split) -> the label of
+         the target holding that IoA (first maximum);
+      3. else a fresh label (``assign_new``) or its own label.
+    Instances that end up with the same label are merged (boxes united, runs joined)."""
 
     def __init__(self, class_id, label_divisor, merge_iou_thr=0.25, merge_ioa_thr=0.25, assign_new=True, **kwargs):
         self.class_id = class_id
@@ -204,54 +211,49 @@ class RLEMatcher:
         self.merge_iou_thr = merge_iou_thr
         self.merge_ioa_thr = merge_ioa_thr
         self.assign_new = assign_new
-        self.next_label = (class_id * label_divisor) + 1
+        self.next_label = class_id * label_divisor + 1
         self.target_rle = None
-        self.last_assignment = None         # [(match label, new label)] of the last call, in match order
+        self.last_assignment = None         # [(incoming label, label it received)] of the last call, in dict order
 
     def initialize_target(self, target_instance_rles):
         self.target_rle = target_instance_rles
-        objs = list(target_instance_rles.keys())
-        if len(objs) > 0:
-            self.next_label = max(objs) + 1
+        if len(target_instance_rles) > 0:               # labels continue after the largest one seen
+            self.next_label = max(target_instance_rles.keys()) + 1
 
     def update_target(self, instance_rles):
         self.target_rle = instance_rles
 
+    def _labels_for(self, incoming, hungarian, target_labels, ioa):
+        """Rule 1-3 above for every incoming label; returns them in order."""
+        by_hungarian = dict(zip(hungarian[1].tolist(), hungarian[0].tolist())) if len(hungarian[0]) else {}
+        if len(ioa) > 0:
+            best, holder = ioa.max(axis=0), ioa.argmax(axis=0)
+        received = []
+        for col, lab in enumerate(incoming):
+            if lab in by_hungarian:
+                received.append(by_hungarian[lab])
+            elif len(ioa) > 0 and best[col] >= self.merge_ioa_thr:
+                received.append(int(target_labels[holder[col]]))
+            elif self.assign_new:
+                received.append(self.next_label)
+                self.next_label += 1
+            else:
+                received.append(lab)
+        return received
+
     def __call__(self, match_instance_rle, update_target=True, inter=None, areas=None):
-        """Matches the given instance segmentation to target"""
         assert self.target_rle is not None, "Initialize target rle before running!"
-        matched_labels, all_labels, matched_ious, ioa_matrix = rle_matcher(
+        hungarian, (target_labels, match_labels), _, ioa = rle_matcher(
             self.target_rle, match_instance_rle, self.merge_iou_thr, return_ioa=True, inter=inter, areas=areas)
-        target_labels, match_labels = all_labels
-        label_matches = {ml: tl for tl, ml in zip(matched_labels[0], matched_labels[1])}
-        matched_rles = {}
-        assignment = []
-        has_ioa = len(ioa_matrix) > 0
-        if has_ioa:                                     # per match instance: best IoA and the target holding it
-            ioa_best = ioa_matrix.max(axis=0)
-            ioa_arg = ioa_matrix.argmax(axis=0)
-        for i, (ml, mattrs) in enumerate(match_instance_rle.items()):
-            if ml in label_matches:
-                new_label = label_matches[ml]
-            else:
-                assert ml == match_labels[i]
-                ioa_max = ioa_best[i] if has_ioa else 0
-                if ioa_max >= self.merge_ioa_thr:
-                    new_label = target_labels[ioa_arg[i]]
-                elif self.assign_new:
-                    new_label = self.next_label
-                    self.next_label += 1
-                else:
-                    new_label = ml
-            assignment.append((ml, new_label))
-            if new_label not in matched_rles:
-                matched_rles[new_label] = mattrs
-            else:
-                matched_rles[new_label] = merge_attrs(matched_rles[new_label], mattrs)
-        self.last_assignment = assignment
+        incoming = [int(k) for k in match_instance_rle.keys()]
+        received = self._labels_for(incoming, hungarian, target_labels, ioa)
+        self.last_assignment = list(zip(incoming, received))
+        relabelled = {}
+        for (old, new), attrs in zip(self.last_assignment, match_instance_rle.values()):
+            relabelled[new] = merge_attrs(relabelled[new], attrs) if new in relabelled else attrs
         if update_target:
-            self.update_target(matched_rles)
-        return matched_rles
+            self.update_target(relabelled)
+        return relabelled
 
 
 class StackMatcher:
