@@ -1622,10 +1622,11 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     const long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
-    // aligned planes take the row-linear kernel (measured 3 % faster than the block walk; the store
-    // policy — .cs / default / .cg — makes no difference); EMP_APPLY_VARIANT=0 forces the block walk
+    // The block walk is the default: on config 2 the row-linear kernel (EMP_APPLY_VARIANT=1..3, the three
+    // store policies measure the same) is 3 % faster, but on dense tiles (config 5: few flagged strips)
+    // it is 15 % slower because its code loads are issued row by row.
     static int variant = -1;
-    if (variant < 0) { const char* e = getenv("EMP_APPLY_VARIANT"); variant = e ? atoi(e) : 1; }
+    if (variant < 0) { const char* e = getenv("EMP_APPLY_VARIANT"); variant = e ? atoi(e) : 0; }
     if (fast && variant > 0 && W % 2 == 0) {
         dim3 g2((unsigned)((H + kItemH - 1) / kItemH), 1, B);
         if (L.code16) {
