@@ -305,6 +305,9 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'alg_bytes_per_px': STAGE_ALG_BYTES_PER_PX[dom], 'avg_launch_ms': dom_ms,
+                         'note': ('achieved counts the algorithmic bytes of the stage (SURVEY 8d: sem 8 + offsets 8 B/px for assign); '
+                                  'traffic is what ncu saw in DRAM for one launch — below it, because offsets are fetched only for '
+                                  'strips holding thing pixels and background strips store no codes'),
                          'pipeline': {'alg_bytes_per_px': ALG_BYTES_PER_PX, 'achieved': pipeline_gbs,
                                       'frac': pipeline_gbs / peak, 'frac_of_8TBs_spec': pipeline_gbs / 8000.0},
                          'stage_ms_per_step': stage_ms},

@@ -63,3 +63,59 @@ EMP_API int emp_rle_pair_overlaps(const int64_t* runs, size_t run_stride, const 
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Dense fill of a z-block — reference array_utils.numpy_fill_instances (array_utils.py:725-736) applied
+// to what the tracker holds after matching: every run (start, length, slot) of slice s paints
+// labels[s][slot] over [start, start + length) of plane s.  Voxels no run covers keep their value (the
+// reference leaves them untouched too); a label < 0 skips the run.  One warp per run, 16-byte stores in
+// the aligned middle of long runs.
+// ---------------------------------------------------------------------------------------------
+namespace emp {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+fill_runs_kernel(const long long* __restrict__ runs, size_t run_stride, const int32_t* __restrict__ n_runs,
+                 const long long* __restrict__ labels, size_t label_stride, T* __restrict__ out, size_t plane)
+{
+    const int s = blockIdx.y;
+    const int n = __ldg(n_runs + s);
+    const long long* R = runs + (size_t)s * run_stride * 3;
+    const long long* lab = labels + (size_t)s * label_stride;
+    T* dst = out + (size_t)s * plane;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int j = warp_global; j < n; j += n_warps) {
+        const long long start = __ldg(R + 3 * (size_t)j), len = __ldg(R + 3 * (size_t)j + 1);
+        const long long v = __ldg(lab + __ldg(R + 3 * (size_t)j + 2));
+        if (v < 0) continue;
+        const T tv = (T)v;
+        for (long long i = lane; i < len; i += 32) dst[start + i] = tv;     // consecutive lanes, consecutive voxels
+    }
+}
+
+}  // namespace emp
+
+EMP_API int emp_fill_runs(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices, int max_runs,
+                          const int64_t* labels, size_t label_stride, void* out, int elem_bytes, size_t plane, void* stream)
+{
+    EMP_REQUIRE(runs && n_runs && labels && out, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(n_slices >= 1 && max_runs >= 0, EMP_ERR_INVALID, "bad sizes");
+    EMP_REQUIRE(elem_bytes == 4 || elem_bytes == 8, EMP_ERR_INVALID, "out must hold 4- or 8-byte integers");
+    if (max_runs == 0) return EMP_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int bx = (max_runs + 7) / 8;                        // one warp per run
+    if (bx > 2048) bx = 2048;
+    dim3 grid(bx, n_slices);
+    if (elem_bytes == 8)
+        fill_runs_kernel<long long><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(runs), run_stride, n_runs,
+                                                          reinterpret_cast<const long long*>(labels), label_stride,
+                                                          static_cast<long long*>(out), plane);
+    else
+        fill_runs_kernel<unsigned><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(runs), run_stride, n_runs,
+                                                         reinterpret_cast<const long long*>(labels), label_stride,
+                                                         static_cast<unsigned*>(out), plane);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}

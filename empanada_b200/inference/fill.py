@@ -1,0 +1,85 @@
+"""
+Dense fill of run-length encoded instances on the GPU — the role of
+``empanada.array_utils.numpy_fill_instances`` (reference array_utils.py:725-736; used by the
+inference scripts to write the labelled volume): every run ``[start, start + length)`` of an instance
+is painted with the instance's label into a flat view of the volume; voxels no run covers keep their
+value.  libempanada_b200 ``emp_fill_runs`` does it with one warp per run.
+
+  * ``fill_instances(volume, instances)`` — the reference's call shape, for a CUDA tensor volume and a
+    dict {label: {'starts', 'runs', ...}} (runs index the flattened volume);
+  * ``fill_block(runs_all, n_runs, labels, shape, dtype)`` — for the z-sharded stack driver: the run
+    tables of a whole z-block are already in HBM, `labels[s][slot]` is each instance's final label.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from empanada_b200 import _cabi as C
+
+__all__ = ['fill_instances', 'fill_block']
+
+
+def _elem_bytes(t):
+    if t.dtype in (torch.int64,):
+        return 8
+    if t.dtype in (torch.int32, torch.uint32):
+        return 4
+    raise TypeError(f'volume must be int64, int32 or uint32 (got {t.dtype})')
+
+
+def _launch(runs, n_runs_dev, max_runs, labels, out2d, device):
+    n_slices, run_stride = int(runs.shape[0]), int(runs.shape[1])
+    with torch.cuda.device(device):
+        C.check(C.lib().emp_fill_runs(ctypes.c_void_p(runs.data_ptr()), run_stride, ctypes.c_void_p(n_runs_dev.data_ptr()),
+                                      n_slices, int(max_runs), ctypes.c_void_p(labels.data_ptr()), int(labels.shape[1]),
+                                      ctypes.c_void_p(out2d.data_ptr()), _elem_bytes(out2d), int(out2d.shape[1]),
+                                      C.stream_ptr(device)))
+
+
+def fill_instances(volume, instances):
+    """Fill a CUDA tensor `volume` (any shape, int64 / int32 / uint32, contiguous) in place with run
+    length encoded instances {label: {'starts': ..., 'runs': ...}} and return it.  Later instances
+    overwrite earlier ones where their runs overlap, as in the reference's loop."""
+    dev = C.require_cuda(volume)
+    assert volume.is_contiguous()
+    if len(instances) == 0:
+        return volume
+    flat = volume.view(1, -1)
+    order = {lab: i for i, lab in enumerate(instances.keys())}
+    starts = [np.asarray(a['starts'], np.int64) for a in instances.values()]
+    lens = [np.asarray(a['runs'], np.int64) for a in instances.values()]
+    slot = np.repeat(np.arange(len(starts), dtype=np.int64), [len(s) for s in starts])
+    table = np.stack([np.concatenate(starts), np.concatenate(lens), slot], 1) if slot.size else np.zeros((0, 3), np.int64)
+    if table.shape[0] == 0:
+        return volume
+    labels = torch.tensor([[int(lab) for lab in order]], dtype=torch.int64, device=dev)
+    # overlapping instances: paint in dict order, one launch per instance, only if any overlap exists
+    s_sorted = np.argsort(table[:, 0], kind='stable')
+    ends = table[s_sorted, 0] + table[s_sorted, 1]
+    overlapping = bool((table[s_sorted, 0][1:] < np.maximum.accumulate(ends)[:-1]).any())
+    groups = [table] if not overlapping else [table[slot == i] for i in range(len(starts))]
+    for g in groups:
+        if g.shape[0] == 0:
+            continue
+        runs = torch.from_numpy(np.ascontiguousarray(g[None])).to(dev)
+        n_runs = torch.tensor([g.shape[0]], dtype=torch.int32, device=dev)
+        _launch(runs, n_runs, g.shape[0], labels, flat, dev)
+    return volume
+
+
+def fill_block(runs_all, n_runs, labels, shape, dtype=torch.int64, out=None):
+    """Labelled planes of a z-block from its run tables: runs_all (n, run_stride, 3) int64 CUDA tensor,
+    n_runs (n,) host counts, labels (n, max_slots) int64 (host array or CUDA tensor; negative = skip),
+    shape (H, W) of a plane.  Returns an (n, H, W) tensor of `dtype` (zeros where nothing was painted)."""
+    dev = runs_all.device
+    n = int(runs_all.shape[0])
+    H, W = shape
+    if out is None:
+        out = torch.zeros((n, H, W), dtype=dtype, device=dev)
+    n_runs = np.asarray(n_runs, np.int64)
+    lab = labels if torch.is_tensor(labels) else torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int64))
+    lab = lab.to(dev).contiguous()
+    nr = torch.from_numpy(n_runs.astype(np.int32)).to(dev)
+    _launch(runs_all, nr, int(n_runs.max()) if n else 0, lab, out.view(n, H * W), dev)
+    return out

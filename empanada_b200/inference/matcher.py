@@ -324,16 +324,19 @@ class StackMatcher:
         m.target_rle = None
         m.assign_new = False
         out = [None] * len(fwd)
+        self.slot_labels = [None] * len(fwd)            # final label of every ORIGINAL instance slot, per slice
         g_next = None
         for z in range(len(fwd) - 1, -1, -1):
             seg = fwd[z]
             if m.target_rle is None:
                 m.initialize_target(seg)
                 out[z], g_next = seg, groups[z]
+                self.slot_labels[z] = np.asarray(g_next[0], np.int64)[g_next[1]] if len(g_next[1]) else np.zeros(0, np.int64)
                 continue
             sa, sb, ov = overlaps[z]                    # pair (z, z+1): a = slots of z, b = slots of z+1
             inter = self._group_inter(g_next, groups[z], sb, sa, ov)
             areas = (self._group_areas(g_next, self.slot_areas[z + 1]), self._group_areas(groups[z], self.slot_areas[z]))
             out[z] = m(seg, inter=inter, areas=areas)
             g_next = self._regroup(groups[z], m.last_assignment)
+            self.slot_labels[z] = np.asarray(g_next[0], np.int64)[g_next[1]] if len(g_next[1]) else np.zeros(0, np.int64)
         return out

@@ -232,6 +232,7 @@ class StackShard:
                 at += k
         # host seconds: enqueueing, waiting for the device, read-back + dict assembly
         self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'assemble_s': time.perf_counter() - t_c}
+        self.tables_shape_ = (int(H), int(W))
         # kept for match(): the run tables stay in HBM, slots index each slice's instances in dict order
         self.tables_ = {'runs_all': runs_all, 'n_runs': np.where(ok, n_runs, 0), 'bad': bad,
                         'inst': [inst_h[i, :n_inst[i]] if ok[i] else None for i in range(n)], 'zs': list(zs),
@@ -254,6 +255,8 @@ class StackShard:
         else:
             pair_rows = mt.block_overlaps(t['runs_all'], t['n_runs'])
         out = {z: dict(segs[z]) for z in zs}
+        # final label of every instance slot (all classes): its own label unless a matcher renames it
+        self.slot_labels_ = [None if t['inst'][i] is None else t['inst'][i][:, 1].copy() for i in range(len(zs))]
         for c in self.labels:
             if c not in e.thing_list:
                 continue
@@ -281,9 +284,27 @@ class StackShard:
             sm = mt.StackMatcher(c, e.label_divisor, merge_iou_thr, merge_ioa_thr)
             fwd, groups = sm.forward(rles, overlaps, areas)
             bwd = sm.backward(fwd, groups, rles, overlaps)
-            for z, seg in zip(zs, bwd):
+            for i, (z, seg) in enumerate(zip(zs, bwd)):
                 out[z][c] = seg
+                if self.slot_labels_[i] is not None:
+                    self.slot_labels_[i][t['inst'][i][:, 0] == c] = sm.slot_labels[i]
         return out
+
+    def fill(self, dtype=torch.int64):
+        """The block as labelled planes (n, H, W) in HBM, painted from the run tables with the labels the
+        last match() assigned (finish() labels if match() was not called): the GPU counterpart of
+        array_utils.numpy_fill_instances over the tracker's instances (array_utils.py:725-736)."""
+        from empanada_b200.inference import fill as fl
+        t = self.tables_
+        assert not t['bad'].any(), 'a slice was redone synchronously: fill from the dicts instead (fill_instances)'
+        labels = getattr(self, 'slot_labels_', None) or [ins[:, 1] for ins in t['inst']]
+        width = max([len(l) for l in labels] + [1])
+        table = np.full((len(labels), width), -1, np.int64)
+        for i, l in enumerate(labels):
+            table[i, :len(l)] = l
+        h = self.heads[t['zs'][0]]
+        H, W = h['size'] if h['size'] is not None else self.tables_shape_
+        return fl.fill_block(t['runs_all'], t['n_runs'], table, (H, W), dtype)
 
     def finish(self):
         from empanada_b200.inference import engines as eng

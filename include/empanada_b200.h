@@ -190,6 +190,15 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
 int emp_rle_pair_overlaps(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices,
                           int max_runs, int32_t* out, int cap, int32_t* count, void* stream);
 
+/* Dense fill of a z-block — array_utils.numpy_fill_instances (array_utils.py:725-736) over the run
+ * tables in HBM: every run (start, length, slot) of slice s paints labels[s][slot] over
+ * [start, start + length) of plane s of `out`; voxels no run covers keep their value; a negative label
+ * skips the run.
+ *   runs / n_runs / max_runs as for emp_rle_pair_overlaps;  labels (n_slices, label_stride) int64;
+ *   out (n_slices, plane) of 4-byte (uint32) or 8-byte (int64) elements. */
+int emp_fill_runs(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices, int max_runs,
+                  const int64_t* labels, size_t label_stride, void* out, int elem_bytes, size_t plane, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -180,5 +180,8 @@ def test_stack_shard_matches_sequential_engine(ks, cuda_device):
             else:
                 seg = mat(seg)
             _rle_equal({1: matched[z][1]}, {1: seg})
+        vol = shard.fill(torch.int64).cpu().numpy()
+        for z in range(D):
+            np.testing.assert_array_equal(vol[z], rle.rle_seg_to_pan_seg(matched[z], (H, W)).astype(np.int64))
         labels0 = set(matched[0][1].keys())
         assert any(set(matched[z][1].keys()) & labels0 for z in range(1, D))      # objects are tracked across slices

@@ -95,10 +95,41 @@ def test_forward_backward_stack(name, api, cuda_device):
         fwd, groups = sm.forward(rles, overlaps)
         assert sm.matcher.next_label == int(g['fwd_next_label'])
         bwd = sm.backward(fwd, groups, rles, overlaps)
+        # dense fill of the block straight from the run tables + the matcher's per-slot labels
+        from empanada_b200.inference import fill as fl
+        width = max(len(l) for l in sm.slot_labels)
+        table = np.full((D, max(width, 1)), -1, np.int64)
+        for z in range(D):
+            table[z, :len(sm.slot_labels[z])] = sm.slot_labels[z]
+        for dt in (torch.int64, torch.int32):
+            vol_out = fl.fill_block(runs_all, n_runs, table, (H, W), dt).cpu().numpy()
+            for z in range(D):
+                np.testing.assert_array_equal(vol_out[z], g[f'bwd_{z}'])
     for z in range(D):
         _same(fwd[z], _unflatten(g[f'fwd_inst_{z}'], g[f'fwd_starts_{z}'], g[f'fwd_runs_{z}']))
         _same(bwd[z], _unflatten(g[f'bwd_inst_{z}'], g[f'bwd_starts_{z}'], g[f'bwd_runs_{z}']))
         np.testing.assert_array_equal(rle.rle_seg_to_pan_seg({1: bwd[z]}, (H, W)), g[f'bwd_{z}'])
+
+
+def test_fill_instances_dict_api(cuda_device):
+    """fill_instances on a flat 3D volume, incl. overlapping instances (later ones win, as in the
+    reference's loop) and untouched voxels keeping their value."""
+    from empanada_b200.inference import fill as fl
+    rng = np.random.default_rng(3)
+    shape = (5, 40, 64)
+    n = int(np.prod(shape))
+    inst = {}
+    for lab in (7, 1003, 20002, 5):
+        starts = np.sort(rng.choice(n - 50, 30, replace=False)).astype(np.int64)
+        inst[lab] = {'box': None, 'starts': starts, 'runs': rng.integers(1, 40, 30).astype(np.int64)}
+    want = np.full(n, 9, np.int64)
+    for lab, a in inst.items():
+        for s0, r0 in zip(a['starts'], a['runs']):
+            want[s0:s0 + r0] = lab
+    vol = torch.full(shape, 9, dtype=torch.int64, device=cuda_device)
+    got = fl.fill_instances(vol, inst)
+    np.testing.assert_array_equal(got.cpu().numpy().ravel(), want)
+    assert fl.fill_instances(torch.zeros(4, 4, dtype=torch.int32, device=cuda_device), {}).sum() == 0
 
 
 def test_merge_rles_host_semantics():
