@@ -489,8 +489,40 @@ def matcher_cases():
         print(f'  {name}: {sum(len(r[1]) for r in rles)} instances in, final labels {len(np.unique(res["bwd_0"])) - 1} in slice 0')
 
 
+# ---------------------------------------------------------------------------------------------
+# tracker: the reference's InstanceTracker along all three axes + its json wire format
+# ---------------------------------------------------------------------------------------------
+def tracker_cases():
+    import tempfile
+    from empanada.inference import tracker as rtrack  # reference
+    rng = np.random.default_rng(77)
+    vol = rng.integers(0, 5, size=(9, 11, 13)).astype(np.int64)
+    vol[vol > 0] += 1000
+    vol[2:5, 3:9, 4:12] = 1007                          # one big object so runs wrap around row ends
+    res = {'in_vol': vol}
+    for axis in ('xy', 'xz', 'yz'):
+        tr = rtrack.InstanceTracker(1, 1000, vol.shape, axis=axis)
+        n = vol.shape[{'xy': 0, 'xz': 1, 'yz': 2}[axis]]
+        for i in range(n):
+            sl = vol[i] if axis == 'xy' else vol[:, i] if axis == 'xz' else vol[..., i]
+            tr.update(rrle.pan_seg_to_rle_seg(np.ascontiguousarray(sl), [1], 1000, [1], False)[1], i)
+        tr.finish()
+        labs = list(tr.instances.keys())
+        res[f'{axis}_labels'] = np.asarray(labs, np.int64)
+        res[f'{axis}_boxes'] = np.asarray([tr.instances[l]['box'] for l in labs], np.int64)
+        res[f'{axis}_counts'] = np.asarray([len(tr.instances[l]['starts']) for l in labs], np.int64)
+        res[f'{axis}_starts'] = np.concatenate([np.asarray(tr.instances[l]['starts'], np.int64) for l in labs])
+        res[f'{axis}_runs'] = np.concatenate([np.asarray(tr.instances[l]['runs'], np.int64) for l in labs])
+        if axis == 'xy':
+            with tempfile.TemporaryDirectory() as d:
+                path = os.path.join(d, 't.json')
+                tr.write_to_json(path)
+                res['xy_json'] = np.frombuffer(open(path, 'rb').read(), dtype=np.uint8)
+    save('tracker_axes', **res)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher']
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker']
     if 'pp' in which:
         pp_cases()
     if 'merge' in which:
@@ -501,3 +533,5 @@ if __name__ == '__main__':
         rle_cases()
     if 'matcher' in which:
         matcher_cases()
+    if 'tracker' in which:
+        tracker_cases()
