@@ -150,3 +150,58 @@ def test_dense_full_size_properties(cuda_device):
     assert torch.equal(merged.reshape(pan.shape), pan)
     # centers are exactly the oracle's (cheap on the CPU even at full size)
     np.testing.assert_array_equal(ctr[0].cpu().numpy(), oracle.find_instance_center(d['ctr_hmp'][0, 0], 0.1, 7))
+
+
+def test_host_buffer_entry_point(cuda_device):
+    """emp_panoptic_batched_host — the end-to-end entry bench.py times: pageable AND pinned host buffers
+    in, H2D / kernels / D2H pipelined over three slots, results identical to the resident path and
+    to the oracle, K and flags reported per tile."""
+    import ctypes
+    from empanada_b200 import _cabi as C
+    H, W, B = 256, 320, 5
+    tiles = [synth_tile(H, W, 30 + 7 * i, seed=700 + i, semi_axes=(5, 16), sigma=3.0) for i in range(B)]
+    sem_h = torch.from_numpy(np.stack([t['sem'][0, 0] for t in tiles]))
+    hm_h = torch.from_numpy(np.stack([t['ctr_hmp'][0, 0] for t in tiles]))
+    off_h = torch.from_numpy(np.stack([t['offsets'][0] for t in tiles]))
+    L = C.lib()
+    things, nt = C.i64_array([1])
+    k_cap = 4096
+    nbytes = L.emp_host_scratch_bytes(H, W, k_cap, nt)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=cuda_device)
+    for pin in (False, True):
+        bufs = [x.pin_memory() if pin else x.clone() for x in (sem_h, hm_h, off_h)]
+        pan_h = torch.empty((B, H, W), dtype=torch.int64)
+        if pin:
+            pan_h = pan_h.pin_memory()
+        k_out, f_out = (ctypes.c_int32 * B)(), (ctypes.c_int32 * B)()
+        with torch.cuda.device(cuda_device):
+            C.check(L.emp_panoptic_batched_host(B, bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), H, W, things, nt,
+                                                1000, 64, 0, 0.1, 7, pan_h.data_ptr(), k_out, f_out, k_cap,
+                                                scratch.data_ptr(), nbytes))
+        for b, t in enumerate(tiles):
+            want_pan, want_ctr = oracle.get_panoptic_segmentation(t['sem'], t['ctr_hmp'], t['offsets'], [1], 1000, 64, 0, 0.1, 7)
+            assert k_out[b] == want_ctr.shape[1] and f_out[b] == 0
+            np.testing.assert_array_equal(pan_h[b].numpy(), want_pan[0, 0])
+
+
+def test_status_flags_through_the_c_abi(cuda_device):
+    """Data-dependent conditions come back through the status block: more centers than k_cap
+    (EMP_FLAG_K_OVERFLOW + true K) and class ids outside [0, 4096) (EMP_FLAG_CLASS_RANGE -> ValueError)."""
+    from empanada_b200 import _cabi as C
+    H, W = 64, 128
+    hm = torch.zeros((1, 1, H, W), device=cuda_device)
+    hm[0, 0, ::8, ::8] = 1.0                                        # 8 x 16 = 128 isolated peaks
+    off = torch.zeros((1, 2, H, W), device=cuda_device)
+    sem = torch.ones((1, 1, H, W), dtype=torch.int64, device=cuda_device)
+    pan, ctr, Ks = pp._panoptic_tiles(sem.reshape(1, H, W), hm.reshape(1, H, W), off, [1], 1000, 0, 0, 0.1, 3, k_cap=16)
+    assert Ks == [128] and ctr.shape[1] >= 128                      # retried with the true K
+    want_pan, want_ctr = oracle.get_panoptic_segmentation(sem.cpu().numpy(), hm.cpu().numpy(), off.cpu().numpy(), [1], 1000, 0, 0, 0.1, 3)
+    np.testing.assert_array_equal(pan.cpu().numpy()[0], want_pan[0, 0])
+    bad = sem.clone()
+    bad[0, 0, 5, 5] = 5000
+    with pytest.raises(ValueError, match='class ids'):
+        pp.get_panoptic_segmentation(bad, hm, off, [1], 1000, 0, 0, 0.1, 3)
+    bad[0, 0, 5, 5] = -3
+    with pytest.raises(ValueError, match='class ids'):
+        pp.get_panoptic_segmentation(bad, hm, off, [1], 1000, 0, 0, 0.1, 3)
+    assert C.lib().emp_version() >= 100
