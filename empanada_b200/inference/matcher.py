@@ -298,12 +298,17 @@ class StackMatcher:
             of_old[i] = j
         return new_labels, of_old[g_old[1]]
 
-    def forward(self, rles, overlaps, slot_areas=None):
+    def forward(self, rles, overlaps, slot_areas=None, prev=None):
         """Returns (matched rles per slice, groups per slice).
-        slot_areas: optional list over slices of per-instance pixel counts (dict order)."""
+        slot_areas: optional list over slices of per-instance pixel counts (dict order).
+        prev: the forward state of the block below (``forward_state`` of the previous rank) plus
+        'overlaps' = (slot in its last slice, slot in rles[0], inter): the chain then continues from
+        that block instead of starting at rles[0]."""
         m = self.matcher
         self.slot_areas = slot_areas if slot_areas is not None else [instance_areas(seg) for seg in rles]
         out, groups = [], []
+        if prev is not None:
+            m.target_rle, m.next_label = prev['target'], prev['next_label']
         for z, seg in enumerate(rles):
             own = (list(seg.keys()), np.arange(len(seg), dtype=np.int64))
             if m.target_rle is None:
@@ -311,32 +316,50 @@ class StackMatcher:
                 out.append(seg)
                 groups.append(own)
                 continue
-            sa, sb, ov = overlaps[z - 1]
-            inter = self._group_inter(groups[-1], own, sa, sb, ov)
-            areas = (self._group_areas(groups[-1], self.slot_areas[z - 1]), self.slot_areas[z])
+            if z == 0:
+                g_t, a_t, (sa, sb, ov) = prev['groups'], prev['areas'], prev['overlaps']
+            else:
+                g_t, a_t, (sa, sb, ov) = groups[-1], self.slot_areas[z - 1], overlaps[z - 1]
+            inter = self._group_inter(g_t, own, sa, sb, ov)
+            areas = (self._group_areas(g_t, a_t), self.slot_areas[z])
             out.append(m(seg, inter=inter, areas=areas))
             groups.append(self._regroup(own, m.last_assignment))
         return out, groups
 
-    def backward(self, fwd, groups, rles, overlaps):
-        """patterns.backward_matching: targets reset, assign_new off, slices in reverse."""
+    def forward_state(self, groups):
+        """What the next block needs to continue the forward chain (picklable)."""
         m = self.matcher
-        m.target_rle = None
+        return {'target': m.target_rle, 'next_label': m.next_label, 'groups': groups[-1], 'areas': self.slot_areas[-1]}
+
+    def backward(self, fwd, groups, rles, overlaps, nxt=None):
+        """patterns.backward_matching: targets reset, assign_new off, slices in reverse.
+        nxt: the backward state of the block above (``backward_state`` of the next rank) plus
+        'overlaps' = (slot in fwd[-1]'s slice, slot in its first slice, inter)."""
+        m = self.matcher
+        m.target_rle = None if nxt is None else nxt['target']
         m.assign_new = False
-        out = [None] * len(fwd)
-        self.slot_labels = [None] * len(fwd)            # final label of every ORIGINAL instance slot, per slice
+        n = len(fwd)
+        out = [None] * n
+        self.slot_labels = [None] * n                   # final label of every ORIGINAL instance slot, per slice
         g_next = None
-        for z in range(len(fwd) - 1, -1, -1):
+        for z in range(n - 1, -1, -1):
             seg = fwd[z]
             if m.target_rle is None:
                 m.initialize_target(seg)
                 out[z], g_next = seg, groups[z]
-                self.slot_labels[z] = np.asarray(g_next[0], np.int64)[g_next[1]] if len(g_next[1]) else np.zeros(0, np.int64)
-                continue
-            sa, sb, ov = overlaps[z]                    # pair (z, z+1): a = slots of z, b = slots of z+1
-            inter = self._group_inter(g_next, groups[z], sb, sa, ov)
-            areas = (self._group_areas(g_next, self.slot_areas[z + 1]), self._group_areas(groups[z], self.slot_areas[z]))
-            out[z] = m(seg, inter=inter, areas=areas)
-            g_next = self._regroup(groups[z], m.last_assignment)
+            else:
+                if z == n - 1:
+                    g_t, a_t, (sa, sb, ov) = nxt['groups'], nxt['areas'], nxt['overlaps']
+                else:
+                    g_t, a_t, (sa, sb, ov) = g_next, self.slot_areas[z + 1], overlaps[z]
+                inter = self._group_inter(g_t, groups[z], sb, sa, ov)      # pair (z, z+1): a = slots of z, b = slots of z+1
+                areas = (self._group_areas(g_t, a_t), self._group_areas(groups[z], self.slot_areas[z]))
+                out[z] = m(seg, inter=inter, areas=areas)
+                g_next = self._regroup(groups[z], m.last_assignment)
             self.slot_labels[z] = np.asarray(g_next[0], np.int64)[g_next[1]] if len(g_next[1]) else np.zeros(0, np.int64)
+        self._g_first = g_next
         return out
+
+    def backward_state(self, out):
+        """What the block below needs to continue the backward chain (picklable)."""
+        return {'target': out[0], 'groups': self._g_first, 'areas': self.slot_areas[0]}

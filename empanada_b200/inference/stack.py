@@ -239,55 +239,106 @@ class StackShard:
                         'slot_areas': slot_areas}
         return segs
 
+    def _class_overlaps(self, pair_rows, inst_a, inst_b, c):
+        """Rows of one slice pair restricted to class c, slots renumbered within the class."""
+        sa, sb, ov = pair_rows
+        ca, cb = inst_a[:, 0] == c, inst_b[:, 0] == c
+        fa = int(np.argmax(ca)) if ca.any() else 0
+        fb = int(np.argmax(cb)) if cb.any() else 0
+        k = ca[sa] & cb[sb]
+        return sa[k] - fa, sb[k] - fb, ov[k]
+
     def match(self, segs, merge_iou_thr=0.25, merge_ioa_thr=0.25):
-        """Forward + backward cross-slice matching of this rank's block (the host loop of
-        patterns.forward_matching / backward_matching, patterns.py:68-112, per thing class), with every
-        IoU / IoA taken from ONE overlap launch over the block's run tables (inference/matcher.py).
-        segs: what finish() returned.  Returns {z: matched rle_seg}.  A single-rank block only: chaining
-        blocks of several ranks needs the last slice's matched labels of rank r-1 and is the caller's job."""
+        """Forward + backward cross-slice matching (the host loops of patterns.forward_matching /
+        backward_matching, patterns.py:68-112, per thing class), with every IoU / IoA taken from ONE
+        overlap launch over the block's run tables (inference/matcher.py).  segs: what finish()
+        returned.  Returns {z: matched rle_seg}.
+
+        With several ranks the chains are inherently sequential in z: rank r continues the forward chain
+        from the state rank r-1 hands over (its last slice's matched instances, label counter and run
+        table, a few hundred KB through torch.distributed's object send/recv), and the backward chain
+        from rank r+1's; only the boundary pair's overlaps are computed on top of the block's own."""
         from empanada_b200.inference import matcher as mt
         e = self.engine
         t = self.tables_
         zs = t['zs']
         assert zs == sorted(segs.keys())
+        assert not t['bad'].any() or self.world == 1, 'multi-rank matching needs the deferred tables of every slice'
+        things = [c for c in self.labels if c in e.thing_list]
+        dev = t['runs_all'].device
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+
+        def exchange(obj, dst, src):
+            """send obj to dst (if any), receive from src (if any) — blocking, object collectives"""
+            got = None
+            if src is not None:
+                box = [None]
+                dist.recv_object_list(box, src=src, group=self.group, device=dev)
+                got = box[0]
+            if dst is not None:
+                dist.send_object_list([obj], dst=dst, group=self.group, device=dev)
+            return got
+
         if t['bad'].any():                              # a slice was redone synchronously: use the dict API
             pair_rows = None
         else:
             pair_rows = mt.block_overlaps(t['runs_all'], t['n_runs'])
-        out = {z: dict(segs[z]) for z in zs}
-        # final label of every instance slot (all classes): its own label unless a matcher renames it
-        self.slot_labels_ = [None if t['inst'][i] is None else t['inst'][i][:, 1].copy() for i in range(len(zs))]
-        for c in self.labels:
-            if c not in e.thing_list:
-                continue
+        per_class = {}
+        for c in things:
             rles = [segs[z][c] for z in zs]
-            areas = None
             if pair_rows is None:
-                overlaps = []
+                overlaps, areas = [], None
                 for a, b in zip(rles[:-1], rles[1:]):
-                    la, _, sa, ra = mt.unpack_rle_attrs(a)
-                    lb, _, sb, rb = mt.unpack_rle_attrs(b)
+                    _, _, sa, ra = mt.unpack_rle_attrs(a)
+                    _, _, sb, rb = mt.unpack_rle_attrs(b)
                     m = mt.pair_overlaps(sa, ra, sb, rb)
                     i, j = np.nonzero(m)
                     overlaps.append((i, j, m[i, j]))
             else:
-                # slots count every class of the slice; keep this class's and renumber from 0
-                overlaps = []
                 areas = [t['slot_areas'][i][t['inst'][i][:, 0] == c] for i in range(len(zs))]
-                for p, (sa, sb, ov) in enumerate(pair_rows):
-                    ia, ib = t['inst'][p], t['inst'][p + 1]
-                    ca, cb = ia[sa, 0] == c, ib[sb, 0] == c
-                    fa = int(np.argmax(ia[:, 0] == c)) if (ia[:, 0] == c).any() else 0
-                    fb = int(np.argmax(ib[:, 0] == c)) if (ib[:, 0] == c).any() else 0
-                    k = ca & cb
-                    overlaps.append((sa[k] - fa, sb[k] - fb, ov[k]))
-            sm = mt.StackMatcher(c, e.label_divisor, merge_iou_thr, merge_ioa_thr)
-            fwd, groups = sm.forward(rles, overlaps, areas)
-            bwd = sm.backward(fwd, groups, rles, overlaps)
+                overlaps = [self._class_overlaps(rows, t['inst'][p], t['inst'][p + 1], c) for p, rows in enumerate(pair_rows)]
+            per_class[c] = (rles, overlaps, areas, mt.StackMatcher(c, e.label_divisor, merge_iou_thr, merge_ioa_thr))
+
+        # ---- forward: continue from the rank below, hand over to the rank above
+        prev = None
+        if multi and self.rank > 0:
+            prev = exchange(None, None, self.rank - 1)
+            # overlaps of the boundary pair (their last slice, my first slice) from the two run tables
+            mine = t['runs_all'][0, :int(t['n_runs'][0])]
+            theirs = torch.from_numpy(prev['runs']).to(dev)
+            stride = max(int(mine.shape[0]), int(theirs.shape[0]), 1)
+            both = torch.zeros((2, stride, 3), dtype=torch.int64, device=dev)
+            both[0, :theirs.shape[0]] = theirs
+            both[1, :mine.shape[0]] = mine
+            rows = mt.block_overlaps(both, [int(theirs.shape[0]), int(mine.shape[0])])[0]
+            self._boundary_below = {c: self._class_overlaps(rows, prev['inst'], t['inst'][0], c) for c in things}
+        fwd = {}
+        for c, (rles, overlaps, areas, sm) in per_class.items():
+            st = None
+            if prev is not None:
+                st = dict(prev['classes'][c], overlaps=self._boundary_below[c])
+            fwd[c] = sm.forward(rles, overlaps, areas, prev=st)
+        if multi and self.rank + 1 < self.world:
+            last = len(zs) - 1
+            exchange({'runs': t['runs_all'][last, :int(t['n_runs'][last])].cpu().numpy(), 'inst': t['inst'][last],
+                      'classes': {c: per_class[c][3].forward_state(fwd[c][1]) for c in things}}, self.rank + 1, None)
+
+        # ---- backward: continue from the rank above, hand over to the rank below
+        nxt = exchange(None, None, self.rank + 1) if multi and self.rank + 1 < self.world else None
+        out = {z: dict(segs[z]) for z in zs}
+        # final label of every instance slot (all classes): its own label unless a matcher renames it
+        self.slot_labels_ = [None if t['inst'][i] is None else t['inst'][i][:, 1].copy() for i in range(len(zs))]
+        down = {}
+        for c, (rles, overlaps, areas, sm) in per_class.items():
+            bwd = sm.backward(fwd[c][0], fwd[c][1], rles, overlaps, nxt=None if nxt is None else nxt[c])
+            down[c] = sm.backward_state(bwd)
             for i, (z, seg) in enumerate(zip(zs, bwd)):
                 out[z][c] = seg
                 if self.slot_labels_[i] is not None:
                     self.slot_labels_[i][t['inst'][i][:, 0] == c] = sm.slot_labels[i]
+        if multi and self.rank > 0:
+            # the rank below matches its last slice against my first: overlaps as (its slot, my slot, inter)
+            exchange({c: dict(down[c], overlaps=self._boundary_below[c]) for c in things}, self.rank - 1, None)
         return out
 
     def fill(self, dtype=torch.int64):
@@ -335,7 +386,8 @@ class StackShard:
                     max_counts[c] = max(max_counts[c], max(seg[c]) - c * e.label_divisor)
             out[z] = seg
         counts = torch.tensor([max_counts[c] for c in self.labels], dtype=torch.int64, device=raw[self.z0].device)
-        offs, _ = label_offsets(counts, self.group)
+        # a single-rank shard never talks to anyone, even inside a larger process group
+        offs = torch.zeros_like(counts) if self.world == 1 else label_offsets(counts, self.group)[0]
         offs = {c: int(o) for c, o in zip(self.labels, offs.tolist())}
         self.label_offsets_ = offs
         return {z: apply_label_offset(s, offs, e.label_divisor, e.thing_list) for z, s in out.items()}

@@ -118,3 +118,37 @@ def test_apply_label_offset():
     assert list(out[1]) == [1041, 1042] and list(out[2]) == [2000]
     with pytest.raises(ValueError):
         stack.apply_label_offset(seg, {1: 998}, 1000, [1])
+
+
+# ---- cross-slice matching across block boundaries (host chain; the overlaps come from the oracle here) ----
+@pytest.mark.parametrize('name', ['matcher_stack_a', 'matcher_stack_b', 'matcher_stack_nofc'])
+def test_matching_chain_continues_across_blocks(name):
+    """StackMatcher.forward/backward with the state handed over between two z-blocks (what two ranks
+    exchange) must equal the single-block chain, i.e. the reference's RLEMatcher loops
+    (tests/golden/matcher_stack_*.npz were produced by the unmodified reference)."""
+    import oracle
+    from conftest import load_golden
+    from oracle import matcher as om
+    from empanada_b200.inference import matcher as mt
+    g = load_golden(name)
+    p = g['params']
+    D = p['D']
+    rles = [oracle.pan_seg_to_rle_seg(g['in_vol'][z], [1], 1000, [1], p['force_connected'])[1] for z in range(D)]
+    ov = []
+    for a, b in zip(rles[:-1], rles[1:]):
+        m = np.array([[om.rle_intersection(x['starts'], x['runs'], y['starts'], y['runs']) for y in b.values()] for x in a.values()],
+                     np.int64).reshape(len(a), len(b))
+        i, j = np.nonzero(m)
+        ov.append((i, j, m[i, j]))
+    for cut in (1, D // 2, D - 1):
+        A, B = rles[:cut], rles[cut:]
+        sm_a, sm_b = mt.StackMatcher(1, 1000, 0.25, 0.25), mt.StackMatcher(1, 1000, 0.25, 0.25)
+        f_a, g_a = sm_a.forward(A, ov[:cut - 1])
+        f_b, g_b = sm_b.forward(B, ov[cut:], prev=dict(sm_a.forward_state(g_a), overlaps=ov[cut - 1]))
+        assert sm_b.matcher.next_label == int(g['fwd_next_label'])
+        b_b = sm_b.backward(f_b, g_b, B, ov[cut:])
+        b_a = sm_a.backward(f_a, g_a, A, ov[:cut - 1], nxt=dict(sm_b.backward_state(b_b), overlaps=ov[cut - 1]))
+        for z, got in enumerate(f_a + f_b):
+            np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg({1: got}, (p['H'], p['W'])), g[f'fwd_{z}'])
+        for z, got in enumerate(b_a + b_b):
+            np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg({1: got}, (p['H'], p['W'])), g[f'bwd_{z}'])
