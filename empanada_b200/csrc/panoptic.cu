@@ -582,6 +582,12 @@ constexpr int kItemW = 64, kItemH = 4, kAssignThreads = 128, kAssignWarps = 4, k
 #endif
 constexpr int kStages = EMP_ASSIGN_STAGES;
 constexpr int kBlkItems = 16;                  // most strips per block (64 rows); small images use shorter blocks
+#ifndef EMP_ASSIGN_STAGE_ITEMS
+#define EMP_ASSIGN_STAGE_ITEMS 1
+#endif
+// strips per TMA box / ring stage.  Measured on config 2: 1 -> assign 0.58 ms, 2 -> 0.67 ms, 4 -> 0.84 ms: halving
+// the barrier waits and issues does not pay for the coarser prefetch (and the larger ring), so one strip per box.
+constexpr int kStageItems = EMP_ASSIGN_STAGE_ITEMS;
 constexpr unsigned kInfoThing = 0x8000u, kInfoBad = 0x4000u;   // per-pixel 16-bit info word
 constexpr unsigned kNoKey = 0xFFFFFFFFu;
 
@@ -841,7 +847,8 @@ assign_kernel(const __grid_constant__ AssignArgs a)
     constexpr bool kTma = FAST && SEM != SEM_NONE;
     constexpr uint32_t kClsBase = (OUT == OUT_CODE16) ? kClsBase16 : kClsBase32;
     constexpr int kRowBytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;       // one staged row of sem
-    constexpr unsigned kStageBytes = kItemH * kRowBytes;
+    constexpr unsigned kItemBytes = kItemH * kRowBytes;
+    constexpr unsigned kStageBytes = kStageItems * kItemBytes;
     extern __shared__ __align__(128) unsigned char dsm[];                   // [warp][stage][row][kRowBytes]
     __shared__ uint64_t s_bar[kAssignWarps][kStages];
 
@@ -879,17 +886,17 @@ assign_kernel(const __grid_constant__ AssignArgs a)
     int nxt = cur < n_blocks ? grab() : n_blocks;
     Blk kc = decode(cur), kn = decode(nxt);
 
-    // ---- TMA ring: one 64 x 4 box of the sem plane per strip, kStages strips ahead ------------------
+    // ---- TMA ring: one box of kStageItems strips (64 x 8 pixels) of the sem plane per stage, kStages boxes ahead ----
     unsigned char* ring = dsm + (size_t)warp * kStages * kStageBytes;
     uint64_t policy = 0;
-    int p_which = 0, p_i = 0, inflight = 0, st_issue = 0;   // prefetch position: block (0 cur, 1 nxt, 2 beyond), strip
+    int p_which = 0, p_i = 0, inflight = 0, st_issue = 0;   // prefetch position: block (0 cur, 1 nxt, 2 beyond), box within it
     auto pump = [&]() {
         while (inflight < kStages && p_which < 2) {
-            const int nit = p_which == 0 ? kc.nitems : kn.nitems;
+            const int nit = ((p_which == 0 ? kc.nitems : kn.nitems) + kStageItems - 1) / kStageItems;     // boxes of the block
             if (p_i < nit) {
                 if (lane == 0) {
                     const int pb = p_which == 0 ? kc.b : kn.b;
-                    const int prow = (p_which == 0 ? kc.row0 : kn.row0) + p_i * kItemH;
+                    const int prow = (p_which == 0 ? kc.row0 : kn.row0) + p_i * (kStageItems * kItemH);
                     const int pcol = p_which == 0 ? kc.colb : kn.colb;
                     mbar_expect_tx(&s_bar[warp][st_issue], kStageBytes);
                     tma_load_3d(ring + (size_t)st_issue * kStageBytes, &a.tmap, pcol, prow, pb, &s_bar[warp][st_issue], policy);
@@ -980,8 +987,9 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 #pragma unroll
             for (int p = 0; p < kPx; ++p) sv[p] = 0;
             if (kTma) {
-                mbar_wait(&s_bar[warp][st_cons], parity);
-                const unsigned char* sp = ring + (size_t)st_cons * kStageBytes;
+                const int sub = it % kStageItems;           // strip within the staged box
+                if (sub == 0) mbar_wait(&s_bar[warp][st_cons], parity);
+                const unsigned char* sp = ring + (size_t)st_cons * kStageBytes + sub * kItemBytes;
 #pragma unroll
                 for (int i = 0; i < kItemH; ++i) {
                     if (SEM == SEM_I64) {
@@ -992,19 +1000,21 @@ assign_kernel(const __grid_constant__ AssignArgs a)
                         sv[2 * i] = u & 255u; sv[2 * i + 1] = u >> 8;
                     }
                 }
-                __syncwarp();                               // every lane has its values: the slot is free
-                --inflight;
-                if (++st_cons == kStages) { st_cons = 0; parity ^= 1u; }
-                if (p_which == 0 && p_i < kc.nitems) {      // common case: the next strip of this block
-                    if (lane == 0) {
-                        mbar_expect_tx(&s_bar[warp][st_issue], kStageBytes);
-                        tma_load_3d(ring + (size_t)st_issue * kStageBytes, &a.tmap, kc.colb, kc.row0 + p_i * kItemH, kc.b,
-                                    &s_bar[warp][st_issue], policy);
+                if (sub == kStageItems - 1 || it + 1 == kc.nitems) {        // last strip of the box: the slot is free
+                    __syncwarp();                           // every lane has its values
+                    --inflight;
+                    if (++st_cons == kStages) { st_cons = 0; parity ^= 1u; }
+                    if (p_which == 0 && p_i * kStageItems < kc.nitems) {    // common case: the next box of this block
+                        if (lane == 0) {
+                            mbar_expect_tx(&s_bar[warp][st_issue], kStageBytes);
+                            tma_load_3d(ring + (size_t)st_issue * kStageBytes, &a.tmap, kc.colb, kc.row0 + p_i * (kStageItems * kItemH),
+                                        kc.b, &s_bar[warp][st_issue], policy);
+                        }
+                        ++p_i; ++inflight;
+                        st_issue = st_issue + 1 == kStages ? 0 : st_issue + 1;
+                    } else {
+                        pump();                             // block boundary: the general state machine
                     }
-                    ++p_i; ++inflight;
-                    st_issue = st_issue + 1 == kStages ? 0 : st_issue + 1;
-                } else {
-                    pump();                                 // block boundary: the general state machine
                 }
             } else if (SEM != SEM_NONE) {
 #pragma unroll
@@ -1522,7 +1532,7 @@ template <int SEM, int IDM, int OUT, bool FAST>
 static int launch_assign_f(const AssignArgs& a, cudaStream_t st)
 {
     constexpr int row_bytes = (SEM == SEM_I64) ? kItemW * 8 : kItemW;
-    constexpr int ring_bytes = kAssignWarps * kStages * kItemH * row_bytes;
+    constexpr int ring_bytes = kAssignWarps * kStages * kStageItems * kItemH * row_bytes;
     const size_t smem = (FAST && SEM != SEM_NONE) ? ring_bytes : 0;
     EMP_CUDA_CHECK(cudaFuncSetAttribute(assign_kernel<SEM, IDM, OUT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
     const long long n_blocks = (long long)a.blocks_x * a.blocks_y * a.B;
@@ -1540,7 +1550,7 @@ static int launch_assign_f(const AssignArgs& a, cudaStream_t st)
 static int make_sem_tensor_map(AssignArgs& a, int sem_mode)
 {
     return make_plane_tensor_map(&a.tmap, sem_mode == SEM_I64 ? CU_TENSOR_MAP_DATA_TYPE_INT64 : CU_TENSOR_MAP_DATA_TYPE_UINT8,
-                                 sem_mode == SEM_I64 ? 8 : 1, a.sem, a.B, a.H, a.W, a.sem_stride, kItemH, kItemW);
+                                 sem_mode == SEM_I64 ? 8 : 1, a.sem, a.B, a.H, a.W, a.sem_stride, kStageItems * kItemH, kItemW);
 }
 
 template <int SEM, int IDM, int OUT>
@@ -1573,7 +1583,7 @@ int launch_assign(int sem_mode, int id_mode, int out_mode, AssignArgs& a, cudaSt
     a.fast = a.vec;
     if (sem_mode == SEM_I64) a.fast = a.vec && aligned16(a.sem) && (a.sem_stride % 2 == 0);
     else if (sem_mode == SEM_U8) a.fast = a.vec && (a.W % 16 == 0) && aligned16(a.sem) && (a.sem_stride % 16 == 0);
-    if (sem_mode != SEM_NONE && (a.W < kItemW || a.H < kItemH)) a.fast = 0;       // the TMA box must fit the tensor
+    if (sem_mode != SEM_NONE && (a.W < kItemW || a.H < kStageItems * kItemH)) a.fast = 0;       // the TMA box must fit the tensor
     if (a.fast && sem_mode != SEM_NONE) {
         const int rc = make_sem_tensor_map(a, sem_mode);
         if (rc) return rc;
