@@ -123,7 +123,10 @@ __device__ __noinline__ bool nms_window_has_bigger(const float* __restrict__ hm,
 #ifndef EMP_NMS_CTAS_PER_SM
 #define EMP_NMS_CTAS_PER_SM 3
 #endif
-constexpr int kNmsRows = 4, kNmsWords = 8, kNmsStages = EMP_NMS_STAGES, kNmsWarps = 4, kNmsBlkItems = 16, kNmsCtasPerSm = EMP_NMS_CTAS_PER_SM;
+#ifndef EMP_NMS_WORDS
+#define EMP_NMS_WORDS 8
+#endif
+constexpr int kNmsRows = 4, kNmsWords = EMP_NMS_WORDS, kNmsStages = EMP_NMS_STAGES, kNmsWarps = 4, kNmsBlkItems = 16, kNmsCtasPerSm = EMP_NMS_CTAS_PER_SM;
 #ifndef EMP_NMS_HALO
 #define EMP_NMS_HALO 1
 #endif
