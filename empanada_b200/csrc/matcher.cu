@@ -119,3 +119,57 @@ EMP_API int emp_fill_runs(const int64_t* runs, size_t run_stride, const int32_t*
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Overlaps between two arbitrary run lists — the intersections behind consensus.object_iou_graph
+// (reference empanada/consensus.py:233-287: rle_iou of every box-overlapping pair of objects from
+// different trackers).  A = all runs of one tracker's objects, B = another's, each as (start, length,
+// slot) rows in ascending start order.  Unlike the slices of a stack, objects of one tracker may
+// overlap each other, so ends are not monotone: a thread takes one run of B, finds the first run of A
+// that starts after (its start - lmax_a) — no earlier run can reach it, lmax_a being A's longest run —
+// and walks while runs start before its end.
+// ---------------------------------------------------------------------------------------------
+namespace emp {
+
+__global__ void __launch_bounds__(256)
+rle_list_overlaps_kernel(const long long* __restrict__ A, int nA, long long lmax_a, const long long* __restrict__ B, int nB,
+                         int32_t* __restrict__ out, int cap, int32_t* __restrict__ count)
+{
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nB; j += gridDim.x * blockDim.x) {
+        const long long bs = B[3 * (size_t)j], be = bs + B[3 * (size_t)j + 1];
+        const int slot_b = (int)B[3 * (size_t)j + 2];
+        int lo = 0, hi = nA;                                    // first A run with start > bs - lmax_a
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (A[3 * (size_t)mid] > bs - lmax_a) hi = mid; else lo = mid + 1;
+        }
+        for (int i = lo; i < nA; ++i) {
+            const long long as = A[3 * (size_t)i];
+            if (as >= be) break;
+            const long long ov = min(as + A[3 * (size_t)i + 1], be) - max(as, bs);
+            if (ov > 0) {
+                const int pos = atomicAdd(count, 1);
+                if (pos < cap) reinterpret_cast<int4*>(out)[pos] = make_int4(0, (int)A[3 * (size_t)i + 2], slot_b, (int)ov);
+            }
+        }
+    }
+}
+
+}  // namespace emp
+
+EMP_API int emp_rle_list_overlaps(const int64_t* runs_a, int n_a, int64_t lmax_a, const int64_t* runs_b, int n_b,
+                                  int32_t* out, int cap, int32_t* count, void* stream)
+{
+    EMP_REQUIRE(runs_a && runs_b && out && count, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(n_a >= 0 && n_b >= 0 && cap >= 0 && lmax_a >= 0, EMP_ERR_INVALID, "bad sizes");
+    EMP_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, EMP_ERR_INVALID, "out must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    EMP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+    if (n_a == 0 || n_b == 0) return EMP_OK;
+    int bx = (n_b + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    rle_list_overlaps_kernel<<<bx, 256, 0, st>>>(reinterpret_cast<const long long*>(runs_a), n_a, (long long)lmax_a,
+                                                 reinterpret_cast<const long long*>(runs_b), n_b, out, cap, count);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}

@@ -190,6 +190,13 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
 int emp_rle_pair_overlaps(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices,
                           int max_runs, int32_t* out, int cap, int32_t* count, void* stream);
 
+/* Orthoplane consensus support — consensus.object_iou_graph (consensus.py:233-287): overlaps between
+ * the objects of two trackers.  runs_a / runs_b: (n, 3) int64 rows (start, length, slot) in ascending
+ * start order; objects of one list may overlap each other; lmax_a = longest run of A.  Output rows
+ * (0, slot_a, slot_b, overlap) as for emp_rle_pair_overlaps; count must be re-checked against cap. */
+int emp_rle_list_overlaps(const int64_t* runs_a, int n_a, int64_t lmax_a, const int64_t* runs_b, int n_b,
+                          int32_t* out, int cap, int32_t* count, void* stream);
+
 /* Dense fill of a z-block — array_utils.numpy_fill_instances (array_utils.py:725-736) over the run
  * tables in HBM: every run (start, length, slot) of slice s paints labels[s][slot] over
  * [start, start + length) of plane s of `out`; voxels no run covers keep their value; a negative label

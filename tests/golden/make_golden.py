@@ -521,8 +521,103 @@ def tracker_cases():
     save('tracker_axes', **res)
 
 
+# ---------------------------------------------------------------------------------------------
+# orthoplane consensus: the reference's merge_objects_from_trackers / merge_semantic_from_trackers
+# ---------------------------------------------------------------------------------------------
+def _ball(r):
+    g = np.arange(-r, r + 1)
+    z, y, x = np.meshgrid(g, g, g, indexing='ij')
+    return (z * z + y * y + x * x <= r * r).astype(np.int64)       # skimage.morphology.ball
+
+
+def _trackers_from_volumes(rtrack, vols, L=1000):
+    trs = []
+    for vol in vols:
+        tr = rtrack.InstanceTracker(1, L, vol.shape, axis='xy')    # tests/test_consensus.py uses 'xy' for all three
+        for i, sl in enumerate(vol):
+            tr.update(rrle.pan_seg_to_rle_seg(np.ascontiguousarray(sl), [1], L, [1], force_connected=False)[1], i)
+        tr.finish()
+        trs.append(tr)
+    return trs
+
+
+def _flat_instances(inst):
+    labs = list(inst.keys())
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.int64)
+    return (np.asarray(labs, np.int64), np.asarray([inst[l]['box'] for l in labs], np.int64).reshape(len(labs), -1),
+            np.asarray([len(inst[l]['starts']) for l in labs], np.int64),
+            cat([np.asarray(inst[l]['starts'], np.int64) for l in labs]), cat([np.asarray(inst[l]['runs'], np.int64) for l in labs]))
+
+
+def consensus_cases():
+    import empanada.array_utils as rau
+    from empanada import consensus as rcons
+    from empanada.inference import tracker as rtrack
+    try:                                            # numba 0.65 cannot compile rle_voting (internal AssertionError):
+        rau.rle_voting(np.array([[0, 5], [2, 8]]), 2)
+    except Exception:                               # run the reference's own Python body of it instead
+        rau.rle_voting = rau.rle_voting.py_func
+        rcons.rle_voting = rau.rle_voting
+    SETTINGS = [(2, 0.75, False), (2, 0.5, False), (1, 0.75, False), (1, 0.75, True), (3, 0.75, False)]
+
+    def run(name, vols):
+        res = {f'in_vol_{i}': v.astype(np.int32) for i, v in enumerate(vols)}
+        for k, (vote, thr, bypass) in enumerate(SETTINGS):
+            trs = _trackers_from_volumes(rtrack, vols)
+            inst = rcons.merge_objects_from_trackers(trs, pixel_vote_thr=vote, cluster_iou_thr=thr, bypass=bypass)
+            for key, arr in zip(('labels', 'boxes', 'counts', 'starts', 'runs'), _flat_instances(inst)):
+                res[f'obj{k}_{key}'] = arr
+            print(f'  {name} objects vote={vote} thr={thr} bypass={bypass}: {len(inst)} instances')
+        for k, vote in enumerate((2, 1, 3)):
+            trs = _trackers_from_volumes(rtrack, vols)
+            for tr in trs:
+                if tr.instances:
+                    tr.instances = {1001: rcons.merge_instances(tr.instances)}
+            inst = rcons.merge_semantic_from_trackers(trs, pixel_vote_thr=vote)
+            for key, arr in zip(('labels', 'boxes', 'counts', 'starts', 'runs'), _flat_instances(inst)):
+                res[f'sem{k}_{key}'] = arr
+        save(name, params=json.dumps(dict(settings=SETTINGS, sem_votes=[2, 1, 3])), **res)
+
+    # 1. the reference's known-answer construction (tests/test_consensus.py:10-60) at half scale
+    shape = (50, 50, 50)
+    s2 = _ball(10)
+    s4 = s2.copy()
+    s4[:, 10:, 10:] = 0
+    xy, xz, yz = (np.zeros(shape, np.int64) for _ in range(3))
+    xy[:21, :21, :21][s2 > 0] = 1001
+    xy[8:29, 8:29, 8:29][s2 > 0] = 1002
+    xz[:21, :21, :21][s2 > 0] = 1005
+    xz[8:29, 8:29, 8:29][s4 > 0] = 1004
+    xz[:21, 29:50, 29:50][s2 > 0] = 1006
+    yz[:21, :21, :21][s2 > 0] = 1003
+    yz[8:29, 8:29, 8:29][s4 > 0] = 1003
+    run('consensus_spheres', [xy, xz, yz])
+
+    # 2. many objects seen three times with independent errors: eroded / shifted / split / missing copies
+    rng = np.random.default_rng(91)
+    shape = (40, 56, 64)
+    zz, yy, xx = np.mgrid[0:shape[0], 0:shape[1], 0:shape[2]]
+    vols = [np.zeros(shape, np.int64) for _ in range(3)]
+    for i in range(26):
+        c = np.array([rng.uniform(4, shape[0] - 4), rng.uniform(5, shape[1] - 5), rng.uniform(5, shape[2] - 5)])
+        r = rng.uniform(3, 7, 3)
+        for v, vol in enumerate(vols):
+            if rng.random() < 0.12:
+                continue                                            # this view missed the object
+            cc = c + rng.normal(0, 0.7, 3)
+            rr = r * rng.uniform(0.85, 1.1)
+            m = ((zz - cc[0]) / rr[0]) ** 2 + ((yy - cc[1]) / rr[1]) ** 2 + ((xx - cc[2]) / rr[2]) ** 2 <= 1
+            lab = 1001 + i + 100 * v
+            if rng.random() < 0.15:                                 # a false split: two labels for one object
+                vol[m & (xx < cc[2])] = lab
+                vol[m & (xx >= cc[2])] = lab + 50
+            else:
+                vol[m] = lab
+    run('consensus_blobs', vols)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker']
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker', 'consensus']
     if 'pp' in which:
         pp_cases()
     if 'merge' in which:
@@ -535,3 +630,5 @@ if __name__ == '__main__':
         matcher_cases()
     if 'tracker' in which:
         tracker_cases()
+    if 'consensus' in which:
+        consensus_cases()
