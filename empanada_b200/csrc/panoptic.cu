@@ -1302,58 +1302,102 @@ __global__ void __launch_bounds__(256)
 apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
     constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
+#ifndef EMP_APPLY_BATCH
+#define EMP_APPLY_BATCH 4
+#endif
+    constexpr int kBatch = EMP_APPLY_BATCH;                         // unflagged strips whose code loads are issued together
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
     const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
     const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
+    const uint4* flags = reinterpret_cast<const uint4*>(ws + a.o_sflags);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = a.H, W = a.W;
-    const int blk = (int)blockIdx.x * 8 + warp;
-    if (blk >= a.blocks_x * a.blocks_y) return;                     // warp-uniform
-    const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
-    const int colb = bx * kItemW, rowb = by * (a.blk_items * kItemH);
-    const int col0 = colb + 2 * lane;
-    const int nitems = min(a.blk_items, (H - rowb + kItemH - 1) / kItemH);
-    const bool cols_full = colb + kItemW <= W;
+    const int n_blocks = a.blocks_x * a.blocks_y;
+    const int stride = (int)gridDim.x * 8;                          // warps along x: each walks blocks blk, blk + stride, ...
+    int blk = (int)blockIdx.x * 8 + warp;
+    if (blk >= n_blocks) return;                                    // warp-uniform
+    uint4 fl_next = __ldg(flags + blk);                             // the next block's flags are always in flight
+    const long long bg = decode<C16>(kClsBase, lut, areas, a);      // label of class-0 stuff, once per warp
 
-    const uint4 fl = *reinterpret_cast<const uint4*>(ws + a.o_sflags + (size_t)blk * kBlkItems);
-    const long long bg = decode<C16>(kClsBase, lut, areas, a);      // label of class-0 stuff
-
-    for (int it = 0; it < nitems; ++it) {
-        const int row0 = rowb + it * kItemH;
-        const unsigned fw = it < 4 ? fl.x : it < 8 ? fl.y : it < 12 ? fl.z : fl.w;
-        const bool flagged = ((fw >> (8 * (it & 3))) & 0xFFu) != 0u;
-        const size_t px0 = (size_t)row0 * W + col0;
-        if (FAST && flagged) {                                      // flagged strips are always full strips
+    for (; blk < n_blocks; blk += stride) {
+        const uint4 fl = fl_next;
+        if (blk + stride < n_blocks) fl_next = __ldg(flags + blk + stride);
+        const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
+        const int colb = bx * kItemW, rowb = by * (a.blk_items * kItemH);
+        const int col0 = colb + 2 * lane;
+        const int nitems = min(a.blk_items, (H - rowb + kItemH - 1) / kItemH);
+        const bool cols_full = colb + kItemW <= W;
+        unsigned fmask = 0;                                         // bit it: strip `it` is flagged (all class-0 stuff)
 #pragma unroll
-            for (int i = 0; i < kItemH; ++i) __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W), make_longlong2(bg, bg));
-            continue;
+        for (int q = 0; q < 4; ++q) {
+            const unsigned wq = q == 0 ? fl.x : q == 1 ? fl.y : q == 2 ? fl.z : fl.w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) fmask |= (((wq >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 * q + k);
         }
-        const bool full = cols_full && row0 + kItemH <= H;
-        if (FAST && full) {
-            unsigned c0[kItemH], c1[kItemH];
+        const unsigned live = (1u << nitems) - 1u;                  // nitems <= 16
+        fmask &= live;
+
+        if (FAST) {
+            // unflagged full strips: issue the code loads of up to kBatch strips together ...
+            unsigned todo = live & ~fmask;
+            if (!cols_full) todo = 0;
+            else if (rowb + nitems * kItemH > H) todo &= ~(1u << (nitems - 1));      // a bottom strip cut by the image edge
+            const unsigned edge = (live & ~fmask) & ~todo;          // partial strips: scalar path below
+            // ... but first the flagged strips (always full strips): pure stores, nothing to wait for
+            for (unsigned m = fmask; m; m &= m - 1) {
+                const size_t px0 = (size_t)(rowb + (__ffs(m) - 1) * kItemH) * W + col0;
 #pragma unroll
-            for (int i = 0; i < kItemH; ++i) {
-                if (C16) {
-                    const unsigned u = __ldcs(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(ws + a.o_codes) + px0 + (size_t)i * W));
-                    c0[i] = u & 0xFFFFu; c1[i] = u >> 16;
-                } else {
-                    const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + px0 + (size_t)i * W));
-                    c0[i] = u.x; c1[i] = u.y;
+                for (int i = 0; i < kItemH; ++i) __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W), make_longlong2(bg, bg));
+            }
+            while (todo) {
+                int its[kBatch];
+                unsigned cw[kBatch][kItemH], ch[kBatch][kItemH];
+#pragma unroll
+                for (int s2 = 0; s2 < kBatch; ++s2) {
+                    its[s2] = todo ? __ffs(todo) - 1 : -1;
+                    todo &= todo - 1;                               // (0 & -1 stays 0)
+#pragma unroll
+                    for (int i = 0; i < kItemH; ++i) {
+                        cw[s2][i] = 0; ch[s2][i] = 0;
+                        if (its[s2] >= 0) {
+                            const size_t e = (size_t)(rowb + its[s2] * kItemH + i) * W + col0;
+                            if (C16) {
+                                cw[s2][i] = __ldcs(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(ws + a.o_codes) + e));
+                            } else {
+                                const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + e));
+                                cw[s2][i] = u.x; ch[s2][i] = u.y;
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int s2 = 0; s2 < kBatch; ++s2) {
+                    if (its[s2] < 0) continue;
+#pragma unroll
+                    for (int i = 0; i < kItemH; ++i) {
+                        const size_t e = (size_t)(rowb + its[s2] * kItemH + i) * W + col0;
+                        const unsigned c0 = C16 ? (cw[s2][i] & 0xFFFFu) : cw[s2][i];
+                        const unsigned c1 = C16 ? (cw[s2][i] >> 16) : ch[s2][i];
+                        __stcs(reinterpret_cast<longlong2*>(pan + e), make_longlong2(decode<C16>(c0, lut, areas, a), decode<C16>(c1, lut, areas, a)));
+                    }
                 }
             }
-#pragma unroll
-            for (int i = 0; i < kItemH; ++i)
-                __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W),
-                       make_longlong2(decode<C16>(c0[i], lut, areas, a), decode<C16>(c1[i], lut, areas, a)));
-        } else {
+            fmask = ~edge;                                          // what is left for the scalar loop: the partial strips
+        }
+
+        for (int it = 0; it < nitems; ++it) {
+            const bool flagged = (fmask >> it) & 1u;
+            if (FAST && flagged) continue;                          // done above
+            const int row0 = rowb + it * kItemH;
+            const size_t px0 = (size_t)row0 * W + col0;
 #pragma unroll
             for (int i = 0; i < kItemH; ++i) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     if (row0 + i < H && col0 + j < W) {
                         const size_t e = px0 + (size_t)i * W + j;
-                        const unsigned code = flagged ? kClsBase
+                        const unsigned code = (!FAST && flagged) ? kClsBase
                                             : C16 ? (unsigned)reinterpret_cast<const unsigned short*>(ws + a.o_codes)[e]
                                                   : reinterpret_cast<const unsigned*>(ws + a.o_codes)[e];
                         pan[e] = decode<C16>(code, lut, areas, a);
@@ -1632,7 +1676,14 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     a.blocks_y = (H + a.blk_items * kItemH - 1) / (a.blk_items * kItemH);
     a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
     const bool fast = aligned16(pan_out) && W % 4 == 0;             // 16-byte label stores, 4-byte code loads
-    const long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
+    long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
+    // One block per warp is the default.  The kernel can also walk several blocks per warp with the next block's
+    // flags prefetched (EMP_APPLY_CTAS_PER_SM = resident CTAs per SM), but every persistent grid measured slower
+    // (config 2, ms per batch: 0 -> 0.391, 3 -> 0.480, 5 -> 0.479, 8 -> 0.451, 12 -> 0.435).
+    static int per_sm = -1;
+    if (per_sm < 0) { const char* e = getenv("EMP_APPLY_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; }
+    const long long want = ((long long)sm_count() * per_sm + B - 1) / B;
+    if (per_sm > 0 && blocks > want) blocks = want;
     dim3 grid((unsigned)blocks, 1, B);
     ProfScope ps(ST_APPLY, st);
     // The block walk is the default: on config 2 the row-linear kernel (EMP_APPLY_VARIANT=1..3, the three
