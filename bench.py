@@ -45,6 +45,42 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print there (NCCL's version banner on the first
+    communicator, nvidia-smi children) are pointed at stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
+def bind_near_gpu(index):
+    """Pin this rank's host threads (and so, by first touch, its pinned staging buffers) to the CPU set NVML
+    reports as closest to the GPU; only matters for the host-buffer path on multi-socket boxes."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception as e:                                   # best effort: an unbound rank is still correct
+        return f'unbound ({type(e).__name__})'
+
+
 def ncu_traffic(kernel):
     """DRAM bytes per pixel of `kernel` from the committed ncu capture of this command
     (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch / pixels per launch)."""
@@ -145,7 +181,7 @@ def run_reference(args, rank):
                              'sample': sample + '; one crop per step'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -164,6 +200,7 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    claim_stdout()
 
     if args.impl == 'reference':
         if args.impl == 'reference' and args.steps > 3:
@@ -183,6 +220,7 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        log(f'[rank {rank}] host threads bound to {bind_near_gpu(local_rank)} cpus near gpu {local_rank}')
     B = args.tiles
     n_px = H * W
 
@@ -318,7 +356,7 @@ def main():
             v, dt, k, threads, sample = cpu_reference_sample()
             line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                     'sample': f'{sample}; {dt:.1f} s'}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

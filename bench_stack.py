@@ -44,6 +44,9 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
+    sys.stdout.flush()
+    json_fd = os.dup(1)                 # stdout carries the ONE JSON line; NCCL's banner etc. go to stderr
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -124,14 +127,14 @@ def main():
         match_cpu = {'ms_per_slice_forward_only': 1e3 * (time.perf_counter() - t) / max(len(zs) - 1, 1), 'slices': len(zs),
                      'kind': 'port', 'cores': 1}
     if rank == 0:
-        print(json.dumps({
+        os.write(json_fd, (json.dumps({
             'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
             'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
             'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
             'matcher_cpu_baseline': match_cpu,
             'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
                        'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
-        }), flush=True)
+        }) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
