@@ -13,7 +13,7 @@ All randomness is ``numpy.random.default_rng(seed)``; the same seed gives the sa
 """
 import numpy as np
 
-__all__ = ['synth_instances', 'synth_tile', 'synth_stack_slices']
+__all__ = ['synth_instances', 'synth_tile', 'synth_stack_slices', 'synth_heads', 'synth_blob_volume']
 
 
 def synth_instances(H, W, n_instances, rng, semi_axes=(12.0, 40.0)):
@@ -178,3 +178,45 @@ def synth_stack_slices(D, H, W, n_blobs, seed, coarse=4, sigma=6.0, noise=0.5,
         p = np.where(ins > 0, np.float32(0.9), np.float32(0.1)).astype(np.float32)
         p += srng.uniform(-0.05, 0.05, p.shape).astype(np.float32)
         yield {'sem_prob': p[None, None], 'ctr_hmp': hm[None, None], 'offsets': off[None], 'ins': ins}
+
+
+def synth_heads(ins, rng, sigma=2.5, noise=0.5, prob_noise=0.22, prob_step=1.0 / 64, off_step=1.0 / 8):
+    """Head tensors for ONE given (H,W) instance slice (any axis of a volume): 'sem_prob' (1,1,H,W),
+    'ctr_hmp' (1,1,H,W), 'offsets' (1,2,H,W), all float32.  The jitter is quantised (prob_step / off_step)
+    so that fixtures holding many slices compress well; ties and near-ties become MORE likely that way."""
+    H, W = ins.shape
+    hm = np.zeros((H, W), np.float32)
+    off = np.zeros((2, H, W), np.float32)
+    if ins.max() > 0:
+        ok, cyc, cxc = _centroids(ins)
+        r = int(np.ceil(4 * sigma))
+        g1 = np.exp(-(np.arange(-r, r + 1, dtype=np.float32) ** 2) / np.float32(2 * sigma * sigma))
+        g2 = np.outer(g1, g1).astype(np.float32)
+        for i in np.flatnonzero(ok):
+            y, x = int(cyc[i]), int(cxc[i])
+            y0, y1 = max(0, y - r), min(H, y + r + 1)
+            x0, x1 = max(0, x - r), min(W, x + r + 1)
+            hm[y0:y1, x0:x1] += g2[y0 - (y - r):y1 - (y - r), x0 - (x - r):x1 - (x - r)]
+        hm /= hm.max()
+        yy, xx = np.nonzero(ins)
+        lab = ins[yy, xx]
+        jit = rng.standard_normal((2, yy.size)) * noise
+        off[0, yy, xx] = np.round((cyc[lab] - yy + jit[0]) / off_step) * off_step
+        off[1, yy, xx] = np.round((cxc[lab] - xx + jit[1]) / off_step) * off_step
+    p = np.where(ins > 0, 0.9, 0.1) + rng.uniform(-prob_noise, prob_noise, ins.shape)
+    p = np.clip(np.round(p / prob_step) * prob_step, prob_step, 1 - prob_step).astype(np.float32)
+    return {'sem_prob': p[None, None], 'ctr_hmp': hm[None, None], 'offsets': off[None]}
+
+
+def synth_blob_volume(shape, n_blobs, seed, radii=(4.0, 9.0)):
+    """(D,H,W) int32 instance volume of axis-aligned ellipsoids (later ones overwrite earlier ones)."""
+    rng = np.random.default_rng(seed)
+    D, H, W = shape
+    zz, yy, xx = np.mgrid[0:D, 0:H, 0:W].astype(np.float32)
+    vol = np.zeros(shape, np.int32)
+    c = rng.uniform(0, 1, (n_blobs, 3)) * np.array(shape)
+    rad = rng.uniform(radii[0], radii[1], (n_blobs, 3))
+    for i in range(n_blobs):
+        m = ((zz - c[i, 0]) / rad[i, 0]) ** 2 + ((yy - c[i, 1]) / rad[i, 1]) ** 2 + ((xx - c[i, 2]) / rad[i, 2]) ** 2 <= 1
+        vol[m] = i + 1
+    return vol

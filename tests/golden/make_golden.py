@@ -616,8 +616,98 @@ def consensus_cases():
     run('consensus_blobs', vols)
 
 
+# ---------------------------------------------------------------------------------------------
+# orthoplane chain (BASELINE configs[3] in miniature): the reference's scripts/pdl_inference3d.py flow
+# — Render engine per slice along xy / xz / yz, RLE, forward + backward matching, trackers, filters,
+# instance consensus, filling — on replayed head tensors of one small blob volume
+# ---------------------------------------------------------------------------------------------
+def _patch_rle_voting():
+    import empanada.array_utils as rau
+    from empanada import consensus as rcons
+    try:
+        rau.rle_voting(np.array([[0, 5], [2, 8]]), 2)
+    except Exception:
+        rau.rle_voting = rau.rle_voting.py_func
+        rcons.rle_voting = rau.rle_voting
+
+
+def ortho_cases():
+    from empanada.inference import patterns as rpat, filters as rfilt
+    from empanada_b200.synth import synth_blob_volume, synth_heads
+    _patch_rle_voting()
+    shape, L, seed = (36, 40, 44), 1000, 7
+    P = dict(thing_list=[1], labels=[1], label_divisor=L, stuff_area=16, void_label=0, nms_threshold=0.1, nms_kernel=3,
+             confidence_thr=0.3, median_kernel_size=3, padding_factor=16, coarse_boundaries=False,
+             merge_iou_thr=0.25, merge_ioa_thr=0.25, min_size=40, min_span=3, pixel_vote_thr=2,
+             cluster_iou_thr=0.75, shape=list(shape))
+    vol = synth_blob_volume(shape, 12, seed)
+    axes = {'xy': 0, 'xz': 1, 'yz': 2}
+    res = {'in_vol': vol}
+    trackers = rpat.create_axis_trackers(axes, P['labels'], L, shape)
+    for name, axis in axes.items():
+        n = shape[axis]
+        h, w = [d for a, d in enumerate(shape) if a != axis]
+        Hp, Wp = -(-h // 16) * 16, -(-w // 16) * 16
+        outs = []
+        for i in range(n):
+            padded = np.zeros((Hp, Wp), np.int32)
+            padded[:h, :w] = np.take(vol, i, axis=axis)
+            hd = synth_heads(padded, np.random.default_rng([seed, axis, i]))
+            o = {'sem_logits': logit(hd['sem_prob']), 'ctr_hmp': hd['ctr_hmp'], 'offsets': hd['offsets']}
+            for k, v in o.items():
+                res[f'in_{name}_{i}_{k}'] = v
+            outs.append({k: t(v) for k, v in o.items()})
+        eng = reng.PanopticDeepLabRenderEngine3d(
+            ReplayModel(outs), thing_list=P['thing_list'], median_kernel_size=P['median_kernel_size'],
+            label_divisor=L, stuff_area=P['stuff_area'], void_label=P['void_label'], nms_threshold=P['nms_threshold'],
+            nms_kernel=P['nms_kernel'], confidence_thr=P['confidence_thr'], padding_factor=P['padding_factor'],
+            coarse_boundaries=False)
+        matchers = rpat.create_matchers(P['thing_list'], L, P['merge_iou_thr'], P['merge_ioa_thr'])
+        rle_stack = []
+
+        def take(pan):
+            seg = rrle.pan_seg_to_rle_seg(pan.squeeze().cpu().numpy(), P['labels'], L, P['thing_list'], force_connected=True)
+            rle_stack.append(rpat.apply_matchers(seg, matchers))
+
+        for i in range(n):
+            pan = eng(torch.zeros(1, 1, h, w), (h, w), upsampling=1)
+            if pan is not None:
+                take(pan)
+        for pan in eng.end(1):
+            take(pan)
+        assert len(rle_stack) == n
+        for index, seg in rpat.backward_matching(rle_stack, matchers, n):
+            rpat.update_trackers(seg, index, trackers[name])
+        # the script fills the per-axis panoptic stack BEFORE finish_tracking (pdl_inference3d.py:198-208), which
+        # raises in numpy_fill_instances (starts are still lists of arrays); the working order is used here
+        rpat.finish_tracking(trackers[name])
+        stack = np.zeros(shape, np.uint32)
+        rpat.fill_panoptic_volume(stack, trackers[name])
+        res[f'out_{name}_stack'] = stack
+        for tr in trackers[name]:
+            rfilt.remove_small_objects(tr, min_size=P['min_size'])
+            rfilt.remove_pancakes(tr, min_span=P['min_span'])
+            for key, arr in zip(('labels', 'boxes', 'counts', 'starts', 'runs'), _flat_instances(tr.instances)):
+                res[f'out_{name}_{key}'] = arr
+        print(f'  ortho {name}: {len(trackers[name][0].instances)} instances after filters, '
+              f'{len(np.unique(stack)) - 1} labels painted')
+    cons = rpat.create_instance_consensus(rpat.get_axis_trackers_by_class(trackers, 1), P['pixel_vote_thr'],
+                                          P['cluster_iou_thr'], False)
+    rfilt.remove_small_objects(cons, min_size=P['min_size'])
+    rfilt.remove_pancakes(cons, min_span=P['min_span'])
+    for key, arr in zip(('labels', 'boxes', 'counts', 'starts', 'runs'), _flat_instances(cons.instances)):
+        res[f'out_cons_{key}'] = arr
+    cvol = np.zeros(shape, np.uint32)
+    rpat.fill_volume(cvol, cons.instances)
+    res['out_cons_vol'] = cvol
+    print(f'  ortho consensus: {len(cons.instances)} instances ({len(np.unique(vol)) - 1} blobs in the volume)')
+    save('ortho_chain', params=json.dumps(P), **res)
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker', 'consensus']
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker', 'consensus', 'ortho']
+    if 'ortho' in which:
+        ortho_cases()
     if 'pp' in which:
         pp_cases()
     if 'merge' in which:
