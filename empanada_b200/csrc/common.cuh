@@ -48,6 +48,7 @@ struct WsLayout {
     size_t status, rowcnt, areas, votes, zero_bytes;
     size_t mask, centers, ctr_i, cell_start, cell_fill, sorted, lut, sflags, codes, total;
     int wd;          // mask words per row
+    int cls_off;     // label LUT: entries [0, k_cap] map instance ids, [cls_off, cls_off + kNumClasses) map stuff classes
     bool code16;
 };
 
@@ -69,7 +70,8 @@ static inline WsLayout ws_layout(int H, int W, int k_cap, int n_things)
     L.cell_start = o; o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
     L.cell_fill = o;  o = align_up(o + sizeof(int) * (kMaxCells + 2), 256);
     L.sorted = o;  o = align_up(o + sizeof(float4) * ((size_t)k_cap + 1), 256);     // (cy, cx, bits of k, -) grouped by cell
-    L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1), 256);
+    L.cls_off = k_cap + 1;
+    L.lut = o;     o = align_up(o + sizeof(int64_t) * ((size_t)k_cap + 1 + kNumClasses), 256);
     // one flag byte per 4 x 64 strip in slots of 16 per block (blocks row-major; a block is 1..16 strips tall)
     L.sflags = o;  o = align_up(o + (size_t)16 * ((W + 63) / 64) * ((H + 3) / 4), 256);
     L.codes = o;   o = align_up(o + (L.code16 ? 2 : 4) * (size_t)H * W, 256);

@@ -1255,10 +1255,21 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 
 // label LUT: one CTA per tile
 __global__ void __launch_bounds__(256)
-build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_votes, size_t o_lut, int k_cap, int k_fixed,
-                 const int32_t* k_dev, const __grid_constant__ Things things, long long label_divisor, long long void_label)
+build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_votes, size_t o_lut, size_t o_areas, int k_cap,
+                 int k_fixed, const int32_t* k_dev, const __grid_constant__ Things things, long long label_divisor,
+                 long long void_label, long long stuff_area, long long n_px)
 {
     char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
+    // stuff classes (postprocess.py:287-294): class c keeps its label c * L if it covers at least stuff_area pixels, else
+    // void; class 0's area is the complement of everything assign counted.  Entries of thing classes are never looked up.
+    {
+        const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + o_areas);
+        long long* cls = reinterpret_cast<long long*>(ws + o_lut) + (k_cap + 1);
+        for (int c = threadIdx.x; c < kNumClasses; c += 256) {
+            const long long area = c ? (long long)__ldcg(areas + c) : n_px - (long long)__ldcg(areas + kNumClasses);
+            cls[c] = area >= stuff_area ? (long long)c * label_divisor : void_label;
+        }
+    }
     __shared__ LutScratch sc;
     __shared__ long long s_k;
     if (threadIdx.x == 0) s_k = lut_extent(k_fixed, k_cap, reinterpret_cast<const int32_t*>(ws + o_status), k_dev);
@@ -1278,27 +1289,25 @@ build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_vote
 // ---------------------------------------------------------------------------------------------
 struct ApplyArgs {
     char* ws; size_t ws_stride;
-    size_t o_codes, o_lut, o_areas, o_sflags;
+    size_t o_codes, o_lut, o_sflags;
     long long* pan; size_t n_px;
     int H, W, blocks_x, blocks_y, blk_items;
-    long long label_divisor, stuff_area, void_label;
+    unsigned cls_off;                                               // lut[cls_off + c]: label of stuff class c
 };
 
+// one table look-up per pixel: build_lut resolved ids AND stuff classes (area test included) into labels
 template <bool C16>
-__device__ __forceinline__ long long decode(unsigned code, const long long* __restrict__ lut,
-                                            const uint32_t* __restrict__ areas, const ApplyArgs& a)
+__device__ __forceinline__ long long decode(unsigned code, const long long* __restrict__ lut, unsigned cls_off)
 {
     constexpr uint32_t base = C16 ? kClsBase16 : kClsBase32;
-    if (code >= base) {
-        const unsigned c = code - base;
-        const long long area = c ? (long long)__ldg(areas + c) : (long long)a.n_px - (long long)__ldg(areas + kNumClasses);
-        return (area >= a.stuff_area) ? (long long)c * a.label_divisor : a.void_label;
-    }
-    return __ldg(lut + code);
+    return __ldg(lut + (code >= base ? code - base + cls_off : code));
 }
 
+#ifndef EMP_APPLY_MIN_CTAS
+#define EMP_APPLY_MIN_CTAS 1
+#endif
 template <bool C16, bool FAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, EMP_APPLY_MIN_CTAS)
 apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
     constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
@@ -1308,7 +1317,6 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
     constexpr int kBatch = EMP_APPLY_BATCH;                         // unflagged strips whose code loads are issued together
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
     const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
-    const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
     const uint4* flags = reinterpret_cast<const uint4*>(ws + a.o_sflags);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1317,8 +1325,11 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
     const int stride = (int)gridDim.x * 8;                          // warps along x: each walks blocks blk, blk + stride, ...
     int blk = (int)blockIdx.x * 8 + warp;
     if (blk >= n_blocks) return;                                    // warp-uniform
-    uint4 fl_next = __ldg(flags + blk);                             // the next block's flags are always in flight
-    const long long bg = decode<C16>(kClsBase, lut, areas, a);      // label of class-0 stuff, once per warp
+#ifndef EMP_APPLY_DEBUG
+#define EMP_APPLY_DEBUG 0                                            // timing experiments only (profiles/README.md): 1 = every strip
+#endif                                                              // flagged, 2 = + constant label, 3 = + no flag load
+    uint4 fl_next = EMP_APPLY_DEBUG >= 3 ? make_uint4(~0u, ~0u, ~0u, ~0u) : __ldg(flags + blk);   // the next block's flags are always in flight
+    const long long bg = EMP_APPLY_DEBUG >= 2 ? 7ll : decode<C16>(kClsBase, lut, a.cls_off);      // label of class-0 stuff, once per warp
 
     for (; blk < n_blocks; blk += stride) {
         const uint4 fl = fl_next;
@@ -1336,6 +1347,7 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
             for (int k = 0; k < 4; ++k) fmask |= (((wq >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 * q + k);
         }
         const unsigned live = (1u << nitems) - 1u;                  // nitems <= 16
+        if (EMP_APPLY_DEBUG >= 1) fmask = ~0u;
         fmask &= live;
 
         if (FAST) {
@@ -1379,7 +1391,7 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
                         const size_t e = (size_t)(rowb + its[s2] * kItemH + i) * W + col0;
                         const unsigned c0 = C16 ? (cw[s2][i] & 0xFFFFu) : cw[s2][i];
                         const unsigned c1 = C16 ? (cw[s2][i] >> 16) : ch[s2][i];
-                        __stcs(reinterpret_cast<longlong2*>(pan + e), make_longlong2(decode<C16>(c0, lut, areas, a), decode<C16>(c1, lut, areas, a)));
+                        __stcs(reinterpret_cast<longlong2*>(pan + e), make_longlong2(decode<C16>(c0, lut, a.cls_off), decode<C16>(c1, lut, a.cls_off)));
                     }
                 }
             }
@@ -1400,11 +1412,100 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
                         const unsigned code = (!FAST && flagged) ? kClsBase
                                             : C16 ? (unsigned)reinterpret_cast<const unsigned short*>(ws + a.o_codes)[e]
                                                   : reinterpret_cast<const unsigned*>(ws + a.o_codes)[e];
-                        pan[e] = decode<C16>(code, lut, areas, a);
+                        pan[e] = decode<C16>(code, lut, a.cls_off);
                     }
                 }
             }
         }
+    }
+}
+
+// apply_lut for the common case (16-bit codes, aligned planes): the same block walk, but ALL code loads of a
+// block are started up front as 4-byte cp.async copies into a per-warp staging area in shared memory (no
+// registers held, up to 64 in flight per lane), the flagged strips are streamed out while they fly, and the
+// unflagged strips are decoded from shared memory after one wait.  The register-batched kernel above needs a
+// DRAM round trip per kBatch strips, under a write stream that makes each one long.  Each 64 x 64 block is shared
+// by EMP_APPLY_SPLIT warps (a pure store stream runs best with little work per warp: profiles/store_patterns.cu).
+// Measured on config 2 (ms per batch): register-batched 0.384, staged split 1 / 2 / 4: 0.3765 / 0.3785 / 0.3749; an
+// L2 evict-first hint on the code copies changes nothing.  With every strip forced "flagged" the kernel takes 0.321
+// and a bare store kernel of this geometry 0.304: what is left above that comes with the code reads of thing strips.
+#ifndef EMP_APPLY_SPLIT
+#define EMP_APPLY_SPLIT 4
+#endif
+constexpr int kApplySplit = EMP_APPLY_SPLIT;                       // warps sharing one block (each takes 16 / split strips)
+constexpr int kApplyPer = kBlkItems / kApplySplit;                  // strips per warp
+__global__ void __launch_bounds__(128)
+apply_lut_staged_kernel(const __grid_constant__ ApplyArgs a)
+{
+    constexpr uint32_t kClsBase = kClsBase16;
+    __shared__ unsigned stage[4][kApplyPer * kItemH][32];          // per warp: its strips' codes (two per word)
+    char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
+    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
+    const unsigned short* codes = reinterpret_cast<const unsigned short*>(ws + a.o_codes);
+    long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.H, W = a.W;
+    const int blk = (int)blockIdx.x * (4 / kApplySplit) + warp / kApplySplit;
+    const int part = warp % kApplySplit;
+    if (blk >= a.blocks_x * a.blocks_y) return;                     // warp-uniform
+    const uint4 fl = __ldg(reinterpret_cast<const uint4*>(ws + a.o_sflags) + blk);
+    const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
+    const int colb = bx * kItemW, rowb = by * (a.blk_items * kItemH);
+    const int col0 = colb + 2 * lane;
+    const int nitems = min(a.blk_items, (H - rowb + kItemH - 1) / kItemH);
+    unsigned fmask = 0;                                             // bit it: strip `it` is flagged (all class-0 stuff)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const unsigned wq = q == 0 ? fl.x : q == 1 ? fl.y : q == 2 ? fl.z : fl.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) fmask |= (((wq >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 * q + k);
+    }
+    const unsigned mine = ((1u << kApplyPer) - 1u) << (part * kApplyPer);        // this warp's strips of the block
+    const unsigned live = ((1u << nitems) - 1u) & mine;             // nitems <= 16
+    if (!live) return;
+    fmask &= live;
+    unsigned todo = live & ~fmask;                                  // unflagged full strips
+    if (colb + kItemW > W) todo = 0;
+    else if (rowb + nitems * kItemH > H) todo &= ~(1u << (nitems - 1));          // a bottom strip cut by the image edge
+    const unsigned edge = (live & ~fmask) & ~todo;                  // partial strips: scalar path at the end
+
+    for (unsigned m = todo; m; m &= m - 1) {                        // 1. start every code load of the block
+        const int it = __ffs(m) - 1;
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i) {
+            const unsigned short* src = codes + (size_t)(rowb + it * kItemH + i) * W + col0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&stage[warp][(it - part * kApplyPer) * kItemH + i][lane])), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const long long bg = decode<true>(kClsBase, lut, a.cls_off);    // label of class-0 stuff
+    for (unsigned m = fmask; m; m &= m - 1) {                       // 2. flagged strips: pure stores
+        const size_t px0 = (size_t)(rowb + (__ffs(m) - 1) * kItemH) * W + col0;
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i) __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W), make_longlong2(bg, bg));
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");            // 3. every lane reads back only what it copied itself
+    for (unsigned m = todo; m; m &= m - 1) {
+        const int it = __ffs(m) - 1;
+        const size_t px0 = (size_t)(rowb + it * kItemH) * W + col0;
+        unsigned w[kItemH];
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i) w[i] = stage[warp][(it - part * kApplyPer) * kItemH + i][lane];
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i)
+            __stcs(reinterpret_cast<longlong2*>(pan + px0 + (size_t)i * W),
+                   make_longlong2(decode<true>(w[i] & 0xFFFFu, lut, a.cls_off), decode<true>(w[i] >> 16, lut, a.cls_off)));
+    }
+    for (unsigned m = edge; m; m &= m - 1) {                        // 4. strips cut by the right / bottom image edge
+        const int row0 = rowb + (__ffs(m) - 1) * kItemH;
+#pragma unroll
+        for (int i = 0; i < kItemH; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (row0 + i < H && col0 + j < W) {
+                    const size_t e = (size_t)(row0 + i) * W + col0 + j;
+                    pan[e] = decode<true>(codes[e], lut, a.cls_off);
+                }
     }
 }
 
@@ -1420,7 +1521,6 @@ apply_rows_kernel(const __grid_constant__ ApplyArgs a)
     constexpr int kSegs = 8;                                        // segments per warp handled at once
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
     const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
-    const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + a.o_areas);
     const unsigned char* sflags = reinterpret_cast<const unsigned char*>(ws + a.o_sflags);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1428,7 +1528,7 @@ apply_rows_kernel(const __grid_constant__ ApplyArgs a)
     const int sr = blockIdx.x;                                      // strip row
     const int row0 = sr * kItemH;
     const int by = sr / a.blk_items, it = sr - by * a.blk_items;
-    const long long bg = decode<C16>(kClsBase, lut, areas, a);
+    const long long bg = decode<C16>(kClsBase, lut, a.cls_off);
     const int nrows = min(kItemH, H - row0);
 
     for (int seg0 = warp; seg0 < a.blocks_x; seg0 += 8 * kSegs) {
@@ -1456,8 +1556,8 @@ apply_rows_kernel(const __grid_constant__ ApplyArgs a)
                         const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + rowpx + col0));
                         c0 = u.x; c1 = u.y;
                     }
-                    v0 = decode<C16>(c0, lut, areas, a);
-                    v1 = decode<C16>(c1, lut, areas, a);
+                    v0 = decode<C16>(c0, lut, a.cls_off);
+                    v1 = decode<C16>(c1, lut, a.cls_off);
                 }
                 longlong2* op = reinterpret_cast<longlong2*>(pan + rowpx + col0);
                 if (POLICY == 0) __stcs(op, make_longlong2(v0, v1));
@@ -1668,13 +1768,12 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     ApplyArgs a;
     memset(&a, 0, sizeof(a));
     a.ws = ws; a.ws_stride = ws_stride;
-    a.o_codes = L.codes; a.o_lut = L.lut; a.o_areas = L.areas; a.o_sflags = L.sflags;
+    a.o_codes = L.codes; a.o_lut = L.lut; a.o_sflags = L.sflags; a.cls_off = (unsigned)L.cls_off;
     a.pan = reinterpret_cast<long long*>(pan_out); a.n_px = (size_t)H * W;
     a.H = H; a.W = W;
     a.blk_items = block_items(H, W);
     a.blocks_x = (W + kItemW - 1) / kItemW;
     a.blocks_y = (H + a.blk_items * kItemH - 1) / (a.blk_items * kItemH);
-    a.label_divisor = label_divisor; a.stuff_area = stuff_area; a.void_label = void_label;
     const bool fast = aligned16(pan_out) && W % 4 == 0;             // 16-byte label stores, 4-byte code loads
     long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
     // One block per warp is the default.  The kernel can also walk several blocks per warp with the next block's
@@ -1705,6 +1804,15 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
         EMP_CUDA_CHECK(cudaGetLastError());
         return EMP_OK;
     }
+    static int staged = -1;
+    if (staged < 0) { const char* e = getenv("EMP_APPLY_STAGED"); staged = e ? atoi(e) : 1; }
+    if (L.code16 && fast && staged) {
+        constexpr int per_cta = 4 / kApplySplit;                   // blocks per 4-warp CTA
+        const long long nb4 = ((long long)a.blocks_x * a.blocks_y + per_cta - 1) / per_cta;
+        apply_lut_staged_kernel<<<dim3((unsigned)nb4, 1, B), 128, 0, st>>>(a);
+        EMP_CUDA_CHECK(cudaGetLastError());
+        return EMP_OK;
+    }
     if (L.code16) {
         if (fast) apply_lut_kernel<true, true><<<grid, 256, 0, st>>>(a);
         else apply_lut_kernel<true, false><<<grid, 256, 0, st>>>(a);
@@ -1717,11 +1825,12 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
 }
 
 int launch_build_lut(int B, const WsLayout& L, char* ws, size_t ws_stride, int k_cap, int k_fixed, const int32_t* k_dev,
-                     const Things& th, long long label_divisor, long long void_label, cudaStream_t st)
+                     const Things& th, long long label_divisor, long long void_label, long long stuff_area, int H, int W,
+                     cudaStream_t st)
 {
     ProfScope ps(ST_LUT, st);
-    build_lut_kernel<<<dim3(1, 1, B), 256, 0, st>>>(ws, ws_stride, L.status, L.votes, L.lut, k_cap, k_fixed, k_dev, th,
-                                                    label_divisor, void_label);
+    build_lut_kernel<<<dim3(1, 1, B), 256, 0, st>>>(ws, ws_stride, L.status, L.votes, L.lut, L.areas, k_cap, k_fixed, k_dev, th,
+                                                    label_divisor, void_label, stuff_area, (long long)H * W);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
@@ -1925,7 +2034,7 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.max_id = max_id;
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
     if ((rc = launch_assign(sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-    if ((rc = launch_build_lut(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, void_label, st))) return rc;
+    if ((rc = launch_build_lut(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, void_label, stuff_area, H, W, st))) return rc;
     return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out, H, W, st);
 }
 
@@ -1990,7 +2099,7 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
         a.B = nb; a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
         a.vec = (W % 4 == 0) && aligned16(a.sem) && aligned16(a.off) && (n_px % 4 == 0 || nb == 1);
         if ((rc = launch_assign(sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
-        if ((rc = launch_build_lut(nb, L, wsg, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, void_label, st))) return rc;
+        if ((rc = launch_build_lut(nb, L, wsg, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, void_label, stuff_area, H, W, st))) return rc;
         if ((rc = launch_apply(nb, L, wsg, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
                                pan_out + (size_t)b0 * n_px, H, W, st))) return rc;
     }
