@@ -273,23 +273,18 @@ nms_peaks_kernel(const __grid_constant__ NmsArgs a)
                 const int y = y0 + r, x = x0 + 32 * j, cs = 32 * j + lane;      // cs: column within the item
                 const float* q = sp + r * kNmsItemW + 32 * j;
                 const float c = FAST ? q[0] : __ldg(hm + (size_t)y * W + x);
-                float m = -CUDART_INF_F;
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (dy == 0 && dx == 0) continue;
-                        if ((dy < 0 || dx < 0) && !before) continue;
-                        if ((dy > 0 || dx > 0) && !after) continue;
-                        float nb;
-                        if (FAST && cs + dx >= 0 && cs + dx < kNmsItemW && (kNmsHalo || (r + dy >= 0 && r + dy < kNmsRows))) {
-                            nb = q[dy * kNmsItemW + dx];
-                        } else {                                        // no staging, or a halo column of the strip
-                            const int yy = y + dy, xx = x + dx;
-                            nb = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(hm + (size_t)yy * W + xx) : -CUDART_INF_F;
-                        }
-                        m = fmaxf(m, nb);
-                    }
+                auto nbr = [&](int dy, int dx) -> float {                    // neighbour (y + dy, x + dx); -inf outside the window / image
+                    if (((dy < 0 || dx < 0) && !before) || ((dy > 0 || dx > 0) && !after)) return -CUDART_INF_F;
+                    if (FAST && cs + dx >= 0 && cs + dx < kNmsItemW && (kNmsHalo || (r + dy >= 0 && r + dy < kNmsRows)))
+                        return q[dy * kNmsItemW + dx];
+                    const int yy = y + dy, xx = x + dx;                    // no staging, or a halo column of the strip
+                    return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(hm + (size_t)yy * W + xx) : -CUDART_INF_F;
+                };
+                // left / right first: on a smooth heat-map they alone reject every pixel off the vertical ridge line
+                float m = fmaxf(nbr(0, -1), nbr(0, 1));
+                if (!(m > c)) {
+                    m = fmaxf(fmaxf(nbr(-1, 0), nbr(1, 0)), m);
+                    if (!(m > c)) m = fmaxf(fmaxf(nbr(-1, -1), nbr(-1, 1)), fmaxf(nbr(1, -1), nbr(1, 1)));
                 }
                 if (!(m > c)) pk |= 1u << bit;
             }
@@ -1265,9 +1260,19 @@ build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_vote
     {
         const uint32_t* areas = reinterpret_cast<const uint32_t*>(ws + o_areas);
         long long* cls = reinterpret_cast<long long*>(ws + o_lut) + (k_cap + 1);
-        for (int c = threadIdx.x; c < kNumClasses; c += 256) {
-            const long long area = c ? (long long)__ldcg(areas + c) : n_px - (long long)__ldcg(areas + kNumClasses);
-            cls[c] = area >= stuff_area ? (long long)c * label_divisor : void_label;
+        static_assert(kNumClasses % 1024 == 0, "class table is read as uint4 by 256 threads");
+        const long long rest = (long long)__ldcg(areas + kNumClasses);
+#pragma unroll
+        for (int r = 0; r < kNumClasses / 1024; ++r) {              // all loads of a thread are in flight together
+            const int c0 = (r * 256 + threadIdx.x) * 4;
+            const uint4 v = __ldcg(reinterpret_cast<const uint4*>(areas) + r * 256 + threadIdx.x);
+            const uint32_t ar[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                const long long area = c ? (long long)ar[j] : n_px - rest;
+                cls[c] = area >= stuff_area ? (long long)c * label_divisor : void_label;
+            }
         }
     }
     __shared__ LutScratch sc;
