@@ -312,6 +312,7 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = world * B * n_px / (e2e_ms * 1e-3) / 1e6
     assert list(k_out) == Ks and all(f == 0 for f in f_out)
+    sem_bpp = float(L.emp_host_sem_bytes_per_px())     # 1.0 when every tile's class map was narrowed on the host
     same = bool(torch.equal(pan_h[B - 1], pan[B - 1].cpu()))
     clocks = sampler.stop(mark) if sampler else None
 
@@ -336,9 +337,11 @@ def main():
                        'thing_list': THINGS, 'label_divisor': LABEL_DIVISOR, 'nms_kernel': NMS_K,
                        'l2': f'inputs {B * n_px * 20 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed',
                        'parallelism': f'dp{world} (independent tiles per rank, no collective on the data path)'},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': B * n_px * 20, 'd2h_bytes_per_step': B * n_px * 8 + B * 64,
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n_px * (12 + sem_bpp)), 'd2h_bytes_per_step': B * n_px * 8 + B * 64,
+                    'host_buffer_bytes_per_step': B * n_px * 20, 'sem_bytes_per_px_on_the_link': sem_bpp,
                     'ms_per_step': e2e_ms, 'steps': args.e2e_steps, 'matches_resident_result': same,
-                    'api': 'emp_panoptic_batched_host (pinned host tensors, 3-slot H2D/compute/D2H pipeline)'},
+                    'api': 'emp_panoptic_batched_host (pinned host tensors, 3-slot H2D/compute/D2H pipeline; int64 class maps '
+                           'narrowed to uint8 by host worker threads before the link)'},
             'gpu_launches': launches,
             'roofline': {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,

@@ -37,6 +37,7 @@ _SIGNATURES = {
     'emp_panoptic_batched': (_i32, [_i32, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                     _f32, _i32, _vp, _vp, _i32, _i32, _vp, _sz, _vp]),
     'emp_host_scratch_bytes': (_sz, [_i32, _i32, _i32, _i32]),
+    'emp_host_sem_bytes_per_px': (ctypes.c_double, []),
     'emp_panoptic_batched_host': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                          _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
     'emp_median_harden': (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp]),

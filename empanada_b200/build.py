@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     '-O3', '-std=c++17',
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo',
-    '-Xcompiler', '-fPIC,-fvisibility=hidden',
+    '-Xcompiler', '-fPIC,-fvisibility=hidden,-pthread',
     '-fmad=false',          # never contract a*b+c: bit parity with torch CPU needs rn(dy*dy) first
     '-cudart', 'static',
 ]
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError('nvcc failed')
     cmd = [nvcc, '-shared', '-cudart', 'static', '-gencode', 'arch=compute_100a,code=sm_100a',
-           '-o', LIB] + objs
+           '-Xcompiler', '-pthread', '-o', LIB] + objs
     subprocess.run(cmd, check=True)
     return LIB
 

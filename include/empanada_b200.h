@@ -137,8 +137,14 @@ int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float* hm, co
 /* Same pipeline with HOST buffers (pinned or pageable): tiles are streamed host->device, processed
  * and streamed back on internal streams (copy/compute overlap); this is the end-to-end entry the
  * benchmark's e2e figure times.  dev_scratch: device buffer of emp_host_scratch_bytes(). Blocks
- * until the batch is complete.  k_out (host, B int32) receives K per tile, flags_out the flags. */
+ * until the batch is complete.  k_out (host, B int32) receives K per tile, flags_out the flags.
+ * The link is the bound of this entry, so sem is narrowed to one byte per pixel on the host (worker
+ * threads, pinned staging owned by the library) before it crosses; a tile with a class id outside
+ * [0, 255] travels as int64.  EMP_HOST_THREADS sets the worker count (0: no narrowing; default: host
+ * threads / visible GPUs, at most 8).  emp_host_sem_bytes_per_px(): what the LAST call sent per sem
+ * pixel on average (1.0 .. 8.0), for byte accounting. */
 size_t emp_host_scratch_bytes(int H, int W, int k_cap, int n_things);
+double emp_host_sem_bytes_per_px(void);
 int emp_panoptic_batched_host(int B, const int64_t* sem_h, const float* hm_h, const float* off_h,
                               int H, int W, const int64_t* thing_list, int n_things,
                               int64_t label_divisor, int64_t stuff_area, int64_t void_label,

@@ -182,6 +182,40 @@ def test_host_buffer_entry_point(cuda_device):
             want_pan, want_ctr = oracle.get_panoptic_segmentation(t['sem'], t['ctr_hmp'], t['offsets'], [1], 1000, 64, 0, 0.1, 7)
             assert k_out[b] == want_ctr.shape[1] and f_out[b] == 0
             np.testing.assert_array_equal(pan_h[b].numpy(), want_pan[0, 0])
+        assert L.emp_host_sem_bytes_per_px() == 1.0                 # every class map crossed the link as bytes
+
+
+def test_host_buffer_entry_wide_class_ids(cuda_device):
+    """The host entry narrows int64 class maps to bytes before the PCIe copy; a tile holding a class id above 255
+    (here a stuff class 300 and 256) or a negative id must travel as int64 and still give the oracle's answer /
+    the class-range flag.  Odd sizes exercise the unaligned head / tail of the packing loop."""
+    import ctypes
+    from empanada_b200 import _cabi as C
+    H, W, B = 131, 203, 6
+    tiles = [synth_tile(H, W, 12 + 3 * i, seed=900 + i, semi_axes=(5, 14), sigma=3.0, stuff_classes=(2,)) for i in range(B)]
+    tiles[1]['sem'][0, 0, 5:40, 7:90][tiles[1]['sem'][0, 0, 5:40, 7:90] == 0] = 300
+    tiles[3]['sem'][0, 0, -1, -1] = 256                               # one pixel, the very last one
+    tiles[4]['sem'][0, 0, 0, 0] = 255                                 # still a byte
+    tiles[5]['sem'][0, 0, 64, 100] = -3                               # out of range: flagged, not narrowed
+    sem_h = torch.from_numpy(np.stack([t['sem'][0, 0] for t in tiles])).pin_memory()
+    hm_h = torch.from_numpy(np.stack([t['ctr_hmp'][0, 0] for t in tiles])).pin_memory()
+    off_h = torch.from_numpy(np.stack([t['offsets'][0] for t in tiles])).pin_memory()
+    pan_h = torch.empty((B, H, W), dtype=torch.int64).pin_memory()
+    L = C.lib()
+    things, nt = C.i64_array([1])
+    k_cap = 2048
+    nbytes = L.emp_host_scratch_bytes(H, W, k_cap, nt)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=cuda_device)
+    k_out, f_out = (ctypes.c_int32 * B)(), (ctypes.c_int32 * B)()
+    with torch.cuda.device(cuda_device):
+        C.check(L.emp_panoptic_batched_host(B, sem_h.data_ptr(), hm_h.data_ptr(), off_h.data_ptr(), H, W, things, nt,
+                                            1000, 20, 0, 0.1, 7, pan_h.data_ptr(), k_out, f_out, k_cap, scratch.data_ptr(), nbytes))
+    for b, t in enumerate(tiles[:5]):
+        want_pan, want_ctr = oracle.get_panoptic_segmentation(t['sem'], t['ctr_hmp'], t['offsets'], [1], 1000, 20, 0, 0.1, 7)
+        assert k_out[b] == want_ctr.shape[1] and f_out[b] == 0
+        np.testing.assert_array_equal(pan_h[b].numpy(), want_pan[0, 0])
+    assert f_out[5] & C.FLAG_CLASS_RANGE
+    assert L.emp_host_sem_bytes_per_px() == (3 * 1.0 + 3 * 8.0) / 6          # tiles 1, 3, 5 went as int64
 
 
 def test_status_flags_through_the_c_abi(cuda_device):
