@@ -1308,37 +1308,25 @@ __device__ __forceinline__ long long decode(unsigned code, const long long* __re
     return __ldg(lut + (code >= base ? code - base + cls_off : code));
 }
 
-#ifndef EMP_APPLY_MIN_CTAS
-#define EMP_APPLY_MIN_CTAS 1
-#endif
+// General kernel (32-bit codes, unaligned planes, odd widths): one 64 x 64 block per warp; with FAST the code loads
+// of up to kBatch unflagged strips are issued together from registers.
 template <bool C16, bool FAST>
-__global__ void __launch_bounds__(256, EMP_APPLY_MIN_CTAS)
+__global__ void __launch_bounds__(256)
 apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 {
     constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
-#ifndef EMP_APPLY_BATCH
-#define EMP_APPLY_BATCH 4
-#endif
-    constexpr int kBatch = EMP_APPLY_BATCH;                         // unflagged strips whose code loads are issued together
+    constexpr int kBatch = 4;                         // unflagged strips whose code loads are issued together
     char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
     const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
     const uint4* flags = reinterpret_cast<const uint4*>(ws + a.o_sflags);
     long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int H = a.H, W = a.W;
-    const int n_blocks = a.blocks_x * a.blocks_y;
-    const int stride = (int)gridDim.x * 8;                          // warps along x: each walks blocks blk, blk + stride, ...
-    int blk = (int)blockIdx.x * 8 + warp;
-    if (blk >= n_blocks) return;                                    // warp-uniform
-#ifndef EMP_APPLY_DEBUG
-#define EMP_APPLY_DEBUG 0                                            // timing experiments only (profiles/README.md): 1 = every strip
-#endif                                                              // flagged, 2 = + constant label, 3 = + no flag load
-    uint4 fl_next = EMP_APPLY_DEBUG >= 3 ? make_uint4(~0u, ~0u, ~0u, ~0u) : __ldg(flags + blk);   // the next block's flags are always in flight
-    const long long bg = EMP_APPLY_DEBUG >= 2 ? 7ll : decode<C16>(kClsBase, lut, a.cls_off);      // label of class-0 stuff, once per warp
-
-    for (; blk < n_blocks; blk += stride) {
-        const uint4 fl = fl_next;
-        if (blk + stride < n_blocks) fl_next = __ldg(flags + blk + stride);
+    const int blk = (int)blockIdx.x * 8 + warp;
+    if (blk >= a.blocks_x * a.blocks_y) return;                     // warp-uniform
+    const uint4 fl = __ldg(flags + blk);
+    const long long bg = decode<C16>(kClsBase, lut, a.cls_off);     // label of class-0 stuff, once per warp
+    {                                                               // the warp's block
         const int by = blk / a.blocks_x, bx = blk - by * a.blocks_x;
         const int colb = bx * kItemW, rowb = by * (a.blk_items * kItemH);
         const int col0 = colb + 2 * lane;
@@ -1352,7 +1340,6 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
             for (int k = 0; k < 4; ++k) fmask |= (((wq >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 * q + k);
         }
         const unsigned live = (1u << nitems) - 1u;                  // nitems <= 16
-        if (EMP_APPLY_DEBUG >= 1) fmask = ~0u;
         fmask &= live;
 
         if (FAST) {
@@ -1430,14 +1417,11 @@ apply_lut_kernel(const __grid_constant__ ApplyArgs a)
 // registers held, up to 64 in flight per lane), the flagged strips are streamed out while they fly, and the
 // unflagged strips are decoded from shared memory after one wait.  The register-batched kernel above needs a
 // DRAM round trip per kBatch strips, under a write stream that makes each one long.  Each 64 x 64 block is shared
-// by EMP_APPLY_SPLIT warps (a pure store stream runs best with little work per warp: profiles/store_patterns.cu).
+// by kApplySplit warps (a pure store stream runs best with little work per warp: profiles/store_patterns.cu).
 // Measured on config 2 (ms per batch): register-batched 0.384, staged split 1 / 2 / 4: 0.3765 / 0.3785 / 0.3749; an
 // L2 evict-first hint on the code copies changes nothing.  With every strip forced "flagged" the kernel takes 0.321
 // and a bare store kernel of this geometry 0.304: what is left above that comes with the code reads of thing strips.
-#ifndef EMP_APPLY_SPLIT
-#define EMP_APPLY_SPLIT 4
-#endif
-constexpr int kApplySplit = EMP_APPLY_SPLIT;                       // warps sharing one block (each takes 16 / split strips)
+constexpr int kApplySplit = 4;                                      // warps sharing one block (each takes 16 / split strips)
 constexpr int kApplyPer = kBlkItems / kApplySplit;                  // strips per warp
 __global__ void __launch_bounds__(128)
 apply_lut_staged_kernel(const __grid_constant__ ApplyArgs a)
@@ -1511,65 +1495,6 @@ apply_lut_staged_kernel(const __grid_constant__ ApplyArgs a)
                     const size_t e = (size_t)(row0 + i) * W + col0 + j;
                     pan[e] = decode<true>(codes[e], lut, a.cls_off);
                 }
-    }
-}
-
-// Row-linear variant of apply_lut for aligned planes: a CTA owns one strip row (4 image rows) of a tile
-// and writes each of its rows left to right — warp w takes the 64-column segments w, w+8, ... — so the
-// label stream leaves the SM as whole rows (32 KB each at W = 4096) like a fill kernel, instead of
-// 512-byte pieces of 64 different rows.  Flags and codes are fetched per segment before the stores.
-template <bool C16, int POLICY>
-__global__ void __launch_bounds__(256)
-apply_rows_kernel(const __grid_constant__ ApplyArgs a)
-{
-    constexpr uint32_t kClsBase = C16 ? kClsBase16 : kClsBase32;
-    constexpr int kSegs = 8;                                        // segments per warp handled at once
-    char* ws = a.ws + (size_t)blockIdx.z * a.ws_stride;
-    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
-    const unsigned char* sflags = reinterpret_cast<const unsigned char*>(ws + a.o_sflags);
-    long long* pan = a.pan + (size_t)blockIdx.z * a.n_px;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int H = a.H, W = a.W;
-    const int sr = blockIdx.x;                                      // strip row
-    const int row0 = sr * kItemH;
-    const int by = sr / a.blk_items, it = sr - by * a.blk_items;
-    const long long bg = decode<C16>(kClsBase, lut, a.cls_off);
-    const int nrows = min(kItemH, H - row0);
-
-    for (int seg0 = warp; seg0 < a.blocks_x; seg0 += 8 * kSegs) {
-        // this warp's segments: seg0, seg0 + 8, ... (kSegs of them)
-        unsigned flagged = 0;
-#pragma unroll
-        for (int k = 0; k < kSegs; ++k) {
-            const int seg = seg0 + 8 * k;
-            if (seg < a.blocks_x && __ldg(sflags + ((size_t)by * a.blocks_x + seg) * kBlkItems + it)) flagged |= 1u << k;
-        }
-        for (int r = 0; r < nrows; ++r) {
-            const size_t rowpx = (size_t)(row0 + r) * W;
-#pragma unroll
-            for (int k = 0; k < kSegs; ++k) {
-                const int seg = seg0 + 8 * k;
-                const int col0 = seg * kItemW + 2 * lane;
-                if (seg >= a.blocks_x || col0 >= W) continue;
-                long long v0 = bg, v1 = bg;
-                if (!((flagged >> k) & 1u)) {
-                    unsigned c0, c1;
-                    if (C16) {
-                        const unsigned u = __ldcs(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned short*>(ws + a.o_codes) + rowpx + col0));
-                        c0 = u & 0xFFFFu; c1 = u >> 16;
-                    } else {
-                        const uint2 u = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned*>(ws + a.o_codes) + rowpx + col0));
-                        c0 = u.x; c1 = u.y;
-                    }
-                    v0 = decode<C16>(c0, lut, a.cls_off);
-                    v1 = decode<C16>(c1, lut, a.cls_off);
-                }
-                longlong2* op = reinterpret_cast<longlong2*>(pan + rowpx + col0);
-                if (POLICY == 0) __stcs(op, make_longlong2(v0, v1));
-                else if (POLICY == 1) *op = make_longlong2(v0, v1);
-                else __stcg(op, make_longlong2(v0, v1));
-            }
-        }
     }
 }
 
@@ -1767,8 +1692,7 @@ void fill_assign_common(AssignArgs& a, const WsLayout& L, const Things& th)
     }
 }
 
-int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long label_divisor, long long stuff_area,
-                 long long void_label, int64_t* pan_out, int H, int W, cudaStream_t st)
+int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, int64_t* pan_out, int H, int W, cudaStream_t st)
 {
     ApplyArgs a;
     memset(&a, 0, sizeof(a));
@@ -1780,49 +1704,18 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, long long
     a.blocks_x = (W + kItemW - 1) / kItemW;
     a.blocks_y = (H + a.blk_items * kItemH - 1) / (a.blk_items * kItemH);
     const bool fast = aligned16(pan_out) && W % 4 == 0;             // 16-byte label stores, 4-byte code loads
-    long long blocks = ((long long)a.blocks_x * a.blocks_y + 7) / 8;
-    // One block per warp is the default.  The kernel can also walk several blocks per warp with the next block's
-    // flags prefetched (EMP_APPLY_CTAS_PER_SM = resident CTAs per SM), but every persistent grid measured slower
-    // (config 2, ms per batch: 0 -> 0.391, 3 -> 0.480, 5 -> 0.479, 8 -> 0.451, 12 -> 0.435).
-    static int per_sm = -1;
-    if (per_sm < 0) { const char* e = getenv("EMP_APPLY_CTAS_PER_SM"); per_sm = e ? atoi(e) : 0; }
-    const long long want = ((long long)sm_count() * per_sm + B - 1) / B;
-    if (per_sm > 0 && blocks > want) blocks = want;
-    dim3 grid((unsigned)blocks, 1, B);
+    const long long n_blocks = (long long)a.blocks_x * a.blocks_y;
     ProfScope ps(ST_APPLY, st);
-    // The block walk is the default: on config 2 the row-linear kernel (EMP_APPLY_VARIANT=1..3, the three
-    // store policies measure the same) is 3 % faster, but on dense tiles (config 5: few flagged strips)
-    // it is 15 % slower because its code loads are issued row by row.
-    static int variant = -1;
-    if (variant < 0) { const char* e = getenv("EMP_APPLY_VARIANT"); variant = e ? atoi(e) : 0; }
-    if (fast && variant > 0 && W % 2 == 0) {
-        dim3 g2((unsigned)((H + kItemH - 1) / kItemH), 1, B);
-        if (L.code16) {
-            if (variant == 1) apply_rows_kernel<true, 0><<<g2, 256, 0, st>>>(a);
-            else if (variant == 2) apply_rows_kernel<true, 1><<<g2, 256, 0, st>>>(a);
-            else apply_rows_kernel<true, 2><<<g2, 256, 0, st>>>(a);
-        } else {
-            if (variant == 1) apply_rows_kernel<false, 0><<<g2, 256, 0, st>>>(a);
-            else if (variant == 2) apply_rows_kernel<false, 1><<<g2, 256, 0, st>>>(a);
-            else apply_rows_kernel<false, 2><<<g2, 256, 0, st>>>(a);
-        }
-        EMP_CUDA_CHECK(cudaGetLastError());
-        return EMP_OK;
-    }
-    static int staged = -1;
-    if (staged < 0) { const char* e = getenv("EMP_APPLY_STAGED"); staged = e ? atoi(e) : 1; }
-    if (L.code16 && fast && staged) {
-        constexpr int per_cta = 4 / kApplySplit;                   // blocks per 4-warp CTA
-        const long long nb4 = ((long long)a.blocks_x * a.blocks_y + per_cta - 1) / per_cta;
-        apply_lut_staged_kernel<<<dim3((unsigned)nb4, 1, B), 128, 0, st>>>(a);
-        EMP_CUDA_CHECK(cudaGetLastError());
-        return EMP_OK;
-    }
-    if (L.code16) {
-        if (fast) apply_lut_kernel<true, true><<<grid, 256, 0, st>>>(a);
-        else apply_lut_kernel<true, false><<<grid, 256, 0, st>>>(a);
+    // Non-persistent grids on purpose: a store stream runs best with little work per warp (profiles/README.md:
+    // grids of 3 ... 12 resident CTAs per SM walking several blocks each were 10 - 25 % slower, a row-linear
+    // variant slower on dense tiles).
+    if (L.code16 && fast) {
+        constexpr int per_cta = 4 / kApplySplit;                    // blocks per 4-warp CTA
+        apply_lut_staged_kernel<<<dim3((unsigned)((n_blocks + per_cta - 1) / per_cta), 1, B), 128, 0, st>>>(a);
     } else {
-        if (fast) apply_lut_kernel<false, true><<<grid, 256, 0, st>>>(a);
+        const dim3 grid((unsigned)((n_blocks + 7) / 8), 1, B);
+        if (L.code16) apply_lut_kernel<true, false><<<grid, 256, 0, st>>>(a);
+        else if (fast) apply_lut_kernel<false, true><<<grid, 256, 0, st>>>(a);
         else apply_lut_kernel<false, false><<<grid, 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
@@ -2040,7 +1933,7 @@ static int merge_common(const void* sem, int sem_mode, int id_mode, const void* 
     a.vec = (W % 4 == 0) && aligned16(sem) && (id_mode != ID_DENSE || aligned16(ids_in));
     if ((rc = launch_assign(sem_mode, id_mode, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
     if ((rc = launch_build_lut(1, L, static_cast<char*>(ws), L.total, k_cap, k_cap, k_dev, th, label_divisor, void_label, stuff_area, H, W, st))) return rc;
-    return launch_apply(1, L, static_cast<char*>(ws), L.total, label_divisor, stuff_area, void_label, pan_out, H, W, st);
+    return launch_apply(1, L, static_cast<char*>(ws), L.total, pan_out, H, W, st);
 }
 
 EMP_API int emp_merge(const int64_t* sem, const int64_t* ins, int H, int W, int64_t label_divisor,
@@ -2105,8 +1998,7 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
         a.vec = (W % 4 == 0) && aligned16(a.sem) && aligned16(a.off) && (n_px % 4 == 0 || nb == 1);
         if ((rc = launch_assign(sem_u8 ? SEM_U8 : SEM_I64, ID_ARGMIN, L.code16 ? OUT_CODE16 : OUT_CODE32, a, st))) return rc;
         if ((rc = launch_build_lut(nb, L, wsg, ws_bytes_per_tile, k_cap, -1, nullptr, th, label_divisor, void_label, stuff_area, H, W, st))) return rc;
-        if ((rc = launch_apply(nb, L, wsg, ws_bytes_per_tile, label_divisor, stuff_area, void_label,
-                               pan_out + (size_t)b0 * n_px, H, W, st))) return rc;
+        if ((rc = launch_apply(nb, L, wsg, ws_bytes_per_tile, pan_out + (size_t)b0 * n_px, H, W, st))) return rc;
     }
     return EMP_OK;
 }
