@@ -44,6 +44,9 @@ _SIGNATURES = {
     'emp_rle_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32, _i64]),
     'emp_rle': (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                        _vp, _sz, _vp]),
+    'emp_stack_slice_scratch_bytes': (_sz, [_i32] * 8 + [_i64]),
+    'emp_stack_slice': (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32, _f32, _i32, _f32, _i32, _vp, _i32, _i64, _i64, _i64,
+                               _i32, _i32, _i32, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     'emp_rle_pair_overlaps': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
     'emp_rle_list_overlaps': (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp]),
     'emp_fill_runs': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _sz, _vp, _i32, _sz, _vp]),

@@ -182,6 +182,26 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
             int force_connected, int64_t* runs_out, int run_cap, int64_t* inst_out, int inst_cap,
             void* ws, size_t ws_bytes, void* stream);
 
+/* One z-slice of the stack path behind the median queue, in one call and with no host synchronisation:
+ * _harden_seg (engines.py:114-121) -> get_instance_cells on the coarse maps (:257-272) -> get_panoptic_seg with the
+ * nearest upsample folded in (:274-292) -> crop to the unpadded size (:305-307) -> pan_seg_to_rle_seg's tables
+ * (rle.py:26-86).  It chains emp_median_harden, emp_coarse_ids, emp_merge_coarse and emp_rle on `stream`.
+ *   sem_prob (C,H,W) f32 probabilities; hm (h,w), off (2,h,w) f32 with (h << shift, w << shift) >= (H, W)
+ *   pan_out  (H,W) int64 or NULL (the padded panoptic map, if the caller wants it)
+ *   runs_out / inst_out as for emp_rle, over the top-left crop_h x crop_w of the map
+ *   status_out  DEVICE int32[3 * EMP_ST_WORDS]: the status blocks of the center search (K, overflow flag), the
+ *               merge (class-range flags) and the encoder (counts, overflow flag), valid once the stream has run
+ *   scratch  device buffer of emp_stack_slice_scratch_bytes(), 256-byte aligned, reusable by the next slice */
+size_t emp_stack_slice_scratch_bytes(int H, int W, int h, int w, int k_cap, int n_things, int run_cap,
+                                     int n_labels, int64_t label_divisor);
+int emp_stack_slice(const float* sem_prob, int C, int H, int W, float confidence_thr, const float* hm,
+                    const float* off, int h, int w, float nms_threshold, int nms_kernel, float step, int shift,
+                    const int64_t* thing_list /* host */, int n_things, int64_t label_divisor,
+                    int64_t stuff_area, int64_t void_label, int k_cap, int crop_h, int crop_w,
+                    const int64_t* labels /* host */, int n_labels, int force_connected, void* scratch,
+                    size_t scratch_bytes, int64_t* pan_out, int64_t* runs_out, int run_cap, int64_t* inst_out,
+                    int inst_cap, int32_t* status_out, void* stream);
+
 /* Cross-slice matcher support — empanada/inference/matcher.py:136-232 (rle_matcher) with
  * array_utils.rle_intersection :371-403 / rle_iou :405-429 / rle_ioa :431-449: pixel overlaps between
  * the instances of consecutive slices, from the run tables emp_rle wrote.  For pair p = (slice p,
