@@ -24,15 +24,15 @@ extern "C" int emp_panoptic_batched(int, const void*, int, const float*, const f
 
 namespace emp {
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 3;                       // 4 and 6 slots measure the same (the link is the bound)
 
 struct HostPipe {
     int device = -1;
-    cudaStream_t streams[kSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t streams[kSlots] = {};
     int32_t* status_pinned = nullptr;   // B * EMP_ST_WORDS
     int status_cap = 0;
-    uint8_t* sem8[kSlots] = {nullptr, nullptr, nullptr};    // pinned staging: one narrowed tile each
-    cudaEvent_t sem8_free[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* sem8[kSlots] = {};     // pinned staging: one narrowed tile each
+    cudaEvent_t sem8_free[kSlots] = {};
     size_t sem8_cap = 0;
     int threads = 0;
     double sem_bytes_per_px = 8.0;  // of the last call
