@@ -41,6 +41,7 @@ _SIGNATURES = {
     'emp_panoptic_batched_host': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                          _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
     'emp_median_harden': (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp]),
+    'emp_median3_compose': (_i32, [_vp, _i32, _i32, _i32, _sz, _vp, _vp, _vp]),
     'emp_rle_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32, _i64]),
     'emp_rle': (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                        _vp, _sz, _vp]),

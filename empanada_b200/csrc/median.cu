@@ -3,6 +3,7 @@
 // optionally written back (the reference stores the filtered plane into the queued entry, which
 // is what makes its median recursive), then hardened into a class map (C == 1: p >= thr,
 // C > 1: first arg-max over channels).  HBM-bound: ks*4*C B/px in, 4*C (+8 or +1) B/px out.
+#include <math_constants.h>
 #include "common.cuh"
 
 namespace emp {
@@ -110,9 +111,56 @@ static int launch_median(const PlanePtrs& pp, int C, size_t hw, float thr, float
     return EMP_OK;
 }
 
+// Recursive median of three as a scan.  With ks = 3 the queue's recursion is f_i = med(f_{i-1}, s_i, s_{i+1}), and
+// a median of three is a clamp of one argument to the range of the other two: f_i = min(max(f_{i-1}, lo_i), hi_i),
+// lo_i / hi_i = min / max(s_i, s_{i+1}).  Clamps compose into clamps, so a whole z-block acts on its incoming plane as
+// ONE clamp (A, B): A <- clamp(A; lo_i, hi_i), B <- clamp(B; lo_i, hi_i) from (-inf, +inf); a raw slice (the first
+// and the last of the stack, which the queue passes through unfiltered) is the constant clamp (s_i, s_i).  A rank
+// can therefore compute (A, B) of its block from its own raw planes alone, and the carry plane crosses all ranks in
+// one clamp per rank instead of one full chain per rank.  Pure selection: bit-exact for non-NaN inputs (the caller
+// compares the result with the chain's own last plane and falls back to the sequential hand-over otherwise).
+__global__ void __launch_bounds__(256)
+median3_compose_kernel(const float* const* __restrict__ planes, int n, int first_raw, int last_raw, size_t count,
+                       float* __restrict__ A_out, float* __restrict__ B_out)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
+        float A = -CUDART_INF_F, B = CUDART_INF_F;
+        float cur = __ldcs(planes[0] + e);
+        for (int z = 0; z < n; ++z) {
+            const bool raw = (z == 0 && first_raw) || (z == n - 1 && last_raw);
+            float lo = cur, hi = cur;
+            if (!raw) {
+                const float nxt = __ldcs(planes[z + 1] + e);        // planes[n] exists whenever the last slice is filtered
+                lo = fminf(cur, nxt); hi = fmaxf(cur, nxt);
+                cur = nxt;
+            } else if (z + 1 < n) {
+                cur = __ldcs(planes[z + 1] + e);
+            }
+            A = fminf(fmaxf(A, lo), hi);
+            B = fminf(fmaxf(B, lo), hi);
+        }
+        A_out[e] = A; B_out[e] = B;
+    }
+}
+
 }  // namespace emp
 
 using namespace emp;
+
+EMP_API int emp_median3_compose(const float* const* planes_dev, int n, int first_raw, int last_raw, size_t count,
+                                float* A_out, float* B_out, void* stream)
+{
+    EMP_REQUIRE(planes_dev && A_out && B_out, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(n >= 1 && count > 0, EMP_ERR_INVALID, "bad block (n=%d)", n);
+    size_t blocks = (count + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    ProfScope ps(ST_MEDIAN, static_cast<cudaStream_t>(stream));
+    median3_compose_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(planes_dev, n, first_raw, last_raw,
+                                                                                             count, A_out, B_out);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}
 
 EMP_API int emp_median_harden(const float* const* planes, int ks, int C, int H, int W, float confidence_thr,
                               float* median_out, void* sem_out, int sem_u8, void* stream)

@@ -28,7 +28,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ['partition_slices', 'halo_range', 'median_chain', 'exchange_carry', 'label_offsets',
+__all__ = ['partition_slices', 'halo_range', 'median_chain', 'exchange_carry', 'exchange_carry_median3', 'compose_median3',
+           'label_offsets',
            'apply_label_offset', 'StackShard']
 
 
@@ -114,6 +115,47 @@ def exchange_carry(chain_fn, rank, world_size, mid, plane_like, group=None):
         for p in nxt:
             dist.send(p.contiguous(), dst=rank + 1, group=group)
     return result
+
+
+def compose_median3(raw, z0, z1, depth, like=None):
+    """The block [z0, z1) of a median_kernel_size == 3 chain as ONE clamp: returns (A, B) with
+    f_{z1-1} = min(max(f_{z0-1}, A), B).  A median of three is a clamp of one argument to the range of the other
+    two, f_i = clamp(f_{i-1}; min(s_i, s_{i+1}), max(s_i, s_{i+1})), clamps compose into clamps, and the raw first /
+    last slice of the stack is the constant clamp (s_i, s_i).  torch restatement of libempanada_b200's
+    emp_median3_compose for tensors on any device (StackShard uses the kernel; the gloo tests use this)."""
+    ref = raw[z0] if z0 < z1 else like
+    A = torch.full_like(ref, float('-inf'))
+    B = torch.full_like(ref, float('inf'))
+    for z in range(z0, z1):
+        if z < 1 or z >= depth - 1:
+            lo = hi = raw[z]
+        else:
+            lo, hi = torch.minimum(raw[z], raw[z + 1]), torch.maximum(raw[z], raw[z + 1])
+        A = torch.minimum(torch.maximum(A, lo), hi)
+        B = torch.minimum(torch.maximum(B, lo), hi)
+    return A, B
+
+
+def exchange_carry_median3(compose_fn, chain_fn, rank, world_size, plane_like, group=None):
+    """exchange_carry for median_kernel_size == 3 without the rank-after-rank wait: every rank first reduces its
+    block to one clamp (compose_fn() -> (A, B), from its own raw planes only), the carry plane then crosses the ranks
+    with ONE clamp per rank, and the real chains (chain_fn(carry) -> (result, next_carry)) run on all ranks at once.
+    Returns (result, mismatch): mismatch is a 0-d int64 tensor, non-zero when the plane this rank handed on is not
+    the chain's own last plane (only possible with NaNs) — the caller must then redo the block with exchange_carry."""
+    carry, sent = [], None
+    if rank + 1 < world_size:
+        A, B = compose_fn()
+    if rank > 0:
+        carry = [torch.empty_like(plane_like)]
+        dist.recv(carry[0], src=rank - 1, group=group)
+    if rank + 1 < world_size:
+        sent = torch.minimum(torch.maximum(carry[0], A), B) if rank > 0 else torch.minimum(A, B)
+        dist.send(sent.contiguous(), dst=rank + 1, group=group)
+    result, nxt = chain_fn(carry)
+    if sent is None:
+        return result, torch.zeros((), dtype=torch.int64, device=plane_like.device)
+    own = nxt[0] if nxt else sent                       # an empty block hands the plane through
+    return result, (own != sent).any().to(torch.int64)  # NaN != NaN: flagged, which is what we want
 
 
 def label_offsets(max_counts, group=None):
@@ -433,6 +475,12 @@ class StackShard:
         H, W = h['size'] if h['size'] is not None else self.tables_shape_
         return fl.fill_block(t['runs_all'], t['n_runs'], table, (H, W), dtype)
 
+    def _all_ranks_agree(self, flag, device):
+        """True iff `flag` holds on every rank (the fast carry hand-over needs all ranks to take it)."""
+        t = torch.tensor([int(bool(flag))], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
+
     def finish(self):
         from empanada_b200.inference import engines as eng
         from empanada_b200.inference import rle
@@ -445,7 +493,30 @@ class StackShard:
         def chain(carry):
             return median_chain(raw, self.z0, self.z1, self.depth, self.ks, carry, med)
 
-        filtered = exchange_carry(chain, self.rank, self.world, self.mid, raw[self.z0], self.group)
+        def compose():
+            """(A, B) of this rank's block from emp_median3_compose over its raw planes (+ the first halo plane)."""
+            from empanada_b200 import _cabi as C
+            last_raw = self.z1 >= self.depth
+            planes = [raw[z].detach() for z in range(self.z0, self.z1 if last_raw else self.z1 + 1)]
+            assert all(p.dtype == torch.float32 and p.is_contiguous() and p.shape == planes[0].shape for p in planes)
+            dev = C.require_cuda(*planes)
+            ptrs = torch.tensor([p.data_ptr() for p in planes], dtype=torch.int64).to(dev)
+            A, B = torch.empty_like(planes[0]), torch.empty_like(planes[0])
+            with torch.cuda.device(dev):
+                C.check(C.lib().emp_median3_compose(ptrs.data_ptr(), self.z1 - self.z0, int(self.z0 == 0), int(last_raw),
+                                                    planes[0].numel(), A.data_ptr(), B.data_ptr(), C.stream_ptr(dev)))
+            return A, B
+
+        # ks == 3 over several ranks: the carry crosses the ranks as one clamp per rank (no rank waits for the chain of
+        # the rank below); anything else — and the NaN fallback — hands the carry on after each rank's chain
+        mismatch = None
+        fast = (self.ks == 3 and self.world > 1 and self.z1 > self.z0 and not getattr(self, '_sequential_carry', False)
+                and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in raw.values()))
+        fast = self._all_ranks_agree(fast, raw[self.z0].device) if self.ks == 3 and self.world > 1 else False
+        if fast:
+            filtered, mismatch = exchange_carry_median3(compose, chain, self.rank, self.world, raw[self.z0], self.group)
+        else:
+            filtered = exchange_carry(chain, self.rank, self.world, self.mid, raw[self.z0], self.group)
         e = self.engine
         zs = list(range(self.z0, self.z1))
         if not zs:
@@ -462,9 +533,18 @@ class StackShard:
                 if c in e.thing_list and seg[c]:
                     max_counts[c] = max(max_counts[c], max(seg[c]) - c * e.label_divisor)
             out[z] = seg
-        counts = torch.tensor([max_counts[c] for c in self.labels], dtype=torch.int64, device=raw[self.z0].device)
+        counts = torch.tensor([max_counts[c] for c in self.labels] + [0], dtype=torch.int64, device=raw[self.z0].device)
+        if mismatch is not None:
+            counts[-1] = mismatch                           # rides along with the instance counts
         # a single-rank shard never talks to anyone, even inside a larger process group
-        offs = torch.zeros_like(counts) if self.world == 1 else label_offsets(counts, self.group)[0]
+        if self.world == 1:
+            offs = torch.zeros_like(counts[:-1])
+        else:
+            offs, table = label_offsets(counts, self.group)
+            if bool(table[:, -1].any()):                    # some rank's composed carry was not its chain's plane (NaNs):
+                self._sequential_carry = True               # every rank sees the same table, so all of them redo the block
+                return self.finish()
+            offs = offs[:-1]
         offs = {c: int(o) for c, o in zip(self.labels, offs.tolist())}
         self.label_offsets_ = offs
         return {z: apply_label_offset(s, offs, e.label_divisor, e.thing_list) for z, s in out.items()}

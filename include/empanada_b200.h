@@ -162,6 +162,16 @@ int emp_median_harden(const float* const* planes /* host array */, int ks, int C
                       float confidence_thr, float* median_out, void* sem_out, int sem_u8,
                       void* stream);
 
+/* The recursive median of _MedianQueue with median_kernel_size == 3 (engines.py:68-90) over a whole z-block as ONE
+ * clamp: f_last = min(max(f_in, A), B), where f_in is the filtered plane below the block.  Lets z-sharded ranks hand
+ * the carry plane on after one clamp instead of one full chain (inference/stack.py).
+ *   planes_dev  DEVICE array of n (+1 unless last_raw) pointers to the block's raw (C*H*W) f32 planes, followed by
+ *               the first plane above the block; first_raw / last_raw: the block starts with the stack's first /
+ *               ends with the stack's last slice (which the queue passes through unfiltered)
+ *   A_out, B_out  (count) f32 */
+int emp_median3_compose(const float* const* planes_dev, int n, int first_raw, int last_raw, size_t count,
+                        float* A_out, float* B_out, void* stream);
+
 /* pan_seg_to_rle_seg — empanada/inference/rle.py:26-86 (+ connected_components :18-24,
  * array_utils.rle_encode array_utils.py:209-235).  One pass over the pixels extracts row-runs
  * (maximal horizontal segments of one selected value); everything after that works on runs:

@@ -112,6 +112,73 @@ def test_sharded_chain_and_offsets_gloo(world, ks):
     assert seen == set(range(D))
 
 
+# ---- ks == 3: the block as one clamp, the carry crossing the ranks without waiting for their chains ----
+@pytest.mark.parametrize('world', [1, 2, 3, 5])
+def test_compose_median3_equals_the_chain(world):
+    """f_last = min(max(f_in, A), B) with (A, B) from the block's own raw planes must be the chain's last plane, for
+    every block of every partition, fed with the true plane below it — including the raw first / last slices, equal
+    neighbours (ties) and multi-channel planes."""
+    rng = np.random.default_rng(100 + world)
+    D = 17
+    planes = [np.round(rng.random((1, 2, 5, 6), dtype=np.float32) * 8) / 8 for _ in range(D)]      # coarse values: many ties
+    want = _sequential([p.copy() for p in planes], 3)
+    for r in range(world):
+        z0, z1 = stack.partition_slices(D, world, r)
+        _, zh = stack.halo_range(D, world, r, 3)
+        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
+        A, B = stack.compose_median3(raw, z0, z1, D)
+        below = torch.from_numpy(want[z0 - 1]) if z0 > 0 else torch.full_like(A, 123.0)     # rank 0: anything
+        got = torch.minimum(torch.maximum(below, A), B)
+        np.testing.assert_array_equal(got.numpy(), want[z1 - 1])
+
+
+def _worker_median3(rank, world, port, D, seed, poison, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(seed)
+        planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]      # same on all ranks
+        if poison:
+            planes[2][0, 0, 1, 3] = np.nan
+        z0, z1 = stack.partition_slices(D, world, rank)
+        _, zh = stack.halo_range(D, world, rank, 3)
+        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
+        got, mismatch = stack.exchange_carry_median3(lambda: stack.compose_median3(raw, z0, z1, D),
+                                                     lambda c: stack.median_chain(raw, z0, z1, D, 3, c, _tmedian),
+                                                     rank, world, raw[z0])
+        ret[rank] = ({z: got[z].numpy() for z in got}, int(mismatch))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_median3_carry_crosses_ranks_as_clamps_gloo(world):
+    D, seed = 11, 9
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_median3, args=(world, port, D, seed, False, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    want = _sequential([rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)], 3)
+    seen = set()
+    for r in range(world):
+        got, mismatch = ret[r]
+        assert mismatch == 0
+        for z, p in got.items():
+            np.testing.assert_array_equal(p, want[z])
+            seen.add(z)
+    assert seen == set(range(D))
+
+
+def test_median3_nan_is_flagged_gloo():
+    """A NaN makes "composed clamp == chain" unprovable: the rank that handed such a plane on must say so (the
+    driver then redoes the block with the sequential hand-over)."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_median3, args=(2, port, 11, 9, True, ret), nprocs=2, join=True)
+    assert ret[0][1] == 1 and ret[1][1] == 0
+
+
 def test_apply_label_offset():
     seg = {1: {1001: {'box': (0, 0, 1, 1)}, 1002: {'box': (1, 1, 2, 2)}}, 2: {2000: {'box': (0, 0, 4, 4)}}}
     out = stack.apply_label_offset(seg, {1: 40, 2: 7}, 1000, [1])
