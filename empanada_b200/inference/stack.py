@@ -11,7 +11,10 @@ for mid <= i < D - mid, raw s_i otherwise.  Rank r owns the contiguous block [z0
   * a carry: the filtered planes f_{z0-mid} .. f_{z0-1} from rank r-1 (one send/recv of `mid`
     (C,H,W) fp32 planes over NCCL/NVLink), available once r-1 has run its — elementwise, cheap —
     median chain.  The CNN forwards, which dominate, never wait on it.
-With median_kernel_size == 1 nothing is exchanged.
+With median_kernel_size == 1 nothing is exchanged.  With median_kernel_size == 3 (the scripts' default) no rank waits
+for the chain of the rank below: a median of three is a clamp of one argument to the range of the other two, clamps
+compose, so every rank first reduces its block to ONE clamp from its own raw planes (emp_median3_compose), the carry
+crosses the ranks with one clamp per rank, and all chains then run at once (exchange_carry_median3).
 
 Labels.  Every slice numbers its instances 1..n per class.  So that labels from different ranks
 never collide before the host-side cross-slice matcher renumbers them, ranks all-gather their
