@@ -38,7 +38,7 @@ def main():
     ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices per rank (cycled)')
     ap.add_argument('--blobs', type=int, default=400)
     ap.add_argument('--repeat', type=int, default=2)
-    ap.add_argument('--streams', type=int, default=4, help='side streams the slices of a block are spread over')
+    ap.add_argument('--block', type=int, default=32, help='slices per emp_stack_block call')
     ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
     ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')
     args = ap.parse_args()
@@ -75,7 +75,7 @@ def main():
 
     def run_once():
         shard = stack.StackShard(eng, labels=[1], depth=D, rank=rank, world_size=world, median_kernel_size=args.ks,
-                                 upsampling=1, force_connected=True, n_streams=args.streams)
+                                 upsampling=1, force_connected=True, block=args.block)
         for z in shard.slices():
             s = slices[z % len(slices)]
             shard.add(z, s['sem_prob'], s['ctr_hmp'], s['offsets'], size=(H, H))
@@ -86,9 +86,11 @@ def main():
         out = shard.finish()
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t
-        n_inst = sum(len(v[1]) for v in out.values())
-        n_runs = sum(len(a['starts']) for v in out.values() for a in v[1].values())
+        n_inst, n_runs = out.counts()
         timing = dict(getattr(shard, 'timing_', {}))
+        t = time.perf_counter()
+        out.materialise()                               # every slice's nested dict (what a dict-walking consumer pays on top)
+        timing['dicts_s'] = time.perf_counter() - t
         if args.match:
             t = time.perf_counter()
             matched = shard.match(out)

@@ -15,6 +15,8 @@ EMP_OK = 0
 ST_K, ST_FLAGS, ST_NROWRUNS, ST_NRUNS, ST_NINST, ST_WORDS = 0, 1, 2, 3, 4, 16
 FLAG_K_OVERFLOW, FLAG_CLASS_RANGE, FLAG_ID_RANGE, FLAG_RLE_OVERFLOW = 1, 2, 4, 8
 MAX_THINGS, MAX_CLASSES, MAX_LABELS = 16, 4096, 64
+# packed output of emp_stack_block (include/empanada_b200.h: EMP_BLK_*)
+BLK_HDR_MAXLAB, BLK_HDR_WORDS, BLK_SLICE_WORDS, BLK_INST_WORDS = 4, 4 + 64, 6, 9
 
 _lib = None
 
@@ -41,19 +43,29 @@ _SIGNATURES = {
     'emp_panoptic_batched_host': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                          _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
     'emp_median_harden': (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp]),
-    'emp_median3_compose': (_i32, [_vp, _i32, _i32, _i32, _sz, _vp, _vp, _vp]),
+    'emp_median_chain': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _f32, _vp, _sz, _vp, _vp, _vp]),
+    'emp_median_chain_repair': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _vp, _f32, _vp, _sz, _vp, _vp, _vp]),
     'emp_rle_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32, _i64]),
     'emp_rle': (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                        _vp, _sz, _vp]),
-    'emp_stack_slice_scratch_bytes': (_sz, [_i32] * 8 + [_i64]),
-    'emp_stack_slice': (_i32, [_vp, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _i32, _f32, _i32, _f32, _i32, _vp, _i32, _i64, _i64, _i64,
-                               _i32, _i32, _i32, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    'emp_stack_block_scratch_bytes': (_sz, [_vp, _i32]),
+    'emp_stack_block_packed_words': (_sz, [_vp, _i32]),
+    'emp_stack_block': (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     'emp_rle_pair_overlaps': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
     'emp_rle_list_overlaps': (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp]),
     'emp_fill_runs': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _sz, _vp, _i32, _sz, _vp]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
+
+
+class StackCfg(ctypes.Structure):
+    """emp_stack_cfg (include/empanada_b200.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ('H', 'W', 'h', 'w', 'shift', 'nms_kernel', 'k_cap', 'crop_h', 'crop_w',
+                                             'n_things', 'n_labels', 'force_connected', 'run_cap', 'inst_cap')] + \
+               [('nms_threshold', ctypes.c_float), ('step', ctypes.c_float),
+                ('label_divisor', ctypes.c_int64), ('stuff_area', ctypes.c_int64), ('void_label', ctypes.c_int64),
+                ('thing_list', ctypes.c_void_p), ('labels', ctypes.c_void_p)]
 
 
 def lib():
@@ -74,7 +86,8 @@ def lib():
 
 
 STAGES = ('nms_peaks', 'emit_centers', 'assign', 'build_lut', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs',
-          'bin_centers')
+          'bin_centers', 'median_chain', 'rle_block_keys', 'rle_block_mark', 'rle_block_emit', 'rle_block_runs',
+          'rle_block_pack')
 
 
 def profile_enable(on):

@@ -89,13 +89,25 @@ int make_things(const int64_t* list, int n, Things* out);
 // Optional per-stage device timing (emp_profile_enable / emp_profile_read): one CUDA event pair
 // around each kernel launch on the launching stream.  Off by default (no events recorded).
 enum { ST_NMS = 0, ST_EMIT = 1, ST_ASSIGN = 2, ST_LUT = 3, ST_APPLY = 4, ST_MEDIAN = 5, ST_RLE_MARK = 6,
-       ST_RLE_RUNS = 7, ST_BIN = 8, ST_COUNT = EMP_PROFILE_STAGES };
+       ST_RLE_RUNS = 7, ST_BIN = 8, ST_CHAIN = 9, ST_BLK_KEYS = 10, ST_BLK_MARK = 11, ST_BLK_EMIT = 12, ST_BLK_RUNS = 13,
+       ST_BLK_PACK = 14, ST_COUNT = EMP_PROFILE_STAGES };
 struct ProfScope {
     ProfScope(int stage, cudaStream_t st);
     ~ProfScope();
     int idx;
     cudaStream_t st;
 };   // sorts + dedups; EMP_ERR_INVALID if > max
+
+// ---- batched building blocks shared with stack_block.cu (defined in panoptic.cu) ---------------
+int assign_block_items(int H, int W);       // strips per 64-column block the assign kernel uses for an H x W plane
+int device_sm_count();
+int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* off, size_t off_stride, int h, int w,
+                       float threshold, int nms_kernel, float step, int32_t* ids_out, size_t ids_stride, int k_cap,
+                       char* ws, size_t ws_stride, cudaStream_t st);
+int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, const int32_t* ids, size_t ids_stride, int hc,
+                        int wc, int shift, int H, int W, const Things& th, long long label_divisor, long long stuff_area,
+                        long long void_label, int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws,
+                        size_t ws_stride, cudaStream_t st);
 
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ int thing_index(long long c, const Things& th)

@@ -167,7 +167,7 @@ EMP_API int emp_rle_list_overlaps(const int64_t* runs_a, int n_a, int64_t lmax_a
     EMP_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
     if (n_a == 0 || n_b == 0) return EMP_OK;
     int bx = (n_b + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
+    if (bx > device_sm_count() * 8) bx = device_sm_count() * 8;
     rle_list_overlaps_kernel<<<bx, 256, 0, st>>>(reinterpret_cast<const long long*>(runs_a), n_a, (long long)lmax_a,
                                                  reinterpret_cast<const long long*>(runs_b), n_b, out, cap, count);
     EMP_CUDA_CHECK(cudaGetLastError());

@@ -30,6 +30,16 @@ __device__ __forceinline__ float median_of(float (&v)[KS])
     return v[(KS - 1) / 2];
 }
 
+// torch.median propagates NaN: a window holding one gives NaN
+template <int KS>
+__device__ __forceinline__ bool any_nan(const float (&v)[KS])
+{
+    bool nan = false;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) nan |= (v[i] != v[i]);
+    return nan;
+}
+
 // One thread per 4 consecutive pixels (VEC) or per pixel; loops over the C channels.
 template <int KS, bool VEC, bool SEM_U8>
 __global__ void __launch_bounds__(256)
@@ -59,14 +69,18 @@ median_harden_kernel(const PlanePtrs planes, int C, size_t hw, float thr, float*
             }
             float m[N];
 #pragma unroll
-            for (int j = 0; j < N; ++j) m[j] = median_of<KS>(v[j]);
+            for (int j = 0; j < N; ++j) {
+                const bool nan = any_nan<KS>(v[j]);
+                m[j] = median_of<KS>(v[j]);
+                if (nan) m[j] = CUDART_NAN_F;
+            }
             if (median_out) {
                 if (VEC) *reinterpret_cast<float4*>(median_out + e) = make_float4(m[0], m[1 % N], m[2 % N], m[3 % N]);
                 else median_out[e] = m[0];
             }
 #pragma unroll
             for (int j = 0; j < N; ++j)
-                if (c == 0 || m[j] > bestv[j]) { bestv[j] = m[j]; bestc[j] = c; }
+                if (c == 0 || m[j] > bestv[j] || (m[j] != m[j] && bestv[j] == bestv[j])) { bestv[j] = m[j]; bestc[j] = c; }   // argmax: NaN is the maximum
         }
         if (sem_out) {
             int cls[N];
@@ -96,7 +110,7 @@ static int launch_median(const PlanePtrs& pp, int C, size_t hw, float thr, float
 {
     const size_t items = vec ? hw / 4 : hw;
     size_t blocks = (items + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (size_t)device_sm_count() * 16) blocks = (size_t)device_sm_count() * 16;
     if (blocks < 1) blocks = 1;
     const unsigned g = (unsigned)blocks;
     ProfScope ps(ST_MEDIAN, st);
@@ -111,56 +125,9 @@ static int launch_median(const PlanePtrs& pp, int C, size_t hw, float thr, float
     return EMP_OK;
 }
 
-// Recursive median of three as a scan.  With ks = 3 the queue's recursion is f_i = med(f_{i-1}, s_i, s_{i+1}), and
-// a median of three is a clamp of one argument to the range of the other two: f_i = min(max(f_{i-1}, lo_i), hi_i),
-// lo_i / hi_i = min / max(s_i, s_{i+1}).  Clamps compose into clamps, so a whole z-block acts on its incoming plane as
-// ONE clamp (A, B): A <- clamp(A; lo_i, hi_i), B <- clamp(B; lo_i, hi_i) from (-inf, +inf); a raw slice (the first
-// and the last of the stack, which the queue passes through unfiltered) is the constant clamp (s_i, s_i).  A rank
-// can therefore compute (A, B) of its block from its own raw planes alone, and the carry plane crosses all ranks in
-// one clamp per rank instead of one full chain per rank.  Pure selection: bit-exact for non-NaN inputs (the caller
-// compares the result with the chain's own last plane and falls back to the sequential hand-over otherwise).
-__global__ void __launch_bounds__(256)
-median3_compose_kernel(const float* const* __restrict__ planes, int n, int first_raw, int last_raw, size_t count,
-                       float* __restrict__ A_out, float* __restrict__ B_out)
-{
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) {
-        float A = -CUDART_INF_F, B = CUDART_INF_F;
-        float cur = __ldcs(planes[0] + e);
-        for (int z = 0; z < n; ++z) {
-            const bool raw = (z == 0 && first_raw) || (z == n - 1 && last_raw);
-            float lo = cur, hi = cur;
-            if (!raw) {
-                const float nxt = __ldcs(planes[z + 1] + e);        // planes[n] exists whenever the last slice is filtered
-                lo = fminf(cur, nxt); hi = fmaxf(cur, nxt);
-                cur = nxt;
-            } else if (z + 1 < n) {
-                cur = __ldcs(planes[z + 1] + e);
-            }
-            A = fminf(fmaxf(A, lo), hi);
-            B = fminf(fmaxf(B, lo), hi);
-        }
-        A_out[e] = A; B_out[e] = B;
-    }
-}
-
 }  // namespace emp
 
 using namespace emp;
-
-EMP_API int emp_median3_compose(const float* const* planes_dev, int n, int first_raw, int last_raw, size_t count,
-                                float* A_out, float* B_out, void* stream)
-{
-    EMP_REQUIRE(planes_dev && A_out && B_out, EMP_ERR_INVALID, "null pointer");
-    EMP_REQUIRE(n >= 1 && count > 0, EMP_ERR_INVALID, "bad block (n=%d)", n);
-    size_t blocks = (count + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    ProfScope ps(ST_MEDIAN, static_cast<cudaStream_t>(stream));
-    median3_compose_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(planes_dev, n, first_raw, last_raw,
-                                                                                             count, A_out, B_out);
-    EMP_CUDA_CHECK(cudaGetLastError());
-    return EMP_OK;
-}
 
 EMP_API int emp_median_harden(const float* const* planes, int ks, int C, int H, int W, float confidence_thr,
                               float* median_out, void* sem_out, int sem_u8, void* stream)

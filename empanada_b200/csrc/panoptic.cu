@@ -1251,9 +1251,10 @@ assign_kernel(const __grid_constant__ AssignArgs a)
 // label LUT: one CTA per tile
 __global__ void __launch_bounds__(256)
 build_lut_kernel(char* ws_base, size_t ws_stride, size_t o_status, size_t o_votes, size_t o_lut, size_t o_areas, int k_cap,
-                 int k_fixed, const int32_t* k_dev, const __grid_constant__ Things things, long long label_divisor,
-                 long long void_label, long long stuff_area, long long n_px)
+                 int k_fixed, const int32_t* k_dev, size_t k_dev_stride, const __grid_constant__ Things things,
+                 long long label_divisor, long long void_label, long long stuff_area, long long n_px)
 {
+    if (k_dev) k_dev += (size_t)blockIdx.z * k_dev_stride;         // per-tile center count (int32 words apart)
     char* ws = ws_base + (size_t)blockIdx.z * ws_stride;
     // stuff classes (postprocess.py:287-294): class c keeps its label c * L if it covers at least stuff_area pixels, else
     // void; class 0's area is the complement of everything assign counted.  Entries of thing classes are never looked up.
@@ -1549,11 +1550,11 @@ static int make_plane_tensor_map(CUtensorMap* out, CUtensorMapDataType dtype, si
 }
 
 int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float step, const WsLayout& L,
-                   char* ws, size_t ws_stride, int k_cap, int64_t* ctr_out, int cap, cudaStream_t st)
+                   char* ws, size_t ws_stride, int k_cap, int64_t* ctr_out, int cap, cudaStream_t st, size_t hm_stride = 0)
 {
     NmsArgs n;
     memset(&n, 0, sizeof(n));
-    n.hm = hm; n.hm_stride = (size_t)H * W;
+    n.hm = hm; n.hm_stride = hm_stride ? hm_stride : (size_t)H * W;
     n.ws = ws; n.ws_stride = ws_stride; n.o_mask = L.mask; n.o_rowcnt = L.rowcnt;
     n.B = B; n.H = H; n.W = W; n.wd = L.wd; n.lo = k / 2; n.hi = k - 1 - n.lo; n.thr = thr;
     n.blocks_x = (W + kNmsItemW - 1) / kNmsItemW;
@@ -1724,11 +1725,11 @@ int launch_apply(int B, const WsLayout& L, char* ws, size_t ws_stride, int64_t* 
 
 int launch_build_lut(int B, const WsLayout& L, char* ws, size_t ws_stride, int k_cap, int k_fixed, const int32_t* k_dev,
                      const Things& th, long long label_divisor, long long void_label, long long stuff_area, int H, int W,
-                     cudaStream_t st)
+                     cudaStream_t st, size_t k_dev_stride = 0)
 {
     ProfScope ps(ST_LUT, st);
-    build_lut_kernel<<<dim3(1, 1, B), 256, 0, st>>>(ws, ws_stride, L.status, L.votes, L.lut, L.areas, k_cap, k_fixed, k_dev, th,
-                                                    label_divisor, void_label, stuff_area, (long long)H * W);
+    build_lut_kernel<<<dim3(1, 1, B), 256, 0, st>>>(ws, ws_stride, L.status, L.votes, L.lut, L.areas, k_cap, k_fixed, k_dev,
+                                                    k_dev_stride, th, label_divisor, void_label, stuff_area, (long long)H * W);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
 }
@@ -1766,6 +1767,61 @@ static int tile_group(int B)
         env = e ? atoi(e) : 0;
     }
     return env > 0 ? env : B;
+}
+
+// ---- batched building blocks of the stack path (stack_block.cu) --------------------------------
+int assign_block_items(int H, int W) { return block_items(H, W); }
+
+int device_sm_count() { return sm_count(); }
+
+// B coarse maps -> nearest-center ids (engines.py:257-272 without the upsample): centers, cell index and the exact
+// argmin, one launch per kernel for the whole batch.  ws: B workspaces of ws_layout(h, w, k_cap, 1), ws_stride apart.
+int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* off, size_t off_stride, int h, int w,
+                       float threshold, int nms_kernel, float step, int32_t* ids_out, size_t ids_stride, int k_cap,
+                       char* ws, size_t ws_stride, cudaStream_t st)
+{
+    const WsLayout L = ws_layout(h, w, k_cap, 1);
+    EMP_REQUIRE(ws_stride >= L.total && ws_stride % 256 == 0, EMP_ERR_WORKSPACE, "coarse workspace stride too small");
+    EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    int rc;
+    if ((rc = launch_centers(B, hm, h, w, threshold, nms_kernel, step, L, ws, ws_stride, k_cap, nullptr, 0, st, hm_stride))) return rc;
+    if ((rc = launch_bin(B, L, ws, ws_stride, h, w, k_cap, -1, step, st))) return rc;
+    AssignArgs a;
+    memset(&a, 0, sizeof(a));
+    a.off = off; a.off_stride = off_stride;
+    a.out = ids_out; a.out_stride = ids_stride;
+    a.ws = ws; a.ws_stride = ws_stride;
+    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none); }
+    a.B = B; a.H = h; a.W = w; a.step = step; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
+    a.vec = (w % 4 == 0) && aligned16(off) && aligned16(ids_out) && (off_stride % 4 == 0) && (ids_stride % 4 == 0);
+    return launch_assign(SEM_NONE, ID_ARGMIN, OUT_IDS32, a, st);
+}
+
+// B hardened class maps (uint8) + their coarse id maps -> code maps, strip flags, votes and label LUTs
+// (postprocess.py:253-294 up to, but without, the write of the int64 label map).  ws: B workspaces of
+// ws_layout(H, W, k_cap, n_things); k_dev: the slices' center counts, k_dev_stride int32 words apart.
+int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, const int32_t* ids, size_t ids_stride, int hc,
+                        int wc, int shift, int H, int W, const Things& th, long long label_divisor, long long stuff_area,
+                        long long void_label, int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws,
+                        size_t ws_stride, cudaStream_t st)
+{
+    const WsLayout L = ws_layout(H, W, k_cap, th.n);
+    EMP_REQUIRE(L.code16, EMP_ERR_INVALID, "the stack block needs 16-bit codes (k_cap < %u)", kClsBase16);
+    EMP_REQUIRE(ws_stride >= L.total && ws_stride % 256 == 0, EMP_ERR_WORKSPACE, "merge workspace stride too small");
+    EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    AssignArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sem = sem8; a.sem_stride = sem_stride;
+    a.ids_in = ids; a.ids_stride = ids_stride; a.wc = wc; a.shift = shift;
+    a.out = ws + L.codes; a.out_stride = ws_stride / 2;
+    a.ws = ws; a.ws_stride = ws_stride;
+    fill_assign_common(a, L, th);
+    a.B = B; a.H = H; a.W = W; a.step = 1.0f; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = k_cap;
+    a.max_id = k_cap;
+    a.vec = (W % 4 == 0) && aligned16(sem8);
+    int rc;
+    if ((rc = launch_assign(SEM_U8, ID_COARSE, OUT_CODE16, a, st))) return rc;
+    return launch_build_lut(B, L, ws, ws_stride, k_cap, k_cap, k_dev, th, label_divisor, void_label, stuff_area, H, W, st, k_dev_stride);
 }
 
 }  // namespace emp

@@ -17,17 +17,9 @@
 //   rle_finish   scan of head flags -> final (start, length, slot) runs in ascending start order
 #include <string.h>
 #include <algorithm>
-#include "common.cuh"
+#include "rle_common.cuh"
 
 namespace emp {
-
-struct RleClasses {
-    long long lo[EMP_MAX_LABELS];        // label * L
-    long long label[EMP_MAX_LABELS];
-    unsigned char ccl[EMP_MAX_LABELS];   // 1: thing class and force_connected
-    long long L;
-    int n;
-};
 
 struct RleLayout {
     size_t status, rowcnt, zero_bytes;
@@ -63,22 +55,6 @@ static RleLayout rle_layout(int H, int W, int run_cap, int n_labels, long long L
     return R;
 }
 
-__device__ __forceinline__ int class_of(long long v, const RleClasses& rc)
-{
-    int c = -1;
-    for (int i = 0; i < rc.n; ++i)
-        if (v >= rc.lo[i] && v < rc.lo[i] + rc.L) c = i;
-    return (v != 0) ? c : -1;
-}
-
-// key-space offset of class ci when n row-runs exist: CCL classes take n keys, others L keys
-__device__ __forceinline__ long long key_offset(int ci, int n, const RleClasses& rc)
-{
-    long long o = 0;
-    for (int i = 0; i < ci; ++i) o += rc.ccl[i] ? (long long)n : rc.L;
-    return o;
-}
-
 // ---------------------------------------------------------------------------------------------
 // rle_mark — the one pass over the pixels.  A warp takes 256 consecutive pixels of a row (8 mask
 // words); lane l loads pixels 32j + l (j = 0..7: eight independent 8-byte loads in flight per lane,
@@ -87,12 +63,6 @@ __device__ __forceinline__ long long key_offset(int ci, int n, const RleClasses&
 // label_divisor <= 2^22 — so that neighbours compare with one shuffle.  An item with no selected pixel
 // (the bulk of an EM slice) stores zeros and moves on.
 constexpr int kMarkWords = 8;
-
-__device__ __forceinline__ unsigned run_key(long long v, const RleClasses& rc)
-{
-    const int c = class_of(v, rc);
-    return c >= 0 ? ((unsigned)(c + 1) << 22) | (unsigned)(v - rc.lo[c]) : 0u;
-}
 
 __global__ void __launch_bounds__(256)
 rle_mark_kernel(const long long* __restrict__ pan, int H, int W, int wd, RleClasses rc,
@@ -234,25 +204,6 @@ rle_emit_kernel(const long long* __restrict__ pan, int H, int W, int wd, RleClas
 }
 
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int uf_find(const int* parent, int x)
-{
-    int p = parent[x];
-    while (p != x) { x = p; p = parent[x]; }
-    return x;
-}
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b)
-{
-    bool done;
-    do {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
-        if (a < b) { const int old = atomicMin(parent + b, a); done = (old == b); b = old; }
-        else if (b < a) { const int old = atomicMin(parent + a, b); done = (old == a); a = old; }
-        else done = true;
-    } while (!done);
-}
-
 __global__ void __launch_bounds__(256)
 rle_union_kernel(const int32_t* __restrict__ status, int run_cap, RleClasses rc, const int* __restrict__ rowoff,
                  const int* __restrict__ r_y, const int* __restrict__ r_xs, const int* __restrict__ r_xe,
@@ -296,36 +247,6 @@ rle_flags_kernel(const int32_t* __restrict__ status, int run_cap, RleClasses rc,
             flags[off + (r_val[i] - rc.lo[c])] = 1;
         }
     }
-}
-
-// exclusive in-place scan of data[0..n) by one 1024-thread CTA, 4 items per thread per round
-__device__ int cta_scan_inplace(int* data, long long n, int* s_w)
-{
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int carry = 0;
-    for (long long base = 0; base < n; base += 4096) {
-        const long long i0 = base + (long long)tid * 4;
-        int v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? data[i0 + k] : 0;
-        const int local = v[0] + v[1] + v[2] + v[3];
-        int wtot;
-        const int wex = warp_excl_scan(local, lane, &wtot);
-        if (lane == 0) s_w[warp] = wtot;
-        __syncthreads();
-        int woff = 0, tot = 0;
-#pragma unroll
-        for (int w = 0; w < 32; ++w) { const int x = s_w[w]; if (w < warp) woff += x; tot += x; }
-        int run = carry + woff + wex;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i0 + k < n) data[i0 + k] = run;
-            run += v[k];
-        }
-        carry += tot;
-        __syncthreads();
-    }
-    return carry;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -446,27 +367,6 @@ rle_finish_kernel(int32_t* __restrict__ status, int run_cap, int out_cap, int in
 
 using namespace emp;
 
-static int make_rle_classes(const int64_t* labels, int n_labels, int64_t L, const int64_t* things, int nt,
-                            int force_connected, RleClasses* rc)
-{
-    EMP_REQUIRE(n_labels >= 0 && n_labels <= EMP_MAX_LABELS, EMP_ERR_INVALID, "at most %d labels (got %d)", EMP_MAX_LABELS, n_labels);
-    EMP_REQUIRE(L > 0 && L <= (1ll << 22), EMP_ERR_INVALID, "label_divisor must be in (0, 2^22] (got %lld)", (long long)L);
-    EMP_REQUIRE(n_labels == 0 || labels, EMP_ERR_INVALID, "labels is null");
-    memset(rc, 0, sizeof(*rc));
-    rc->n = n_labels;
-    rc->L = L;
-    for (int i = 0; i < n_labels; ++i) {
-        EMP_REQUIRE(labels[i] >= 0 && labels[i] < (1ll << 40), EMP_ERR_INVALID, "label %lld out of range", (long long)labels[i]);
-        for (int j = 0; j < i; ++j) EMP_REQUIRE(labels[j] != labels[i], EMP_ERR_INVALID, "duplicate label %lld", (long long)labels[i]);
-        rc->label[i] = labels[i];
-        rc->lo[i] = labels[i] * L;
-        bool thing = false;
-        for (int t = 0; t < nt; ++t) thing |= (things[t] == labels[i]);
-        rc->ccl[i] = (force_connected && thing) ? 1 : 0;
-    }
-    return EMP_OK;
-}
-
 EMP_API size_t emp_rle_workspace_bytes(int H, int W, int run_cap, int n_labels, int64_t label_divisor)
 {
     if (H <= 0 || W <= 0 || run_cap < 1 || label_divisor <= 0) return 0;
@@ -509,7 +409,7 @@ EMP_API int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels, int
     EMP_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * R.flags_len, st));
 
     const size_t chunks = (size_t)H * ((R.wd + kMarkWords - 1) / kMarkWords);      // 256-pixel items, one per warp
-    unsigned g_mark = (unsigned)std::min<size_t>((chunks + 7) / 8, (size_t)148 * 16);
+    unsigned g_mark = (unsigned)std::min<size_t>((chunks + 7) / 8, (size_t)device_sm_count() * 16);
     if (g_mark < 1) g_mark = 1;
     {
         ProfScope ps(ST_RLE_MARK, st);
@@ -520,7 +420,7 @@ EMP_API int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels, int
     rle_emit_kernel<<<(H + 31) / 32, 256, 0, st>>>(panp, H, W, R.wd, rc, smask, emask, rowcnt, rowoff, r_y, r_xs, r_xe,
                                                    r_cls, r_val, parent, status, run_cap);
     EMP_CUDA_CHECK(cudaGetLastError());
-    const unsigned g_runs = (unsigned)std::min<size_t>(((size_t)run_cap + 255) / 256, (size_t)148 * 8);
+    const unsigned g_runs = (unsigned)std::min<size_t>(((size_t)run_cap + 255) / 256, (size_t)device_sm_count() * 8);
     bool any_ccl = false;
     for (int i = 0; i < rc.n; ++i) any_ccl |= rc.ccl[i] != 0;
     if (any_ccl) {

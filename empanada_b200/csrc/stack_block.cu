@@ -1,0 +1,988 @@
+// stack_block.cu — the 3D stack path, a z-block at a time (one launch per kernel for B slices).
+//
+//   emp_median_chain         _MedianQueue + _harden_seg over a whole z-block (engines.py:47-90, :114-121): every thread
+//                            owns 4 pixels and walks the block in z with the recursion's state in registers — each raw
+//                            probability is read ONCE (4 B/voxel) and only the hardened class byte is written (1 B/voxel)
+//   emp_median_chain_repair  the same block re-run from a corrected carry, per pixel only as far as the two chains differ
+//                            (the z-sharded stack starts every rank's chain from a guessed carry: inference/stack.py)
+//   emp_stack_block          hardened classes + coarse heat-maps / offsets of B slices -> RLE tables, packed for one D2H:
+//                              coarse centers + nearest-center ids          (panoptic.cu, batched; engines.py:257-272)
+//                              upsample-fused merge -> 16-bit code map, strip flags, label LUT
+//                                                                           (panoptic.cu, batched; postprocess.py:253-294)
+//                              rle_block_keys   label LUT -> 32-bit run keys (class index, label - class base)
+//                              rle_block_mark   code map + strip flags -> run start / end bit masks (rle.py:57-71)
+//                              rle_block_emit   masks -> row-runs in raster order
+//                              rle_block_runs   one CTA per slice: 8-connected union-find over row-runs, instance slots
+//                                               in the reference's dict order, per-instance run lists merged across row
+//                                               ends (array_utils.rle_encode :209-235), boxes, areas
+//                              rle_block_pack   instance tables of all slices packed behind the run lists
+//                            The int64 label map the reference materialises between merge and RLE (8 B/px written, 8 B/px
+//                            read back) never exists: runs are cut from the 2 B/px code map, and only for strips that
+//                            hold something other than class-0 background.
+#include <math_constants.h>
+#include <string.h>
+#include <algorithm>
+#include "rle_common.cuh"
+
+namespace emp {
+
+// =====================================================================================================
+// 1. recursive median chain
+// =====================================================================================================
+constexpr int kChainPf = 3;         // raw planes loaded ahead of the window (loads in flight per thread)
+
+struct ChainArgs {
+    const float* const* planes;     // device array: planes[j] = raw (C,H,W) probabilities of slice z0 + j, j < n_planes
+    const float* const* carry_in;   // device array of mid pointers: filtered planes z0-mid .. z0-1 (null: none)
+    const float* const* carry_new;  // repair: the corrected carry
+    float* const* carry_out;        // device array of mid pointers (null: not wanted): filtered planes z0+n-mid .. z0+n-1
+    int n, n_planes, z0, depth, c;
+    size_t hw;                      // elements per channel plane
+    float thr;
+    unsigned char* sem8; size_t sem8_stride;
+    float* best;                    // C > 1: running maximum over the channels seen so far, [n][hw]
+    int multi;                      // C > 1
+    int32_t* changed;               // repair: set to 1 if the block's outgoing carry changed
+};
+
+// middle order statistic of KS values; NaN if any of them is NaN (torch.median propagates NaN)
+template <int KS>
+__device__ __forceinline__ float median_nan(const float (&w)[KS])
+{
+    float v[KS];
+    bool nan = false;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) { v[i] = w[i]; nan |= (w[i] != w[i]); }
+#pragma unroll
+    for (int pass = 0; pass < KS; ++pass) {
+#pragma unroll
+        for (int i = (pass & 1); i + 1 < KS; i += 2) {
+            const float lo = fminf(v[i], v[i + 1]);
+            const float hi = fmaxf(v[i], v[i + 1]);
+            v[i] = lo; v[i + 1] = hi;
+        }
+    }
+    return nan ? CUDART_NAN_F : v[(KS - 1) / 2];
+}
+
+template <int N>
+__device__ __forceinline__ void load_px(float (&dst)[N], const float* p)
+{
+    if (N == 4) {
+        const float4 u = __ldcs(reinterpret_cast<const float4*>(p));
+        dst[0] = u.x; dst[1 % N] = u.y; dst[2 % N] = u.z; dst[3 % N] = u.w;
+    } else {
+        dst[0] = __ldcs(p);
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void store_px(float* p, const float (&src)[N])
+{
+    if (N == 4) *reinterpret_cast<float4*>(p) = make_float4(src[0], src[1 % N], src[2 % N], src[3 % N]);
+    else p[0] = src[0];
+}
+
+// One thread per N consecutive pixels of one channel; the z loop keeps the last MID filtered values and the raw
+// window (+ kChainPf planes of look-ahead) in registers.  REPAIR runs the chain from two carries at once and stops
+// as soon as their states agree bit for bit (from there on the outputs are identical by construction).
+template <int KS, int N, bool REPAIR>
+__global__ void __launch_bounds__(256)
+median_chain_kernel(const ChainArgs a)
+{
+    constexpr int MID = KS / 2, MS = MID > 0 ? MID : 1, WIN = MID + 1 + kChainPf;
+    const size_t items = a.hw / N;
+    const size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= items) return;
+    const size_t px = it * N;
+    const size_t e = (size_t)a.c * a.hw + px;
+    float f[MS][N], g[MS][N], r[WIN][N];
+#pragma unroll
+    for (int j = 0; j < MS; ++j)
+#pragma unroll
+        for (int q = 0; q < N; ++q) { f[j][q] = 0.f; g[j][q] = 0.f; }
+    if (MID > 0 && a.carry_in) {
+#pragma unroll
+        for (int j = 0; j < MID; ++j) load_px<N>(f[j], a.carry_in[j] + e);
+    }
+    if (REPAIR) {
+#pragma unroll
+        for (int j = 0; j < MID; ++j) load_px<N>(g[j], a.carry_new[j] + e);
+    }
+#pragma unroll
+    for (int j = 0; j < WIN; ++j) {
+#pragma unroll
+        for (int q = 0; q < N; ++q) r[j][q] = 0.f;
+        if (j < a.n_planes) load_px<N>(r[j], a.planes[j] + e);
+    }
+    bool differs = REPAIR;
+#pragma unroll 1
+    for (int i = 0; i < a.n; ++i) {
+        if (REPAIR) {
+            differs = false;
+#pragma unroll
+            for (int j = 0; j < MID; ++j)
+#pragma unroll
+                for (int q = 0; q < N; ++q) differs |= __float_as_uint(f[j][q]) != __float_as_uint(g[j][q]);
+            if (!differs) break;
+        }
+        const int z = a.z0 + i;
+        const bool raw = (z < MID) || (z >= a.depth - MID);        // the queue passes the stack's ends through unfiltered
+        float o[N], og[N];
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+            o[q] = r[0][q]; og[q] = r[0][q];
+            if (KS > 1 && !raw) {
+                float w[KS];
+#pragma unroll
+                for (int j = 0; j < MID; ++j) w[j] = f[j][q];
+#pragma unroll
+                for (int j = 0; j <= MID; ++j) w[MID + j] = r[j][q];
+                o[q] = median_nan<KS>(w);
+                if (REPAIR) {
+#pragma unroll
+                    for (int j = 0; j < MID; ++j) w[j] = g[j][q];
+#pragma unroll
+                    for (int j = 0; j <= MID; ++j) w[MID + j] = r[j][q];
+                    og[q] = median_nan<KS>(w);
+                }
+            }
+        }
+        const float (&res)[N] = REPAIR ? og : o;                    // the values that count
+        unsigned char* sp = a.sem8 + (size_t)i * a.sem8_stride + px;
+        if (!a.multi) {
+            unsigned bits = 0;
+#pragma unroll
+            for (int q = 0; q < N; ++q) bits |= (res[q] >= a.thr ? 1u : 0u) << (8 * q);
+            if (N == 4) *reinterpret_cast<unsigned*>(sp) = bits;
+            else sp[0] = (unsigned char)bits;
+        } else {                                                    // first arg-max over channels, NaN counts as the maximum
+            float* bp = a.best + (size_t)i * a.hw + px;
+            if (a.c == 0) {
+                store_px<N>(bp, res);
+#pragma unroll
+                for (int q = 0; q < N; ++q) sp[q] = 0;
+            } else {
+                float b[N];
+                load_px<N>(b, bp);
+#pragma unroll
+                for (int q = 0; q < N; ++q)
+                    if (res[q] > b[q] || (res[q] != res[q] && b[q] == b[q])) { bp[q] = res[q]; sp[q] = (unsigned char)a.c; }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
+#pragma unroll
+            for (int j = 0; j + 1 < MID; ++j) { f[j][q] = f[j + 1][q]; g[j][q] = g[j + 1][q]; }
+            if constexpr (MID > 0) { f[MID - 1][q] = o[q]; g[MID - 1][q] = og[q]; }
+#pragma unroll
+            for (int j = 0; j + 1 < WIN; ++j) r[j][q] = r[j + 1][q];
+        }
+        if (i + WIN < a.n_planes) load_px<N>(r[WIN - 1], a.planes[i + WIN] + e);
+    }
+    if (MID > 0 && a.carry_out) {
+        if (!REPAIR) {
+#pragma unroll
+            for (int j = 0; j < MID; ++j) store_px<N>(a.carry_out[j] + e, f[j]);
+        } else if (differs) {                                       // still apart at the block's end: the carry moves on
+#pragma unroll
+            for (int j = 0; j < MID; ++j) store_px<N>(a.carry_out[j] + e, g[j]);
+            *a.changed = 1;
+        }
+    }
+}
+
+template <int KS, bool REPAIR>
+static int launch_chain_ks(const ChainArgs& a, bool vec, cudaStream_t st)
+{
+    const size_t items = vec ? a.hw / 4 : a.hw;
+    const unsigned grid = (unsigned)((items + 255) / 256);
+    ProfScope ps(ST_CHAIN, st);
+    if (vec) median_chain_kernel<KS, 4, REPAIR><<<grid, 256, 0, st>>>(a);
+    else median_chain_kernel<KS, 1, REPAIR><<<grid, 256, 0, st>>>(a);
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}
+
+template <bool REPAIR>
+static int launch_chain(int ks, const ChainArgs& a, bool vec, cudaStream_t st)
+{
+    switch (ks) {
+        case 1:  return REPAIR ? EMP_OK : launch_chain_ks<1, false>(a, vec, st);
+        case 3:  return launch_chain_ks<3, REPAIR>(a, vec, st);
+        case 5:  return launch_chain_ks<5, REPAIR>(a, vec, st);
+        case 7:  return launch_chain_ks<7, REPAIR>(a, vec, st);
+        case 9:  return launch_chain_ks<9, REPAIR>(a, vec, st);
+        case 11: return launch_chain_ks<11, REPAIR>(a, vec, st);
+        case 13: return launch_chain_ks<13, REPAIR>(a, vec, st);
+        default: return launch_chain_ks<15, REPAIR>(a, vec, st);
+    }
+}
+
+// =====================================================================================================
+// 2. RLE tables from code maps
+// =====================================================================================================
+// per-slice scratch of the encoder (B of them, rs_stride apart)
+struct BlkLayout {
+    size_t status, rowcnt, flags, cnt, zero_bytes;          // [0, zero_bytes) is cleared per call
+    size_t keylut, smask, emask, rowoff, r_y, r_xs, r_xe, r_key, parent, slot_of, ymin, ymax, inst, total;
+    size_t flags_len;
+    int wd;
+};
+
+static BlkLayout blk_layout(int crop_h, int crop_w, int run_cap, int inst_cap, int n_labels, long long L, int k_cap)
+{
+    BlkLayout R;
+    R.wd = (crop_w + 31) / 32;
+    if (n_labels < 1) n_labels = 1;
+    // key space per class: row-runs for CCL classes, label - base (<= number of centers) otherwise
+    const size_t key_space = (size_t)std::max<long long>((long long)run_cap, std::min<long long>(L, (long long)k_cap + 1));
+    R.flags_len = key_space * (size_t)n_labels + 1;
+    size_t o = 0;
+    R.status = o;  o = align_up(o + sizeof(int32_t) * EMP_ST_WORDS, 256);
+    R.rowcnt = o;  o = align_up(o + sizeof(uint32_t) * (size_t)crop_h, 256);
+    R.flags = o;   o = align_up(o + sizeof(int) * R.flags_len, 256);
+    R.cnt = o;     o = align_up(o + sizeof(int) * ((size_t)inst_cap + 1), 256);
+    R.zero_bytes = o;
+    R.keylut = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1 + kNumClasses), 256);
+    R.smask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);
+    R.emask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);
+    R.rowoff = o;  o = align_up(o + sizeof(int) * ((size_t)crop_h + 1), 256);
+    R.r_y = o;     o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
+    R.r_xs = o;    o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
+    R.r_xe = o;    o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
+    R.r_key = o;   o = align_up(o + sizeof(uint32_t) * (size_t)run_cap, 256);
+    R.parent = o;  o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
+    R.slot_of = o; o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
+    R.ymin = o;    o = align_up(o + sizeof(int) * (size_t)inst_cap, 256);
+    R.ymax = o;    o = align_up(o + sizeof(int) * (size_t)inst_cap, 256);
+    R.inst = o;    o = align_up(o + sizeof(long long) * EMP_BLK_INST_WORDS * (size_t)inst_cap, 256);
+    R.total = o;
+    return R;
+}
+
+struct BlkArgs {
+    char* ws; size_t ws_stride;             // merge workspaces (ws_layout): codes, strip flags, label LUT, status
+    size_t o_codes, o_sflags, o_lut, o_status;
+    char* cs; size_t cs_stride; size_t o_cstatus;   // coarse workspaces: status (center count K)
+    char* rs; size_t rs_stride;             // encoder scratch (BlkLayout)
+    BlkLayout R;
+    RleClasses rc;
+    int B, W, crop_h, crop_w;               // W: row pitch of the code map (the padded plane)
+    int blocks_x, blk_items;                // strip-flag geometry of the assign kernel
+    unsigned cls_off;
+    int k_cap, run_cap, inst_cap;
+    int vec;                                // 16-byte code loads allowed
+    long long* packed;                      // EMP_BLK_* layout
+    long long* runs3; size_t runs3_stride;  // optional (start, length, slot) row-runs per slice, int64 triples
+};
+
+// label LUT -> run keys: 0 if the label belongs to no selected class, else (class index + 1) << 22 | (label - base)
+__global__ void __launch_bounds__(256)
+rle_block_keys_kernel(const BlkArgs a)
+{
+    const int b = blockIdx.z;
+    const char* ws = a.ws + (size_t)b * a.ws_stride;
+    const long long* lut = reinterpret_cast<const long long*>(ws + a.o_lut);
+    uint32_t* keylut = reinterpret_cast<uint32_t*>(a.rs + (size_t)b * a.rs_stride + a.R.keylut);
+    const int K = min(max(__ldcg(reinterpret_cast<const int32_t*>(a.cs + (size_t)b * a.cs_stride + a.o_cstatus) + EMP_ST_K), 0), a.k_cap);
+    const int n = K + 1 + kNumClasses;              // ids 0..K, then the class entries at cls_off
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int idx = i <= K ? i : (int)a.cls_off + (i - K - 1);
+        keylut[idx] = run_key(lut[idx], a.rc);
+    }
+}
+
+// run key of pixel (y, x) of slice-local planes: strip flag -> code -> key
+struct CodeView {
+    const unsigned short* codes;
+    const unsigned char* sflags;
+    const uint32_t* keylut;
+    int W, blocks_x, blk_items;
+    unsigned cls_off;
+};
+
+__device__ __forceinline__ unsigned code_index(unsigned code, unsigned cls_off)
+{
+    return code >= kClsBase16 ? code - kClsBase16 + cls_off : code;
+}
+
+__device__ __forceinline__ size_t flag_index(const CodeView& v, int y, int x)
+{
+    return ((size_t)(y / (v.blk_items * 4)) * v.blocks_x + (x >> 6)) * 16 + ((y >> 2) % v.blk_items);
+}
+
+__device__ __forceinline__ unsigned key_at(const CodeView& v, int y, int x)
+{
+    const unsigned code = v.sflags[flag_index(v, y, x)] ? kClsBase16 : v.codes[(size_t)y * v.W + x];
+    return __ldg(v.keylut + code_index(code, v.cls_off));
+}
+
+__device__ __forceinline__ CodeView code_view(const BlkArgs& a, int b)
+{
+    CodeView v;
+    const char* ws = a.ws + (size_t)b * a.ws_stride;
+    v.codes = reinterpret_cast<const unsigned short*>(ws + a.o_codes);
+    v.sflags = reinterpret_cast<const unsigned char*>(ws + a.o_sflags);
+    v.keylut = reinterpret_cast<const uint32_t*>(a.rs + (size_t)b * a.rs_stride + a.R.keylut);
+    v.W = a.W; v.blocks_x = a.blocks_x; v.blk_items = a.blk_items; v.cls_off = a.cls_off;
+    return v;
+}
+
+// The one pass over the (cropped) code maps.  A warp takes 256 consecutive pixels of a row; lane l owns pixels
+// 8l .. 8l+7 (one 16-byte load of codes — or none at all when its 64-column strip is flagged "all class-0
+// background", the bulk of an EM slice).  Start / end bits are formed per lane and gathered into the row's mask
+// words with three shuffles.
+__global__ void __launch_bounds__(256)
+rle_block_mark_kernel(const BlkArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int groups = (a.crop_w + 255) / 256;
+    const size_t per_slice = (size_t)a.crop_h * groups;
+    const size_t items = per_slice * a.B;
+    const int wd = a.R.wd;
+    for (size_t it = warp_global; it < items; it += n_warps) {
+        const int b = (int)(it / per_slice);
+        const size_t r = it - (size_t)b * per_slice;
+        const int y = (int)(r / groups), g = (int)(r % groups);
+        const CodeView v = code_view(a, b);
+        char* rs = a.rs + (size_t)b * a.rs_stride;
+        uint32_t* smask = reinterpret_cast<uint32_t*>(rs + a.R.smask) + (size_t)y * wd;
+        uint32_t* emask = reinterpret_cast<uint32_t*>(rs + a.R.emask) + (size_t)y * wd;
+        const int xb = g * 256, x0 = xb + lane * 8;
+        const unsigned bgkey = __ldg(v.keylut + a.cls_off);             // class-0 background
+        const bool inside = x0 < a.crop_w;
+        const bool flagged = inside && v.sflags[flag_index(v, y, x0)] != 0;
+        unsigned key[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) key[p] = 0u;
+        if (flagged) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) key[p] = (x0 + p < a.crop_w) ? bgkey : 0u;
+        } else if (inside) {
+            unsigned code[8];
+            const unsigned short* cp = v.codes + (size_t)y * a.W + x0;
+            if (a.vec) {                                                // W % 8 == 0: the whole group lies inside the plane
+                const uint4 u = __ldcs(reinterpret_cast<const uint4*>(cp));
+                code[0] = u.x & 0xFFFFu; code[1] = u.x >> 16; code[2] = u.y & 0xFFFFu; code[3] = u.y >> 16;
+                code[4] = u.z & 0xFFFFu; code[5] = u.z >> 16; code[6] = u.w & 0xFFFFu; code[7] = u.w >> 16;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) code[p] = (x0 + p < a.crop_w) ? cp[p] : 0u;
+            }
+            unsigned prev_code = 0xFFFFFFFFu, prev_key = 0u;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                if (code[p] != prev_code) { prev_code = code[p]; prev_key = __ldg(v.keylut + code_index(code[p], a.cls_off)); }
+                key[p] = (x0 + p < a.crop_w) ? prev_key : 0u;
+            }
+        }
+        unsigned any = 0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) any |= key[p];
+        const int w0 = g * 8;
+        if (!__any_sync(0xffffffffu, any != 0u)) {                      // warp-uniform: nothing selected here
+            if (lane < 8 && w0 + lane < wd) { smask[w0 + lane] = 0u; emask[w0 + lane] = 0u; }
+            continue;
+        }
+        unsigned left = __shfl_up_sync(0xffffffffu, key[7], 1);
+        unsigned right = __shfl_down_sync(0xffffffffu, key[0], 1);
+        if (lane == 0) left = xb > 0 ? key_at(v, y, xb - 1) : 0u;
+        if (lane == 31) right = xb + 256 < a.crop_w ? key_at(v, y, xb + 256) : 0u;
+        unsigned sb = 0, eb = 0;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const unsigned l = p ? key[p - 1] : left, rr = p < 7 ? key[p + 1] : right;
+            sb |= (key[p] != 0u && l != key[p] ? 1u : 0u) << p;
+            eb |= (key[p] != 0u && rr != key[p] ? 1u : 0u) << p;
+        }
+        const unsigned mine = sb | (eb << 8);
+        const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
+                       m3 = __shfl_down_sync(0xffffffffu, mine, 3);
+        unsigned cnt = 0;
+        if ((lane & 3) == 0) {
+            const unsigned sw = (mine & 0xFFu) | ((m1 & 0xFFu) << 8) | ((m2 & 0xFFu) << 16) | ((m3 & 0xFFu) << 24);
+            const unsigned ew = ((mine >> 8) & 0xFFu) | (((m1 >> 8) & 0xFFu) << 8) | (((m2 >> 8) & 0xFFu) << 16) | (((m3 >> 8) & 0xFFu) << 24);
+            const int wi = w0 + (lane >> 2);
+            if (wi < wd) { smask[wi] = sw; emask[wi] = ew; }
+            cnt = (unsigned)__popc(sw);
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<uint32_t*>(rs + a.R.rowcnt) + y, cnt);
+    }
+}
+
+// masks -> row-runs in raster order: a CTA owns 32 rows of one slice (prefix = the row counts above them)
+__global__ void __launch_bounds__(256)
+rle_block_emit_kernel(const BlkArgs a)
+{
+    __shared__ int s_part[8];
+    __shared__ int s_off[33];
+    const int b = blockIdx.z;
+    const CodeView v = code_view(a, b);
+    char* rs = a.rs + (size_t)b * a.rs_stride;
+    const uint32_t* rowcnt = reinterpret_cast<const uint32_t*>(rs + a.R.rowcnt);
+    const uint32_t* smask = reinterpret_cast<const uint32_t*>(rs + a.R.smask);
+    const uint32_t* emask = reinterpret_cast<const uint32_t*>(rs + a.R.emask);
+    int* rowoff = reinterpret_cast<int*>(rs + a.R.rowoff);
+    int* r_y = reinterpret_cast<int*>(rs + a.R.r_y);
+    int* r_xs = reinterpret_cast<int*>(rs + a.R.r_xs);
+    int* r_xe = reinterpret_cast<int*>(rs + a.R.r_xe);
+    uint32_t* r_key = reinterpret_cast<uint32_t*>(rs + a.R.r_key);
+    int* parent = reinterpret_cast<int*>(rs + a.R.parent);
+    const int H = a.crop_h, wd = a.R.wd, run_cap = a.run_cap;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * 32;
+
+    int part = 0;
+    for (int i = tid; i < r0; i += 256) part += (int)rowcnt[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int prefix = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) prefix += s_part[w];
+        const int c = (r0 + lane < H) ? (int)rowcnt[r0 + lane] : 0;
+        int tot;
+        const int ex = warp_excl_scan(c, lane, &tot);
+        s_off[lane] = prefix + ex;
+        if (lane == 31) s_off[32] = prefix + tot;
+        if (r0 + lane < H) rowoff[r0 + lane] = prefix + ex;
+        if (r0 + 32 >= H && lane == 31) rowoff[H] = prefix + tot;
+    }
+    __syncthreads();
+
+    for (int j = 0; j < 4; ++j) {
+        const int rr = warp * 4 + j;
+        const int y = r0 + rr;
+        if (y >= H) break;
+        const int base = s_off[rr];
+        const int cnt = s_off[rr + 1] - base;
+        if (cnt == 0) continue;
+        int run_s = 0, run_e = 0;
+        for (int wb = 0; wb < wd; wb += 32) {
+            const int wi = wb + lane;
+            unsigned sw = wi < wd ? smask[(size_t)y * wd + wi] : 0u;
+            unsigned ew = wi < wd ? emask[(size_t)y * wd + wi] : 0u;
+            int tot_s, tot_e;
+            int ps = base + run_s + warp_excl_scan(__popc(sw), lane, &tot_s);
+            int pe = base + run_e + warp_excl_scan(__popc(ew), lane, &tot_e);
+            while (sw) {
+                const int bit = __ffs(sw) - 1;
+                sw &= sw - 1;
+                const int x = wi * 32 + bit;
+                if (ps < run_cap) { r_y[ps] = y; r_xs[ps] = x; r_key[ps] = key_at(v, y, x); parent[ps] = ps; }
+                ++ps;
+            }
+            while (ew) {
+                const int bit = __ffs(ew) - 1;
+                ew &= ew - 1;
+                if (pe < run_cap) r_xe[pe] = wi * 32 + bit + 1;         // exclusive end
+                ++pe;
+            }
+            run_s += tot_s;
+            run_e += tot_e;
+            if (run_s >= cnt && run_e >= cnt) break;
+        }
+    }
+}
+
+// union-find on row-run indices inside ONE CTA: parent links only ever decrease (atomicMin), reads go to L2
+__device__ __forceinline__ int ufb_find(const int* parent, int x)
+{
+    int p = __ldcg(parent + x);
+    while (p != x) { x = p; p = __ldcg(parent + x); }
+    return x;
+}
+
+__device__ __forceinline__ void ufb_union(int* parent, int a, int b)
+{
+    bool done;
+    do {
+        a = ufb_find(parent, a);
+        b = ufb_find(parent, b);
+        if (a < b) { const int old = atomicMin(parent + b, a); done = (old == b); b = old; }
+        else if (b < a) { const int old = atomicMin(parent + a, b); done = (old == a); a = old; }
+        else done = true;
+    } while (!done);
+}
+
+__device__ __forceinline__ int block_sum(int v, int* s_w)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if (lane == 0) s_w[warp] = v;
+    __syncthreads();
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) tot += s_w[w];
+    return tot;
+}
+
+// rows of the run region of the packed output this slice's runs start at: the row-runs of the slices before it
+__device__ __forceinline__ void block_prefix(const BlkArgs& a, int b, int* s_w, int* my_off, int* total)
+{
+    int before = 0, all = 0;
+    for (int j = threadIdx.x; j < a.B; j += blockDim.x) {
+        const int* ro = reinterpret_cast<const int*>(a.rs + (size_t)j * a.rs_stride + a.R.rowoff);
+        const int nj = min(__ldcg(ro + a.crop_h), a.run_cap);
+        all += nj;
+        if (j < b) before += nj;
+    }
+    *my_off = block_sum(before, s_w);
+    *total = block_sum(all, s_w);
+}
+
+// Everything behind the row-runs of one slice, by one 1024-thread CTA (a 2048^2 EM slice has a few thousand row-runs):
+//   1  8-connected union of touching equal-key runs of CCL classes (root = lowest run index = raster-first pixel)
+//   2  key flags (CCL: root runs; else label - base) -> exclusive scan -> instance slots in the reference's dict
+//      order (class order of `labels`, ascending label: rle.py:57-84), table rows
+//   3  slot per row-run, run count and row band per slot; scan of the counts -> where each slot's run list starts
+//   4  a warp per slot walks the row-runs of its row band, keeps its own, merges a run that starts where the slot's
+//      previous run ended (array_utils.rle_encode only breaks where idx[i] != idx[i-1]+1: a run reaching the last column
+//      continues in column 0 of the next row) and writes (start, length) in ascending order; box and area on the way
+__global__ void __launch_bounds__(1024)
+rle_block_runs_kernel(const BlkArgs a)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_base[EMP_MAX_LABELS + 1];
+    const int b = blockIdx.x;
+    char* rs = a.rs + (size_t)b * a.rs_stride;
+    int32_t* status = reinterpret_cast<int32_t*>(rs + a.R.status);
+    const int* rowoff = reinterpret_cast<const int*>(rs + a.R.rowoff);
+    const int* r_y = reinterpret_cast<const int*>(rs + a.R.r_y);
+    const int* r_xs = reinterpret_cast<const int*>(rs + a.R.r_xs);
+    const int* r_xe = reinterpret_cast<const int*>(rs + a.R.r_xe);
+    const uint32_t* r_key = reinterpret_cast<const uint32_t*>(rs + a.R.r_key);
+    int* parent = reinterpret_cast<int*>(rs + a.R.parent);
+    int* slot_of = reinterpret_cast<int*>(rs + a.R.slot_of);
+    int* flags = reinterpret_cast<int*>(rs + a.R.flags);
+    int* cnt = reinterpret_cast<int*>(rs + a.R.cnt);
+    int* ymin = reinterpret_cast<int*>(rs + a.R.ymin);
+    int* ymax = reinterpret_cast<int*>(rs + a.R.ymax);
+    long long* inst = reinterpret_cast<long long*>(rs + a.R.inst);
+    const RleClasses& rc = a.rc;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = a.crop_h, Wc = a.crop_w, inst_cap = a.inst_cap;
+    const int n_all = __ldcg(rowoff + H);
+    const int n = min(n_all, a.run_cap);
+    int my_off, total_rr;
+    block_prefix(a, b, s_w, &my_off, &total_rr);
+    long long* starts_out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + my_off;
+    long long* lens_out = starts_out + total_rr;
+    if (tid == 0) {
+        status[EMP_ST_NROWRUNS] = n_all;
+        if (n_all > a.run_cap) atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
+    }
+    // key-space offsets of the classes: CCL classes take n keys, the others min(L, k_cap + 1)
+    const long long plain_keys = min(rc.L, (long long)a.k_cap + 1);
+    auto key_off = [&](int ci) {
+        long long o = 0;
+        for (int i = 0; i < ci; ++i) o += rc.ccl[i] ? (long long)n : plain_keys;
+        return o;
+    };
+    // ---- 1
+    for (int i = tid; i < n; i += 1024) {
+        const uint32_t key = r_key[i];
+        const int c = (int)(key >> 22) - 1;
+        const int y = r_y[i];
+        if (c < 0 || !rc.ccl[c] || y == 0) continue;
+        const int lo = min(rowoff[y - 1], n), hi = min(rowoff[y], n);
+        const int xs = r_xs[i], xe = r_xe[i];
+        int p = lo, q = hi;                                     // first run of the row above with r_xe >= xs
+        while (p < q) {
+            const int m = (p + q) >> 1;
+            if (r_xe[m] >= xs) q = m; else p = m + 1;
+        }
+        for (int j = p; j < hi && r_xs[j] <= xe; ++j)
+            if (r_key[j] == key) ufb_union(parent, i, j);
+    }
+    __syncthreads();
+    // ---- 2
+    for (int i = tid; i < n; i += 1024) {
+        const uint32_t key = r_key[i];
+        const int c = (int)(key >> 22) - 1;
+        if (c < 0) continue;
+        const long long off = key_off(c);
+        if (rc.ccl[c]) {
+            if (ufb_find(parent, i) == i) flags[off + i] = 1;
+        } else {
+            const long long kv = (long long)(key & 0x3FFFFFu);
+            if (kv < plain_keys) flags[off + kv] = 1;
+            else atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);     // cannot happen: labels are 1 + rank <= K
+        }
+    }
+    __syncthreads();
+    const long long F = key_off(rc.n);
+    const int n_inst_all = cta_scan_inplace(flags, F, s_w);
+    if (tid == 0) {
+        flags[F] = n_inst_all;
+        status[EMP_ST_NINST] = n_inst_all;
+        if (n_inst_all > inst_cap) atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
+    }
+    __syncthreads();
+    if (tid <= rc.n) s_base[tid] = flags[key_off(tid)];
+    __syncthreads();
+    const int n_inst = min(n_inst_all, inst_cap);
+    for (long long p = tid; p < F; p += 1024) {
+        const int slot = flags[p];
+        if (flags[p + 1] - slot != 1 || slot >= inst_cap) continue;
+        int ci = 0;
+        long long off = 0;
+        for (; ci < rc.n; ++ci) {
+            const long long sz = rc.ccl[ci] ? (long long)n : plain_keys;
+            if (p < off + sz) break;
+            off += sz;
+        }
+        long long* row = inst + (size_t)slot * EMP_BLK_INST_WORDS;
+        row[0] = rc.label[ci];
+        row[1] = rc.ccl[ci] ? rc.lo[ci] + (long long)(slot - s_base[ci]) + 1 : rc.lo[ci] + (p - off);
+        ymin[slot] = INT_MAX; ymax[slot] = -1;
+    }
+    __syncthreads();
+    // ---- 3
+    long long* r3 = a.runs3 ? a.runs3 + (size_t)b * a.runs3_stride : nullptr;
+    for (int i = tid; i < n; i += 1024) {
+        const uint32_t key = r_key[i];
+        const int c = (int)(key >> 22) - 1;
+        int slot = -1;
+        if (c >= 0) {
+            const long long off = key_off(c);
+            const long long kv = rc.ccl[c] ? (long long)ufb_find(parent, i) : (long long)(key & 0x3FFFFFu);
+            slot = (rc.ccl[c] || kv < plain_keys) ? flags[off + kv] : -1;
+        }
+        slot_of[i] = slot;
+        const int y = r_y[i];
+        if (slot >= 0 && slot < inst_cap) {
+            atomicAdd(cnt + slot, 1);
+            atomicMin(ymin + slot, y);
+            atomicMax(ymax + slot, y);
+        }
+        if (r3) {
+            r3[(size_t)i * 3] = (long long)y * Wc + r_xs[i];
+            r3[(size_t)i * 3 + 1] = r_xe[i] - r_xs[i];
+            r3[(size_t)i * 3 + 2] = slot;
+        }
+    }
+    __syncthreads();
+    cta_scan_inplace(cnt, n_inst, s_w);                         // cnt[slot] = first row of the slot's run list (slice-local)
+    __syncthreads();
+    // ---- 4
+    for (int slot = warp; slot < n_inst; slot += 32) {
+        const int ya = __ldcg(ymin + slot), yb = __ldcg(ymax + slot);
+        const int base = __ldcg(cnt + slot);
+        long long* row = inst + (size_t)slot * EMP_BLK_INST_WORDS;
+        if (yb < 0) {                                           // cannot happen (a slot exists because a run carries it)
+            if (lane == 0) { row[2] = 0; row[3] = 0; row[4] = 0; row[5] = 0; row[6] = 0; row[7] = my_off + base; row[8] = 0; }
+            continue;
+        }
+        const int ja = min(rowoff[ya], n), jb = min(rowoff[yb + 1], n);
+        int n_final = 0, x0 = INT_MAX, x1 = -1;
+        long long carry_start = -1, carry_end = -1, area = 0;   // the slot's last run so far (flat indices)
+        for (int j0 = ja; j0 < jb; j0 += 32) {
+            const int j = j0 + lane;
+            const bool mine = j < jb && slot_of[j] == slot;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (!m) continue;                                   // warp-uniform
+            long long start = 0, end = 0;
+            if (mine) {
+                const int y = r_y[j], xs = r_xs[j], xe = r_xe[j];
+                start = (long long)y * Wc + xs;
+                end = (long long)y * Wc + xe;
+                x0 = min(x0, xs); x1 = max(x1, xe);
+                area += xe - xs;
+            }
+            const unsigned below = m & lanemask_lt();
+            const int prev_lane = below ? 31 - __clz(below) : 0;
+            long long prev_end = __shfl_sync(0xffffffffu, end, prev_lane);
+            if (!below) prev_end = carry_end;
+            const bool head = mine && prev_end != start;
+            const unsigned hb = __ballot_sync(0xffffffffu, head);
+            // start of the final run this row-run belongs to: the nearest head at or below this lane, else the carried one
+            const unsigned hle = hb & (lanemask_lt() | (1u << lane));
+            const int head_lane = hle ? 31 - __clz(hle) : 0;
+            long long fstart = __shfl_sync(0xffffffffu, start, head_lane);
+            if (!hle) fstart = carry_start;
+            const int fidx = n_final + __popc(hle) - 1;         // index of that final run within the slot (>= 0 once a head exists)
+            // the last row-run of a final run inside this chunk writes its length (a continuation in a later chunk overwrites it)
+            const unsigned above = m & ~(lanemask_lt() | (1u << lane));
+            const int next_lane = above ? __ffs(above) - 1 : 32;
+            const bool last_of_final = mine && (next_lane == 32 || ((hb >> next_lane) & 1u));
+            if (head) starts_out[base + fidx] = start;
+            if (last_of_final) lens_out[base + fidx] = end - fstart;
+            // carry: the slot's last row-run of this chunk
+            const int last_lane = 31 - __clz(m);
+            carry_end = __shfl_sync(0xffffffffu, end, last_lane);
+            carry_start = __shfl_sync(0xffffffffu, fstart, last_lane);
+            n_final += __popc(hb);
+            __syncwarp();
+        }
+        x0 = __reduce_min_sync(0xffffffffu, x0);
+        x1 = __reduce_max_sync(0xffffffffu, x1);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) area += __shfl_xor_sync(0xffffffffu, area, d);
+        if (lane == 0) {
+            row[2] = ya; row[3] = x0; row[4] = yb + 1; row[5] = x1;
+            row[6] = n_final; row[7] = my_off + base; row[8] = area;
+        }
+    }
+}
+
+// instance tables of all slices packed behind the run lists + the header the host parses
+__global__ void __launch_bounds__(256)
+rle_block_pack_kernel(const BlkArgs a)
+{
+    __shared__ int s_w[32];
+    __shared__ long long s_max[EMP_MAX_LABELS];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    int before = 0, all = 0, rr_before = 0, rr_all = 0;
+    for (int j = tid; j < a.B; j += blockDim.x) {
+        const char* rs = a.rs + (size_t)j * a.rs_stride;
+        const int ni = min(__ldcg(reinterpret_cast<const int32_t*>(rs + a.R.status) + EMP_ST_NINST), a.inst_cap);
+        const int nr = min(__ldcg(reinterpret_cast<const int*>(rs + a.R.rowoff) + a.crop_h), a.run_cap);
+        all += ni; rr_all += nr;
+        if (j < b) { before += ni; rr_before += nr; }
+    }
+    // block_sum needs 32 warps' worth of slots; with 256 threads the upper ones are zero
+    if (tid < 32) s_w[tid] = 0;
+    __syncthreads();
+    auto sum256 = [&](int v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        __syncthreads();
+        if ((tid & 31) == 0) s_w[tid >> 5] = v;
+        __syncthreads();
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        return t;
+    };
+    const int inst_off = sum256(before), total_inst = sum256(all), rr_off = sum256(rr_before), total_rr = sum256(rr_all);
+    const char* rs = a.rs + (size_t)b * a.rs_stride;
+    const int32_t* status = reinterpret_cast<const int32_t*>(rs + a.R.status);
+    const int n_inst = min(__ldcg(status + EMP_ST_NINST), a.inst_cap);
+    const long long* inst = reinterpret_cast<const long long*>(rs + a.R.inst);
+    long long* hdr = a.packed;
+    long long* out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + 2 * (size_t)total_rr +
+                     (size_t)inst_off * EMP_BLK_INST_WORDS;
+    for (int i = tid; i < n_inst * EMP_BLK_INST_WORDS; i += blockDim.x) out[i] = inst[i];
+    // largest label - class base per class over the block (the z-sharded stack's label offsets)
+    if (tid < EMP_MAX_LABELS) s_max[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_inst; i += blockDim.x) {
+        const long long cls = inst[(size_t)i * EMP_BLK_INST_WORDS], lab = inst[(size_t)i * EMP_BLK_INST_WORDS + 1];
+        for (int ci = 0; ci < a.rc.n; ++ci)
+            if (a.rc.label[ci] == cls) atomicMax(reinterpret_cast<unsigned long long*>(s_max + ci), (unsigned long long)(lab - a.rc.lo[ci]));
+    }
+    __syncthreads();
+    if (tid < a.rc.n && s_max[tid] > 0)
+        atomicMax(reinterpret_cast<unsigned long long*>(hdr + EMP_BLK_HDR_MAXLAB + tid), (unsigned long long)s_max[tid]);
+    if (tid == 0) {
+        const int32_t* cstat = reinterpret_cast<const int32_t*>(a.cs + (size_t)b * a.cs_stride + a.o_cstatus);
+        const int32_t* mstat = reinterpret_cast<const int32_t*>(a.ws + (size_t)b * a.ws_stride + a.o_status);
+        long long* s = hdr + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * b;
+        s[0] = n_inst;
+        s[1] = inst_off;
+        s[2] = rr_off;
+        s[3] = min(__ldcg(status + EMP_ST_NROWRUNS), a.run_cap);
+        s[4] = (long long)(__ldcg(cstat + EMP_ST_FLAGS) | __ldcg(mstat + EMP_ST_FLAGS) | __ldcg(status + EMP_ST_FLAGS));
+        s[5] = __ldcg(cstat + EMP_ST_K);
+        if (b == 0) { hdr[0] = a.B; hdr[1] = total_rr; hdr[2] = total_inst; hdr[3] = EMP_BLK_INST_WORDS; }
+    }
+}
+
+}  // namespace emp
+
+using namespace emp;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+EMP_API int emp_median_chain(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, int C, size_t hw,
+                             const float* const* carry_in_dev, float confidence_thr, uint8_t* sem8_out, size_t sem8_stride,
+                             float* best_scratch, float* const* carry_out_dev, void* stream)
+{
+    EMP_REQUIRE(planes_dev && sem8_out, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(ks >= 1 && ks <= 15 && (ks & 1), EMP_ERR_INVALID, "median kernel size must be odd and <= 15 (got %d)", ks);
+    EMP_REQUIRE(n >= 1 && n_planes >= n && z0 >= 0 && z0 + n <= depth && C >= 1 && C <= 256 && hw > 0, EMP_ERR_INVALID,
+                "bad block (n=%d, n_planes=%d, z0=%d, depth=%d, C=%d)", n, n_planes, z0, depth, C);
+    const int mid = ks / 2;
+    EMP_REQUIRE(n_planes >= std::min(n + mid, depth - z0), EMP_ERR_INVALID, "the block needs %d raw planes (got %d)",
+                std::min(n + mid, depth - z0), n_planes);
+    EMP_REQUIRE(mid == 0 || z0 == 0 || (z0 >= mid && carry_in_dev), EMP_ERR_INVALID,
+                "a block that starts at z0=%d needs z0 >= %d and the carry planes", z0, mid);
+    EMP_REQUIRE(C == 1 || best_scratch, EMP_ERR_INVALID, "multi-channel chains need the running-maximum scratch");
+    EMP_REQUIRE(sem8_stride >= hw, EMP_ERR_INVALID, "sem8 stride smaller than a plane");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the planes themselves are only known on the device; torch planes are 256-byte aligned, channel planes hw apart
+    const bool vec = (hw % 4 == 0) && (sem8_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(sem8_out) & 3u) == 0) &&
+                     (!best_scratch || (reinterpret_cast<uintptr_t>(best_scratch) & 15u) == 0);
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.planes = planes_dev; a.carry_in = (mid > 0 && z0 >= mid) ? carry_in_dev : nullptr; a.carry_out = carry_out_dev;
+    a.n = n; a.n_planes = n_planes; a.z0 = z0; a.depth = depth; a.hw = hw; a.thr = confidence_thr;
+    a.sem8 = sem8_out; a.sem8_stride = sem8_stride; a.best = best_scratch; a.multi = C > 1;
+    for (int c = 0; c < C; ++c) {
+        a.c = c;
+        const int rc = launch_chain<false>(ks, a, vec, st);
+        if (rc) return rc;
+    }
+    return EMP_OK;
+}
+
+EMP_API int emp_median_chain_repair(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, size_t hw,
+                                    const float* const* carry_old_dev, const float* const* carry_new_dev,
+                                    float confidence_thr, uint8_t* sem8, size_t sem8_stride, float* const* carry_out_dev,
+                                    int32_t* changed, void* stream)
+{
+    EMP_REQUIRE(planes_dev && sem8 && carry_old_dev && carry_new_dev && carry_out_dev && changed, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(ks >= 3 && ks <= 15 && (ks & 1), EMP_ERR_INVALID, "median kernel size must be odd, 3 .. 15 (got %d)", ks);
+    const int mid = ks / 2;
+    EMP_REQUIRE(n >= 1 && z0 >= mid && z0 + n <= depth && hw > 0 && n_planes >= std::min(n + mid, depth - z0), EMP_ERR_INVALID,
+                "bad block (n=%d, n_planes=%d, z0=%d, depth=%d)", n, n_planes, z0, depth);
+    EMP_REQUIRE(sem8_stride >= hw, EMP_ERR_INVALID, "sem8 stride smaller than a plane");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (hw % 4 == 0) && (sem8_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(sem8) & 3u) == 0);
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.planes = planes_dev; a.carry_in = carry_old_dev; a.carry_new = carry_new_dev; a.carry_out = carry_out_dev;
+    a.n = n; a.n_planes = n_planes; a.z0 = z0; a.depth = depth; a.hw = hw; a.thr = confidence_thr;
+    a.sem8 = sem8; a.sem8_stride = sem8_stride; a.changed = changed;
+    return launch_chain<true>(ks, a, vec, st);
+}
+
+namespace {
+
+struct BlockPlan {
+    WsLayout Lc, Lm;            // coarse / merge workspaces
+    BlkLayout R;
+    size_t o_ids, o_cs, o_ws, o_rs, total;
+    size_t ids_stride;          // int32 elements
+    Things th;
+    RleClasses rc;
+};
+
+int plan_block(const emp_stack_cfg* c, int B, BlockPlan* P)
+{
+    EMP_REQUIRE(c != nullptr, EMP_ERR_INVALID, "cfg is null");
+    EMP_REQUIRE(B >= 1 && B <= 4096, EMP_ERR_INVALID, "bad block size %d", B);
+    EMP_REQUIRE(c->H > 0 && c->W > 0 && c->h > 0 && c->w > 0 && (long long)c->H * c->W < (1ll << 31), EMP_ERR_INVALID, "bad shape");
+    EMP_REQUIRE(c->shift >= 0 && c->shift < 16 && ((c->H - 1) >> c->shift) < c->h && ((c->W - 1) >> c->shift) < c->w, EMP_ERR_INVALID,
+                "coarse map %d x %d << %d does not cover %d x %d", c->h, c->w, c->shift, c->H, c->W);
+    EMP_REQUIRE(c->crop_h >= 1 && c->crop_h <= c->H && c->crop_w >= 1 && c->crop_w <= c->W, EMP_ERR_INVALID, "bad crop %d x %d",
+                c->crop_h, c->crop_w);
+    EMP_REQUIRE(c->nms_kernel >= 1 && c->k_cap >= 1 && c->run_cap >= 1 && c->inst_cap >= 1, EMP_ERR_INVALID, "bad nms_kernel / capacities");
+    int rc;
+    if ((rc = make_things(c->thing_list, c->n_things, &P->th))) return rc;
+    if ((rc = make_rle_classes(c->labels, c->n_labels, c->label_divisor, c->thing_list, c->n_things, c->force_connected, &P->rc))) return rc;
+    P->Lc = ws_layout(c->h, c->w, c->k_cap, 1);
+    P->Lm = ws_layout(c->H, c->W, c->k_cap, P->th.n);
+    EMP_REQUIRE(P->Lm.code16, EMP_ERR_INVALID, "k_cap must stay below %u", kClsBase16);
+    P->R = blk_layout(c->crop_h, c->crop_w, c->run_cap, c->inst_cap, c->n_labels, c->label_divisor, c->k_cap);
+    P->ids_stride = align_up((size_t)c->h * c->w, 64);
+    size_t o = 0;
+    P->o_ids = o; o = align_up(o + sizeof(int32_t) * P->ids_stride * B, 256);
+    P->o_cs = o;  o = align_up(o + P->Lc.total * B, 256);
+    P->o_ws = o;  o = align_up(o + P->Lm.total * B, 256);
+    P->o_rs = o;  o = align_up(o + P->R.total * B, 256);
+    P->total = o;
+    return EMP_OK;
+}
+
+}  // namespace
+
+EMP_API size_t emp_stack_block_scratch_bytes(const emp_stack_cfg* cfg, int B)
+{
+    BlockPlan P;
+    if (plan_block(cfg, B, &P)) return 0;
+    return P.total;
+}
+
+EMP_API size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B)
+{
+    if (!cfg || B < 1 || cfg->run_cap < 1 || cfg->inst_cap < 1) return 0;
+    return (size_t)EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * B +
+           (size_t)B * (2 * (size_t)cfg->run_cap + (size_t)EMP_BLK_INST_WORDS * cfg->inst_cap);
+}
+
+EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+                            size_t hm_stride, const float* off, size_t off_stride, void* scratch, size_t scratch_bytes,
+                            int64_t* packed_out, size_t packed_words, int64_t* runs3_out, void* stream)
+{
+    BlockPlan P;
+    int rc = plan_block(cfg, B, &P);
+    if (rc) return rc;
+    EMP_REQUIRE(sem8 && hm && off && scratch && packed_out, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255u) == 0 && scratch_bytes >= P.total, EMP_ERR_WORKSPACE,
+                "scratch too small or misaligned: %zu < %zu", scratch_bytes, P.total);
+    EMP_REQUIRE(packed_words >= emp_stack_block_packed_words(cfg, B), EMP_ERR_WORKSPACE, "packed output too small");
+    EMP_REQUIRE(sem8_stride >= (size_t)cfg->H * cfg->W && hm_stride >= (size_t)cfg->h * cfg->w &&
+                off_stride >= 2 * (size_t)cfg->h * cfg->w, EMP_ERR_INVALID, "plane strides smaller than the planes");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char* base = static_cast<char*>(scratch);
+    int32_t* ids = reinterpret_cast<int32_t*>(base + P.o_ids);
+    char* cs = base + P.o_cs;
+    char* ws = base + P.o_ws;
+    char* rs = base + P.o_rs;
+
+    if ((rc = coarse_ids_batched(B, hm, hm_stride, off, off_stride, cfg->h, cfg->w, cfg->nms_threshold, cfg->nms_kernel, cfg->step,
+                                 ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st)))
+        return rc;
+    const int32_t* k_dev = reinterpret_cast<const int32_t*>(cs + P.Lc.status) + EMP_ST_K;
+    if ((rc = merge_codes_batched(B, sem8, sem8_stride, ids, P.ids_stride, cfg->h, cfg->w, cfg->shift, cfg->H, cfg->W, P.th,
+                                  cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev, P.Lc.total / 4, ws,
+                                  P.Lm.total, st)))
+        return rc;
+
+    BlkArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ws = ws; a.ws_stride = P.Lm.total; a.o_codes = P.Lm.codes; a.o_sflags = P.Lm.sflags; a.o_lut = P.Lm.lut; a.o_status = P.Lm.status;
+    a.cs = cs; a.cs_stride = P.Lc.total; a.o_cstatus = P.Lc.status;
+    a.rs = rs; a.rs_stride = P.R.total; a.R = P.R; a.rc = P.rc;
+    a.B = B; a.W = cfg->W; a.crop_h = cfg->crop_h; a.crop_w = cfg->crop_w;
+    a.blk_items = assign_block_items(cfg->H, cfg->W);
+    a.blocks_x = (cfg->W + 63) / 64;
+    a.cls_off = (unsigned)P.Lm.cls_off;
+    a.k_cap = cfg->k_cap; a.run_cap = cfg->run_cap; a.inst_cap = cfg->inst_cap;
+    a.vec = (cfg->W % 8 == 0);
+    a.packed = reinterpret_cast<long long*>(packed_out);
+    a.runs3 = reinterpret_cast<long long*>(runs3_out); a.runs3_stride = 3 * (size_t)cfg->run_cap;
+
+    EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
+    EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
+    const int sms = device_sm_count();
+    {
+        ProfScope ps(ST_BLK_KEYS, st);
+        rle_block_keys_kernel<<<dim3(8, 1, B), 256, 0, st>>>(a);
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    {
+        const size_t items = (size_t)B * cfg->crop_h * ((cfg->crop_w + 255) / 256);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 16));
+        ProfScope ps(ST_BLK_MARK, st);
+        rle_block_mark_kernel<<<grid, 256, 0, st>>>(a);
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    {
+        ProfScope ps(ST_BLK_EMIT, st);
+        rle_block_emit_kernel<<<dim3((cfg->crop_h + 31) / 32, 1, B), 256, 0, st>>>(a);
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    {
+        ProfScope ps(ST_BLK_RUNS, st);
+        rle_block_runs_kernel<<<B, 1024, 0, st>>>(a);
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    {
+        ProfScope ps(ST_BLK_PACK, st);
+        rle_block_pack_kernel<<<B, 256, 0, st>>>(a);
+    }
+    EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}

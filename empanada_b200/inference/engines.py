@@ -256,15 +256,18 @@ class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
         return ids, ws, k_cap
 
     @torch.no_grad()
-    def _fused_enqueue(self, sem_prob, ctr_hmp, offsets, upsampling, k_cap=None):
+    def _fused_enqueue(self, sem_prob, ctr_hmp, offsets, upsampling, k_cap=None, sem8=None):
         """Enqueue median-queue output -> pan (1,H,W) int64 on the current stream, with no dense
         intermediate besides uint8 sem and NO host synchronisation.  Returns (pan, coarse workspace,
         merge workspace, k_cap); the status blocks at the start of the two workspaces (K / overflow
         flag, class-range flags) are valid once the stream has run — and only until the next call
         reuses the cached workspaces, so callers that defer the check copy them out first."""
-        dev = sem_prob.device
         step = 4 if self.coarse_boundaries else 1
-        _, sem = median_harden([sem_prob], self.confidence_thr, want_median=False, want_sem='u8')
+        if sem8 is None:
+            _, sem = median_harden([sem_prob], self.confidence_thr, want_median=False, want_sem='u8')
+        else:
+            sem = sem8                                  # already hardened (the z-block chain of inference/stack.py)
+        dev = sem.device
         H, W = sem.shape[-2:]
         h, w = ctr_hmp.shape[-2:]
         s = int(upsampling * step)
@@ -283,12 +286,12 @@ class PanopticDeepLabRenderEngine(PanopticDeepLabEngine):
         return pan, cws, ws, k_cap
 
     @torch.no_grad()
-    def _fused_postprocess(self, sem_prob, ctr_hmp, offsets, upsampling):
+    def _fused_postprocess(self, sem_prob, ctr_hmp, offsets, upsampling, sem8=None):
         """median-queue output -> pan (1,H,W) int64; reads the status blocks back (one sync) and
         retries with a larger center table in the (rare) overflow case."""
         k_cap = None
         while True:
-            pan, cws, ws, k_cap = self._fused_enqueue(sem_prob, ctr_hmp, offsets, upsampling, k_cap)
+            pan, cws, ws, k_cap = self._fused_enqueue(sem_prob, ctr_hmp, offsets, upsampling, k_cap, sem8)
             st = C.read_status(cws)
             if not (int(st[C.ST_FLAGS]) & C.FLAG_K_OVERFLOW):
                 break

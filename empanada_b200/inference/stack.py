@@ -8,19 +8,27 @@ Sharding.  Slices are independent except for the recursive median queue (engines
     m_i = median(f_{i-mid}, ..., f_{i-1}, s_i, s_{i+1}, ..., s_{i+mid}),   f_j = m_j (j >= mid) else s_j
 for mid <= i < D - mid, raw s_i otherwise.  Rank r owns the contiguous block [z0, z1).  It needs
   * a look-ahead halo: the raw probabilities of slices z1 .. z1+mid-1 (it runs the CNN on them too);
-  * a carry: the filtered planes f_{z0-mid} .. f_{z0-1} from rank r-1 (one send/recv of `mid`
-    (C,H,W) fp32 planes over NCCL/NVLink), available once r-1 has run its — elementwise, cheap —
-    median chain.  The CNN forwards, which dominate, never wait on it.
-With median_kernel_size == 1 nothing is exchanged.  With median_kernel_size == 3 (the scripts' default) no rank waits
-for the chain of the rank below: a median of three is a clamp of one argument to the range of the other two, clamps
-compose, so every rank first reduces its block to ONE clamp from its own raw planes (emp_median3_compose), the carry
-crosses the ranks with one clamp per rank, and all chains then run at once (exchange_carry_median3).
+  * a carry: the filtered planes f_{z0-mid} .. f_{z0-1} of rank r-1.
+No rank waits for the chain of the rank below.  Every rank runs its whole chain at once from a GUESSED carry
+(its own first raw plane; one emp_median_chain launch, each probability read once), sends the `mid` planes it
+ends with to rank r+1 (one NCCL send/recv per neighbour pair over NVLink, all pairs at the same time) and then
+REPAIRS its block from the carry it received: per pixel the guessed and the true chain advance together until
+their states agree bit for bit — an order-statistic filter forgets its start within a few slices — and only that
+prefix is redone (emp_median_chain_repair).  A rank whose repair reached the end of its block says so; the flag
+rides along with the instance counts, and only then (never seen on EM data; NaNs force it) the ranks settle with
+further rounds, each one correcting at least one more rank, before the block is post-processed again.
+
+Blocks.  Behind the chain a z-block is processed `block` slices at a time: ONE emp_stack_block call — a dozen
+launches — per sub-block, its run tables packed into one buffer that crosses PCIe in one copy while the next
+sub-block runs.  The int64 label map is never materialised; the dicts of the reference's format are built lazily
+from the packed tables (RleStack).
 
 Labels.  Every slice numbers its instances 1..n per class.  So that labels from different ranks
 never collide before the host-side cross-slice matcher renumbers them, ranks all-gather their
 per-class maximum instance count (one int64 per class) and add the exclusive prefix as an offset;
 rank 0 keeps offset 0, which is what the reference's matcher sees for the first slice.
 """
+import collections.abc
 import contextlib
 import ctypes
 import gc
@@ -31,9 +39,8 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ['partition_slices', 'halo_range', 'median_chain', 'exchange_carry', 'exchange_carry_median3', 'compose_median3',
-           'label_offsets',
-           'apply_label_offset', 'StackShard']
+__all__ = ['partition_slices', 'halo_range', 'median_chain', 'exchange_planes', 'carry_rounds', 'label_offsets',
+           'apply_label_offset', 'RleStack', 'StackShard']
 
 
 @contextlib.contextmanager
@@ -50,16 +57,25 @@ def _gc_paused():
             gc.enable()
 
 
-_stream_cache = {}
+_copy_streams = {}
+_pinned = {}
+_words_per_slice = {}       # (device, H, W) -> packed words per slice seen so far (sizes the one D2H copy per sub-block)
 
 
-def _side_streams(device, n):
-    """n side streams of `device`, created once per process: the per-stream scratch buffers (C.workspace) and the
-    caching allocator's per-stream pools stay warm from block to block."""
-    have = _stream_cache.setdefault(device.index, [])
-    while len(have) < n:
-        have.append(torch.cuda.Stream(device))
-    return have[:n]
+def _copy_stream(device):
+    s = _copy_streams.get(device.index)
+    if s is None:
+        s = _copy_streams[device.index] = torch.cuda.Stream(device)
+    return s
+
+
+def _pinned_words(device, slot, n_words):
+    """Pinned int64 staging buffer `slot` of this device, grown and never shrunk."""
+    key = (device.index, slot)
+    t = _pinned.get(key)
+    if t is None or t.numel() < n_words:
+        t = _pinned[key] = torch.empty(int(n_words), dtype=torch.int64).pin_memory()
+    return t
 
 
 def partition_slices(depth, world_size, rank):
@@ -77,13 +93,13 @@ def halo_range(depth, world_size, rank, median_kernel_size):
 
 
 def median_chain(raw, z0, z1, depth, ks, carry, median_fn):
-    """Recursive median over the block [z0, z1).
+    """Recursive median over the block [z0, z1), plane by plane — the restatement of the reference's queue the
+    kernels are tested against (tests/test_stack_host.py, tests/test_gpu_stack_block.py).
 
     raw      dict {z: sem plane} for z in [z0, min(depth, z1 + mid))
     carry    list of the `mid` planes f_{z0-mid} .. f_{z0-1} (filtered where z >= mid, else raw);
              ignored for z0 == 0
-    median_fn(list of ks planes) -> plane   (libempanada_b200's emp_median_harden on the GPU,
-             any odd-count median on the CPU in tests)
+    median_fn(list of ks planes) -> plane
     Returns (filtered {z: plane} for z in [z0, z1), carry for the next rank).
     """
     mid = (ks - 1) // 2
@@ -104,61 +120,41 @@ def median_chain(raw, z0, z1, depth, ks, carry, median_fn):
     return out, nxt
 
 
-def exchange_carry(chain_fn, rank, world_size, mid, plane_like, group=None):
-    """Run `chain_fn(carry) -> (result, next_carry)` on every rank in rank order, handing the
-    carry planes from rank r to r+1 with point-to-point send/recv (NCCL on CUDA tensors, gloo on
-    CPU tensors).  plane_like: a tensor with the carry planes' shape / dtype / device."""
-    carry = []
-    if mid > 0 and rank > 0 and world_size > 1:
-        carry = [torch.empty_like(plane_like) for _ in range(mid)]
-        for p in carry:
-            dist.recv(p, src=rank - 1, group=group)
-    result, nxt = chain_fn(carry)
-    if mid > 0 and rank + 1 < world_size:
-        for p in nxt:
-            dist.send(p.contiguous(), dst=rank + 1, group=group)
-    return result
-
-
-def compose_median3(raw, z0, z1, depth, like=None):
-    """The block [z0, z1) of a median_kernel_size == 3 chain as ONE clamp: returns (A, B) with
-    f_{z1-1} = min(max(f_{z0-1}, A), B).  A median of three is a clamp of one argument to the range of the other
-    two, f_i = clamp(f_{i-1}; min(s_i, s_{i+1}), max(s_i, s_{i+1})), clamps compose into clamps, and the raw first /
-    last slice of the stack is the constant clamp (s_i, s_i).  torch restatement of libempanada_b200's
-    emp_median3_compose for tensors on any device (StackShard uses the kernel; the gloo tests use this)."""
-    ref = raw[z0] if z0 < z1 else like
-    A = torch.full_like(ref, float('-inf'))
-    B = torch.full_like(ref, float('inf'))
-    for z in range(z0, z1):
-        if z < 1 or z >= depth - 1:
-            lo = hi = raw[z]
-        else:
-            lo, hi = torch.minimum(raw[z], raw[z + 1]), torch.maximum(raw[z], raw[z + 1])
-        A = torch.minimum(torch.maximum(A, lo), hi)
-        B = torch.minimum(torch.maximum(B, lo), hi)
-    return A, B
-
-
-def exchange_carry_median3(compose_fn, chain_fn, rank, world_size, plane_like, group=None):
-    """exchange_carry for median_kernel_size == 3 without the rank-after-rank wait: every rank first reduces its
-    block to one clamp (compose_fn() -> (A, B), from its own raw planes only), the carry plane then crosses the ranks
-    with ONE clamp per rank, and the real chains (chain_fn(carry) -> (result, next_carry)) run on all ranks at once.
-    Returns (result, mismatch): mismatch is a 0-d int64 tensor, non-zero when the plane this rank handed on is not
-    the chain's own last plane (only possible with NaNs) — the caller must then redo the block with exchange_carry."""
-    carry, sent = [], None
+def exchange_planes(send, recv, rank, world_size, group=None):
+    """Every rank hands `send` (list of tensors) to rank + 1 and fills `recv` from rank - 1, all neighbour pairs at
+    the same time (one batched NCCL send/recv; gloo on CPU tensors)."""
+    ops = []
     if rank + 1 < world_size:
-        A, B = compose_fn()
+        ops += [dist.P2POp(dist.isend, t, rank + 1, group) for t in send]
     if rank > 0:
-        carry = [torch.empty_like(plane_like)]
-        dist.recv(carry[0], src=rank - 1, group=group)
-    if rank + 1 < world_size:
-        sent = torch.minimum(torch.maximum(carry[0], A), B) if rank > 0 else torch.minimum(A, B)
-        dist.send(sent.contiguous(), dst=rank + 1, group=group)
-    result, nxt = chain_fn(carry)
-    if sent is None:
-        return result, torch.zeros((), dtype=torch.int64, device=plane_like.device)
-    own = nxt[0] if nxt else sent                       # an empty block hands the plane through
-    return result, (own != sent).any().to(torch.int64)  # NaN != NaN: flagged, which is what we want
+        ops += [dist.P2POp(dist.irecv, t, rank - 1, group) for t in recv]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def carry_rounds(rank, world_size, chain, repair, exchange, any_changed=None):
+    """The carry hand-over of a z-sharded recursive median without a rank-after-rank wait.
+
+    chain()            run this rank's chain from the guessed carry (rank 0: exact), leaving its outgoing carry
+    exchange()         outgoing carry -> rank + 1, rank - 1's -> this rank's `received` buffer
+    repair(round)      redo the block's prefix from the received carry against the one used before (round 0: the
+                       guess); returns a flag (tensor) that is non-zero when the outgoing carry changed
+    any_changed(flag)  None: ONE round, the flag is returned for the caller to share later (the common path: if no
+                       rank's flag is set, every block is exact — rank r's repair saw rank r-1's final carry);
+                       else a callable reducing the flag over all ranks: rounds repeat until no carry moves (each
+                       round settles at least one more rank, so world_size - 1 rounds always suffice)
+    """
+    chain()
+    flag = None
+    for rnd in range(max(world_size - 1, 1)):
+        exchange()
+        flag = repair(rnd) if rank > 0 else None
+        if any_changed is None:
+            return flag
+        if not any_changed(flag):
+            return None
+    return None
 
 
 def label_offsets(max_counts, group=None):
@@ -194,37 +190,171 @@ def apply_label_offset(rle_seg, offsets_by_class, label_divisor, thing_list):
     return out
 
 
-def _slice_sync(engine, head, sem_prob, labels, upsampling, force_connected):
+class _BlockTables:
+    """Host copy of one emp_stack_block packed output (include/empanada_b200.h)."""
+    __slots__ = ('slices', 'starts', 'lens', 'inst')
+
+    def __init__(self, words, B):
+        from empanada_b200 import _cabi as C
+        R, I = int(words[1]), int(words[2])
+        s0 = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B
+        # owned copies: the pinned staging buffer is reused by the next block
+        self.slices = words[C.BLK_HDR_WORDS:s0].reshape(B, C.BLK_SLICE_WORDS).copy()
+        self.starts = words[s0:s0 + R].copy()
+        self.lens = words[s0 + R:s0 + 2 * R].copy()
+        self.inst = words[s0 + 2 * R:s0 + 2 * R + C.BLK_INST_WORDS * I].reshape(I, C.BLK_INST_WORDS).copy()
+
+    @staticmethod
+    def words_needed(words, B):
+        from empanada_b200 import _cabi as C
+        return C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B + 2 * int(words[1]) + C.BLK_INST_WORDS * int(words[2])
+
+
+class RleStack(collections.abc.Mapping):
+    """{z: rle_seg} of a z-block in the reference's format ({class: {label: {'box', 'starts', 'runs'}}},
+    rle.py:26-86), built per slice on first access from the packed run / instance tables the GPU returned: the
+    tables hold everything (instance rows in dict order, each instance's starts / runs contiguous), so consumers
+    that work on arrays — the cross-slice matcher, counters, fill — never pay for ~200 small dicts per slice."""
+
+    def __init__(self, labels, thing_list, label_divisor):
+        self.labels, self.thing_list, self.label_divisor = [int(l) for l in labels], list(thing_list), int(label_divisor)
+        self._where = {}        # z -> (block tables, index in block) | dict (a slice redone synchronously)
+        self._cache = {}
+        self.offsets = {}
+
+    def _add(self, z, tables, b):
+        self._where[z] = (tables, b)
+
+    def _add_dict(self, z, seg):
+        self._where[z] = seg
+
+    def __len__(self):
+        return len(self._where)
+
+    def __iter__(self):
+        return iter(sorted(self._where))
+
+    def inst_rows(self, z):
+        """(n, 9) int64 rows of slice z: class, label (before the rank offset), y0, x0, y1, x1, n runs, first run, area;
+        None for a slice that was redone synchronously."""
+        w = self._where[z]
+        if isinstance(w, dict):
+            return None
+        t, b = w
+        n, first = int(t.slices[b, 0]), int(t.slices[b, 1])
+        return t.inst[first:first + n]
+
+    def counts(self):
+        """(instances, runs) over the block without building a dict."""
+        n_inst = n_runs = 0
+        for z, w in self._where.items():
+            if isinstance(w, dict):
+                n_inst += sum(len(v) for v in w.values())
+                n_runs += sum(len(a['starts']) for v in w.values() for a in v.values())
+            else:
+                rows = self.inst_rows(z)
+                n_inst += rows.shape[0]
+                n_runs += int(rows[:, 6].sum())
+        return n_inst, n_runs
+
+    def __getitem__(self, z):
+        seg = self._cache.get(z)
+        if seg is not None:
+            return seg
+        w = self._where[z]
+        if isinstance(w, dict):
+            seg = apply_label_offset(w, self.offsets, self.label_divisor, self.thing_list)
+        else:
+            t, _ = w
+            rows = self.inst_rows(z)
+            seg = {l: {} for l in self.labels}
+            if rows.shape[0]:
+                cls = rows[:, 0].tolist()
+                labs = rows[:, 1].tolist()
+                boxes = rows[:, 2:6].tolist()
+                cnt = rows[:, 6].tolist()
+                first = rows[:, 7].tolist()
+                starts, lens = t.starts, t.lens
+                offs = {c: (int(self.offsets.get(c, 0)) if c in self.thing_list else 0) for c in self.labels}
+                for i in range(len(cls)):
+                    c = cls[i]
+                    lab = labs[i] + offs[c]
+                    if lab >= (c + 1) * self.label_divisor:
+                        raise ValueError(f'label {labs[i]} + offset {offs[c]} leaves class {c}\'s range; '
+                                         f'raise label_divisor (reference default for 3D is 20000)')
+                    a, e = first[i], first[i] + cnt[i]
+                    seg[c][lab] = {'box': tuple(boxes[i]), 'starts': starts[a:e], 'runs': lens[a:e]}
+        self._cache[z] = seg
+        return seg
+
+    def materialise(self):
+        """Build every slice's dict now (what a consumer iterating over .items() pays)."""
+        with _gc_paused():
+            for z in self._where:
+                self[z]
+        return self
+
+
+def _slice_sync(engine, head, sem8, labels, upsampling, force_connected):
     """One slice, synchronously (status read-backs and retries inside): the fallback for a slice
     whose deferred run overflowed a table."""
     from empanada_b200.inference import rle
-    pan = engine._fused_postprocess(sem_prob, head['ctr_hmp'], head['offsets'], upsampling)
+    pan = engine._fused_postprocess(None, head['ctr_hmp'], head['offsets'], upsampling, sem8=sem8)
     if head['size'] is not None:
         pan = pan[..., :head['size'][0], :head['size'][1]]
     return rle.pan_seg_to_rle_seg(pan, labels, engine.label_divisor, engine.thing_list, force_connected)
 
 
+def _f32c(t):
+    t = t.detach()
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def _batched(tensors):
+    """(base tensor, stride in elements) of equal-shape contiguous tensors: zero-copy when they already sit evenly
+    spaced in one allocation (views of a batch), else one torch.stack."""
+    t0 = tensors[0]
+    n = len(tensors)
+    if n == 1:
+        return t0, t0.numel()
+    step = tensors[1].data_ptr() - t0.data_ptr()
+    if step >= t0.numel() * 4 and step % 16 == 0 and all(tensors[i].data_ptr() - t0.data_ptr() == i * step for i in range(2, n)) \
+            and t0.untyped_storage().data_ptr() == tensors[-1].untyped_storage().data_ptr():
+        return t0, step // 4
+    st = torch.stack([t.reshape(-1) for t in tensors])
+    return st, st.shape[1]
+
+
 class StackShard:
     """One rank's share of a stack: feed it the head tensors of its slices (block + halo) in z
-    order, then `finish()` returns {z: rle_seg} for the block.
+    order, then `finish()` returns {z: rle_seg} (an RleStack) for the block.
 
     engine: a PanopticDeepLabRenderEngine(3d) (its post-processing parameters and fused kernels
     are used; its own median queue is bypassed in favour of the sharded chain above).
+    block: slices per emp_stack_block call (sub-block); keep_tables: keep the (start, length, slot) row-run tables
+    in HBM for match() / fill().
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, n_streams=4):
+                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
         self.rank, self.world, self.ks = rank, world_size, median_kernel_size
         self.mid = (median_kernel_size - 1) // 2
+        if depth < median_kernel_size:
+            raise ValueError(f'stack of {depth} slices is shallower than the median kernel ({median_kernel_size})')
+        if world_size > 1 and depth // world_size < max(self.mid, 1):
+            # every rank sees the same arguments, so every rank raises: nobody is left waiting in a collective
+            raise ValueError(f'{depth} slices over {world_size} ranks leaves blocks shorter than {max(self.mid, 1)} slice(s); '
+                             f'use fewer ranks')
         self.upsampling, self.force_connected, self.group = upsampling, force_connected, group
         self.z0, self.z1 = partition_slices(depth, world_size, rank)
         _, self.z_halo = halo_range(depth, world_size, rank, median_kernel_size)
         self.heads = {}
-        self.n_streams = max(1, int(n_streams))   # side streams the block's slices are spread over
-        self._streams = None
+        self.block = max(1, int(block))
+        self.keep_tables = bool(keep_tables)
+        self._settle = False
 
     def slices(self):
         """z indices this rank must run the CNN on, in order."""
@@ -236,125 +366,181 @@ class StackShard:
         assert self.z0 <= z < self.z_halo
         self.heads[z] = {'sem': sem_prob, 'ctr_hmp': ctr_hmp, 'offsets': offsets, 'size': size}
 
-    def _finish_block_gpu(self, zs, filtered):
-        """Post-process + RLE-encode the block's slices in two phases: (A) enqueue every slice's
-        kernels on the current stream with no host synchronisation — one emp_stack_slice call per
-        slice; run / instance tables and the three status blocks of every slice stay in HBM — then ONE
-        synchronisation (the status read-back); (B) read the tables back in two bulk copies and
-        assemble the reference's nested dicts on the host.  A slice that overflowed a table (more
-        centers or runs than the deferred capacities) is simply redone synchronously."""
+    # ------------------------------------------------------------------------------------------------------
+    def _chain(self, planes, dev, hw, Cn):
+        """Recursive median + harden over the rank's block: sem8 (n, hw) uint8 in HBM.  Multi-rank blocks start from a
+        guessed carry and are repaired from the true one (module docstring).  Returns (sem8, changed flag or None)."""
+        from empanada_b200 import _cabi as C
+        e, L = self.engine, C.lib()
+        n, mid, ks = self.z1 - self.z0, self.mid, self.ks
+        stream = C.stream_ptr(dev)
+        vp = ctypes.c_void_p
+        sem8 = torch.empty((n, hw), dtype=torch.uint8, device=dev)
+        multi = self.world > 1 and mid > 0 and dist.is_available() and dist.is_initialized()
+        words = [p.data_ptr() for p in planes]
+        carry = {}
+        if multi:
+            for name in ('out', 'a', 'b'):
+                carry[name] = [torch.empty((Cn * hw,), dtype=torch.float32, device=dev) for _ in range(mid)]
+                words += [t.data_ptr() for t in carry[name]]
+            words += [planes[0].data_ptr()] * mid                      # the guess: this rank's first raw plane
+        tab = torch.tensor(words, dtype=torch.int64).to(dev)
+        base = tab.data_ptr()
+        at = {'planes': base}
+        o = len(planes)
+        for name in ('out', 'a', 'b', 'guess'):
+            at[name] = base + 8 * o
+            o += mid
+        best = torch.empty((n, hw), dtype=torch.float32, device=dev) if Cn > 1 else None
+        thr = float(e.confidence_thr)
+        self._keep = (tab, carry, best)                                 # alive until the stream has run
+
+        def chain(carry_in):
+            with torch.cuda.device(dev):
+                C.check(L.emp_median_chain(vp(at['planes']), n, len(planes), self.z0, self.depth, ks, Cn, hw,
+                                           vp(carry_in) if carry_in else None, thr, vp(sem8.data_ptr()), hw,
+                                           vp(best.data_ptr()) if best is not None else None,
+                                           vp(at['out']) if multi else None, stream))
+
+        if not multi:
+            chain(None)
+            return sem8, None
+        if Cn > 1:
+            # multi-channel blocks keep a running arg-max the repair cannot redo: hand the carry on rank after rank
+            if self.rank > 0:
+                for t in carry['a']:
+                    dist.recv(t, src=self.rank - 1, group=self.group)
+            chain(at['a'] if self.rank > 0 else None)
+            if self.rank + 1 < self.world:
+                for t in carry['out']:
+                    dist.send(t, dst=self.rank + 1, group=self.group)
+            return sem8, None
+
+        changed = torch.zeros((1,), dtype=torch.int32, device=dev)
+        state = {'old': 'guess', 'new': 'a'}
+
+        def repair(rnd):
+            changed.zero_()
+            with torch.cuda.device(dev):
+                C.check(L.emp_median_chain_repair(vp(at['planes']), n, len(planes), self.z0, self.depth, ks, hw,
+                                                  vp(at[state['old']]), vp(at[state['new']]), thr, vp(sem8.data_ptr()), hw,
+                                                  vp(at['out']), vp(changed.data_ptr()), stream))
+            state['old'], state['new'] = state['new'], ('b' if state['new'] == 'a' else 'a')
+            return changed
+
+        def exchange():
+            exchange_planes(carry['out'], carry[state['new']], self.rank, self.world, self.group)
+
+        def any_changed(flag):
+            t = (flag if flag is not None else torch.zeros((1,), dtype=torch.int32, device=dev)).to(torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return bool(t.item())
+
+        flag = carry_rounds(self.rank, self.world, lambda: chain(at['guess'] if self.rank > 0 else None), repair, exchange,
+                            any_changed if self._settle else None)
+        return sem8, flag
+
+    def _enqueue_blocks(self, zs, sem8, dev, H, W):
+        """Phase A: one emp_stack_block call per sub-block on the current stream, each followed by ONE device->host
+        copy of its packed tables on the copy stream.  No host synchronisation."""
         from empanada_b200 import _cabi as C
         from empanada_b200.inference import postprocess as pp
-        e = self.engine
+        e, L = self.engine, C.lib()
         n = len(zs)
-        dev = filtered[zs[0]].device
-        H, W = filtered[zs[0]].shape[-2:]
-        run_cap = max(1 << 14, (H * W * self.upsampling * self.upsampling) // 256)
-        inst_cap = max(1 << 12, run_cap // 4)
-        runs_all = torch.empty((n, run_cap, 3), dtype=torch.int64, device=dev)
-        inst_all = torch.empty((n, inst_cap, 8), dtype=torch.int64, device=dev)
-        status_dev = torch.zeros((n, 3, C.ST_WORDS), dtype=torch.int32, device=dev)
-        # ---- phase A: one emp_stack_slice call per slice (harden, coarse ids, merge, crop, RLE tables, status gather)
-        L = C.lib()
-        things, nt = C.i64_array(e.thing_list)
-        labels, nl = C.i64_array(self.labels)
+        h0 = self.heads[zs[0]]
+        hh, ww = h0['ctr_hmp'].shape[-2:]
+        size = h0['size']
+        assert all(self.heads[z]['size'] == size for z in zs), 'slices of one block must share their unpadded size'
+        crop = (H, W) if size is None else (min(int(size[0]), H), min(int(size[1]), W))
         step = 4 if e.coarse_boundaries else 1
         s_up = int(self.upsampling * step)
         shift = int(math.log2(s_up))
         assert (1 << shift) == s_up
-
-        def f32c(t):
-            t = t.detach()
-            return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
-
-        # The kernels of one 2048^2 slice are small (~25 launches of a few microseconds each), so slices go round-robin
-        # over a few side streams and overlap on the GPU; every stream has its own scratch (C.workspace is per stream).
+        things, nt = C.i64_array(e.thing_list)
+        labels, nl = C.i64_array(self.labels)
+        run_cap = max(1 << 14, (H * W) // 256)
+        inst_cap = max(1 << 12, run_cap // 4)
+        cfg = C.StackCfg(H=H, W=W, h=hh, w=ww, shift=shift, nms_kernel=int(e.nms_kernel), k_cap=min(pp.DEFAULT_K_CAP, hh * ww),
+                         crop_h=crop[0], crop_w=crop[1], n_things=nt, n_labels=nl, force_connected=int(bool(self.force_connected)),
+                         run_cap=run_cap, inst_cap=inst_cap, nms_threshold=float(e.nms_threshold), step=float(step),
+                         label_divisor=int(e.label_divisor), stuff_area=int(e.stuff_area), void_label=int(e.void_label),
+                         thing_list=ctypes.cast(things, ctypes.c_void_p), labels=ctypes.cast(labels, ctypes.c_void_p))
+        SB = min(self.block, n)
+        n_sub = (n + SB - 1) // SB
+        packed_words = int(L.emp_stack_block_packed_words(ctypes.byref(cfg), SB))
+        scratch_bytes = int(L.emp_stack_block_scratch_bytes(ctypes.byref(cfg), SB))
+        if packed_words == 0 or scratch_bytes == 0:
+            raise ValueError('bad arguments to emp_stack_block: ' + L.emp_last_error().decode(errors='replace'))
+        scratch = C.workspace(dev, scratch_bytes, 'stack_block')
+        packed = torch.empty((n_sub, packed_words), dtype=torch.int64, device=dev)
+        runs_all = torch.empty((n, run_cap, 3), dtype=torch.int64, device=dev) if self.keep_tables else None
+        counts = torch.zeros((nl,), dtype=torch.int64, device=dev)
         main = torch.cuda.current_stream(dev)
-        self._streams = _side_streams(dev, self.n_streams)
-        ready = torch.cuda.Event()
-        ready.record(main)                                  # the median chain's planes and the tables above exist
-        for sd in self._streams:
-            sd.wait_event(ready)
-        t_a = time.perf_counter()
+        side = _copy_stream(dev)
+        fixed = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * SB
+        per_slice = _words_per_slice.get((dev.index, H, W), 1 << 14)
+        subs = []
         with torch.cuda.device(dev):
-            for i, z in enumerate(zs):
-                h = self.heads[z]
-                sd = self._streams[i % len(self._streams)]
-                with torch.cuda.stream(sd):                 # conversions (if any), scratch and kernels all on the side stream
-                    sem, hm, off = f32c(filtered[z]), f32c(h['ctr_hmp']), f32c(h['offsets'])
-                    C.require_cuda(sem, hm, off)
-                    assert sem.size(0) == 1 and hm.size(0) == 1 and off.size(0) == 1
-                    cc, Hs, Ws = sem.shape[1:]
-                    hh, ww = hm.shape[-2:]
-                    crop = (Hs, Ws) if h['size'] is None else (min(int(h['size'][0]), Hs), min(int(h['size'][1]), Ws))
-                    k_cap = min(pp.DEFAULT_K_CAP, hh * ww)
-                    nbytes = L.emp_stack_slice_scratch_bytes(Hs, Ws, hh, ww, k_cap, nt, run_cap, nl, int(e.label_divisor))
-                    if nbytes == 0:
-                        raise ValueError('bad arguments to emp_stack_slice')
-                    scratch = C.workspace(dev, nbytes, 'stack_slice')
-                    C.check(L.emp_stack_slice(sem.data_ptr(), cc, Hs, Ws, float(e.confidence_thr), hm.data_ptr(), off.data_ptr(),
-                                              hh, ww, float(e.nms_threshold), int(e.nms_kernel), float(step), shift, things, nt,
-                                              int(e.label_divisor), int(e.stuff_area), int(e.void_label), k_cap, crop[0], crop[1],
-                                              labels, nl, int(bool(self.force_connected)), scratch.data_ptr(), scratch.numel(),
-                                              None, runs_all[i].data_ptr(), run_cap, inst_all[i].data_ptr(), inst_cap,
-                                              status_dev[i].data_ptr(), ctypes.c_void_p(sd.cuda_stream)))
-        for sd in self._streams:                            # the block is complete when every side stream is
-            done = torch.cuda.Event()
-            done.record(sd)
-            main.wait_event(done)
-        t_b = time.perf_counter()
-        status = status_dev.cpu()                           # the one synchronisation of the block
-        t_c = time.perf_counter()
-        st = status.numpy()                                 # ---- phase B: read back, assemble
-        n_runs = st[:, 2, C.ST_NRUNS].astype(np.int64)
-        n_inst = st[:, 2, C.ST_NINST].astype(np.int64)
-        bad = ((st[:, 0, C.ST_FLAGS] & C.FLAG_K_OVERFLOW) != 0) | ((st[:, 2, C.ST_FLAGS] & C.FLAG_RLE_OVERFLOW) != 0)
-        for f in st[:, 1, C.ST_FLAGS]:
-            pp._check_flags(int(f))
-        ok = ~bad
-        mr = int(n_runs[ok].max()) if ok.any() else 0
-        mi = int(n_inst[ok].max()) if ok.any() else 0
-        # group every slice's runs by instance slot with ONE device sort over the block:
-        # key = slice << 44 | slot << 24 | position (runs are in ascending start order already)
-        nr_dev = torch.from_numpy(np.where(ok, n_runs, 0)).to(dev)
-        rv = runs_all[:, :max(mr, 1)]
-        pos = torch.arange(rv.shape[1], device=dev, dtype=torch.int64)
-        key = (torch.arange(n, device=dev, dtype=torch.int64)[:, None] << 44) | (rv[:, :, 2] << 24) | pos[None]
-        key = torch.where(pos[None] < nr_dev[:, None], key, torch.full_like(key, torch.iinfo(torch.int64).max))
-        perm = torch.sort(key.reshape(-1)).indices[:int(nr_dev.sum())]
-        starts_h = rv[:, :, 0].reshape(-1)[perm].cpu().numpy()
-        lens_h = rv[:, :, 1].reshape(-1)[perm].cpu().numpy()
-        inst_h = inst_all[:, :max(mi, 1)].cpu().numpy()
-        segs, slot_areas, at = {}, [None] * n, 0
-        with _gc_paused():
-            self._assemble(zs, segs, slot_areas, bad, n_runs, n_inst, inst_h, starts_h, lens_h, filtered)
-        # host seconds: enqueueing, waiting for the device, read-back + dict assembly
-        self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'assemble_s': time.perf_counter() - t_c}
-        self.tables_shape_ = (int(H), int(W))
-        # kept for match(): the run tables stay in HBM, slots index each slice's instances in dict order
-        self.tables_ = {'runs_all': runs_all, 'n_runs': np.where(ok, n_runs, 0), 'bad': bad,
-                        'inst': [inst_h[i, :n_inst[i]] if ok[i] else None for i in range(n)], 'zs': list(zs),
-                        'slot_areas': slot_areas}
-        return segs
+            for bi in range(n_sub):
+                i0 = bi * SB
+                B = min(SB, n - i0)
+                hm, hm_stride = _batched([_f32c(self.heads[z]['ctr_hmp']) for z in zs[i0:i0 + B]])
+                off, off_stride = _batched([_f32c(self.heads[z]['offsets']) for z in zs[i0:i0 + B]])
+                C.require_cuda(hm, off)
+                C.check(L.emp_stack_block(ctypes.byref(cfg), B, ctypes.c_void_p(sem8[i0].data_ptr()), H * W,
+                                          ctypes.c_void_p(hm.data_ptr()), hm_stride, ctypes.c_void_p(off.data_ptr()), off_stride,
+                                          ctypes.c_void_p(scratch.data_ptr()), scratch.numel(),
+                                          ctypes.c_void_p(packed[bi].data_ptr()), packed_words,
+                                          ctypes.c_void_p(runs_all[i0].data_ptr()) if runs_all is not None else None,
+                                          ctypes.c_void_p(main.cuda_stream)))
+                torch.maximum(counts, packed[bi, C.BLK_HDR_MAXLAB:C.BLK_HDR_MAXLAB + nl], out=counts)
+                guess = min(packed_words, fixed + B * int(per_slice * 1.25))
+                host = _pinned_words(dev, bi, guess)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                done = torch.cuda.Event()
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    host[:guess].copy_(packed[bi, :guess], non_blocking=True)
+                    done.record(side)
+                subs.append({'i0': i0, 'B': B, 'host': host, 'guess': guess, 'done': done, 'keep': (hm, off)})
+        return subs, packed, runs_all, counts, cfg
 
-    def _assemble(self, zs, segs, slot_areas, bad, n_runs, n_inst, inst_h, starts_h, lens_h, filtered):
-        """Phase B's host loop: the reference's nested dicts per slice from the grouped run tables."""
-        from empanada_b200.inference import rle
-        e = self.engine
-        at = 0
-        for i, z in enumerate(zs):
-            if bad[i]:
-                segs[z] = _slice_sync(e, self.heads[z], filtered[z], self.labels, self.upsampling, self.force_connected)
-            else:
-                k = int(n_runs[i])
-                ins = inst_h[i, :n_inst[i]]
-                segs[z] = rle.grouped_to_rle_seg(ins, starts_h[at:at + k], lens_h[at:at + k], self.labels)
-                if ins.shape[0]:                        # pixels per instance slot (runs are grouped by slot)
-                    first = np.concatenate(([0], np.cumsum(ins[:-1, 6])))
-                    slot_areas[i] = np.add.reduceat(lens_h[at:at + k], first) if k else np.zeros(0, np.int64)
-                else:
-                    slot_areas[i] = np.zeros(0, np.int64)
-                at += k
+    def _collect(self, zs, subs, packed, sem8, out):
+        """Phase B: wait for each sub-block's copy, take owned copies of its tables, register the slices with `out`."""
+        from empanada_b200 import _cabi as C
+        from empanada_b200.inference import postprocess as pp
+        dev = packed.device
+        n = len(zs)
+        bad = np.zeros(n, dtype=bool)
+        n_runs = np.zeros(n, dtype=np.int64)
+        inst = [None] * n
+        worst = 0
+        for bi, sb in enumerate(subs):
+            sb['done'].synchronize()
+            words = sb['host'].numpy()
+            need = _BlockTables.words_needed(words, sb['B'])
+            if need > sb['guess']:                                  # the guess was short: fetch the rest (rare)
+                host = _pinned_words(dev, bi, need)
+                host[:need].copy_(packed[bi, :need])
+                words = host.numpy()
+            t = _BlockTables(words, sb['B'])
+            worst = max(worst, (need - C.BLK_HDR_WORDS) // sb['B'] + 1)
+            for b in range(sb['B']):
+                i = sb['i0'] + b
+                flags = int(t.slices[b, 4])
+                if flags & (C.FLAG_K_OVERFLOW | C.FLAG_RLE_OVERFLOW):
+                    bad[i] = True
+                    out._add_dict(zs[i], _slice_sync(self.engine, self.heads[zs[i]], sem8[i].view(1, 1, *self._plane), self.labels,
+                                                     self.upsampling, self.force_connected))
+                    continue
+                pp._check_flags(flags)
+                out._add(zs[i], t, b)
+                n_runs[i] = int(t.slices[b, 3])
+                inst[i] = out.inst_rows(zs[i])
+        key = (dev.index,) + tuple(self._plane)
+        _words_per_slice[key] = max(_words_per_slice.get(key, 0), worst)
+        return bad, n_runs, inst
 
     def _class_overlaps(self, pair_rows, inst_a, inst_b, c):
         """Rows of one slice pair restricted to class c, slots renumbered within the class."""
@@ -478,76 +664,63 @@ class StackShard:
         H, W = h['size'] if h['size'] is not None else self.tables_shape_
         return fl.fill_block(t['runs_all'], t['n_runs'], table, (H, W), dtype)
 
-    def _all_ranks_agree(self, flag, device):
-        """True iff `flag` holds on every rank (the fast carry hand-over needs all ranks to take it)."""
-        t = torch.tensor([int(bool(flag))], dtype=torch.int64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        return bool(t.item())
-
     def finish(self):
-        from empanada_b200.inference import engines as eng
-        from empanada_b200.inference import rle
-
-        raw = {z: h['sem'] for z, h in self.heads.items()}
-
-        def med(window):
-            return eng.median_harden(window, 0.0)[0]
-
-        def chain(carry):
-            return median_chain(raw, self.z0, self.z1, self.depth, self.ks, carry, med)
-
-        def compose():
-            """(A, B) of this rank's block from emp_median3_compose over its raw planes (+ the first halo plane)."""
-            from empanada_b200 import _cabi as C
-            last_raw = self.z1 >= self.depth
-            planes = [raw[z].detach() for z in range(self.z0, self.z1 if last_raw else self.z1 + 1)]
-            assert all(p.dtype == torch.float32 and p.is_contiguous() and p.shape == planes[0].shape for p in planes)
-            dev = C.require_cuda(*planes)
-            ptrs = torch.tensor([p.data_ptr() for p in planes], dtype=torch.int64).to(dev)
-            A, B = torch.empty_like(planes[0]), torch.empty_like(planes[0])
-            with torch.cuda.device(dev):
-                C.check(C.lib().emp_median3_compose(ptrs.data_ptr(), self.z1 - self.z0, int(self.z0 == 0), int(last_raw),
-                                                    planes[0].numel(), A.data_ptr(), B.data_ptr(), C.stream_ptr(dev)))
-            return A, B
-
-        # ks == 3 over several ranks: the carry crosses the ranks as one clamp per rank (no rank waits for the chain of
-        # the rank below); anything else — and the NaN fallback — hands the carry on after each rank's chain
-        mismatch = None
-        fast = (self.ks == 3 and self.world > 1 and self.z1 > self.z0 and not getattr(self, '_sequential_carry', False)
-                and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in raw.values()))
-        fast = self._all_ranks_agree(fast, raw[self.z0].device) if self.ks == 3 and self.world > 1 else False
-        if fast:
-            filtered, mismatch = exchange_carry_median3(compose, chain, self.rank, self.world, raw[self.z0], self.group)
-        else:
-            filtered = exchange_carry(chain, self.rank, self.world, self.mid, raw[self.z0], self.group)
+        """Post-process + RLE-encode this rank's block.  Returns an RleStack ({z: rle_seg}, dicts built on access)."""
+        from empanada_b200 import _cabi as C
         e = self.engine
         zs = list(range(self.z0, self.z1))
-        if not zs:
-            segs = {}
-        elif filtered[self.z0].is_cuda:
-            with _gc_paused():
-                segs = self._finish_block_gpu(zs, filtered)
-        else:
+        assert all(z in self.heads for z in range(self.z0, self.z_halo)), 'add() every slice of slices() first'
+        planes = [_f32c(self.heads[z]['sem']) for z in range(self.z0, self.z_halo)]
+        if not planes[0].is_cuda:
             raise RuntimeError('StackShard runs on CUDA tensors only (there is no CPU fallback)')
-        out, max_counts = {}, {c: 0 for c in self.labels}
-        for z in zs:
-            seg = segs[z]
-            for c in self.labels:
-                if c in e.thing_list and seg[c]:
-                    max_counts[c] = max(max_counts[c], max(seg[c]) - c * e.label_divisor)
-            out[z] = seg
-        counts = torch.tensor([max_counts[c] for c in self.labels] + [0], dtype=torch.int64, device=raw[self.z0].device)
-        if mismatch is not None:
-            counts[-1] = mismatch                           # rides along with the instance counts
-        # a single-rank shard never talks to anyone, even inside a larger process group
-        if self.world == 1:
-            offs = torch.zeros_like(counts[:-1])
-        else:
-            offs, table = label_offsets(counts, self.group)
-            if bool(table[:, -1].any()):                    # some rank's composed carry was not its chain's plane (NaNs):
-                self._sequential_carry = True               # every rank sees the same table, so all of them redo the block
-                return self.finish()
-            offs = offs[:-1]
-        offs = {c: int(o) for c, o in zip(self.labels, offs.tolist())}
+        dev = C.require_cuda(*planes)
+        assert all(p.dim() == 4 and p.size(0) == 1 and p.shape == planes[0].shape for p in planes)
+        Cn, H, W = planes[0].shape[1:]
+        self._plane = (int(H), int(W))
+        t_a = time.perf_counter()
+        sem8, changed = self._chain(planes, dev, H * W, Cn)
+        subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W)
+        # instance counts per class (+ the "my outgoing carry moved" flag) over all ranks
+        multi = self.world > 1 and dist.is_available() and dist.is_initialized()
+        table_h = None
+        if multi:
+            mine = torch.cat([counts, (changed if changed is not None else torch.zeros((1,), dtype=torch.int32, device=dev)).to(torch.int64)])
+            gathered = torch.empty((self.world, mine.numel()), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            table_h = torch.empty(gathered.shape, dtype=torch.int64).pin_memory()
+            table_h.copy_(gathered, non_blocking=True)
+        t_b = time.perf_counter()
+        out = RleStack(self.labels, e.thing_list, e.label_divisor)
+        bad, n_runs, inst = self._collect(zs, subs, packed, sem8, out)
+        torch.cuda.current_stream(dev).synchronize()
+        t_c = time.perf_counter()
+        offs = {c: 0 for c in self.labels}
+        if multi:
+            table = table_h.numpy()
+            if table[:, -1].any() and not self._settle:
+                # some rank's repair reached the end of its block: its neighbour's carry was not final.  Every rank
+                # sees the same table, so all of them settle the carries with further rounds and redo the block.
+                self._settle = True
+                try:
+                    return self.finish()
+                finally:
+                    self._settle = False
+            per_class = table[:, :-1]
+            if bad.any():                                           # a slice redone synchronously is not in the device counts
+                raise RuntimeError('a slice overflowed the deferred tables on a multi-rank stack; raise the capacities')
+            before = per_class[:self.rank].sum(0)
+            worst = per_class.sum(0)
+            for c, b, w in zip(self.labels, before.tolist(), worst.tolist()):
+                if c in e.thing_list:
+                    if w >= e.label_divisor:                        # identical on every rank: all of them raise
+                        raise ValueError(f'class {c}: {w} instance labels over {self.world} ranks leave the class range; '
+                                         f'raise label_divisor (reference default for 3D is 20000)')
+                    offs[c] = int(b)
+        out.offsets = offs
         self.label_offsets_ = offs
-        return {z: apply_label_offset(s, offs, e.label_divisor, e.thing_list) for z, s in out.items()}
+        self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b}
+        self.tables_shape_ = self._plane
+        self.tables_ = {'runs_all': runs_all, 'n_runs': n_runs, 'bad': bad, 'inst': inst, 'zs': zs,
+                        'slot_areas': [None if r is None else r[:, 8] for r in inst]}
+        self._keep = None
+        return out

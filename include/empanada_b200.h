@@ -50,7 +50,7 @@ extern "C" {
 #define EMP_ST_GSHIFT 5     /* internal: log2 of the center-index cell size in pixels */
 #define EMP_ST_TICKET 6     /* internal: block hand-out counter of the assign kernel */
 #define EMP_ST_WORDS 16
-#define EMP_PROFILE_STAGES 9
+#define EMP_PROFILE_STAGES 15
 
 #define EMP_FLAG_K_OVERFLOW 1     /* more centers than k_cap: result invalid, retry with larger cap */
 #define EMP_FLAG_CLASS_RANGE 2    /* a semantic class id outside [0, EMP_MAX_CLASSES) was seen */
@@ -63,7 +63,8 @@ const char* emp_last_error(void);
 /* Optional per-stage device timing for benchmarks: while enabled, every kernel launch is
  * bracketed by a CUDA event pair on its stream.  emp_profile_read() waits for the recorded events
  * and returns, per stage (0 nms_peaks, 1 emit_centers, 2 assign, 3 build_lut, 4 apply_lut,
- * 5 median_harden, 6 rle_mark, 7 rle run kernels, 8 bin_centers), the summed milliseconds and the
+ * 5 median_harden, 6 rle_mark, 7 rle run kernels, 8 bin_centers, 9 median_chain, 10..14 the stack block's
+ * rle keys / mark / emit / runs / pack), the summed milliseconds and the
  * number of launches since the last read.  Both arrays have EMP_PROFILE_STAGES entries (host). */
 int emp_profile_enable(int on);
 int emp_profile_read(double* ms_per_stage, int* launches_per_stage);
@@ -162,15 +163,28 @@ int emp_median_harden(const float* const* planes /* host array */, int ks, int C
                       float confidence_thr, float* median_out, void* sem_out, int sem_u8,
                       void* stream);
 
-/* The recursive median of _MedianQueue with median_kernel_size == 3 (engines.py:68-90) over a whole z-block as ONE
- * clamp: f_last = min(max(f_in, A), B), where f_in is the filtered plane below the block.  Lets z-sharded ranks hand
- * the carry plane on after one clamp instead of one full chain (inference/stack.py).
- *   planes_dev  DEVICE array of n (+1 unless last_raw) pointers to the block's raw (C*H*W) f32 planes, followed by
- *               the first plane above the block; first_raw / last_raw: the block starts with the stack's first /
- *               ends with the stack's last slice (which the queue passes through unfiltered)
- *   A_out, B_out  (count) f32 */
-int emp_median3_compose(const float* const* planes_dev, int n, int first_raw, int last_raw, size_t count,
-                        float* A_out, float* B_out, void* stream);
+/* _MedianQueue + _harden_seg over a whole z-block — engines.py:47-90 (enqueue / get_next / end), :114-121.
+ * The queue's filter is recursive: m_z = median(m_{z-mid} .. m_{z-1}, s_z .. s_{z+mid}) for mid <= z < depth - mid, and the
+ * first / last mid slices of the stack pass through raw.  One launch (per channel) walks the block [z0, z0 + n) in z with
+ * that state in registers: every raw plane is read once, only the hardened class byte is written.
+ *   planes_dev   DEVICE array of n_planes pointers: raw (C,H,W) f32 probabilities of slices z0, z0+1, ... — the block and
+ *                its look-ahead halo, n_planes >= min(n + mid, depth - z0)
+ *   carry_in_dev DEVICE array of mid pointers: the filtered planes z0-mid .. z0-1 (ignored / may be NULL when z0 == 0)
+ *   carry_out_dev DEVICE array of mid pointers or NULL: receives the filtered planes z0+n-mid .. z0+n-1 (n >= mid)
+ *   sem8_out     (n, sem8_stride) uint8 class maps: C == 1: p >= confidence_thr; C > 1: first arg-max (NaN counts as max)
+ *   best_scratch (n, hw) f32, only for C > 1
+ * A NaN in a window gives a NaN median, as torch.median does. */
+int emp_median_chain(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, int C, size_t hw,
+                     const float* const* carry_in_dev, float confidence_thr, uint8_t* sem8_out, size_t sem8_stride,
+                     float* best_scratch, float* const* carry_out_dev, void* stream);
+
+/* The same block (C == 1) re-run from a corrected carry: per pixel, both chains (old carry, new carry) advance together
+ * until their states agree bit for bit; only that prefix of sem8 is rewritten.  Pixels still apart at the block's end
+ * store the new state into carry_out_dev and set *changed (device int32, zeroed by the caller) — the z-sharded stack
+ * starts every rank's chain from a guessed carry and repairs it once the true one arrives (inference/stack.py). */
+int emp_median_chain_repair(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, size_t hw,
+                            const float* const* carry_old_dev, const float* const* carry_new_dev, float confidence_thr,
+                            uint8_t* sem8, size_t sem8_stride, float* const* carry_out_dev, int32_t* changed, void* stream);
 
 /* pan_seg_to_rle_seg — empanada/inference/rle.py:26-86 (+ connected_components :18-24,
  * array_utils.rle_encode array_utils.py:209-235).  One pass over the pixels extracts row-runs
@@ -192,25 +206,44 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
             int force_connected, int64_t* runs_out, int run_cap, int64_t* inst_out, int inst_cap,
             void* ws, size_t ws_bytes, void* stream);
 
-/* One z-slice of the stack path behind the median queue, in one call and with no host synchronisation:
- * _harden_seg (engines.py:114-121) -> get_instance_cells on the coarse maps (:257-272) -> get_panoptic_seg with the
- * nearest upsample folded in (:274-292) -> crop to the unpadded size (:305-307) -> pan_seg_to_rle_seg's tables
- * (rle.py:26-86).  It chains emp_median_harden, emp_coarse_ids, emp_merge_coarse and emp_rle on `stream`.
- *   sem_prob (C,H,W) f32 probabilities; hm (h,w), off (2,h,w) f32 with (h << shift, w << shift) >= (H, W)
- *   pan_out  (H,W) int64 or NULL (the padded panoptic map, if the caller wants it)
- *   runs_out / inst_out as for emp_rle, over the top-left crop_h x crop_w of the map
- *   status_out  DEVICE int32[3 * EMP_ST_WORDS]: the status blocks of the center search (K, overflow flag), the
- *               merge (class-range flags) and the encoder (counts, overflow flag), valid once the stream has run
- *   scratch  device buffer of emp_stack_slice_scratch_bytes(), 256-byte aligned, reusable by the next slice */
-size_t emp_stack_slice_scratch_bytes(int H, int W, int h, int w, int k_cap, int n_things, int run_cap,
-                                     int n_labels, int64_t label_divisor);
-int emp_stack_slice(const float* sem_prob, int C, int H, int W, float confidence_thr, const float* hm,
-                    const float* off, int h, int w, float nms_threshold, int nms_kernel, float step, int shift,
-                    const int64_t* thing_list /* host */, int n_things, int64_t label_divisor,
-                    int64_t stuff_area, int64_t void_label, int k_cap, int crop_h, int crop_w,
-                    const int64_t* labels /* host */, int n_labels, int force_connected, void* scratch,
-                    size_t scratch_bytes, int64_t* pan_out, int64_t* runs_out, int run_cap, int64_t* inst_out,
-                    int inst_cap, int32_t* status_out, void* stream);
+/* B z-slices of the stack path behind the median queue, one launch per kernel for the whole block and no host
+ * synchronisation: get_instance_cells on the coarse maps (engines.py:257-272) -> get_panoptic_seg with the nearest
+ * upsample folded in (:274-292) -> crop to the unpadded size (:305-307) -> pan_seg_to_rle_seg's tables (rle.py:26-86),
+ * cut straight from the 16-bit code map + label LUT (the int64 label map is never written).
+ *   sem8 (B, sem8_stride) uint8 hardened classes (emp_median_chain); hm (B, hm_stride) f32 (h,w) heat-maps;
+ *   off (B, off_stride) f32 (2,h,w) offsets, with (h << shift, w << shift) >= (H, W)
+ *   scratch   device buffer of emp_stack_block_scratch_bytes(), 256-byte aligned, reusable by the next block
+ *   packed_out  device int64[emp_stack_block_packed_words()], everything the host needs in ONE contiguous prefix:
+ *       [0] B  [1] R = row-runs of all slices  [2] I = instances of all slices  [3] EMP_BLK_INST_WORDS
+ *       [EMP_BLK_HDR_MAXLAB + i]  largest (label - labels[i] * label_divisor) in the block
+ *       per slice b at EMP_BLK_HDR_WORDS + EMP_BLK_SLICE_WORDS * b:
+ *           n instances, first instance row, first run row, row-runs, OR of the EMP_FLAG_* bits, K (centers found)
+ *       starts[R], lengths[R] (flat indices into the crop_h x crop_w map; grouped by instance, ascending inside one)
+ *       I instance rows of EMP_BLK_INST_WORDS: class label, instance label, y0, x0, y1, x1, n runs, first run row
+ *           (into starts / lengths), area — slices in order, instances in the reference's dict order
+ *   runs3_out  optional device (B, run_cap, 3) int64: (start, length, instance slot) of every row-run in ascending
+ *              start order — the layout emp_rle_pair_overlaps / emp_fill_runs consume. */
+typedef struct emp_stack_cfg {
+    int32_t H, W, h, w;                 /* padded plane, coarse maps */
+    int32_t shift;                      /* log2 of the coarse -> full upsampling */
+    int32_t nms_kernel, k_cap;
+    int32_t crop_h, crop_w;
+    int32_t n_things, n_labels, force_connected;
+    int32_t run_cap, inst_cap;          /* row-runs / instances per slice */
+    float nms_threshold, step;
+    int64_t label_divisor, stuff_area, void_label;
+    const int64_t* thing_list;          /* host */
+    const int64_t* labels;              /* host */
+} emp_stack_cfg;
+#define EMP_BLK_HDR_MAXLAB 4
+#define EMP_BLK_HDR_WORDS (4 + EMP_MAX_LABELS)
+#define EMP_BLK_SLICE_WORDS 6
+#define EMP_BLK_INST_WORDS 9
+size_t emp_stack_block_scratch_bytes(const emp_stack_cfg* cfg, int B);
+size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B);
+int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+                    size_t hm_stride, const float* off, size_t off_stride, void* scratch, size_t scratch_bytes,
+                    int64_t* packed_out, size_t packed_words, int64_t* runs3_out, void* stream);
 
 /* Cross-slice matcher support — empanada/inference/matcher.py:136-232 (rle_matcher) with
  * array_utils.rle_intersection :371-403 / rle_iou :405-429 / rle_ioa :431-449: pixel overlaps between

@@ -185,28 +185,3 @@ def test_stack_shard_matches_sequential_engine(ks, cuda_device):
             np.testing.assert_array_equal(vol[z], rle.rle_seg_to_pan_seg(matched[z], (H, W)).astype(np.int64))
         labels0 = set(matched[0][1].keys())
         assert any(set(matched[z][1].keys()) & labels0 for z in range(1, D))      # objects are tracked across slices
-
-
-@pytest.mark.parametrize('z0,z1,depth', [(0, 9, 20), (5, 12, 20), (13, 20, 20), (0, 6, 6), (4, 5, 9)])
-def test_median3_compose_kernel(z0, z1, depth, cuda_device):
-    """emp_median3_compose (a z-block of the ks = 3 recursive median as one clamp) against the torch restatement the
-    gloo tests pin to the reference's queue (tests/test_stack_host.py), and against the chain itself."""
-    import ctypes
-    from empanada_b200 import _cabi as C
-    from empanada_b200.inference import stack
-    rng = np.random.default_rng(z0 * 100 + z1)
-    last_raw = z1 >= depth
-    raw = {z: torch.from_numpy(np.round(rng.random((1, 2, 37, 50), dtype=np.float32) * 16) / 16).to(cuda_device)
-           for z in range(z0, z1 if last_raw else z1 + 1)}
-    want_A, want_B = stack.compose_median3(raw, z0, z1, depth)
-    planes = [raw[z] for z in sorted(raw)]
-    ptrs = torch.tensor([p.data_ptr() for p in planes], dtype=torch.int64).to(cuda_device)
-    A, B = torch.empty_like(planes[0]), torch.empty_like(planes[0])
-    with torch.cuda.device(cuda_device):
-        C.check(C.lib().emp_median3_compose(ptrs.data_ptr(), z1 - z0, int(z0 == 0), int(last_raw), planes[0].numel(),
-                                            A.data_ptr(), B.data_ptr(), C.stream_ptr(cuda_device)))
-    assert torch.equal(A, want_A) and torch.equal(B, want_B)
-    # and the clamp applied to a plane below the block is what the chain produces
-    below = torch.from_numpy(rng.random((1, 2, 37, 50), dtype=np.float32)).to(cuda_device)
-    got, nxt = stack.median_chain(raw, z0, z1, depth, 3, [below] if z0 > 0 else [], lambda w: eng.median_harden(w, 0.0)[0])
-    assert torch.equal(torch.minimum(torch.maximum(below, A), B), nxt[0])

@@ -71,112 +71,93 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ks, D, seed, ret):
+def _worker(rank, world, port, ks, D, seed, sticky, ret):
+    """One rank of the guessed-carry hand-over (stack.carry_rounds) with torch restatements of the two kernels: chain
+    from a carry, and "repair" as a full re-run that reports whether the outgoing carry moved."""
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
-        rng = np.random.default_rng(seed)
-        planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]      # same on all ranks
+        planes = _planes(D, seed, sticky)                                            # same on all ranks
         z0, z1 = stack.partition_slices(D, world, rank)
         _, zh = stack.halo_range(D, world, rank, ks)
         raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
         mid = (ks - 1) // 2
-        got = stack.exchange_carry(lambda c: stack.median_chain(raw, z0, z1, D, ks, c, _tmedian),
-                                   rank, world, mid, raw[z0])
+        st = {'got': None, 'out': [torch.zeros_like(raw[z0]) for _ in range(mid)], 'recv': [torch.zeros_like(raw[z0]) for _ in range(mid)],
+              'rounds': 0}
+
+        def run(carry):
+            got, nxt = stack.median_chain(raw, z0, z1, D, ks, carry, _tmedian)
+            moved = any(not torch.equal(a, b) for a, b in zip(st['out'], nxt))
+            for a, b in zip(st['out'], nxt):
+                a.copy_(b)
+            st['got'] = got
+            return moved
+
+        def repair(rnd):
+            st['rounds'] += 1
+            return torch.tensor([int(run([t.clone() for t in st['recv']]))])
+
+        def any_changed(flag):
+            t = flag.clone() if flag is not None else torch.zeros(1, dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return bool(t.item())
+
+        for settle in (False, True):
+            flag = stack.carry_rounds(rank, world, lambda: run([raw[z0]] * mid), repair,
+                                      lambda: stack.exchange_planes(st['out'], st['recv'], rank, world),
+                                      any_changed if settle else None)
+            if not settle:
+                first_flag = int(flag.item()) if flag is not None else 0
+                one_round = {z: st['got'][z].numpy().copy() for z in st['got']}
         counts = torch.tensor([10 * (rank + 1), 3 + rank], dtype=torch.int64)
         offs, table = stack.label_offsets(counts)
-        ret[rank] = ({z: got[z].numpy() for z in got}, offs.tolist(), table.tolist())
+        ret[rank] = ({z: st['got'][z].numpy() for z in st['got']}, offs.tolist(), table.tolist(), first_flag, one_round)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,ks', [(2, 3), (2, 5), (3, 3)])
-def test_sharded_chain_and_offsets_gloo(world, ks):
-    D, seed = 11, 5
+def _planes(D, seed, sticky):
+    rng = np.random.default_rng(seed)
+    if sticky:      # alternating 0 / 10 planes: every window's middle values are carried ones, the filter never forgets its start
+        return [np.full((1, 1, 4, 8), 10.0 * (z % 2), np.float32) + (rng.random((1, 1, 4, 8), dtype=np.float32) if z == 1 else 0)
+                for z in range(D)]
+    return [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]
+
+
+@pytest.mark.parametrize('world,ks,sticky', [(2, 3, False), (2, 5, False), (3, 3, False), (3, 3, True), (4, 5, True)])
+def test_guessed_carry_rounds_and_offsets_gloo(world, ks, sticky):
+    """Every rank starts its chain from a guessed carry, one exchange + repair makes all blocks exact unless some
+    rank reports that its outgoing carry moved; the settle rounds then converge to the sequential queue's result."""
+    D, seed = 13, 5
     port = _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ks, D, seed, ret), nprocs=world, join=True)
-    rng = np.random.default_rng(seed)
-    planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]
-    want = _sequential(planes, ks)
+    mp.spawn(_worker, args=(world, port, ks, D, seed, sticky, ret), nprocs=world, join=True)
+    want = _sequential(_planes(D, seed, sticky), ks)
     seen = set()
+    flags = [ret[r][3] for r in range(world)]
     for r in range(world):
-        got, offs, table = ret[r]
+        got, offs, table, _, one_round = ret[r]
         for z, p in got.items():
             np.testing.assert_array_equal(p, want[z])
+            if not any(flags):                       # nobody's carry moved: the single round was already exact
+                np.testing.assert_array_equal(one_round[z], want[z])
             seen.add(z)
         assert offs == [sum(10 * (q + 1) for q in range(r)), sum(3 + q for q in range(r))]
         assert table == [[10 * (q + 1), 3 + q] for q in range(world)]
     assert seen == set(range(D))
+    if sticky and world > 2:
+        assert any(flags[1:])                        # the case the settle rounds exist for
 
 
-# ---- ks == 3: the block as one clamp, the carry crossing the ranks without waiting for their chains ----
-@pytest.mark.parametrize('world', [1, 2, 3, 5])
-def test_compose_median3_equals_the_chain(world):
-    """f_last = min(max(f_in, A), B) with (A, B) from the block's own raw planes must be the chain's last plane, for
-    every block of every partition, fed with the true plane below it — including the raw first / last slices, equal
-    neighbours (ties) and multi-channel planes."""
-    rng = np.random.default_rng(100 + world)
-    D = 17
-    planes = [np.round(rng.random((1, 2, 5, 6), dtype=np.float32) * 8) / 8 for _ in range(D)]      # coarse values: many ties
-    want = _sequential([p.copy() for p in planes], 3)
-    for r in range(world):
-        z0, z1 = stack.partition_slices(D, world, r)
-        _, zh = stack.halo_range(D, world, r, 3)
-        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
-        A, B = stack.compose_median3(raw, z0, z1, D)
-        below = torch.from_numpy(want[z0 - 1]) if z0 > 0 else torch.full_like(A, 123.0)     # rank 0: anything
-        got = torch.minimum(torch.maximum(below, A), B)
-        np.testing.assert_array_equal(got.numpy(), want[z1 - 1])
-
-
-def _worker_median3(rank, world, port, D, seed, poison, ret):
-    os.environ['MASTER_ADDR'] = '127.0.0.1'
-    os.environ['MASTER_PORT'] = str(port)
-    dist.init_process_group('gloo', rank=rank, world_size=world)
-    try:
-        rng = np.random.default_rng(seed)
-        planes = [rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)]      # same on all ranks
-        if poison:
-            planes[2][0, 0, 1, 3] = np.nan
-        z0, z1 = stack.partition_slices(D, world, rank)
-        _, zh = stack.halo_range(D, world, rank, 3)
-        raw = {z: torch.from_numpy(planes[z]) for z in range(z0, zh)}
-        got, mismatch = stack.exchange_carry_median3(lambda: stack.compose_median3(raw, z0, z1, D),
-                                                     lambda c: stack.median_chain(raw, z0, z1, D, 3, c, _tmedian),
-                                                     rank, world, raw[z0])
-        ret[rank] = ({z: got[z].numpy() for z in got}, int(mismatch))
-    finally:
-        dist.destroy_process_group()
-
-
-@pytest.mark.parametrize('world', [2, 3])
-def test_median3_carry_crosses_ranks_as_clamps_gloo(world):
-    D, seed = 11, 9
-    port = _free_port()
-    ret = mp.Manager().dict()
-    mp.spawn(_worker_median3, args=(world, port, D, seed, False, ret), nprocs=world, join=True)
-    rng = np.random.default_rng(seed)
-    want = _sequential([rng.random((1, 1, 4, 8), dtype=np.float32) for _ in range(D)], 3)
-    seen = set()
-    for r in range(world):
-        got, mismatch = ret[r]
-        assert mismatch == 0
-        for z, p in got.items():
-            np.testing.assert_array_equal(p, want[z])
-            seen.add(z)
-    assert seen == set(range(D))
-
-
-def test_median3_nan_is_flagged_gloo():
-    """A NaN makes "composed clamp == chain" unprovable: the rank that handed such a plane on must say so (the
-    driver then redoes the block with the sequential hand-over)."""
-    port = _free_port()
-    ret = mp.Manager().dict()
-    mp.spawn(_worker_median3, args=(2, port, 11, 9, True, ret), nprocs=2, join=True)
-    assert ret[0][1] == 1 and ret[1][1] == 0
+def test_shard_rejects_blocks_shorter_than_the_window():
+    """depth < world_size * mid cannot be sharded; every rank sees the same arguments, so every rank raises before any
+    collective (nobody is left waiting)."""
+    with pytest.raises(ValueError):
+        stack.StackShard(None, [1], depth=6, rank=1, world_size=4, median_kernel_size=7)
+    with pytest.raises(ValueError):
+        stack.StackShard(None, [1], depth=2, rank=0, world_size=1, median_kernel_size=3)
 
 
 def test_apply_label_offset():
