@@ -109,6 +109,9 @@ int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, con
                         long long void_label, int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws,
                         size_t ws_stride, cudaStream_t st);
 
+int build_luts_batched(int B, int H, int W, const Things& th, long long label_divisor, long long stuff_area, long long void_label,
+                       int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws, size_t ws_stride, cudaStream_t st);
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ int thing_index(long long c, const Things& th)
 {

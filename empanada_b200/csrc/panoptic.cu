@@ -1824,6 +1824,14 @@ int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, con
     return launch_build_lut(B, L, ws, ws_stride, k_cap, k_cap, k_dev, th, label_divisor, void_label, stuff_area, H, W, st, k_dev_stride);
 }
 
+// label LUTs of B tiles from their votes / areas (build_lut_kernel), for merge kernels defined elsewhere
+int build_luts_batched(int B, int H, int W, const Things& th, long long label_divisor, long long stuff_area, long long void_label,
+                       int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws, size_t ws_stride, cudaStream_t st)
+{
+    const WsLayout L = ws_layout(H, W, k_cap, th.n);
+    return launch_build_lut(B, L, ws, ws_stride, k_cap, k_cap, k_dev, th, label_divisor, void_label, stuff_area, H, W, st, k_dev_stride);
+}
+
 }  // namespace emp
 
 // =============================================================================================

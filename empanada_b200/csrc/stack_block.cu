@@ -29,6 +29,7 @@ namespace emp {
 // =====================================================================================================
 // 1. recursive median chain
 // =====================================================================================================
+constexpr unsigned kNoVote = 0xFFFFFFFFu;
 constexpr int kChainPf = 3;         // raw planes loaded ahead of the window (loads in flight per thread)
 
 struct ChainArgs {
@@ -220,12 +221,141 @@ static int launch_chain(int ks, const ChainArgs& a, bool vec, cudaStream_t st)
 }
 
 // =====================================================================================================
-// 2. RLE tables from code maps
+// 2. upsample-fused merge for uint8 class maps + coarse id maps (the stack path's common case)
+// =====================================================================================================
+// get_panoptic_seg (engines.py:277-292) up to the label LUT, as the general assign kernel of panoptic.cu does it for
+// (SEM_U8, ID_COARSE), but without anything the nearest-center search needs: ~60 registers, 8 CTAs per SM, and a
+// background strip costs four 16-byte loads and one flag byte.  A warp takes a strip row (4 rows) x 512 columns = 8
+// strips of 4 x 64; four lanes share a strip, each owning 16 consecutive pixels of its 4 rows.  Same outputs as the
+// general kernel: strip flags, 16-bit codes (only for strips that are not all class-0 background), votes per
+// (id, thing class), stuff areas by complement.  Needs W % 16 == 0 and thing classes < 64 (else the general kernel).
+struct LeanArgs {
+    const unsigned char* sem8; size_t sem_stride;
+    const int32_t* ids; size_t ids_stride;
+    char* ws; size_t ws_stride;
+    size_t o_votes, o_areas, o_sflags, o_codes;
+    int B, H, W, wc, shift, blocks_x, blk_items, T;
+    unsigned long long thing_bits;
+};
+
+__global__ void __launch_bounds__(256, 4)
+merge_lean_kernel(const LeanArgs a)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 2, q = lane & 3;
+    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const int groups = (a.W + 511) / 512, srows = (a.H + 3) / 4;
+    const size_t per_slice = (size_t)srows * groups;
+    const size_t items = per_slice * a.B;
+    const bool class0_stuff = !(a.thing_bits & 1ull);
+    const bool multi = a.T > 1;
+    int cur_b = -1;
+    unsigned deficit = 0;                                               // in-image pixels of the slice that are NOT class-0 stuff
+    char* ws = nullptr;
+    auto flush = [&]() {                                                // warp-uniform call sites
+        if (cur_b < 0) return;
+        const unsigned d = __reduce_add_sync(0xffffffffu, deficit);
+        if (d && lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(ws + a.o_areas) + kNumClasses, d);
+        deficit = 0;
+    };
+    for (size_t it = warp_global; it < items; it += n_warps) {
+        const int b = (int)(it / per_slice);
+        const size_t r = it - (size_t)b * per_slice;
+        const int sy = (int)(r / groups), g = (int)(r % groups);
+        if (b != cur_b) {
+            flush();
+            cur_b = b;
+            ws = a.ws + (size_t)b * a.ws_stride;
+        }
+        const int y0 = sy * 4, xs = g * 512 + grp * 64;                 // the strip of this lane's group
+        const int x0 = xs + q * 16;
+        const bool in_x = x0 < a.W;                                     // W % 16 == 0: a lane is inside or outside as a whole
+        const unsigned char* sp = a.sem8 + (size_t)b * a.sem_stride + (size_t)y0 * a.W + x0;
+        uint4 raw[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            raw[rr] = make_uint4(0u, 0u, 0u, 0u);
+            if (in_x && y0 + rr < a.H) raw[rr] = __ldcs(reinterpret_cast<const uint4*>(sp + (size_t)rr * a.W));
+        }
+        unsigned orall = 0;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) orall |= raw[rr].x | raw[rr].y | raw[rr].z | raw[rr].w;
+        const unsigned zero4 = __ballot_sync(0xffffffffu, orall == 0u);  // before any lane leaves the iteration
+        if (xs >= a.W) continue;                                        // the whole group lies right of the plane (4 lanes agree)
+        const bool full = xs + 64 <= a.W && y0 + 4 <= a.H;
+        const unsigned gmask = 0xFu << (lane & ~3);
+        const bool bg = full && class0_stuff && ((zero4 & gmask) == gmask);
+        unsigned char* flagp = reinterpret_cast<unsigned char*>(ws + a.o_sflags) +
+                               ((size_t)(y0 / (a.blk_items * 4)) * a.blocks_x + (xs >> 6)) * 16 + ((y0 >> 2) % a.blk_items);
+        if (bg) {
+            if (q == 0) *flagp = 1;
+            continue;
+        }
+        if (q == 0) *flagp = 0;
+        if (!in_x) continue;
+        uint32_t* votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
+        uint32_t* areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
+        const int32_t* ids = a.ids + (size_t)b * a.ids_stride;
+        unsigned short* codes = reinterpret_cast<unsigned short*>(ws + a.o_codes);
+        unsigned vkey = kNoVote, vcnt = 0;                              // pending vote: pixels in a row of equal (id, class)
+        unsigned akey = kNoVote, acnt = 0;                              // pending stuff-area count of one non-zero class
+        int last_cell = -1, last_id = 0;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int y = y0 + rr;
+            if (y >= a.H) break;
+            const unsigned w4[4] = {raw[rr].x, raw[rr].y, raw[rr].z, raw[rr].w};
+            const int crow = (y >> a.shift) * a.wc;
+            unsigned out[8];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                const unsigned c = (w4[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+                const bool thing = c < 64u && ((a.thing_bits >> c) & 1ull);
+                unsigned code;
+                if (thing) {
+                    const int cell = crow + ((x0 + p) >> a.shift);
+                    if (cell != last_cell) { last_cell = cell; last_id = __ldg(ids + cell); }
+                    code = (unsigned)last_id;                           // 0: a thing pixel without an instance stays void
+                    if (last_id > 0) {
+                        const unsigned t = multi ? (unsigned)__popcll(a.thing_bits & ((1ull << c) - 1ull)) : 0u;
+                        const unsigned key = (unsigned)last_id * (unsigned)a.T + t;
+                        if (key != vkey) {
+                            if (vcnt) atomicAdd(votes + vkey, vcnt);
+                            vkey = key; vcnt = 0;
+                        }
+                        ++vcnt;
+                    }
+                    ++deficit;
+                } else {
+                    code = kClsBase16 + c;
+                    if (c != 0u) {
+                        ++deficit;
+                        if (c != akey) {
+                            if (acnt) atomicAdd(areas + akey, acnt);
+                            akey = c; acnt = 0;
+                        }
+                        ++acnt;
+                    }
+                }
+                if (p & 1) out[p >> 1] |= code << 16; else out[p >> 1] = code;
+            }
+            uint4* cp = reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x0);
+            cp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            cp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+        if (vcnt) atomicAdd(votes + vkey, vcnt);
+        if (acnt) atomicAdd(areas + akey, acnt);
+    }
+    flush();
+}
+
+// =====================================================================================================
+// 3. RLE tables from code maps
 // =====================================================================================================
 // per-slice scratch of the encoder (B of them, rs_stride apart)
 struct BlkLayout {
-    size_t status, rowcnt, flags, cnt, zero_bytes;          // [0, zero_bytes) is cleared per call
-    size_t keylut, smask, emask, rowoff, r_y, r_xs, r_xe, r_key, parent, slot_of, ymin, ymax, inst, total;
+    size_t status, rowcnt, flags, cnt, smask, emask, zero_bytes;    // [0, zero_bytes) is cleared per call
+    size_t keylut, rowoff, r_y, r_xs, r_xe, r_key, parent, slot_of, ymin, ymax, inst, total;
     size_t flags_len;
     int wd;
 };
@@ -243,10 +373,10 @@ static BlkLayout blk_layout(int crop_h, int crop_w, int run_cap, int inst_cap, i
     R.rowcnt = o;  o = align_up(o + sizeof(uint32_t) * (size_t)crop_h, 256);
     R.flags = o;   o = align_up(o + sizeof(int) * R.flags_len, 256);
     R.cnt = o;     o = align_up(o + sizeof(int) * ((size_t)inst_cap + 1), 256);
+    R.smask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);     // mark only writes words that hold a run boundary
+    R.emask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);
     R.zero_bytes = o;
     R.keylut = o;  o = align_up(o + sizeof(uint32_t) * ((size_t)k_cap + 1 + kNumClasses), 256);
-    R.smask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);
-    R.emask = o;   o = align_up(o + sizeof(uint32_t) * (size_t)crop_h * R.wd, 256);
     R.rowoff = o;  o = align_up(o + sizeof(int) * ((size_t)crop_h + 1), 256);
     R.r_y = o;     o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
     R.r_xs = o;    o = align_up(o + sizeof(int) * (size_t)run_cap, 256);
@@ -329,10 +459,11 @@ __device__ __forceinline__ CodeView code_view(const BlkArgs& a, int b)
     return v;
 }
 
-// The one pass over the (cropped) code maps.  A warp takes 256 consecutive pixels of a row; lane l owns pixels
-// 8l .. 8l+7 (one 16-byte load of codes — or none at all when its 64-column strip is flagged "all class-0
-// background", the bulk of an EM slice).  Start / end bits are formed per lane and gathered into the row's mask
-// words with three shuffles.
+// The one pass over the (cropped) code maps.  A warp takes a strip row (4 rows) x 256 columns; lane l owns pixels
+// 8l .. 8l+7 of each row (one 16-byte load of codes per row — or none at all when its 4 x 64 strip is flagged "all
+// class-0 background", the bulk of an EM slice: such an item costs one flag byte).  Start / end bits are formed per
+// lane and gathered into the row's mask words with three shuffles; the masks are pre-zeroed, so only words of items
+// that hold a selected pixel are written.
 __global__ void __launch_bounds__(256)
 rle_block_mark_kernel(const BlkArgs a)
 {
@@ -340,77 +471,100 @@ rle_block_mark_kernel(const BlkArgs a)
     const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const int groups = (a.crop_w + 255) / 256;
-    const size_t per_slice = (size_t)a.crop_h * groups;
+    const int srows = (a.crop_h + 3) / 4;
+    const size_t per_slice = (size_t)srows * groups;
     const size_t items = per_slice * a.B;
     const int wd = a.R.wd;
+    int cur_b = -1;
+    unsigned bgkey = 0, key0 = 0;
+    CodeView v;
+    char* rs = nullptr;
     for (size_t it = warp_global; it < items; it += n_warps) {
         const int b = (int)(it / per_slice);
         const size_t r = it - (size_t)b * per_slice;
-        const int y = (int)(r / groups), g = (int)(r % groups);
-        const CodeView v = code_view(a, b);
-        char* rs = a.rs + (size_t)b * a.rs_stride;
-        uint32_t* smask = reinterpret_cast<uint32_t*>(rs + a.R.smask) + (size_t)y * wd;
-        uint32_t* emask = reinterpret_cast<uint32_t*>(rs + a.R.emask) + (size_t)y * wd;
+        const int sy = (int)(r / groups), g = (int)(r % groups);
+        if (b != cur_b) {                                               // warp-uniform
+            cur_b = b;
+            v = code_view(a, b);
+            rs = a.rs + (size_t)b * a.rs_stride;
+            bgkey = __ldg(v.keylut + a.cls_off);                        // class-0 background
+            key0 = __ldg(v.keylut);                                     // void
+        }
+        const int y0 = sy * 4;
         const int xb = g * 256, x0 = xb + lane * 8;
-        const unsigned bgkey = __ldg(v.keylut + a.cls_off);             // class-0 background
         const bool inside = x0 < a.crop_w;
-        const bool flagged = inside && v.sflags[flag_index(v, y, x0)] != 0;
-        unsigned key[8];
+        const bool flagged = inside && v.sflags[flag_index(v, y0, x0)] != 0;
+        if (bgkey == 0u && __all_sync(0xffffffffu, flagged || !inside)) continue;      // nothing selected in this item
+        uint4 raw[4];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) key[p] = 0u;
-        if (flagged) {
+        for (int rr = 0; rr < 4; ++rr) {
+            raw[rr] = make_uint4(0u, 0u, 0u, 0u);
+            if (inside && !flagged && y0 + rr < a.crop_h && a.vec)
+                raw[rr] = __ldcs(reinterpret_cast<const uint4*>(v.codes + (size_t)(y0 + rr) * a.W + x0));
+        }
 #pragma unroll
-            for (int p = 0; p < 8; ++p) key[p] = (x0 + p < a.crop_w) ? bgkey : 0u;
-        } else if (inside) {
-            unsigned code[8];
-            const unsigned short* cp = v.codes + (size_t)y * a.W + x0;
-            if (a.vec) {                                                // W % 8 == 0: the whole group lies inside the plane
-                const uint4 u = __ldcs(reinterpret_cast<const uint4*>(cp));
-                code[0] = u.x & 0xFFFFu; code[1] = u.x >> 16; code[2] = u.y & 0xFFFFu; code[3] = u.y >> 16;
-                code[4] = u.z & 0xFFFFu; code[5] = u.z >> 16; code[6] = u.w & 0xFFFFu; code[7] = u.w >> 16;
-            } else {
+        for (int rr = 0; rr < 4; ++rr) {
+            const int y = y0 + rr;
+            if (y >= a.crop_h) break;                                   // warp-uniform
+            unsigned key[8];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) code[p] = (x0 + p < a.crop_w) ? cp[p] : 0u;
+            for (int p = 0; p < 8; ++p) key[p] = 0u;
+            if (flagged) {
+#pragma unroll
+                for (int p = 0; p < 8; ++p) key[p] = (x0 + p < a.crop_w) ? bgkey : 0u;
+            } else if (inside) {
+                unsigned code[8];
+                if (a.vec) {                                            // W % 8 == 0: the whole group lies inside the plane
+                    const uint4 u = raw[rr];
+                    code[0] = u.x & 0xFFFFu; code[1] = u.x >> 16; code[2] = u.y & 0xFFFFu; code[3] = u.y >> 16;
+                    code[4] = u.z & 0xFFFFu; code[5] = u.z >> 16; code[6] = u.w & 0xFFFFu; code[7] = u.w >> 16;
+                } else {
+                    const unsigned short* cp = v.codes + (size_t)y * a.W + x0;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) code[p] = (x0 + p < a.crop_w) ? cp[p] : 0u;
+                }
+                unsigned prev_code = 0u, prev_key = key0;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    if (code[p] != prev_code) {
+                        prev_code = code[p];
+                        prev_key = code[p] == 0u ? key0 : code[p] == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(code[p], a.cls_off));
+                    }
+                    key[p] = (x0 + p < a.crop_w) ? prev_key : 0u;
+                }
             }
-            unsigned prev_code = 0xFFFFFFFFu, prev_key = 0u;
+            unsigned any = 0;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) any |= key[p];
+            if (!__any_sync(0xffffffffu, any != 0u)) continue;          // warp-uniform: nothing selected in this row
+            unsigned left = __shfl_up_sync(0xffffffffu, key[7], 1);
+            unsigned right = __shfl_down_sync(0xffffffffu, key[0], 1);
+            if (lane == 0) left = xb > 0 ? key_at(v, y, xb - 1) : 0u;
+            if (lane == 31) right = xb + 256 < a.crop_w ? key_at(v, y, xb + 256) : 0u;
+            unsigned sb = 0, eb = 0;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                if (code[p] != prev_code) { prev_code = code[p]; prev_key = __ldg(v.keylut + code_index(code[p], a.cls_off)); }
-                key[p] = (x0 + p < a.crop_w) ? prev_key : 0u;
+                const unsigned l = p ? key[p - 1] : left, rn = p < 7 ? key[p + 1] : right;
+                sb |= (key[p] != 0u && l != key[p] ? 1u : 0u) << p;
+                eb |= (key[p] != 0u && rn != key[p] ? 1u : 0u) << p;
             }
+            const unsigned mine = sb | (eb << 8);
+            const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
+                           m3 = __shfl_down_sync(0xffffffffu, mine, 3);
+            unsigned cnt = 0;
+            if ((lane & 3) == 0) {
+                const unsigned sw = (mine & 0xFFu) | ((m1 & 0xFFu) << 8) | ((m2 & 0xFFu) << 16) | ((m3 & 0xFFu) << 24);
+                const unsigned ew = ((mine >> 8) & 0xFFu) | (((m1 >> 8) & 0xFFu) << 8) | (((m2 >> 8) & 0xFFu) << 16) | (((m3 >> 8) & 0xFFu) << 24);
+                const int wi = g * 8 + (lane >> 2);
+                if (wi < wd && (sw | ew)) {
+                    reinterpret_cast<uint32_t*>(rs + a.R.smask)[(size_t)y * wd + wi] = sw;
+                    reinterpret_cast<uint32_t*>(rs + a.R.emask)[(size_t)y * wd + wi] = ew;
+                }
+                cnt = (unsigned)__popc(sw);
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0 && cnt) atomicAdd(reinterpret_cast<uint32_t*>(rs + a.R.rowcnt) + y, cnt);
         }
-        unsigned any = 0;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) any |= key[p];
-        const int w0 = g * 8;
-        if (!__any_sync(0xffffffffu, any != 0u)) {                      // warp-uniform: nothing selected here
-            if (lane < 8 && w0 + lane < wd) { smask[w0 + lane] = 0u; emask[w0 + lane] = 0u; }
-            continue;
-        }
-        unsigned left = __shfl_up_sync(0xffffffffu, key[7], 1);
-        unsigned right = __shfl_down_sync(0xffffffffu, key[0], 1);
-        if (lane == 0) left = xb > 0 ? key_at(v, y, xb - 1) : 0u;
-        if (lane == 31) right = xb + 256 < a.crop_w ? key_at(v, y, xb + 256) : 0u;
-        unsigned sb = 0, eb = 0;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const unsigned l = p ? key[p - 1] : left, rr = p < 7 ? key[p + 1] : right;
-            sb |= (key[p] != 0u && l != key[p] ? 1u : 0u) << p;
-            eb |= (key[p] != 0u && rr != key[p] ? 1u : 0u) << p;
-        }
-        const unsigned mine = sb | (eb << 8);
-        const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
-                       m3 = __shfl_down_sync(0xffffffffu, mine, 3);
-        unsigned cnt = 0;
-        if ((lane & 3) == 0) {
-            const unsigned sw = (mine & 0xFFu) | ((m1 & 0xFFu) << 8) | ((m2 & 0xFFu) << 16) | ((m3 & 0xFFu) << 24);
-            const unsigned ew = ((mine >> 8) & 0xFFu) | (((m1 >> 8) & 0xFFu) << 8) | (((m2 >> 8) & 0xFFu) << 16) | (((m3 >> 8) & 0xFFu) << 24);
-            const int wi = w0 + (lane >> 2);
-            if (wi < wd) { smask[wi] = sw; emask[wi] = ew; }
-            cnt = (unsigned)__popc(sw);
-        }
-        cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<uint32_t*>(rs + a.R.rowcnt) + y, cnt);
     }
 }
 
@@ -491,208 +645,236 @@ rle_block_emit_kernel(const BlkArgs a)
     }
 }
 
-// union-find on row-run indices inside ONE CTA: parent links only ever decrease (atomicMin), reads go to L2
-__device__ __forceinline__ int ufb_find(const int* parent, int x)
-{
-    int p = __ldcg(parent + x);
-    while (p != x) { x = p; p = __ldcg(parent + x); }
-    return x;
-}
+constexpr int kStBlkOff = 7, kStBlkTotal = 8;       // internal status words: this slice's first run row / run rows of the block
 
-__device__ __forceinline__ void ufb_union(int* parent, int a, int b)
-{
-    bool done;
-    do {
-        a = ufb_find(parent, a);
-        b = ufb_find(parent, b);
-        if (a < b) { const int old = atomicMin(parent + b, a); done = (old == b); b = old; }
-        else if (b < a) { const int old = atomicMin(parent + a, b); done = (old == a); a = old; }
-        else done = true;
-    } while (!done);
-}
+// Everything behind the row-runs (a 2048^2 EM slice has a few thousand of them), one thread per row-run and all slices
+// of the block per launch:
+//   union    8-connected union of touching equal-key runs of CCL classes (root = lowest run index = raster-first pixel)
+//   flags    key flags (CCL: root runs; else label - base)
+//   slots    per slice: exclusive scan of the flags -> instance slots in the reference's dict order (class order of
+//            `labels`, ascending label: rle.py:57-84), class / label of every table row
+//   assign   slot per row-run, run count and row band per slot, (start, length, slot) triples for the matcher
+//   offsets  per slice: scan of the counts -> where each slot's run list starts; the slice's place in the packed output
+//   lists    a warp per slot walks the row-runs of its row band, keeps its own, merges a run that starts where the
+//            slot's previous run ended (array_utils.rle_encode only breaks where idx[i] != idx[i-1]+1: a run reaching
+//            the last column continues in column 0 of the next row) and writes (start, length) in ascending order; box
+//            and area on the way
+struct SliceRuns {
+    int32_t* status;
+    const int *rowoff, *r_y, *r_xs, *r_xe;
+    const uint32_t* r_key;
+    int *parent, *slot_of, *flags, *cnt, *ymin, *ymax;
+    long long* inst;
+    int n_all, n;
+};
 
-__device__ __forceinline__ int block_sum(int v, int* s_w)
+__device__ __forceinline__ SliceRuns slice_runs(const BlkArgs& a, int b)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-    __syncthreads();
-    if (lane == 0) s_w[warp] = v;
-    __syncthreads();
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) tot += s_w[w];
-    return tot;
-}
-
-// rows of the run region of the packed output this slice's runs start at: the row-runs of the slices before it
-__device__ __forceinline__ void block_prefix(const BlkArgs& a, int b, int* s_w, int* my_off, int* total)
-{
-    int before = 0, all = 0;
-    for (int j = threadIdx.x; j < a.B; j += blockDim.x) {
-        const int* ro = reinterpret_cast<const int*>(a.rs + (size_t)j * a.rs_stride + a.R.rowoff);
-        const int nj = min(__ldcg(ro + a.crop_h), a.run_cap);
-        all += nj;
-        if (j < b) before += nj;
-    }
-    *my_off = block_sum(before, s_w);
-    *total = block_sum(all, s_w);
-}
-
-// Everything behind the row-runs of one slice, by one 1024-thread CTA (a 2048^2 EM slice has a few thousand row-runs):
-//   1  8-connected union of touching equal-key runs of CCL classes (root = lowest run index = raster-first pixel)
-//   2  key flags (CCL: root runs; else label - base) -> exclusive scan -> instance slots in the reference's dict
-//      order (class order of `labels`, ascending label: rle.py:57-84), table rows
-//   3  slot per row-run, run count and row band per slot; scan of the counts -> where each slot's run list starts
-//   4  a warp per slot walks the row-runs of its row band, keeps its own, merges a run that starts where the slot's
-//      previous run ended (array_utils.rle_encode only breaks where idx[i] != idx[i-1]+1: a run reaching the last column
-//      continues in column 0 of the next row) and writes (start, length) in ascending order; box and area on the way
-__global__ void __launch_bounds__(1024)
-rle_block_runs_kernel(const BlkArgs a)
-{
-    __shared__ int s_w[32];
-    __shared__ int s_base[EMP_MAX_LABELS + 1];
-    const int b = blockIdx.x;
+    SliceRuns s;
     char* rs = a.rs + (size_t)b * a.rs_stride;
-    int32_t* status = reinterpret_cast<int32_t*>(rs + a.R.status);
-    const int* rowoff = reinterpret_cast<const int*>(rs + a.R.rowoff);
-    const int* r_y = reinterpret_cast<const int*>(rs + a.R.r_y);
-    const int* r_xs = reinterpret_cast<const int*>(rs + a.R.r_xs);
-    const int* r_xe = reinterpret_cast<const int*>(rs + a.R.r_xe);
-    const uint32_t* r_key = reinterpret_cast<const uint32_t*>(rs + a.R.r_key);
-    int* parent = reinterpret_cast<int*>(rs + a.R.parent);
-    int* slot_of = reinterpret_cast<int*>(rs + a.R.slot_of);
-    int* flags = reinterpret_cast<int*>(rs + a.R.flags);
-    int* cnt = reinterpret_cast<int*>(rs + a.R.cnt);
-    int* ymin = reinterpret_cast<int*>(rs + a.R.ymin);
-    int* ymax = reinterpret_cast<int*>(rs + a.R.ymax);
-    long long* inst = reinterpret_cast<long long*>(rs + a.R.inst);
-    const RleClasses& rc = a.rc;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = a.crop_h, Wc = a.crop_w, inst_cap = a.inst_cap;
-    const int n_all = __ldcg(rowoff + H);
-    const int n = min(n_all, a.run_cap);
-    int my_off, total_rr;
-    block_prefix(a, b, s_w, &my_off, &total_rr);
-    long long* starts_out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + my_off;
-    long long* lens_out = starts_out + total_rr;
-    if (tid == 0) {
-        status[EMP_ST_NROWRUNS] = n_all;
-        if (n_all > a.run_cap) atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
-    }
-    // key-space offsets of the classes: CCL classes take n keys, the others min(L, k_cap + 1)
-    const long long plain_keys = min(rc.L, (long long)a.k_cap + 1);
-    auto key_off = [&](int ci) {
-        long long o = 0;
-        for (int i = 0; i < ci; ++i) o += rc.ccl[i] ? (long long)n : plain_keys;
-        return o;
-    };
-    // ---- 1
-    for (int i = tid; i < n; i += 1024) {
-        const uint32_t key = r_key[i];
+    s.status = reinterpret_cast<int32_t*>(rs + a.R.status);
+    s.rowoff = reinterpret_cast<const int*>(rs + a.R.rowoff);
+    s.r_y = reinterpret_cast<const int*>(rs + a.R.r_y);
+    s.r_xs = reinterpret_cast<const int*>(rs + a.R.r_xs);
+    s.r_xe = reinterpret_cast<const int*>(rs + a.R.r_xe);
+    s.r_key = reinterpret_cast<const uint32_t*>(rs + a.R.r_key);
+    s.parent = reinterpret_cast<int*>(rs + a.R.parent);
+    s.slot_of = reinterpret_cast<int*>(rs + a.R.slot_of);
+    s.flags = reinterpret_cast<int*>(rs + a.R.flags);
+    s.cnt = reinterpret_cast<int*>(rs + a.R.cnt);
+    s.ymin = reinterpret_cast<int*>(rs + a.R.ymin);
+    s.ymax = reinterpret_cast<int*>(rs + a.R.ymax);
+    s.inst = reinterpret_cast<long long*>(rs + a.R.inst);
+    s.n_all = s.rowoff[a.crop_h];
+    s.n = min(s.n_all, a.run_cap);
+    return s;
+}
+
+// key-space offset of class ci when the slice has n row-runs: CCL classes take n keys, the others min(L, k_cap + 1)
+__device__ __forceinline__ long long blk_key_off(const BlkArgs& a, int ci, int n)
+{
+    const long long plain = min(a.rc.L, (long long)a.k_cap + 1);
+    long long o = 0;
+    for (int i = 0; i < ci; ++i) o += a.rc.ccl[i] ? (long long)n : plain;
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+rle_block_union_kernel(const BlkArgs a)
+{
+    const SliceRuns s = slice_runs(a, blockIdx.z);
+    const int n = s.n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = s.r_key[i];
         const int c = (int)(key >> 22) - 1;
-        const int y = r_y[i];
-        if (c < 0 || !rc.ccl[c] || y == 0) continue;
-        const int lo = min(rowoff[y - 1], n), hi = min(rowoff[y], n);
-        const int xs = r_xs[i], xe = r_xe[i];
+        const int y = s.r_y[i];
+        if (c < 0 || !a.rc.ccl[c] || y == 0) continue;
+        const int lo = min(s.rowoff[y - 1], n), hi = min(s.rowoff[y], n);
+        const int xs = s.r_xs[i], xe = s.r_xe[i];
         int p = lo, q = hi;                                     // first run of the row above with r_xe >= xs
         while (p < q) {
             const int m = (p + q) >> 1;
-            if (r_xe[m] >= xs) q = m; else p = m + 1;
+            if (s.r_xe[m] >= xs) q = m; else p = m + 1;
         }
-        for (int j = p; j < hi && r_xs[j] <= xe; ++j)
-            if (r_key[j] == key) ufb_union(parent, i, j);
+        for (int j = p; j < hi && s.r_xs[j] <= xe; ++j)
+            if (s.r_key[j] == key) uf_union(s.parent, i, j);
     }
-    __syncthreads();
-    // ---- 2
-    for (int i = tid; i < n; i += 1024) {
-        const uint32_t key = r_key[i];
+}
+
+__global__ void __launch_bounds__(256)
+rle_block_flags_kernel(const BlkArgs a)
+{
+    const SliceRuns s = slice_runs(a, blockIdx.z);
+    const int n = s.n;
+    const long long plain = min(a.rc.L, (long long)a.k_cap + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        s.status[EMP_ST_NROWRUNS] = s.n_all;
+        if (s.n_all > a.run_cap) atomicOr(s.status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = s.r_key[i];
         const int c = (int)(key >> 22) - 1;
         if (c < 0) continue;
-        const long long off = key_off(c);
-        if (rc.ccl[c]) {
-            if (ufb_find(parent, i) == i) flags[off + i] = 1;
+        const long long off = blk_key_off(a, c, n);
+        if (a.rc.ccl[c]) {
+            // no path compression: parent[] is read by other threads' finds and a root's self-link must survive
+            if (uf_find(s.parent, i) == i) s.flags[off + i] = 1;
         } else {
             const long long kv = (long long)(key & 0x3FFFFFu);
-            if (kv < plain_keys) flags[off + kv] = 1;
-            else atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);     // cannot happen: labels are 1 + rank <= K
+            if (kv < plain) s.flags[off + kv] = 1;
+            else atomicOr(s.status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);      // cannot happen: labels are 1 + rank <= K
         }
     }
-    __syncthreads();
-    const long long F = key_off(rc.n);
-    const int n_inst_all = cta_scan_inplace(flags, F, s_w);
+}
+
+__global__ void __launch_bounds__(1024)
+rle_block_slots_kernel(const BlkArgs a)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_base[EMP_MAX_LABELS + 1];
+    const SliceRuns s = slice_runs(a, blockIdx.x);
+    const RleClasses& rc = a.rc;
+    const int tid = threadIdx.x, n = s.n, inst_cap = a.inst_cap;
+    const long long plain = min(rc.L, (long long)a.k_cap + 1);
+    const long long F = blk_key_off(a, rc.n, n);
+    const int n_inst_all = cta_scan_inplace(s.flags, F, s_w);
     if (tid == 0) {
-        flags[F] = n_inst_all;
-        status[EMP_ST_NINST] = n_inst_all;
-        if (n_inst_all > inst_cap) atomicOr(status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
+        s.flags[F] = n_inst_all;
+        s.status[EMP_ST_NINST] = n_inst_all;
+        if (n_inst_all > inst_cap) atomicOr(s.status + EMP_ST_FLAGS, EMP_FLAG_RLE_OVERFLOW);
     }
     __syncthreads();
-    if (tid <= rc.n) s_base[tid] = flags[key_off(tid)];
+    if (tid <= rc.n) s_base[tid] = s.flags[blk_key_off(a, tid, n)];
     __syncthreads();
-    const int n_inst = min(n_inst_all, inst_cap);
     for (long long p = tid; p < F; p += 1024) {
-        const int slot = flags[p];
-        if (flags[p + 1] - slot != 1 || slot >= inst_cap) continue;
+        const int slot = s.flags[p];
+        if (s.flags[p + 1] - slot != 1 || slot >= inst_cap) continue;
         int ci = 0;
         long long off = 0;
         for (; ci < rc.n; ++ci) {
-            const long long sz = rc.ccl[ci] ? (long long)n : plain_keys;
+            const long long sz = rc.ccl[ci] ? (long long)n : plain;
             if (p < off + sz) break;
             off += sz;
         }
-        long long* row = inst + (size_t)slot * EMP_BLK_INST_WORDS;
+        long long* row = s.inst + (size_t)slot * EMP_BLK_INST_WORDS;
         row[0] = rc.label[ci];
         row[1] = rc.ccl[ci] ? rc.lo[ci] + (long long)(slot - s_base[ci]) + 1 : rc.lo[ci] + (p - off);
-        ymin[slot] = INT_MAX; ymax[slot] = -1;
+        s.ymin[slot] = INT_MAX; s.ymax[slot] = -1;
     }
-    __syncthreads();
-    // ---- 3
+}
+
+__global__ void __launch_bounds__(256)
+rle_block_assign_kernel(const BlkArgs a)
+{
+    const int b = blockIdx.z;
+    const SliceRuns s = slice_runs(a, b);
+    const int n = s.n, Wc = a.crop_w, inst_cap = a.inst_cap;
+    const long long plain = min(a.rc.L, (long long)a.k_cap + 1);
     long long* r3 = a.runs3 ? a.runs3 + (size_t)b * a.runs3_stride : nullptr;
-    for (int i = tid; i < n; i += 1024) {
-        const uint32_t key = r_key[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t key = s.r_key[i];
         const int c = (int)(key >> 22) - 1;
         int slot = -1;
         if (c >= 0) {
-            const long long off = key_off(c);
-            const long long kv = rc.ccl[c] ? (long long)ufb_find(parent, i) : (long long)(key & 0x3FFFFFu);
-            slot = (rc.ccl[c] || kv < plain_keys) ? flags[off + kv] : -1;
+            const long long off = blk_key_off(a, c, n);
+            const long long kv = a.rc.ccl[c] ? (long long)uf_find(s.parent, i) : (long long)(key & 0x3FFFFFu);
+            slot = (a.rc.ccl[c] || kv < plain) ? s.flags[off + kv] : -1;
         }
-        slot_of[i] = slot;
-        const int y = r_y[i];
+        s.slot_of[i] = slot;
+        const int y = s.r_y[i];
         if (slot >= 0 && slot < inst_cap) {
-            atomicAdd(cnt + slot, 1);
-            atomicMin(ymin + slot, y);
-            atomicMax(ymax + slot, y);
+            atomicAdd(s.cnt + slot, 1);
+            atomicMin(s.ymin + slot, y);
+            atomicMax(s.ymax + slot, y);
         }
         if (r3) {
-            r3[(size_t)i * 3] = (long long)y * Wc + r_xs[i];
-            r3[(size_t)i * 3 + 1] = r_xe[i] - r_xs[i];
+            r3[(size_t)i * 3] = (long long)y * Wc + s.r_xs[i];
+            r3[(size_t)i * 3 + 1] = s.r_xe[i] - s.r_xs[i];
             r3[(size_t)i * 3 + 2] = slot;
         }
     }
+}
+
+__global__ void __launch_bounds__(1024)
+rle_block_offsets_kernel(const BlkArgs a)
+{
+    __shared__ int s_w[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const SliceRuns s = slice_runs(a, b);
+    const int n_inst = min(s.status[EMP_ST_NINST], a.inst_cap);
+    cta_scan_inplace(s.cnt, n_inst, s_w);                       // cnt[slot] = first row of the slot's run list (slice-local)
+    // this slice's place in the packed run region: the row-runs of the slices before it
+    int before = 0, all = 0;
+    for (int j = tid; j < a.B; j += 1024) {
+        const int* ro = reinterpret_cast<const int*>(a.rs + (size_t)j * a.rs_stride + a.R.rowoff);
+        const int nj = min(ro[a.crop_h], a.run_cap);
+        all += nj;
+        if (j < b) before += nj;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { before += __shfl_xor_sync(0xffffffffu, before, d); all += __shfl_xor_sync(0xffffffffu, all, d); }
+    __shared__ int s_b[32], s_a[32];
+    if (lane == 0) { s_b[warp] = before; s_a[warp] = all; }
     __syncthreads();
-    cta_scan_inplace(cnt, n_inst, s_w);                         // cnt[slot] = first row of the slot's run list (slice-local)
-    __syncthreads();
-    // ---- 4
-    for (int slot = warp; slot < n_inst; slot += 32) {
-        const int ya = __ldcg(ymin + slot), yb = __ldcg(ymax + slot);
-        const int base = __ldcg(cnt + slot);
-        long long* row = inst + (size_t)slot * EMP_BLK_INST_WORDS;
+    if (tid == 0) {
+        int tb = 0, ta = 0;
+        for (int w = 0; w < 32; ++w) { tb += s_b[w]; ta += s_a[w]; }
+        s.status[kStBlkOff] = tb;
+        s.status[kStBlkTotal] = ta;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rle_block_lists_kernel(const BlkArgs a)
+{
+    const int b = blockIdx.z;
+    const SliceRuns s = slice_runs(a, b);
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int n = s.n, Wc = a.crop_w;
+    const int n_inst = min(s.status[EMP_ST_NINST], a.inst_cap);
+    const int my_off = s.status[kStBlkOff], total_rr = s.status[kStBlkTotal];
+    long long* starts_out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + my_off;
+    long long* lens_out = starts_out + total_rr;
+    for (int slot = warp; slot < n_inst; slot += n_warps) {
+        const int ya = s.ymin[slot], yb = s.ymax[slot];
+        const int base = s.cnt[slot];
+        long long* row = s.inst + (size_t)slot * EMP_BLK_INST_WORDS;
         if (yb < 0) {                                           // cannot happen (a slot exists because a run carries it)
             if (lane == 0) { row[2] = 0; row[3] = 0; row[4] = 0; row[5] = 0; row[6] = 0; row[7] = my_off + base; row[8] = 0; }
             continue;
         }
-        const int ja = min(rowoff[ya], n), jb = min(rowoff[yb + 1], n);
+        const int ja = min(s.rowoff[ya], n), jb = min(s.rowoff[yb + 1], n);
         int n_final = 0, x0 = INT_MAX, x1 = -1;
         long long carry_start = -1, carry_end = -1, area = 0;   // the slot's last run so far (flat indices)
         for (int j0 = ja; j0 < jb; j0 += 32) {
             const int j = j0 + lane;
-            const bool mine = j < jb && slot_of[j] == slot;
+            const bool mine = j < jb && s.slot_of[j] == slot;
             const unsigned m = __ballot_sync(0xffffffffu, mine);
             if (!m) continue;                                   // warp-uniform
             long long start = 0, end = 0;
             if (mine) {
-                const int y = r_y[j], xs = r_xs[j], xe = r_xe[j];
+                const int y = s.r_y[j], xs = s.r_xs[j], xe = s.r_xe[j];
                 start = (long long)y * Wc + xs;
                 end = (long long)y * Wc + xe;
                 x0 = min(x0, xs); x1 = max(x1, xe);
@@ -709,15 +891,14 @@ rle_block_runs_kernel(const BlkArgs a)
             const int head_lane = hle ? 31 - __clz(hle) : 0;
             long long fstart = __shfl_sync(0xffffffffu, start, head_lane);
             if (!hle) fstart = carry_start;
-            const int fidx = n_final + __popc(hle) - 1;         // index of that final run within the slot (>= 0 once a head exists)
+            const int fidx = n_final + __popc(hle) - 1;         // index of that final run within the slot
             // the last row-run of a final run inside this chunk writes its length (a continuation in a later chunk overwrites it)
             const unsigned above = m & ~(lanemask_lt() | (1u << lane));
             const int next_lane = above ? __ffs(above) - 1 : 32;
             const bool last_of_final = mine && (next_lane == 32 || ((hb >> next_lane) & 1u));
             if (head) starts_out[base + fidx] = start;
             if (last_of_final) lens_out[base + fidx] = end - fstart;
-            // carry: the slot's last row-run of this chunk
-            const int last_lane = 31 - __clz(m);
+            const int last_lane = 31 - __clz(m);                // carry: the slot's last row-run of this chunk
             carry_end = __shfl_sync(0xffffffffu, end, last_lane);
             carry_start = __shfl_sync(0xffffffffu, fstart, last_lane);
             n_final += __popc(hb);
@@ -935,10 +1116,38 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
                                  ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st)))
         return rc;
     const int32_t* k_dev = reinterpret_cast<const int32_t*>(cs + P.Lc.status) + EMP_ST_K;
-    if ((rc = merge_codes_batched(B, sem8, sem8_stride, ids, P.ids_stride, cfg->h, cfg->w, cfg->shift, cfg->H, cfg->W, P.th,
-                                  cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev, P.Lc.total / 4, ws,
-                                  P.Lm.total, st)))
+    unsigned long long thing_bits = 0ull;
+    bool things_small = true;
+    for (int i = 0; i < P.th.n; ++i) {
+        if (P.th.v[i] >= 0 && P.th.v[i] < 64) thing_bits |= 1ull << P.th.v[i];
+        else things_small = false;
+    }
+    const int sms = device_sm_count();
+    if (things_small && cfg->W % 16 == 0 && (reinterpret_cast<uintptr_t>(sem8) & 15u) == 0 && sem8_stride % 16 == 0) {
+        EMP_CUDA_CHECK(cudaMemset2DAsync(ws, P.Lm.total, 0, P.Lm.zero_bytes, (size_t)B, st));
+        LeanArgs m;
+        memset(&m, 0, sizeof(m));
+        m.sem8 = sem8; m.sem_stride = sem8_stride; m.ids = ids; m.ids_stride = P.ids_stride;
+        m.ws = ws; m.ws_stride = P.Lm.total;
+        m.o_votes = P.Lm.votes; m.o_areas = P.Lm.areas; m.o_sflags = P.Lm.sflags; m.o_codes = P.Lm.codes;
+        m.B = B; m.H = cfg->H; m.W = cfg->W; m.wc = cfg->w; m.shift = cfg->shift;
+        m.blocks_x = (cfg->W + 63) / 64; m.blk_items = assign_block_items(cfg->H, cfg->W);
+        m.T = P.th.n > 0 ? P.th.n : 1; m.thing_bits = thing_bits;
+        const size_t items = (size_t)B * ((cfg->H + 3) / 4) * ((cfg->W + 511) / 512);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 8));
+        {
+            ProfScope ps(ST_ASSIGN, st);
+            merge_lean_kernel<<<grid, 256, 0, st>>>(m);
+        }
+        EMP_CUDA_CHECK(cudaGetLastError());
+        if ((rc = build_luts_batched(B, cfg->H, cfg->W, P.th, cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev,
+                                     P.Lc.total / 4, ws, P.Lm.total, st)))
+            return rc;
+    } else if ((rc = merge_codes_batched(B, sem8, sem8_stride, ids, P.ids_stride, cfg->h, cfg->w, cfg->shift, cfg->H, cfg->W, P.th,
+                                         cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev, P.Lc.total / 4,
+                                         ws, P.Lm.total, st))) {
         return rc;
+    }
 
     BlkArgs a;
     memset(&a, 0, sizeof(a));
@@ -956,15 +1165,14 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
 
     EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
     EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
-    const int sms = device_sm_count();
     {
         ProfScope ps(ST_BLK_KEYS, st);
         rle_block_keys_kernel<<<dim3(8, 1, B), 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     {
-        const size_t items = (size_t)B * cfg->crop_h * ((cfg->crop_w + 255) / 256);
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 16));
+        const size_t items = (size_t)B * ((cfg->crop_h + 3) / 4) * ((cfg->crop_w + 255) / 256);
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 8));
         ProfScope ps(ST_BLK_MARK, st);
         rle_block_mark_kernel<<<grid, 256, 0, st>>>(a);
     }
@@ -975,8 +1183,17 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     {
-        ProfScope ps(ST_BLK_RUNS, st);
-        rle_block_runs_kernel<<<B, 1024, 0, st>>>(a);
+        ProfScope ps(ST_BLK_RUNS, st);                          // union .. lists as one interval
+        const unsigned gx = (unsigned)std::min(((size_t)cfg->run_cap + 255) / 256, (size_t)64);
+        bool any_ccl = false;
+        for (int i = 0; i < P.rc.n; ++i) any_ccl |= P.rc.ccl[i] != 0;
+        if (any_ccl) rle_block_union_kernel<<<dim3(gx, 1, B), 256, 0, st>>>(a);
+        rle_block_flags_kernel<<<dim3(gx, 1, B), 256, 0, st>>>(a);
+        rle_block_slots_kernel<<<B, 1024, 0, st>>>(a);
+        rle_block_assign_kernel<<<dim3(gx, 1, B), 256, 0, st>>>(a);
+        rle_block_offsets_kernel<<<B, 1024, 0, st>>>(a);
+        const unsigned gl = (unsigned)std::min(((size_t)cfg->inst_cap + 7) / 8, (size_t)32);
+        rle_block_lists_kernel<<<dim3(gl, 1, B), 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     {
