@@ -39,6 +39,7 @@ def main():
     ap.add_argument('--blobs', type=int, default=400)
     ap.add_argument('--repeat', type=int, default=2)
     ap.add_argument('--block', type=int, default=32, help='slices per emp_stack_block call')
+    ap.add_argument('--profile', action='store_true', help='one extra run with per-stage CUDA events (ms per stage over the block)')
     ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
     ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')
     args = ap.parse_args()
@@ -106,6 +107,13 @@ def main():
         r = run_once()
         best = r if best is None or r[0] < best[0] else best
     dt, n_slices, n_inst, n_runs, timing = best
+    stages = None
+    if args.profile:
+        from empanada_b200 import _cabi as C
+        C.profile_enable(True)
+        run_once()
+        stages = {k: [round(v[0], 4), v[1]] for k, v in C.profile_read().items() if v[1]}
+        C.profile_enable(False)
     if world > 1:
         t = torch.tensor([dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -134,7 +142,7 @@ def main():
             'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
             'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
             'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
-            'matcher_cpu_baseline': match_cpu,
+            'matcher_cpu_baseline': match_cpu, 'stage_ms_and_launches': stages,
             'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
                        'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
         }) + '\n').encode())

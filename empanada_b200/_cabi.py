@@ -43,14 +43,14 @@ _SIGNATURES = {
     'emp_panoptic_batched_host': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                          _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
     'emp_median_harden': (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp]),
-    'emp_median_chain': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _f32, _vp, _sz, _vp, _vp, _vp]),
-    'emp_median_chain_repair': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _vp, _f32, _vp, _sz, _vp, _vp, _vp]),
+    'emp_median_chain': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _f32, _vp, _sz, _vp, _vp, _vp, _vp]),
+    'emp_median_chain_repair': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _vp, _f32, _vp, _sz, _vp, _vp, _vp, _vp]),
     'emp_rle_workspace_bytes': (_sz, [_i32, _i32, _i32, _i32, _i64]),
     'emp_rle': (_i32, [_vp, _i32, _i32, _vp, _i32, _i64, _vp, _i32, _i32, _vp, _i32, _vp, _i32,
                        _vp, _sz, _vp]),
     'emp_stack_block_scratch_bytes': (_sz, [_vp, _i32]),
     'emp_stack_block_packed_words': (_sz, [_vp, _i32]),
-    'emp_stack_block': (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    'emp_stack_block': (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     'emp_rle_pair_overlaps': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
     'emp_rle_list_overlaps': (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp]),
     'emp_fill_runs': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _sz, _vp, _i32, _sz, _vp]),
@@ -83,6 +83,12 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+class NeedMap(ctypes.Structure):
+    """emp_need_map (include/empanada_b200.h)."""
+    _fields_ = [('map', ctypes.c_void_p), ('stride', ctypes.c_size_t), ('W', ctypes.c_int32), ('shift', ctypes.c_int32),
+                ('wc', ctypes.c_int32), ('thing_bits', ctypes.c_uint64)]
 
 
 STAGES = ('nms_peaks', 'emit_centers', 'assign', 'build_lut', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs',

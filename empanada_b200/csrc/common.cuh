@@ -103,7 +103,7 @@ int assign_block_items(int H, int W);       // strips per 64-column block the as
 int device_sm_count();
 int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* off, size_t off_stride, int h, int w,
                        float threshold, int nms_kernel, float step, int32_t* ids_out, size_t ids_stride, int k_cap,
-                       char* ws, size_t ws_stride, cudaStream_t st);
+                       char* ws, size_t ws_stride, cudaStream_t st, const unsigned char* need = nullptr, size_t need_stride = 0);
 int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, const int32_t* ids, size_t ids_stride, int hc,
                         int wc, int shift, int H, int W, const Things& th, long long label_divisor, long long stuff_area,
                         long long void_label, int k_cap, const int32_t* k_dev, size_t k_dev_stride, char* ws,

@@ -1778,7 +1778,7 @@ int device_sm_count() { return sm_count(); }
 // argmin, one launch per kernel for the whole batch.  ws: B workspaces of ws_layout(h, w, k_cap, 1), ws_stride apart.
 int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* off, size_t off_stride, int h, int w,
                        float threshold, int nms_kernel, float step, int32_t* ids_out, size_t ids_stride, int k_cap,
-                       char* ws, size_t ws_stride, cudaStream_t st)
+                       char* ws, size_t ws_stride, cudaStream_t st, const unsigned char* need, size_t need_stride)
 {
     const WsLayout L = ws_layout(h, w, k_cap, 1);
     EMP_REQUIRE(ws_stride >= L.total && ws_stride % 256 == 0, EMP_ERR_WORKSPACE, "coarse workspace stride too small");
@@ -1791,9 +1791,17 @@ int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* of
     a.off = off; a.off_stride = off_stride;
     a.out = ids_out; a.out_stride = ids_stride;
     a.ws = ws; a.ws_stride = ws_stride;
-    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none); }
     a.B = B; a.H = h; a.W = w; a.step = step; a.chunksize = 20; a.k_cap = k_cap; a.k_fixed = -1;
     a.vec = (w % 4 == 0) && aligned16(off) && aligned16(ids_out) && (off_stride % 4 == 0) && (ids_stride % 4 == 0);
+    if (need) {
+        // only cells that hold a thing pixel need their nearest center (everywhere else the id is multiplied by 0,
+        // engines.py:283-285): the need map plays the class map of get_instance_segmentation with thing class 1
+        Things one; memset(&one, 0, sizeof(one)); one.n = 1; one.v[0] = 1;
+        fill_assign_common(a, L, one);
+        a.sem = need; a.sem_stride = need_stride;
+        return launch_assign(SEM_U8, ID_ARGMIN, OUT_IDS32, a, st);
+    }
+    { Things none; memset(&none, 0, sizeof(none)); fill_assign_common(a, L, none); }
     return launch_assign(SEM_NONE, ID_ARGMIN, OUT_IDS32, a, st);
 }
 

@@ -20,6 +20,7 @@
 //                            read back) never exists: runs are cut from the 2 B/px code map, and only for strips that
 //                            hold something other than class-0 background.
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "rle_common.cuh"
@@ -44,6 +45,9 @@ struct ChainArgs {
     float* best;                    // C > 1: running maximum over the channels seen so far, [n][hw]
     int multi;                      // C > 1
     int32_t* changed;               // repair: set to 1 if the block's outgoing carry changed
+    unsigned char* need; size_t need_stride;        // optional (n, need_stride) coarse maps: 1 where a cell holds a thing pixel
+    int W, shift, wc;               // plane width, log2 of the cell size, cells per coarse row
+    unsigned long long thing_bits;
 };
 
 // middle order statistic of KS values; NaN if any of them is NaN (torch.median propagates NaN)
@@ -72,6 +76,9 @@ __device__ __forceinline__ void load_px(float (&dst)[N], const float* p)
     if (N == 4) {
         const float4 u = __ldcs(reinterpret_cast<const float4*>(p));
         dst[0] = u.x; dst[1 % N] = u.y; dst[2 % N] = u.z; dst[3 % N] = u.w;
+    } else if (N == 2) {
+        const float2 u = __ldcs(reinterpret_cast<const float2*>(p));
+        dst[0] = u.x; dst[1 % N] = u.y;
     } else {
         dst[0] = __ldcs(p);
     }
@@ -81,6 +88,7 @@ template <int N>
 __device__ __forceinline__ void store_px(float* p, const float (&src)[N])
 {
     if (N == 4) *reinterpret_cast<float4*>(p) = make_float4(src[0], src[1 % N], src[2 % N], src[3 % N]);
+    else if (N == 2) *reinterpret_cast<float2*>(p) = make_float2(src[0], src[1 % N]);
     else p[0] = src[0];
 }
 
@@ -97,6 +105,15 @@ median_chain_kernel(const ChainArgs a)
     if (it >= items) return;
     const size_t px = it * N;
     const size_t e = (size_t)a.c * a.hw + px;
+    int cell[N];                                                    // coarse cell of each pixel (need map)
+    if (a.need) {
+        const int y = (int)(px / (size_t)a.W), x = (int)(px - (size_t)y * a.W);
+#pragma unroll
+        for (int q = 0; q < N; ++q) {                                // N == 4 only with W % 4 == 0: the pixels share a row
+            const int xx = x + q;
+            cell[q] = ((y + xx / a.W) >> a.shift) * a.wc + ((xx % a.W) >> a.shift);
+        }
+    }
     float f[MS][N], g[MS][N], r[WIN][N];
 #pragma unroll
     for (int j = 0; j < MS; ++j)
@@ -151,24 +168,39 @@ median_chain_kernel(const ChainArgs a)
         }
         const float (&res)[N] = REPAIR ? og : o;                    // the values that count
         unsigned char* sp = a.sem8 + (size_t)i * a.sem8_stride + px;
+        unsigned set = 0;                                           // bit q: pixel q's class was (re)written by this launch
+        unsigned bits = 0;                                          // class bytes
         if (!a.multi) {
-            unsigned bits = 0;
 #pragma unroll
             for (int q = 0; q < N; ++q) bits |= (res[q] >= a.thr ? 1u : 0u) << (8 * q);
             if (N == 4) *reinterpret_cast<unsigned*>(sp) = bits;
+            else if (N == 2) *reinterpret_cast<unsigned short*>(sp) = (unsigned short)bits;
             else sp[0] = (unsigned char)bits;
+            set = (1u << N) - 1u;
         } else {                                                    // first arg-max over channels, NaN counts as the maximum
             float* bp = a.best + (size_t)i * a.hw + px;
             if (a.c == 0) {
                 store_px<N>(bp, res);
 #pragma unroll
                 for (int q = 0; q < N; ++q) sp[q] = 0;
+                set = (1u << N) - 1u;
             } else {
                 float b[N];
                 load_px<N>(b, bp);
 #pragma unroll
                 for (int q = 0; q < N; ++q)
-                    if (res[q] > b[q] || (res[q] != res[q] && b[q] == b[q])) { bp[q] = res[q]; sp[q] = (unsigned char)a.c; }
+                    if (res[q] > b[q] || (res[q] != res[q] && b[q] == b[q])) {
+                        bp[q] = res[q]; sp[q] = (unsigned char)a.c;
+                        set |= 1u << q; bits |= (unsigned)a.c << (8 * q);
+                    }
+            }
+        }
+        if (a.need) {                                               // a superset is fine: a stale 1 only costs an unused id
+            unsigned char* np = a.need + (size_t)i * a.need_stride;
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+                const unsigned cls = (bits >> (8 * q)) & 0xFFu;
+                if (((set >> q) & 1u) && cls < 64u && ((a.thing_bits >> cls) & 1ull)) np[cell[q]] = 1;
             }
         }
 #pragma unroll
@@ -196,10 +228,17 @@ median_chain_kernel(const ChainArgs a)
 template <int KS, bool REPAIR>
 static int launch_chain_ks(const ChainArgs& a, bool vec, cudaStream_t st)
 {
-    const size_t items = vec ? a.hw / 4 : a.hw;
+    static int width = -1;                  // pixels per thread of the vector path (tuning knob: EMP_CHAIN_N = 2 | 4)
+    if (width < 0) {
+        const char* e = getenv("EMP_CHAIN_N");
+        width = (e && atoi(e) == 2) ? 2 : 4;
+    }
+    const int N = vec ? width : 1;
+    const size_t items = a.hw / N;
     const unsigned grid = (unsigned)((items + 255) / 256);
     ProfScope ps(ST_CHAIN, st);
-    if (vec) median_chain_kernel<KS, 4, REPAIR><<<grid, 256, 0, st>>>(a);
+    if (N == 4) median_chain_kernel<KS, 4, REPAIR><<<grid, 256, 0, st>>>(a);
+    else if (N == 2) median_chain_kernel<KS, 2, REPAIR><<<grid, 256, 0, st>>>(a);
     else median_chain_kernel<KS, 1, REPAIR><<<grid, 256, 0, st>>>(a);
     EMP_CUDA_CHECK(cudaGetLastError());
     return EMP_OK;
@@ -242,11 +281,11 @@ __global__ void __launch_bounds__(256, 4)
 merge_lean_kernel(const LeanArgs a)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 2, q = lane & 3;
-    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const int groups = (a.W + 511) / 512, srows = (a.H + 3) / 4;
-    const size_t per_slice = (size_t)srows * groups;
-    const size_t items = per_slice * a.B;
+    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned groups = (a.W + 511) / 512, srows = (a.H + 3) / 4;
+    const unsigned per_slice = srows * groups;
+    const unsigned items = per_slice * a.B;                             // host: < 2^31
     const bool class0_stuff = !(a.thing_bits & 1ull);
     const bool multi = a.T > 1;
     int cur_b = -1;
@@ -258,62 +297,58 @@ merge_lean_kernel(const LeanArgs a)
         if (d && lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(ws + a.o_areas) + kNumClasses, d);
         deficit = 0;
     };
-    for (size_t it = warp_global; it < items; it += n_warps) {
+    for (unsigned it = warp_global; it < items; it += n_warps) {
         const int b = (int)(it / per_slice);
-        const size_t r = it - (size_t)b * per_slice;
+        const unsigned r = it - (unsigned)b * per_slice;
         const int sy = (int)(r / groups), g = (int)(r % groups);
         if (b != cur_b) {
             flush();
             cur_b = b;
             ws = a.ws + (size_t)b * a.ws_stride;
         }
+        // ---- streaming part: 4 rows x 512 columns, 16 bytes per lane and row; which of the 8 strips are pure background?
         const int y0 = sy * 4, xs = g * 512 + grp * 64;                 // the strip of this lane's group
         const int x0 = xs + q * 16;
-        const bool in_x = x0 < a.W;                                     // W % 16 == 0: a lane is inside or outside as a whole
-        const unsigned char* sp = a.sem8 + (size_t)b * a.sem_stride + (size_t)y0 * a.W + x0;
-        uint4 raw[4];
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            raw[rr] = make_uint4(0u, 0u, 0u, 0u);
-            if (in_x && y0 + rr < a.H) raw[rr] = __ldcs(reinterpret_cast<const uint4*>(sp + (size_t)rr * a.W));
-        }
+        const unsigned char* plane = a.sem8 + (size_t)b * a.sem_stride;
         unsigned orall = 0;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) orall |= raw[rr].x | raw[rr].y | raw[rr].z | raw[rr].w;
-        const unsigned zero4 = __ballot_sync(0xffffffffu, orall == 0u);  // before any lane leaves the iteration
-        if (xs >= a.W) continue;                                        // the whole group lies right of the plane (4 lanes agree)
+        for (int rr = 0; rr < 4; ++rr) {
+            if (x0 < a.W && y0 + rr < a.H) {                            // W % 16 == 0: a lane is inside or outside as a whole
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(plane + (size_t)(y0 + rr) * a.W + x0));
+                orall |= u.x | u.y | u.z | u.w;
+            }
+        }
+        const unsigned zero4 = __ballot_sync(0xffffffffu, orall == 0u);
         const bool full = xs + 64 <= a.W && y0 + 4 <= a.H;
         const unsigned gmask = 0xFu << (lane & ~3);
         const bool bg = full && class0_stuff && ((zero4 & gmask) == gmask);
-        unsigned char* flagp = reinterpret_cast<unsigned char*>(ws + a.o_sflags) +
-                               ((size_t)(y0 / (a.blk_items * 4)) * a.blocks_x + (xs >> 6)) * 16 + ((y0 >> 2) % a.blk_items);
-        if (bg) {
-            if (q == 0) *flagp = 1;
-            continue;
-        }
-        if (q == 0) *flagp = 0;
-        if (!in_x) continue;
+        if (q == 0 && xs < a.W)
+            reinterpret_cast<unsigned char*>(ws + a.o_sflags)[((size_t)(y0 / (a.blk_items * 4)) * a.blocks_x + (xs >> 6)) * 16 +
+                                                              ((y0 >> 2) % a.blk_items)] = bg ? 1 : 0;
+        unsigned todo = __ballot_sync(0xffffffffu, q == 0 && xs < a.W && !bg);
+        // ---- strips that hold something: the whole warp takes one strip at a time, lane l 8 pixels of row l / 8
         uint32_t* votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
         uint32_t* areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
         const int32_t* ids = a.ids + (size_t)b * a.ids_stride;
         unsigned short* codes = reinterpret_cast<unsigned short*>(ws + a.o_codes);
-        unsigned vkey = kNoVote, vcnt = 0;                              // pending vote: pixels in a row of equal (id, class)
-        unsigned akey = kNoVote, acnt = 0;                              // pending stuff-area count of one non-zero class
-        int last_cell = -1, last_id = 0;
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int y = y0 + rr;
-            if (y >= a.H) break;
-            const unsigned w4[4] = {raw[rr].x, raw[rr].y, raw[rr].z, raw[rr].w};
+        for (; todo; todo &= todo - 1) {
+            const int sx = g * 512 + ((__ffs(todo) - 1) >> 2) * 64;     // first column of the strip
+            const int y = y0 + (lane >> 3), x = sx + (lane & 7) * 8;
+            if (y >= a.H || x >= a.W) continue;                         // lanes past the plane's edge (partial strips only)
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(plane + (size_t)y * a.W + x));    // just read: an L1 hit
+            const unsigned w2[2] = {u.x, u.y};
             const int crow = (y >> a.shift) * a.wc;
-            unsigned out[8];
+            unsigned out[4];
+            unsigned vkey = kNoVote, vcnt = 0;                          // pending vote: neighbours of equal (id, class)
+            unsigned akey = kNoVote, acnt = 0;                          // pending stuff-area count of one non-zero class
+            int last_cell = -1, last_id = 0;
 #pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                const unsigned c = (w4[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+            for (int p = 0; p < 8; ++p) {
+                const unsigned c = (w2[p >> 2] >> (8 * (p & 3))) & 0xFFu;
                 const bool thing = c < 64u && ((a.thing_bits >> c) & 1ull);
                 unsigned code;
                 if (thing) {
-                    const int cell = crow + ((x0 + p) >> a.shift);
+                    const int cell = crow + ((x + p) >> a.shift);
                     if (cell != last_cell) { last_cell = cell; last_id = __ldg(ids + cell); }
                     code = (unsigned)last_id;                           // 0: a thing pixel without an instance stays void
                     if (last_id > 0) {
@@ -339,12 +374,10 @@ merge_lean_kernel(const LeanArgs a)
                 }
                 if (p & 1) out[p >> 1] |= code << 16; else out[p >> 1] = code;
             }
-            uint4* cp = reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x0);
-            cp[0] = make_uint4(out[0], out[1], out[2], out[3]);
-            cp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            *reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x) = make_uint4(out[0], out[1], out[2], out[3]);
+            if (vcnt) atomicAdd(votes + vkey, vcnt);
+            if (acnt) atomicAdd(areas + akey, acnt);
         }
-        if (vcnt) atomicAdd(votes + vkey, vcnt);
-        if (acnt) atomicAdd(areas + akey, acnt);
     }
     flush();
 }
@@ -468,20 +501,20 @@ __global__ void __launch_bounds__(256)
 rle_block_mark_kernel(const BlkArgs a)
 {
     const int lane = threadIdx.x & 31;
-    const size_t warp_global = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const int groups = (a.crop_w + 255) / 256;
-    const int srows = (a.crop_h + 3) / 4;
-    const size_t per_slice = (size_t)srows * groups;
-    const size_t items = per_slice * a.B;
+    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned groups = (a.crop_w + 255) / 256;
+    const unsigned srows = (a.crop_h + 3) / 4;
+    const unsigned per_slice = srows * groups;
+    const unsigned items = per_slice * a.B;                             // host: < 2^31
     const int wd = a.R.wd;
     int cur_b = -1;
     unsigned bgkey = 0, key0 = 0;
     CodeView v;
     char* rs = nullptr;
-    for (size_t it = warp_global; it < items; it += n_warps) {
+    for (unsigned it = warp_global; it < items; it += n_warps) {
         const int b = (int)(it / per_slice);
-        const size_t r = it - (size_t)b * per_slice;
+        const unsigned r = it - (unsigned)b * per_slice;
         const int sy = (int)(r / groups), g = (int)(r % groups);
         if (b != cur_b) {                                               // warp-uniform
             cur_b = b;
@@ -493,25 +526,37 @@ rle_block_mark_kernel(const BlkArgs a)
         const int y0 = sy * 4;
         const int xb = g * 256, x0 = xb + lane * 8;
         const bool inside = x0 < a.crop_w;
+        // the pixel just outside the item on this lane's side (lanes 0 / 31): its key decides whether a run starts / ends here
+        const int ex = lane == 0 ? xb - 1 : (lane == 31 ? xb + 256 : -1);
+        const bool edge = ex >= 0 && ex < a.crop_w;
+        // ---- round trip 1: strip flags
         const bool flagged = inside && v.sflags[flag_index(v, y0, x0)] != 0;
+        const bool eflagged = edge && v.sflags[flag_index(v, y0, ex)] != 0;
         if (bgkey == 0u && __all_sync(0xffffffffu, flagged || !inside)) continue;      // nothing selected in this item
+        // ---- round trip 2: codes of the 4 rows (and of the edge pixels)
         uint4 raw[4];
+        unsigned ecode[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             raw[rr] = make_uint4(0u, 0u, 0u, 0u);
-            if (inside && !flagged && y0 + rr < a.crop_h && a.vec)
+            ecode[rr] = kClsBase16;
+            const bool row_in = y0 + rr < a.crop_h;
+            if (inside && !flagged && row_in && a.vec)
                 raw[rr] = __ldcs(reinterpret_cast<const uint4*>(v.codes + (size_t)(y0 + rr) * a.W + x0));
+            if (edge && !eflagged && row_in) ecode[rr] = v.codes[(size_t)(y0 + rr) * a.W + ex];
         }
+        // ---- round trip 3: run keys of the codes that are neither void nor background
+        unsigned key[4][8], ekey[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const int y = y0 + rr;
-            if (y >= a.crop_h) break;                                   // warp-uniform
-            unsigned key[8];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) key[p] = 0u;
+            for (int p = 0; p < 8; ++p) key[rr][p] = 0u;
+            ekey[rr] = 0u;
+            if (y >= a.crop_h) continue;
             if (flagged) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) key[p] = (x0 + p < a.crop_w) ? bgkey : 0u;
+                for (int p = 0; p < 8; ++p) key[rr][p] = (x0 + p < a.crop_w) ? bgkey : 0u;
             } else if (inside) {
                 unsigned code[8];
                 if (a.vec) {                                            // W % 8 == 0: the whole group lies inside the plane
@@ -530,23 +575,33 @@ rle_block_mark_kernel(const BlkArgs a)
                         prev_code = code[p];
                         prev_key = code[p] == 0u ? key0 : code[p] == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(code[p], a.cls_off));
                     }
-                    key[p] = (x0 + p < a.crop_w) ? prev_key : 0u;
+                    key[rr][p] = (x0 + p < a.crop_w) ? prev_key : 0u;
                 }
             }
+            if (edge) {
+                const unsigned c = ecode[rr];
+                ekey[rr] = c == 0u ? key0 : c == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(c, a.cls_off));
+            }
+        }
+        // ---- start / end bits, gathered into mask words
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int y = y0 + rr;
+            if (y >= a.crop_h) break;                                   // warp-uniform
             unsigned any = 0;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) any |= key[p];
+            for (int p = 0; p < 8; ++p) any |= key[rr][p];
             if (!__any_sync(0xffffffffu, any != 0u)) continue;          // warp-uniform: nothing selected in this row
-            unsigned left = __shfl_up_sync(0xffffffffu, key[7], 1);
-            unsigned right = __shfl_down_sync(0xffffffffu, key[0], 1);
-            if (lane == 0) left = xb > 0 ? key_at(v, y, xb - 1) : 0u;
-            if (lane == 31) right = xb + 256 < a.crop_w ? key_at(v, y, xb + 256) : 0u;
+            unsigned left = __shfl_up_sync(0xffffffffu, key[rr][7], 1);
+            unsigned right = __shfl_down_sync(0xffffffffu, key[rr][0], 1);
+            if (lane == 0) left = ekey[rr];
+            if (lane == 31) right = ekey[rr];
             unsigned sb = 0, eb = 0;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const unsigned l = p ? key[p - 1] : left, rn = p < 7 ? key[p + 1] : right;
-                sb |= (key[p] != 0u && l != key[p] ? 1u : 0u) << p;
-                eb |= (key[p] != 0u && rn != key[p] ? 1u : 0u) << p;
+                const unsigned l = p ? key[rr][p - 1] : left, rn = p < 7 ? key[rr][p + 1] : right;
+                sb |= (key[rr][p] != 0u && l != key[rr][p] ? 1u : 0u) << p;
+                eb |= (key[rr][p] != 0u && rn != key[rr][p] ? 1u : 0u) << p;
             }
             const unsigned mine = sb | (eb << 8);
             const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
@@ -985,9 +1040,20 @@ using namespace emp;
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
+static int set_need(ChainArgs& a, const emp_need_map* need, size_t hw)
+{
+    if (!need || !need->map) return EMP_OK;
+    EMP_REQUIRE(need->W > 0 && hw % (size_t)need->W == 0 && need->shift >= 0 && need->shift < 16 && need->wc > 0 &&
+                ((need->W - 1) >> need->shift) < need->wc, EMP_ERR_INVALID, "bad need-map geometry");
+    EMP_REQUIRE(need->stride >= (size_t)need->wc * (((hw / need->W - 1) >> need->shift) + 1), EMP_ERR_INVALID, "need-map stride too small");
+    a.need = need->map; a.need_stride = need->stride; a.W = need->W; a.shift = need->shift; a.wc = need->wc;
+    a.thing_bits = need->thing_bits;
+    return EMP_OK;
+}
+
 EMP_API int emp_median_chain(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, int C, size_t hw,
                              const float* const* carry_in_dev, float confidence_thr, uint8_t* sem8_out, size_t sem8_stride,
-                             float* best_scratch, float* const* carry_out_dev, void* stream)
+                             float* best_scratch, float* const* carry_out_dev, const emp_need_map* need, void* stream)
 {
     EMP_REQUIRE(planes_dev && sem8_out, EMP_ERR_INVALID, "null pointer");
     EMP_REQUIRE(ks >= 1 && ks <= 15 && (ks & 1), EMP_ERR_INVALID, "median kernel size must be odd and <= 15 (got %d)", ks);
@@ -1009,6 +1075,8 @@ EMP_API int emp_median_chain(const float* const* planes_dev, int n, int n_planes
     a.planes = planes_dev; a.carry_in = (mid > 0 && z0 >= mid) ? carry_in_dev : nullptr; a.carry_out = carry_out_dev;
     a.n = n; a.n_planes = n_planes; a.z0 = z0; a.depth = depth; a.hw = hw; a.thr = confidence_thr;
     a.sem8 = sem8_out; a.sem8_stride = sem8_stride; a.best = best_scratch; a.multi = C > 1;
+    int rcn;
+    if ((rcn = set_need(a, need, hw))) return rcn;
     for (int c = 0; c < C; ++c) {
         a.c = c;
         const int rc = launch_chain<false>(ks, a, vec, st);
@@ -1020,7 +1088,7 @@ EMP_API int emp_median_chain(const float* const* planes_dev, int n, int n_planes
 EMP_API int emp_median_chain_repair(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, size_t hw,
                                     const float* const* carry_old_dev, const float* const* carry_new_dev,
                                     float confidence_thr, uint8_t* sem8, size_t sem8_stride, float* const* carry_out_dev,
-                                    int32_t* changed, void* stream)
+                                    int32_t* changed, const emp_need_map* need, void* stream)
 {
     EMP_REQUIRE(planes_dev && sem8 && carry_old_dev && carry_new_dev && carry_out_dev && changed, EMP_ERR_INVALID, "null pointer");
     EMP_REQUIRE(ks >= 3 && ks <= 15 && (ks & 1), EMP_ERR_INVALID, "median kernel size must be odd, 3 .. 15 (got %d)", ks);
@@ -1035,6 +1103,8 @@ EMP_API int emp_median_chain_repair(const float* const* planes_dev, int n, int n
     a.planes = planes_dev; a.carry_in = carry_old_dev; a.carry_new = carry_new_dev; a.carry_out = carry_out_dev;
     a.n = n; a.n_planes = n_planes; a.z0 = z0; a.depth = depth; a.hw = hw; a.thr = confidence_thr;
     a.sem8 = sem8; a.sem8_stride = sem8_stride; a.changed = changed;
+    int rcn;
+    if ((rcn = set_need(a, need, hw))) return rcn;
     return launch_chain<true>(ks, a, vec, st);
 }
 
@@ -1093,8 +1163,9 @@ EMP_API size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B)
 }
 
 EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
-                            size_t hm_stride, const float* off, size_t off_stride, void* scratch, size_t scratch_bytes,
-                            int64_t* packed_out, size_t packed_words, int64_t* runs3_out, void* stream)
+                            size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
+                            void* scratch, size_t scratch_bytes, int64_t* packed_out, size_t packed_words, int64_t* runs3_out,
+                            void* stream)
 {
     BlockPlan P;
     int rc = plan_block(cfg, B, &P);
@@ -1104,7 +1175,8 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
                 "scratch too small or misaligned: %zu < %zu", scratch_bytes, P.total);
     EMP_REQUIRE(packed_words >= emp_stack_block_packed_words(cfg, B), EMP_ERR_WORKSPACE, "packed output too small");
     EMP_REQUIRE(sem8_stride >= (size_t)cfg->H * cfg->W && hm_stride >= (size_t)cfg->h * cfg->w &&
-                off_stride >= 2 * (size_t)cfg->h * cfg->w, EMP_ERR_INVALID, "plane strides smaller than the planes");
+                off_stride >= 2 * (size_t)cfg->h * cfg->w && (!need || need_stride >= (size_t)cfg->h * cfg->w), EMP_ERR_INVALID,
+                "plane strides smaller than the planes");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char* base = static_cast<char*>(scratch);
     int32_t* ids = reinterpret_cast<int32_t*>(base + P.o_ids);
@@ -1113,7 +1185,7 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     char* rs = base + P.o_rs;
 
     if ((rc = coarse_ids_batched(B, hm, hm_stride, off, off_stride, cfg->h, cfg->w, cfg->nms_threshold, cfg->nms_kernel, cfg->step,
-                                 ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st)))
+                                 ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st, need, need_stride)))
         return rc;
     const int32_t* k_dev = reinterpret_cast<const int32_t*>(cs + P.Lc.status) + EMP_ST_K;
     unsigned long long thing_bits = 0ull;

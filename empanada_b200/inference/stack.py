@@ -367,15 +367,32 @@ class StackShard:
         self.heads[z] = {'sem': sem_prob, 'ctr_hmp': ctr_hmp, 'offsets': offsets, 'size': size}
 
     # ------------------------------------------------------------------------------------------------------
-    def _chain(self, planes, dev, hw, Cn):
+    def _geometry(self, H, W):
+        """(coarse h, w, shift) of the block: the coarse maps are 2^shift times smaller than the H x W planes."""
+        hh, ww = self.heads[self.z0]['ctr_hmp'].shape[-2:]
+        s_up = int(self.upsampling * (4 if self.engine.coarse_boundaries else 1))
+        shift = int(math.log2(s_up))
+        assert (1 << shift) == s_up
+        return int(hh), int(ww), shift
+
+    def _chain(self, planes, dev, hw, Cn, need=None):
         """Recursive median + harden over the rank's block: sem8 (n, hw) uint8 in HBM.  Multi-rank blocks start from a
-        guessed carry and are repaired from the true one (module docstring).  Returns (sem8, changed flag or None)."""
+        guessed carry and are repaired from the true one (module docstring).  need: optional (n, h*w) uint8 zeros the
+        kernels mark with the coarse cells that hold a thing pixel.  Returns (sem8, changed flag or None)."""
         from empanada_b200 import _cabi as C
         e, L = self.engine, C.lib()
         n, mid, ks = self.z1 - self.z0, self.mid, self.ks
         stream = C.stream_ptr(dev)
         vp = ctypes.c_void_p
         sem8 = torch.empty((n, hw), dtype=torch.uint8, device=dev)
+        need_arg = None
+        if need is not None:
+            hh, ww, shift = self._geometry(*self._plane)
+            bits = 0
+            for c in e.thing_list:
+                bits |= 1 << int(c)
+            nm = C.NeedMap(map=need.data_ptr(), stride=need.shape[1], W=self._plane[1], shift=shift, wc=ww, thing_bits=bits)
+            need_arg = ctypes.byref(nm)
         multi = self.world > 1 and mid > 0 and dist.is_available() and dist.is_initialized()
         words = [p.data_ptr() for p in planes]
         carry = {}
@@ -400,7 +417,7 @@ class StackShard:
                 C.check(L.emp_median_chain(vp(at['planes']), n, len(planes), self.z0, self.depth, ks, Cn, hw,
                                            vp(carry_in) if carry_in else None, thr, vp(sem8.data_ptr()), hw,
                                            vp(best.data_ptr()) if best is not None else None,
-                                           vp(at['out']) if multi else None, stream))
+                                           vp(at['out']) if multi else None, need_arg, stream))
 
         if not multi:
             chain(None)
@@ -424,7 +441,7 @@ class StackShard:
             with torch.cuda.device(dev):
                 C.check(L.emp_median_chain_repair(vp(at['planes']), n, len(planes), self.z0, self.depth, ks, hw,
                                                   vp(at[state['old']]), vp(at[state['new']]), thr, vp(sem8.data_ptr()), hw,
-                                                  vp(at['out']), vp(changed.data_ptr()), stream))
+                                                  vp(at['out']), vp(changed.data_ptr()), need_arg, stream))
             state['old'], state['new'] = state['new'], ('b' if state['new'] == 'a' else 'a')
             return changed
 
@@ -440,7 +457,7 @@ class StackShard:
                             any_changed if self._settle else None)
         return sem8, flag
 
-    def _enqueue_blocks(self, zs, sem8, dev, H, W):
+    def _enqueue_blocks(self, zs, sem8, dev, H, W, need=None):
         """Phase A: one emp_stack_block call per sub-block on the current stream, each followed by ONE device->host
         copy of its packed tables on the copy stream.  No host synchronisation."""
         from empanada_b200 import _cabi as C
@@ -448,14 +465,11 @@ class StackShard:
         e, L = self.engine, C.lib()
         n = len(zs)
         h0 = self.heads[zs[0]]
-        hh, ww = h0['ctr_hmp'].shape[-2:]
+        hh, ww, shift = self._geometry(H, W)
         size = h0['size']
         assert all(self.heads[z]['size'] == size for z in zs), 'slices of one block must share their unpadded size'
         crop = (H, W) if size is None else (min(int(size[0]), H), min(int(size[1]), W))
         step = 4 if e.coarse_boundaries else 1
-        s_up = int(self.upsampling * step)
-        shift = int(math.log2(s_up))
-        assert (1 << shift) == s_up
         things, nt = C.i64_array(e.thing_list)
         labels, nl = C.i64_array(self.labels)
         run_cap = max(1 << 14, (H * W) // 256)
@@ -489,6 +503,8 @@ class StackShard:
                 C.require_cuda(hm, off)
                 C.check(L.emp_stack_block(ctypes.byref(cfg), B, ctypes.c_void_p(sem8[i0].data_ptr()), H * W,
                                           ctypes.c_void_p(hm.data_ptr()), hm_stride, ctypes.c_void_p(off.data_ptr()), off_stride,
+                                          ctypes.c_void_p(need[i0].data_ptr()) if need is not None else None,
+                                          need.shape[1] if need is not None else 0,
                                           ctypes.c_void_p(scratch.data_ptr()), scratch.numel(),
                                           ctypes.c_void_p(packed[bi].data_ptr()), packed_words,
                                           ctypes.c_void_p(runs_all[i0].data_ptr()) if runs_all is not None else None,
@@ -678,8 +694,12 @@ class StackShard:
         Cn, H, W = planes[0].shape[1:]
         self._plane = (int(H), int(W))
         t_a = time.perf_counter()
-        sem8, changed = self._chain(planes, dev, H * W, Cn)
-        subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W)
+        need = None
+        if all(0 <= int(c) < 64 for c in e.thing_list):
+            hh, ww, _ = self._geometry(H, W)
+            need = torch.zeros((len(zs), hh * ww), dtype=torch.uint8, device=dev)
+        sem8, changed = self._chain(planes, dev, H * W, Cn, need)
+        subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W, need)
         # instance counts per class (+ the "my outgoing carry moved" flag) over all ranks
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         table_h = None

@@ -173,10 +173,20 @@ int emp_median_harden(const float* const* planes /* host array */, int ks, int C
  *   carry_out_dev DEVICE array of mid pointers or NULL: receives the filtered planes z0+n-mid .. z0+n-1 (n >= mid)
  *   sem8_out     (n, sem8_stride) uint8 class maps: C == 1: p >= confidence_thr; C > 1: first arg-max (NaN counts as max)
  *   best_scratch (n, hw) f32, only for C > 1
+ *   need         optional: coarse (n, stride) uint8 maps, zeroed by the caller, in which the kernel marks every cell
+ *                (y >> shift, x >> shift) that holds a pixel of a thing class — the only cells whose nearest-center id
+ *                get_panoptic_seg ever looks at (engines.py:283-285); emp_stack_block skips the search elsewhere
  * A NaN in a window gives a NaN median, as torch.median does. */
+typedef struct emp_need_map {
+    uint8_t* map;                   /* device (n, stride) */
+    size_t stride;
+    int32_t W, shift, wc;           /* plane width, log2 of the cell size, cells per coarse row */
+    uint64_t thing_bits;            /* bit c set <=> class c (< 64) is a thing class */
+} emp_need_map;
 int emp_median_chain(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, int C, size_t hw,
                      const float* const* carry_in_dev, float confidence_thr, uint8_t* sem8_out, size_t sem8_stride,
-                     float* best_scratch, float* const* carry_out_dev, void* stream);
+                     float* best_scratch, float* const* carry_out_dev, const emp_need_map* need /* host, may be NULL */,
+                     void* stream);
 
 /* The same block (C == 1) re-run from a corrected carry: per pixel, both chains (old carry, new carry) advance together
  * until their states agree bit for bit; only that prefix of sem8 is rewritten.  Pixels still apart at the block's end
@@ -184,7 +194,8 @@ int emp_median_chain(const float* const* planes_dev, int n, int n_planes, int z0
  * starts every rank's chain from a guessed carry and repairs it once the true one arrives (inference/stack.py). */
 int emp_median_chain_repair(const float* const* planes_dev, int n, int n_planes, int z0, int depth, int ks, size_t hw,
                             const float* const* carry_old_dev, const float* const* carry_new_dev, float confidence_thr,
-                            uint8_t* sem8, size_t sem8_stride, float* const* carry_out_dev, int32_t* changed, void* stream);
+                            uint8_t* sem8, size_t sem8_stride, float* const* carry_out_dev, int32_t* changed,
+                            const emp_need_map* need /* host, may be NULL */, void* stream);
 
 /* pan_seg_to_rle_seg — empanada/inference/rle.py:26-86 (+ connected_components :18-24,
  * array_utils.rle_encode array_utils.py:209-235).  One pass over the pixels extracts row-runs
@@ -212,6 +223,8 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
  * cut straight from the 16-bit code map + label LUT (the int64 label map is never written).
  *   sem8 (B, sem8_stride) uint8 hardened classes (emp_median_chain); hm (B, hm_stride) f32 (h,w) heat-maps;
  *   off (B, off_stride) f32 (2,h,w) offsets, with (h << shift, w << shift) >= (H, W)
+ *   need  optional (B, need_stride) uint8 (h,w) maps from emp_median_chain: the nearest-center search runs only in cells
+ *         marked there (NULL: everywhere, as the reference does — the ids differ only where nobody reads them)
  *   scratch   device buffer of emp_stack_block_scratch_bytes(), 256-byte aligned, reusable by the next block
  *   packed_out  device int64[emp_stack_block_packed_words()], everything the host needs in ONE contiguous prefix:
  *       [0] B  [1] R = row-runs of all slices  [2] I = instances of all slices  [3] EMP_BLK_INST_WORDS
@@ -242,8 +255,9 @@ typedef struct emp_stack_cfg {
 size_t emp_stack_block_scratch_bytes(const emp_stack_cfg* cfg, int B);
 size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B);
 int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
-                    size_t hm_stride, const float* off, size_t off_stride, void* scratch, size_t scratch_bytes,
-                    int64_t* packed_out, size_t packed_words, int64_t* runs3_out, void* stream);
+                    size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
+                    void* scratch, size_t scratch_bytes, int64_t* packed_out, size_t packed_words, int64_t* runs3_out,
+                    void* stream);
 
 /* Cross-slice matcher support — empanada/inference/matcher.py:136-232 (rle_matcher) with
  * array_utils.rle_intersection :371-403 / rle_iou :405-429 / rle_ioa :431-449: pixel overlaps between

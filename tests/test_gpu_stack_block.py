@@ -39,7 +39,8 @@ def _run_chain(dev, raw, z0, z1, depth, ks, carry, thr, want_carry=True):
         C.check(C.lib().emp_median_chain(vp(tab.data_ptr()), n, len(planes), z0, depth, ks, Cn, hw,
                                          vp(tab.data_ptr() + 8 * (len(planes) + mid)) if carry else None, float(thr),
                                          vp(sem8.data_ptr()), hw, vp(best.data_ptr()) if best is not None else None,
-                                         vp(tab.data_ptr() + 8 * len(planes)) if (want_carry and mid) else None, C.stream_ptr(dev)))
+                                         vp(tab.data_ptr() + 8 * len(planes)) if (want_carry and mid) else None, None,
+                                         C.stream_ptr(dev)))
     torch.cuda.synchronize(dev)
     return sem8.view(n, H, W), [t.view(1, Cn, H, W) for t in out]
 
@@ -112,7 +113,7 @@ def test_median_chain_repair(ks, kind, cuda_device):
     with torch.cuda.device(dev):
         C.check(C.lib().emp_median_chain_repair(vp(tab.data_ptr()), n, P, z0, depth, ks, hw, vp(tab.data_ptr() + 8 * P),
                                                 vp(tab.data_ptr() + 8 * (P + mid)), thr, vp(sem8.data_ptr()), hw,
-                                                vp(tab.data_ptr() + 8 * (P + 2 * mid)), vp(changed.data_ptr()), C.stream_ptr(dev)))
+                                                vp(tab.data_ptr() + 8 * (P + 2 * mid)), vp(changed.data_ptr()), None, C.stream_ptr(dev)))
     torch.cuda.synchronize(dev)
     assert torch.equal(sem8.view(n, H, W), want_sem)
     moved = any(not torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(spec_carry, want_carry))
