@@ -141,44 +141,103 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(rows)}
 
 
-def cpu_reference_sample(seed=0):
-    """The reference's CPU op sequence on a bounded crop of the workload: 1024x1024 with the same
-    center density (500 per 4096^2 -> 31 per 1024^2 -> 2 chunks of 20 centers)."""
+def reference_postprocess():
+    """The reference's own post-processing module when build() staged it (oracle/_ref/postprocess.py: the unmodified
+    file, copied from /root/reference in the build container; git-ignored, it travels with the snapshot), else the
+    oracle's op-sequence port.  Returns (find_instance_center, group_pixels, merge_semantic_and_instance, kind)."""
+    path = os.path.join(ROOT, 'oracle', '_ref', 'postprocess.py')
+    if os.path.exists(path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location('empanada_reference_postprocess', path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.find_instance_center, mod.group_pixels, mod.merge_semantic_and_instance, 'reference'
+    from oracle import torch_port as tp
+    return (lambda hm, thr, k: tp.centers_by_maxpool(hm, thr, k), lambda ctr, off: tp.pixel_ids(ctr, off),
+            tp.vote_and_paste, 'port')
+
+
+_REF_TILE = {}
+
+
+def cpu_reference_sample(seed=0, win_centers=1024, win_group=160, win_merge=512):
+    """One bounded sample of the workload on the host cores, through the reference's own functions
+    (postprocess.py:38-76, :118-169, :223-296), with the per-pixel cost of the FULL tile:
+
+      find_instance_center  on a win_centers^2 window of the tile's heat-map            (x 4096^2 / win_centers^2)
+      group_pixels          on a win_group^2 window of the offsets with ALL ~500 centers of the tile, i.e. the tile's
+                            25 chunks of 20 centers per pixel                            (x 4096^2 / win_group^2)
+      merge_semantic_and_instance  on a win_merge^2 window (its instance loop costs instances x pixels)
+                                                                  (x 4096^2 / win_merge^2 x K / instances in the window)
+    Returns (Mpix/s of a whole tile extrapolated from the three timings, seconds spent, K, threads, description)."""
     import torch
-    from oracle import torch_port
     from empanada_b200.synth import synth_tile
-    side, n = 1024, max(1, N_INST // 16)
-    d = synth_tile(side, side, n, seed)
+    find_centers, group_pixels, merge, kind = reference_postprocess()
+    if seed not in _REF_TILE:
+        _REF_TILE.clear()
+        _REF_TILE[seed] = synth_tile(H, W, N_INST, seed)
+    d = _REF_TILE[seed]
     sem, hm, off = (torch.from_numpy(d[k]) for k in ('sem', 'ctr_hmp', 'offsets'))
+    # all centers of the tile (not timed: the oracle's closed form; the timed part below runs the reference)
+    import oracle
+    ctr_all = torch.from_numpy(oracle.find_instance_center(d['ctr_hmp'], THR, NMS_K))
+    K = int(ctr_all.shape[0])
+    y0 = x0 = (H - win_centers) // 2
     t0 = time.perf_counter()
-    pan, ctr = torch_port.panoptic(sem, hm, off, THINGS, LABEL_DIVISOR, STUFF_AREA, VOID, THR, NMS_K)
-    dt = time.perf_counter() - t0
-    return side * side / dt / 1e6, dt, int(ctr.shape[1]), torch.get_num_threads(), \
-        f'{side}x{side} crop, {int(ctr.shape[1])} centers (same density), torch {torch.__version__} CPU ops'
+    find_centers(hm[:, :, y0:y0 + win_centers, x0:x0 + win_centers].contiguous(), THR, NMS_K)
+    t_c = time.perf_counter() - t0
+    # a window around a center, centers shifted into its frame: every pixel still meets all K centers
+    cy, cx = [int(v) for v in ctr_all[K // 2]]
+    gy, gx = min(max(cy - win_group // 2, 0), H - win_group), min(max(cx - win_group // 2, 0), W - win_group)
+    shifted = ctr_all - torch.tensor([gy, gx])
+    t0 = time.perf_counter()
+    ids = group_pixels(shifted, off[:, :, gy:gy + win_group, gx:gx + win_group].contiguous())
+    t_g = time.perf_counter() - t0
+    my, mx = min(max(cy - win_merge // 2, 0), H - win_merge), min(max(cx - win_merge // 2, 0), W - win_merge)
+    sem_w = sem[:, :, my:my + win_merge, mx:mx + win_merge].contiguous()
+    ins_w = torch.from_numpy(d['ins'][my:my + win_merge, mx:mx + win_merge].astype('int64'))[None] * (sem_w[0] > 0)   # GT ids: same instance count / sizes
+    k_w = max(int(torch.unique(ins_w).numel()) - 1, 1)
+    t0 = time.perf_counter()
+    merge(sem_w, ins_w, LABEL_DIVISOR, THINGS, STUFF_AREA, VOID)
+    t_m = time.perf_counter() - t0
+    n_px = H * W
+    t_tile = t_c * n_px / win_centers ** 2 + t_g * n_px / win_group ** 2 + t_m * (n_px / win_merge ** 2) * (K / k_w)
+    desc = (f'{kind}: find_instance_center on {win_centers}^2 + group_pixels on {win_group}^2 with all {K} centers of the tile '
+            f'(25 chunks) + merge on {win_merge}^2 ({k_w} instances), each scaled to the 4096^2 tile '
+            f'({t_c:.2f} / {t_g:.2f} / {t_m:.2f} s measured -> {t_tile:.0f} s per tile); torch {torch.__version__} CPU')
+    return n_px / t_tile / 1e6, t_c + t_g + t_m, K, torch.get_num_threads(), desc, kind
+
+
+def workload_config(world, B, Ks, dense=False):
+    return {'workload': WORKLOAD if not dense else 'postproc_16x4096x4096_dense_k5000', 'tiles_per_gpu': B, 'tile': [H, W],
+            'centers_per_tile': Ks, 'thing_list': THINGS, 'label_divisor': LABEL_DIVISOR, 'nms_kernel': NMS_K,
+            'l2': f'inputs {B * H * W * 20 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed',
+            'parallelism': f'dp{world} (independent tiles per rank, no collective on the data path)'}
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU post-processing (op-sequence port; /root/reference does
-    not travel to the GPU box) on the host cores, one bounded crop per step."""
+    """--impl reference: the reference's CPU post-processing on the host cores, all threads, one bounded sample of the
+    workload per step (cpu_reference_sample: full-tile per-pixel cost, extrapolated to Mpix/s of whole tiles)."""
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    vals, sample = [], ''
+    vals, sample, kind = [], '', 'port'
     for i in range(args.warmup + args.steps):
-        v, dt, k, threads, sample = cpu_reference_sample(seed=i)
-        log(f'[reference] step {i}: {v:.4f} Mpix/s ({dt:.1f} s, K={k})')
+        v, dt, k, threads, sample, kind = cpu_reference_sample(seed=0)
+        log(f'[reference] step {i}: {v:.5f} Mpix/s ({dt:.1f} s of samples, K={k})')
         if i >= args.warmup:
             vals.append((v, dt))
-    value = sum(1024 * 1024 / 1e6 for _ in vals) / sum(dt for _, dt in vals)
+    value = len(vals) / sum(1.0 / v for v, _ in vals)              # tiles per second over the timed steps, in Mpix/s
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'sample': sample},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': sample + '; one crop per step'},
+            'config': workload_config(args.gpus, TILES, [N_INST - 2, N_INST]),
+            'sample': sample,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind,
+                             'sample': sample + '; one sample per step, ms_per_step = seconds of samples per step'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
@@ -195,7 +254,10 @@ def main():
     ap.add_argument('--tiles', type=int, default=TILES)
     ap.add_argument('--instances', type=int, default=N_INST)
     ap.add_argument('--thr', type=float, default=THR, help='center threshold (experiments; the workload uses 0.1)')
-    ap.add_argument('--dense', action='store_true', help='BASELINE configs[4]: ~5000 instances of semi-axes 4..12 px per tile')
+    ap.add_argument('--dense', action='store_true', help='BASELINE configs[4] as the main workload: ~5000 instances of semi-axes 4..12 px per tile')
+    ap.add_argument('--no-stack', action='store_true', help='skip the configs[2] stack sub-record')
+    ap.add_argument('--no-dense', action='store_true', help='skip the configs[4] dense sub-record (N = 1)')
+    ap.add_argument('--dense-tiles', type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -203,9 +265,7 @@ def main():
     claim_stdout()
 
     if args.impl == 'reference':
-        if args.impl == 'reference' and args.steps > 3:
-            args.steps, args.warmup = min(args.steps, 3), min(args.warmup, 1)   # ~10 s per step
-        run_reference(args, rank)
+        run_reference(args, rank)               # a few seconds of CPU per step: --steps 20 --warmup 5 ends within minutes
         return
 
     import torch
@@ -313,8 +373,84 @@ def main():
     e2e_value = world * B * n_px / (e2e_ms * 1e-3) / 1e6
     assert list(k_out) == Ks and all(f == 0 for f in f_out)
     sem_bpp = float(L.emp_host_sem_bytes_per_px())     # 1.0 when every tile's class map was narrowed on the host
-    same = bool(torch.equal(pan_h[B - 1], pan[B - 1].cpu()))
+    same = all(bool(torch.equal(pan_h[b], pan[b].cpu())) for b in range(B))      # every tile, not just the last
+    # the same bytes over the same link with no kernel in between: what the host fabric allows this rank right now
+    sem8_h = torch.empty((B, H, W), dtype=torch.uint8).pin_memory()
+    sem8_d = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_floor():
+        for b in range(B):
+            with torch.cuda.stream(s_in):
+                sem8_d.copy_(sem8_h[b], non_blocking=True)
+                hm[b].copy_(hm_h[b], non_blocking=True)
+                off[b].copy_(off_h[b], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                pan_h[b].copy_(pan[b], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    copy_floor()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        copy_floor()
+    floor_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([floor_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        floor_ms = float(t.item())
+    del sem8_h
     clocks = sampler.stop(mark) if sampler else None
+
+    # ---- BASELINE configs[2]: the z-sharded stack (strong scaling: the 512 x 2048^2 volume is split over the ranks) ----
+    stack_rec = None
+    if not args.no_stack:
+        import bench_stack as bs
+        t0 = time.time()
+        slices = bs.make_slices(dev, 2048)
+        log(f'[rank {rank}] stack: {len(slices)} distinct slices ready in {time.time() - t0:.1f} s')
+        stack_rec, s_out_, _, _ = bs.run_stack(dev, rank, world, slices, 512, 2048, ks=3, repeats=3, profile=(world == 1))
+        if world > 1:
+            bs.add_parity(stack_rec, s_out_, dev, rank, world, slices, 512, 2048, 3, 32, 4096)
+        peak_, _src = measured_peak()
+        stack_rec['roofline'] = {'bound': 'hbm', 'alg_bytes_per_voxel': bs.ALG_BYTES_PER_VOXEL,
+                                 'achieved': bs.ALG_BYTES_PER_VOXEL * stack_rec['value'] / 1e9 / world, 'peak': peak_, 'unit': 'GB/s per GPU',
+                                 'frac': bs.ALG_BYTES_PER_VOXEL * stack_rec['value'] / 1e9 / world / peak_,
+                                 'note': 'host-visible time (enqueue, kernels, D2H of the tables, collectives) against the algorithmic bytes of '
+                                         'SURVEY 8d; the fused path never writes or re-reads the int64 label map those bytes include'}
+        del slices, s_out_
+
+    # ---- BASELINE configs[4]: dense-instance stress, a few tiles through the same fused entry point ----
+    dense_rec = None
+    if world == 1 and not args.no_dense and not args.dense:
+        t0 = time.time()
+        Bd = args.dense_tiles
+        ds = [synth_tile(H, W, 5000, seed=7000 + b, semi_axes=(4.0, 12.0), sigma=2.0) for b in range(Bd)]
+        sem_d = torch.stack([torch.from_numpy(d['sem'][0, 0]) for d in ds]).to(dev)
+        hm_d = torch.stack([torch.from_numpy(d['ctr_hmp'][0, 0]) for d in ds]).to(dev)
+        off_d = torch.stack([torch.from_numpy(d['offsets'][0]) for d in ds]).to(dev)
+        del ds
+        log(f'[rank 0] dense tiles ready in {time.time() - t0:.1f} s')
+
+        def dense_step():
+            C.check(L.emp_panoptic_batched(Bd, sem_d.data_ptr(), 0, hm_d.data_ptr(), off_d.data_ptr(), H, W, things, nt,
+                                           LABEL_DIVISOR, STUFF_AREA, VOID, THR, NMS_K, pan.data_ptr(), None, 0, k_cap,
+                                           ws.data_ptr(), per_tile, ctypes.c_void_p(stream.cuda_stream)))
+        for _ in range(3):
+            dense_step()
+        torch.cuda.synchronize(dev)
+        Kd = [int(v) for v in C.read_status(ws, Bd, per_tile).reshape(Bd, -1)[:, C.ST_K]]
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(stream)
+        for _ in range(10):
+            dense_step()
+        d1.record(stream)
+        torch.cuda.synchronize(dev)
+        dms = d0.elapsed_time(d1) / 10
+        dense_rec = {'workload': f'postproc_{Bd}x4096x4096_dense_k5000', 'value': Bd * n_px / (dms * 1e-3) / 1e6, 'unit': UNIT,
+                     'ms_per_step': dms, 'tiles': Bd, 'centers_per_tile': [min(Kd), max(Kd)],
+                     'hbm_frac_of_measured': ALG_BYTES_PER_PX * Bd * n_px / (dms * 1e-3) / 1e9 / measured_peak()[0]}
+        del sem_d, hm_d, off_d
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -333,13 +469,13 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'int64/f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD if not args.dense else 'postproc_16x4096x4096_dense_k5000', 'tiles_per_gpu': B, 'tile': [H, W], 'centers_per_tile': [min(Ks), max(Ks)],
-                       'thing_list': THINGS, 'label_divisor': LABEL_DIVISOR, 'nms_kernel': NMS_K,
-                       'l2': f'inputs {B * n_px * 20 / 1e9:.1f} GB per step >> 126 MB L2, no flush needed',
-                       'parallelism': f'dp{world} (independent tiles per rank, no collective on the data path)'},
+            'config': workload_config(world, B, [min(Ks), max(Ks)], args.dense),
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n_px * (12 + sem_bpp)), 'd2h_bytes_per_step': B * n_px * 8 + B * 64,
                     'host_buffer_bytes_per_step': B * n_px * 20, 'sem_bytes_per_px_on_the_link': sem_bpp,
                     'ms_per_step': e2e_ms, 'steps': args.e2e_steps, 'matches_resident_result': same,
+                    'copy_only_floor_ms_per_step': floor_ms,
+                    'copy_only_floor_note': 'the same H2D / D2H bytes on two streams with no kernel launched, max over ranks: the '
+                                            'share of e2e time the host memory / PCIe fabric of the box dictates',
                     'api': 'emp_panoptic_batched_host (pinned host tensors, 3-slot H2D/compute/D2H pipeline; int64 class maps '
                            'narrowed to uint8 by host worker threads before the link)'},
             'gpu_launches': launches,
@@ -353,12 +489,14 @@ def main():
                                       'frac': pipeline_gbs / peak, 'frac_of_8TBs_spec': pipeline_gbs / 8000.0},
                          'stage_ms_per_step': stage_ms},
             'clocks': clocks,
+            'stack': stack_rec,
+            'dense': dense_rec,
         }
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            v, dt, k, threads, sample = cpu_reference_sample()
-            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                    'sample': f'{sample}; {dt:.1f} s'}
+            v, dt, k, threads, sample, kind = cpu_reference_sample()
+            line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind,
+                                    'sample': f'{sample}; {dt:.1f} s of CPU'}
         emit(line)
     if world > 1:
         dist.barrier()

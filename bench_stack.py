@@ -4,20 +4,22 @@ bench_stack.py — BASELINE.json configs[2]: the 3D stack post-processing path o
 512 x 2048 x 2048 anisotropic volume, z-sharded over N GPUs of one node, RLE out.
 
 What is timed (per rank, max over ranks): everything between "the CNN heads of my z-block are in HBM"
-and "every slice's RLE dict is on the host with globally unique labels" — the recursive median
+and "every slice's RLE tables are on the host with globally unique labels" — the recursive median
 chain + harden (engines.py:47-90,114-121), coarse center search + group_pixels(step=4) on the
 512 x 512 maps (:257-272), the upsample-fused merge (:274-292), pan_seg -> RLE (rle.py:26-86),
 the D2H of the run tables, the carry-plane exchange between neighbouring ranks and the all-gather of
 instance counts (inference/stack.py).  The CNN forward is the unchanged PyTorch/cuDNN model and is
-not part of this path (its heads are synthetic here, cycled from a few distinct slices per rank).
+not part of this path (its heads are synthetic here, cycled from a few distinct slices; slice z is
+the same on every rank, so a sharded run can be compared with a single block).
 
     python bench_stack.py [--depth 512] [--hw 2048] [--ks 3]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bench_stack.py --gpus N
 
 Prints one JSON line (rank 0): voxels/s over all ranks, ms per slice, scaling "strong" (the volume is
-fixed, ranks split it).  This is a secondary figure; the driver's bench is bench.py (configs[1]).
+fixed, ranks split it).  bench.py runs the same function at every N and puts the record on its line.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -28,6 +30,133 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+ALG_BYTES_PER_VOXEL = 20.75     # sem prob 4 + (ctr 4 + off 8) / 16 + pan 8 (post-proc) + pan 8 (RLE read)
+
+
+def make_slices(dev, hw, distinct=12, blobs=400, seed=100):
+    """`distinct` head-tensor slices of a synthetic blob volume (slices 40.. of it, so blobs are live)."""
+    import torch
+    from empanada_b200.synth import synth_stack_slices
+    slices = []
+    for i, s in enumerate(synth_stack_slices(40 + distinct, hw, hw, blobs, seed=seed, coarse=4)):
+        if i >= 40:
+            slices.append({k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')})
+    return slices
+
+
+def make_engine():
+    """pdl_inference3d.py defaults (:28-37): nms kernel 3, threshold 0.1, confidence 0.3, label divisor 20000"""
+    import torch
+    from empanada_b200.inference import engines
+    return engines.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0,
+                                               nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3, coarse_boundaries=True)
+
+
+def slice_digests(out):
+    """{z: digest} over everything a slice's RLE dict holds (labels before the rank offset)."""
+    dig = {}
+    for z in out:
+        rows = out.inst_rows(z)
+        h = hashlib.blake2b(digest_size=12)
+        if rows is None:                                    # a slice redone synchronously: hash the dict
+            for c, d in out[z].items():
+                for lab, a in d.items():
+                    h.update(np.asarray([c, lab, *a['box']], np.int64).tobytes())
+                    h.update(np.ascontiguousarray(a['starts']).tobytes())
+                    h.update(np.ascontiguousarray(a['runs']).tobytes())
+        else:
+            t, _ = out._where[z]
+            h.update(np.ascontiguousarray(rows[:, [0, 1, 2, 3, 4, 5, 6, 8]]).tobytes())
+            for first, cnt in zip(rows[:, 7].tolist(), rows[:, 6].tolist()):
+                h.update(t.starts[first:first + cnt].tobytes())
+                h.update(t.lens[first:first + cnt].tobytes())
+        dig[int(z)] = h.hexdigest()
+    return dig
+
+
+def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=32, chain_chunk=4096, repeats=3, warmup=2, group=None,
+              profile=False, match=False, lanes=2):
+    """Times StackShard.finish() on this rank's z-block; returns (record, last RleStack, shard, matched)."""
+    import torch
+    import torch.distributed as dist
+    from empanada_b200.inference import stack
+    eng = make_engine()
+
+    def run_once():
+        shard = stack.StackShard(eng, labels=[1], depth=depth, rank=rank, world_size=world, median_kernel_size=ks,
+                                 upsampling=1, force_connected=True, block=block, chain_chunk=chain_chunk, group=group, lanes=lanes)
+        for z in shard.slices():
+            s = slices[z % len(slices)]
+            shard.add(z, s['sem_prob'], s['ctr_hmp'], s['offsets'], size=(hw, hw))
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=group)
+            torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        out = shard.finish()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t
+        if world > 1:                                       # the job is done when its slowest rank is
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
+            dt = float(tt.item())
+        return dt, out, shard
+
+    for _ in range(warmup):
+        run_once()
+    times, out, shard = [], None, None
+    for _ in range(repeats):
+        dt, out, shard = run_once()
+        times.append(dt)
+    n_inst, n_runs = out.counts()
+    timing = dict(getattr(shard, 'timing_', {}))
+    t = time.perf_counter()
+    out.materialise()                                       # every slice's nested dict (what a dict-walking consumer pays on top)
+    timing['dicts_s'] = time.perf_counter() - t
+    matched = None
+    if match:
+        t = time.perf_counter()
+        matched = shard.match(out)
+        torch.cuda.synchronize(dev)
+        timing['match_s'] = time.perf_counter() - t
+    stages = None
+    if profile:
+        from empanada_b200 import _cabi as C
+        C.profile_enable(True)
+        run_once()
+        stages = {k: [round(v[0], 4), v[1]] for k, v in C.profile_read().items() if v[1]}
+        C.profile_enable(False)
+    if world > 1:
+        c = torch.tensor([n_inst, n_runs], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, group=group)
+        n_inst, n_runs = int(c[0]), int(c[1])
+    sec = sum(times) / len(times)
+    rec = {'metric': 'stack_postproc_throughput', 'value': depth * hw * hw / sec, 'unit': 'voxels/s', 'n_gpus': world,
+           'seconds': sec, 'seconds_best': min(times), 'repeats': repeats, 'ms_per_slice_per_rank': 1e3 * sec / max(len(out), 1),
+           'scaling': 'strong', 'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
+           'stage_ms_and_launches': stages,
+           'config': {'workload': f'stack_{depth}x{hw}x{hw}_coarse4_ks{ks}', 'slices_per_rank': len(out), 'block': block,
+                      'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'}}
+    return rec, out, shard, matched
+
+
+def add_parity(rec, out, dev, rank, world, slices, depth, hw, ks, block, chain_chunk, group=None):
+    """N > 1: every rank's slices must equal the same stack run as ONE block (rank 0 runs and times it)."""
+    import torch.distributed as dist
+    mine = slice_digests(out)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    if rank == 0:
+        one, whole, _, _ = run_stack(dev, 0, 1, slices, depth, hw, ks, block, chain_chunk, 2, warmup=1)
+        want = slice_digests(whole)
+        got = {}
+        for g in gathered:
+            got.update(g)
+        rec['parity'] = 'bit-equal to single-block on rank 0' if got == want else 'MISMATCH vs single-block on rank 0'
+        rec['single_gpu_seconds_same_run'] = one['seconds']
+        rec['speedup_vs_n1'] = one['seconds'] / rec['seconds']
+    dist.barrier(group=group)
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -35,10 +164,12 @@ def main():
     ap.add_argument('--depth', type=int, default=512)
     ap.add_argument('--hw', type=int, default=2048)
     ap.add_argument('--ks', type=int, default=3)
-    ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices per rank (cycled)')
+    ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices (cycled)')
     ap.add_argument('--blobs', type=int, default=400)
-    ap.add_argument('--repeat', type=int, default=2)
+    ap.add_argument('--repeat', type=int, default=3)
     ap.add_argument('--block', type=int, default=32, help='slices per emp_stack_block call')
+    ap.add_argument('--chain-chunk', type=int, default=4096, help='slices per emp_median_chain launch')
+    ap.add_argument('--lanes', type=int, default=2, help='streams the sub-blocks alternate between')
     ap.add_argument('--profile', action='store_true', help='one extra run with per-stage CUDA events (ms per stage over the block)')
     ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
     ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')
@@ -52,80 +183,24 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from empanada_b200.inference import engines, stack
-    from empanada_b200.synth import synth_stack_slices
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     D, H = args.depth, args.hw
-
-    # a few distinct slices of a blob volume (slices 40.. of a 64-slice volume so blobs are live)
     t0 = time.time()
-    slices = []
-    for i, s in enumerate(synth_stack_slices(40 + args.distinct, H, H, args.blobs, seed=100 + rank, coarse=4)):
-        if i >= 40:
-            slices.append({k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')})
+    slices = make_slices(dev, H, args.distinct, args.blobs)
     if rank == 0:
         print(f'[rank 0] {len(slices)} distinct slices ready in {time.time() - t0:.1f} s', file=sys.stderr, flush=True)
-
-    # pdl_inference3d.py defaults (:28-37): nms kernel 3, threshold 0.1, confidence 0.3, label divisor 20000
-    eng = engines.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0,
-                                              nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3, coarse_boundaries=True)
-
-    def run_once():
-        shard = stack.StackShard(eng, labels=[1], depth=D, rank=rank, world_size=world, median_kernel_size=args.ks,
-                                 upsampling=1, force_connected=True, block=args.block)
-        for z in shard.slices():
-            s = slices[z % len(slices)]
-            shard.add(z, s['sem_prob'], s['ctr_hmp'], s['offsets'], size=(H, H))
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        t = time.perf_counter()
-        out = shard.finish()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t
-        n_inst, n_runs = out.counts()
-        timing = dict(getattr(shard, 'timing_', {}))
-        t = time.perf_counter()
-        out.materialise()                               # every slice's nested dict (what a dict-walking consumer pays on top)
-        timing['dicts_s'] = time.perf_counter() - t
-        if args.match:
-            t = time.perf_counter()
-            matched = shard.match(out)
-            torch.cuda.synchronize(dev)
-            timing['match_s'] = time.perf_counter() - t
-            timing['match_objects_in_first_slice'] = len(matched[min(matched)][1])
-            run_once.last = (out, matched)
-        return dt, len(out), n_inst, n_runs, timing
-
-    run_once()                                          # warm-up (workspaces, module load)
-    best = None
-    for _ in range(args.repeat):
-        r = run_once()
-        best = r if best is None or r[0] < best[0] else best
-    dt, n_slices, n_inst, n_runs, timing = best
-    stages = None
-    if args.profile:
-        from empanada_b200 import _cabi as C
-        C.profile_enable(True)
-        run_once()
-        stages = {k: [round(v[0], 4), v[1]] for k, v in C.profile_read().items() if v[1]}
-        C.profile_enable(False)
+    rec, out, shard, matched = run_stack(dev, rank, world, slices, D, H, args.ks, args.block, args.chain_chunk, args.repeat,
+                                         profile=args.profile, match=args.match, lanes=args.lanes)
     if world > 1:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        c = torch.tensor([n_inst, n_runs], device=dev, dtype=torch.int64)
-        dist.all_reduce(c)
-        n_inst, n_runs = int(c[0]), int(c[1])
+        add_parity(rec, out, dev, rank, world, slices, D, H, args.ks, args.block, args.chain_chunk)
     match_cpu = None
     if args.match and rank == 0:
         # the reference's matcher on the host (oracle port, numpy): forward chain over the first slices
         from oracle import matcher as om
-        out, _ = run_once.last
         zs = sorted(out)[:args.match_cpu_slices]
         t = time.perf_counter()
         m = om.RLEMatcher(1, 20000, 0.25, 0.25, True)
@@ -138,14 +213,8 @@ def main():
         match_cpu = {'ms_per_slice_forward_only': 1e3 * (time.perf_counter() - t) / max(len(zs) - 1, 1), 'slices': len(zs),
                      'kind': 'port', 'cores': 1}
     if rank == 0:
-        os.write(json_fd, (json.dumps({
-            'metric': 'stack_postproc_throughput', 'value': D * H * H / dt, 'unit': 'voxels/s', 'n_gpus': world,
-            'ms_per_slice_per_rank': 1e3 * dt / n_slices, 'seconds': dt, 'scaling': 'strong',
-            'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
-            'matcher_cpu_baseline': match_cpu, 'stage_ms_and_launches': stages,
-            'config': {'workload': f'stack_{D}x{H}x{H}_coarse4_ks{args.ks}', 'slices_per_rank': n_slices,
-                       'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'},
-        }) + '\n').encode())
+        rec['matcher_cpu_baseline'] = match_cpu
+        os.write(json_fd, (json.dumps(rec) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

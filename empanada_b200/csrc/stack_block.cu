@@ -50,24 +50,44 @@ struct ChainArgs {
     unsigned long long thing_bits;
 };
 
-// middle order statistic of KS values; NaN if any of them is NaN (torch.median propagates NaN)
+// min / max that return NaN when either operand is NaN (fminf / fmaxf drop it): with these a sorting network carries
+// a NaN to every output it can reach — for an odd-even transposition network of KS passes that includes the middle
+// one — which is torch.median's "a window holding a NaN gives NaN"
+__device__ __forceinline__ float min_nan(float a, float b)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// middle order statistic of KS values; NaN if any of them is NaN
 template <int KS>
 __device__ __forceinline__ float median_nan(const float (&w)[KS])
 {
-    float v[KS];
-    bool nan = false;
+    if constexpr (KS == 3) {
+        return max_nan(min_nan(w[0], w[1]), min_nan(max_nan(w[0], w[1]), w[2]));
+    } else {
+        float v[KS];
 #pragma unroll
-    for (int i = 0; i < KS; ++i) { v[i] = w[i]; nan |= (w[i] != w[i]); }
+        for (int i = 0; i < KS; ++i) v[i] = w[i];
 #pragma unroll
-    for (int pass = 0; pass < KS; ++pass) {
+        for (int pass = 0; pass < KS; ++pass) {
 #pragma unroll
-        for (int i = (pass & 1); i + 1 < KS; i += 2) {
-            const float lo = fminf(v[i], v[i + 1]);
-            const float hi = fmaxf(v[i], v[i + 1]);
-            v[i] = lo; v[i + 1] = hi;
+            for (int i = (pass & 1); i + 1 < KS; i += 2) {
+                const float lo = min_nan(v[i], v[i + 1]);
+                const float hi = max_nan(v[i], v[i + 1]);
+                v[i] = lo; v[i + 1] = hi;
+            }
         }
+        return v[(KS - 1) / 2];
     }
-    return nan ? CUDART_NAN_F : v[(KS - 1) / 2];
 }
 
 template <int N>
@@ -93,8 +113,9 @@ __device__ __forceinline__ void store_px(float* p, const float (&src)[N])
 }
 
 // One thread per N consecutive pixels of one channel; the z loop keeps the last MID filtered values and the raw
-// window (+ kChainPf planes of look-ahead) in registers.  REPAIR runs the chain from two carries at once and stops
-// as soon as their states agree bit for bit (from there on the outputs are identical by construction).
+// window (+ kChainPf planes of look-ahead) in registers — the window as a ring whose slots are named at compile time
+// (the loop is unrolled by the ring's length), so advancing costs no moves.  REPAIR runs the chain from two carries at
+// once and stops as soon as their states agree bit for bit (from there on the outputs are identical by construction).
 template <int KS, int N, bool REPAIR>
 __global__ void __launch_bounds__(256)
 median_chain_kernel(const ChainArgs a)
@@ -109,7 +130,7 @@ median_chain_kernel(const ChainArgs a)
     if (a.need) {
         const int y = (int)(px / (size_t)a.W), x = (int)(px - (size_t)y * a.W);
 #pragma unroll
-        for (int q = 0; q < N; ++q) {                                // N == 4 only with W % 4 == 0: the pixels share a row
+        for (int q = 0; q < N; ++q) {                                // N > 1 only with hw % N == 0; pixels may wrap into the next row
             const int xx = x + q;
             cell[q] = ((y + xx / a.W) >> a.shift) * a.wc + ((xx % a.W) >> a.shift);
         }
@@ -134,84 +155,93 @@ median_chain_kernel(const ChainArgs a)
         if (j < a.n_planes) load_px<N>(r[j], a.planes[j] + e);
     }
     bool differs = REPAIR;
+    bool done = false;
 #pragma unroll 1
-    for (int i = 0; i < a.n; ++i) {
-        if (REPAIR) {
-            differs = false;
+    for (int i0 = 0; i0 < a.n && !done; i0 += WIN) {
 #pragma unroll
-            for (int j = 0; j < MID; ++j)
+        for (int u = 0; u < WIN; ++u) {                             // slice i0 + u: its window is ring slots u, u+1, ... (mod WIN)
+            const int i = i0 + u;
+            if (i >= a.n) { done = true; break; }
+            if (REPAIR) {
+                differs = false;
 #pragma unroll
-                for (int q = 0; q < N; ++q) differs |= __float_as_uint(f[j][q]) != __float_as_uint(g[j][q]);
-            if (!differs) break;
-        }
-        const int z = a.z0 + i;
-        const bool raw = (z < MID) || (z >= a.depth - MID);        // the queue passes the stack's ends through unfiltered
-        float o[N], og[N];
+                for (int j = 0; j < MID; ++j)
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
-            o[q] = r[0][q]; og[q] = r[0][q];
-            if (KS > 1 && !raw) {
-                float w[KS];
-#pragma unroll
-                for (int j = 0; j < MID; ++j) w[j] = f[j][q];
-#pragma unroll
-                for (int j = 0; j <= MID; ++j) w[MID + j] = r[j][q];
-                o[q] = median_nan<KS>(w);
-                if (REPAIR) {
-#pragma unroll
-                    for (int j = 0; j < MID; ++j) w[j] = g[j][q];
-#pragma unroll
-                    for (int j = 0; j <= MID; ++j) w[MID + j] = r[j][q];
-                    og[q] = median_nan<KS>(w);
-                }
+                    for (int q = 0; q < N; ++q) differs |= __float_as_uint(f[j][q]) != __float_as_uint(g[j][q]);
+                if (!differs) { done = true; break; }
             }
-        }
-        const float (&res)[N] = REPAIR ? og : o;                    // the values that count
-        unsigned char* sp = a.sem8 + (size_t)i * a.sem8_stride + px;
-        unsigned set = 0;                                           // bit q: pixel q's class was (re)written by this launch
-        unsigned bits = 0;                                          // class bytes
-        if (!a.multi) {
-#pragma unroll
-            for (int q = 0; q < N; ++q) bits |= (res[q] >= a.thr ? 1u : 0u) << (8 * q);
-            if (N == 4) *reinterpret_cast<unsigned*>(sp) = bits;
-            else if (N == 2) *reinterpret_cast<unsigned short*>(sp) = (unsigned short)bits;
-            else sp[0] = (unsigned char)bits;
-            set = (1u << N) - 1u;
-        } else {                                                    // first arg-max over channels, NaN counts as the maximum
-            float* bp = a.best + (size_t)i * a.hw + px;
-            if (a.c == 0) {
-                store_px<N>(bp, res);
-#pragma unroll
-                for (int q = 0; q < N; ++q) sp[q] = 0;
-                set = (1u << N) - 1u;
-            } else {
-                float b[N];
-                load_px<N>(b, bp);
-#pragma unroll
-                for (int q = 0; q < N; ++q)
-                    if (res[q] > b[q] || (res[q] != res[q] && b[q] == b[q])) {
-                        bp[q] = res[q]; sp[q] = (unsigned char)a.c;
-                        set |= 1u << q; bits |= (unsigned)a.c << (8 * q);
-                    }
-            }
-        }
-        if (a.need) {                                               // a superset is fine: a stale 1 only costs an unused id
-            unsigned char* np = a.need + (size_t)i * a.need_stride;
+            const int z = a.z0 + i;
+            const bool raw = (z < MID) || (z >= a.depth - MID);    // the queue passes the stack's ends through unfiltered
+            float o[N], og[N];
 #pragma unroll
             for (int q = 0; q < N; ++q) {
-                const unsigned cls = (bits >> (8 * q)) & 0xFFu;
-                if (((set >> q) & 1u) && cls < 64u && ((a.thing_bits >> cls) & 1ull)) np[cell[q]] = 1;
+                o[q] = r[u][q]; og[q] = r[u][q];
+                if (KS > 1 && !raw) {
+                    float w[KS];
+#pragma unroll
+                    for (int j = 0; j < MID; ++j) w[j] = f[j][q];
+#pragma unroll
+                    for (int j = 0; j <= MID; ++j) w[MID + j] = r[(u + j) % WIN][q];
+                    o[q] = median_nan<KS>(w);
+                    if (REPAIR) {
+#pragma unroll
+                        for (int j = 0; j < MID; ++j) w[j] = g[j][q];
+                        og[q] = median_nan<KS>(w);
+                    }
+                }
             }
+            const float (&res)[N] = REPAIR ? og : o;                // the values that count
+            unsigned char* sp = a.sem8 + (size_t)i * a.sem8_stride + px;
+            unsigned set = 0;                                       // bit q: pixel q's class was (re)written by this launch
+            unsigned bits = 0;                                      // class bytes
+            if (!a.multi) {
+#pragma unroll
+                for (int q = 0; q < N; ++q) bits |= (res[q] >= a.thr ? 1u : 0u) << (8 * q);
+                if (N == 4) *reinterpret_cast<unsigned*>(sp) = bits;
+                else if (N == 2) *reinterpret_cast<unsigned short*>(sp) = (unsigned short)bits;
+                else sp[0] = (unsigned char)bits;
+                set = (1u << N) - 1u;
+            } else {                                                // first arg-max over channels, NaN counts as the maximum
+                float* bp = a.best + (size_t)i * a.hw + px;
+                if (a.c == 0) {
+                    store_px<N>(bp, res);
+#pragma unroll
+                    for (int q = 0; q < N; ++q) sp[q] = 0;
+                    set = (1u << N) - 1u;
+                } else {
+                    float b[N];
+                    load_px<N>(b, bp);
+#pragma unroll
+                    for (int q = 0; q < N; ++q)
+                        if (res[q] > b[q] || (res[q] != res[q] && b[q] == b[q])) {
+                            bp[q] = res[q]; sp[q] = (unsigned char)a.c;
+                            set |= 1u << q; bits |= (unsigned)a.c << (8 * q);
+                        }
+                }
+            }
+            if (a.need && (bits != 0u || (a.thing_bits & 1ull))) {  // a superset is fine: a stale 1 only costs an unused id
+                unsigned char* np = a.need + (size_t)i * a.need_stride;
+#pragma unroll
+                for (int q = 0; q < N; ++q) {
+                    const unsigned cls = (bits >> (8 * q)) & 0xFFu;
+                    if (((set >> q) & 1u) && cls < 64u && ((a.thing_bits >> cls) & 1ull)) np[cell[q]] = 1;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < N; ++q) {
+#pragma unroll
+                for (int j = 0; j + 1 < MID; ++j) { f[j][q] = f[j + 1][q]; g[j][q] = g[j + 1][q]; }
+                if constexpr (MID > 0) { f[MID - 1][q] = o[q]; g[MID - 1][q] = og[q]; }
+            }
+            if (i + WIN < a.n_planes) load_px<N>(r[u], a.planes[i + WIN] + e);     // slot u is free: it takes slice i + WIN
         }
+    }
+    if (REPAIR && differs) {                                        // ran to the block's end: are the final states still apart?
+        differs = false;
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
+        for (int j = 0; j < MID; ++j)
 #pragma unroll
-            for (int j = 0; j + 1 < MID; ++j) { f[j][q] = f[j + 1][q]; g[j][q] = g[j + 1][q]; }
-            if constexpr (MID > 0) { f[MID - 1][q] = o[q]; g[MID - 1][q] = og[q]; }
-#pragma unroll
-            for (int j = 0; j + 1 < WIN; ++j) r[j][q] = r[j + 1][q];
-        }
-        if (i + WIN < a.n_planes) load_px<N>(r[WIN - 1], a.planes[i + WIN] + e);
+            for (int q = 0; q < N; ++q) differs |= __float_as_uint(f[j][q]) != __float_as_uint(g[j][q]);
     }
     if (MID > 0 && a.carry_out) {
         if (!REPAIR) {
