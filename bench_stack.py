@@ -75,7 +75,7 @@ def slice_digests(out):
 
 
 def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=32, chain_chunk=4096, repeats=3, warmup=2, group=None,
-              profile=False, match=False, lanes=2):
+              profile=False, match=False, lanes=1):
     """Times StackShard.finish() on this rank's z-block; returns (record, last RleStack, shard, matched)."""
     import torch
     import torch.distributed as dist
@@ -169,7 +169,7 @@ def main():
     ap.add_argument('--repeat', type=int, default=3)
     ap.add_argument('--block', type=int, default=32, help='slices per emp_stack_block call')
     ap.add_argument('--chain-chunk', type=int, default=4096, help='slices per emp_median_chain launch')
-    ap.add_argument('--lanes', type=int, default=2, help='streams the sub-blocks alternate between')
+    ap.add_argument('--lanes', type=int, default=1, help='streams the sub-blocks alternate between')
     ap.add_argument('--profile', action='store_true', help='one extra run with per-stage CUDA events (ms per stage over the block)')
     ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
     ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')

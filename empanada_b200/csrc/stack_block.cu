@@ -305,6 +305,8 @@ struct LeanArgs {
     size_t o_votes, o_areas, o_sflags, o_codes;
     int B, H, W, wc, shift, blocks_x, blk_items, T;
     unsigned long long thing_bits;
+    int simple;                 // one thing class (thing_class, != 0) and cells of >= 4 pixels: the byte-mask path applies
+    unsigned thing_class;
 };
 
 __global__ void __launch_bounds__(256, 4)
@@ -361,52 +363,95 @@ merge_lean_kernel(const LeanArgs a)
         uint32_t* areas = reinterpret_cast<uint32_t*>(ws + a.o_areas);
         const int32_t* ids = a.ids + (size_t)b * a.ids_stride;
         unsigned short* codes = reinterpret_cast<unsigned short*>(ws + a.o_codes);
-        for (; todo; todo &= todo - 1) {
+        for (; todo; todo &= todo - 1) {                                // warp-uniform trip count, no lane leaves early
             const int sx = g * 512 + ((__ffs(todo) - 1) >> 2) * 64;     // first column of the strip
             const int y = y0 + (lane >> 3), x = sx + (lane & 7) * 8;
-            if (y >= a.H || x >= a.W) continue;                         // lanes past the plane's edge (partial strips only)
-            const uint2 u = __ldg(reinterpret_cast<const uint2*>(plane + (size_t)y * a.W + x));    // just read: an L1 hit
-            const unsigned w2[2] = {u.x, u.y};
+            const bool valid = y < a.H && x < a.W;                      // lanes past the plane's edge (partial strips only)
+            uint2 u = make_uint2(0u, 0u);
+            if (valid) u = __ldg(reinterpret_cast<const uint2*>(plane + (size_t)y * a.W + x));     // just read: an L1 hit
             const int crow = (y >> a.shift) * a.wc;
             unsigned out[4];
-            unsigned vkey = kNoVote, vcnt = 0;                          // pending vote: neighbours of equal (id, class)
-            unsigned akey = kNoVote, acnt = 0;                          // pending stuff-area count of one non-zero class
-            int last_cell = -1, last_id = 0;
+            unsigned k1 = kNoVote, c1 = 0, k2 = kNoVote, c2 = 0;        // up to two (vote key, count) pairs leave the lane aggregated
+            const unsigned tcx4 = a.thing_class * 0x01010101u;
+            const unsigned t0 = __vcmpeq4(u.x, tcx4), t1 = __vcmpeq4(u.y, tcx4);          // 0xFF per byte of the (one) thing class
+            const unsigned z0 = __vcmpeq4(u.x, 0u), z1 = __vcmpeq4(u.y, 0u);              // 0xFF per class-0 byte
+            if (a.simple && ((t0 | z0) & (t1 | z1)) == 0xFFFFFFFFu) {
+                // ---- one thing class, cells of >= 4 aligned pixels, nothing but that class and class 0 here: a word of 4
+                // pixels meets one cell; codes and votes come from byte masks
+                const unsigned tm[2] = {t0, t1};
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const unsigned c = (w2[p >> 2] >> (8 * (p & 3))) & 0xFFu;
-                const bool thing = c < 64u && ((a.thing_bits >> c) & 1ull);
-                unsigned code;
-                if (thing) {
-                    const int cell = crow + ((x + p) >> a.shift);
-                    if (cell != last_cell) { last_cell = cell; last_id = __ldg(ids + cell); }
-                    code = (unsigned)last_id;                           // 0: a thing pixel without an instance stays void
-                    if (last_id > 0) {
-                        const unsigned t = multi ? (unsigned)__popcll(a.thing_bits & ((1ull << c) - 1ull)) : 0u;
-                        const unsigned key = (unsigned)last_id * (unsigned)a.T + t;
-                        if (key != vkey) {
-                            if (vcnt) atomicAdd(votes + vkey, vcnt);
-                            vkey = key; vcnt = 0;
-                        }
-                        ++vcnt;
-                    }
-                    ++deficit;
-                } else {
-                    code = kClsBase16 + c;
-                    if (c != 0u) {
-                        ++deficit;
-                        if (c != akey) {
-                            if (acnt) atomicAdd(areas + akey, acnt);
-                            akey = c; acnt = 0;
-                        }
-                        ++acnt;
+                for (int k = 0; k < 2; ++k) {
+                    unsigned id = 0;
+                    if (tm[k]) id = (unsigned)__ldg(ids + crow + ((x + 4 * k) >> a.shift));
+                    const unsigned n_thing = (unsigned)__popc(tm[k]) >> 3;
+                    deficit += n_thing;
+                    const unsigned idid = id | (id << 16);
+                    const unsigned bg2 = kClsBase16 | (kClsBase16 << 16);
+                    const unsigned m_lo = __byte_perm(tm[k], 0u, 0x1100), m_hi = __byte_perm(tm[k], 0u, 0x3322);
+                    out[2 * k] = (m_lo & idid) | (~m_lo & bg2);          // a thing pixel without an instance (id 0) stays void
+                    out[2 * k + 1] = (m_hi & idid) | (~m_hi & bg2);
+                    if (id > 0u && n_thing) {
+                        if (k == 0 || k1 == kNoVote) { k1 = id; c1 = n_thing; }              // T == 1: key = id
+                        else if (k1 == id) c1 += n_thing;
+                        else { k2 = id; c2 = n_thing; }
                     }
                 }
-                if (p & 1) out[p >> 1] |= code << 16; else out[p >> 1] = code;
+            } else if (valid) {
+                // ---- anything else: pixel by pixel
+                const unsigned w2[2] = {u.x, u.y};
+                unsigned vkey = kNoVote, vcnt = 0;                      // pending vote: neighbours of equal (id, class)
+                unsigned akey = kNoVote, acnt = 0;                      // pending stuff-area count of one non-zero class
+                int last_cell = -1, last_id = 0;
+                auto push_vote = [&]() {
+                    if (!vcnt) return;
+                    if (k1 == kNoVote) { k1 = vkey; c1 = vcnt; }
+                    else if (k1 == vkey) c1 += vcnt;
+                    else if (k2 == kNoVote) { k2 = vkey; c2 = vcnt; }
+                    else if (k2 == vkey) c2 += vcnt;
+                    else atomicAdd(votes + vkey, vcnt);
+                };
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const unsigned c = (w2[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+                    const bool thing = c < 64u && ((a.thing_bits >> c) & 1ull);
+                    unsigned code;
+                    if (thing) {
+                        const int cell = crow + ((x + p) >> a.shift);
+                        if (cell != last_cell) { last_cell = cell; last_id = __ldg(ids + cell); }
+                        code = (unsigned)last_id;                       // 0: a thing pixel without an instance stays void
+                        if (last_id > 0) {
+                            const unsigned t = multi ? (unsigned)__popcll(a.thing_bits & ((1ull << c) - 1ull)) : 0u;
+                            const unsigned key = (unsigned)last_id * (unsigned)a.T + t;
+                            if (key != vkey) { push_vote(); vkey = key; vcnt = 0; }
+                            ++vcnt;
+                        }
+                        ++deficit;
+                    } else {
+                        code = kClsBase16 + c;
+                        if (c != 0u) {
+                            ++deficit;
+                            if (c != akey) {
+                                if (acnt) atomicAdd(areas + akey, acnt);
+                                akey = c; acnt = 0;
+                            }
+                            ++acnt;
+                        }
+                    }
+                    if (p & 1) out[p >> 1] |= code << 16; else out[p >> 1] = code;
+                }
+                push_vote();
+                if (acnt) atomicAdd(areas + akey, acnt);
             }
-            *reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x) = make_uint4(out[0], out[1], out[2], out[3]);
-            if (vcnt) atomicAdd(votes + vkey, vcnt);
-            if (acnt) atomicAdd(areas + akey, acnt);
+            if (valid) *reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x) = make_uint4(out[0], out[1], out[2], out[3]);
+            // votes: lanes holding the same key (the rows of a strip share their cells) add up first
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const unsigned key = sl ? k2 : k1, cnt = sl ? c2 : c1;
+                if (!__any_sync(0xffffffffu, key != kNoVote)) continue; // warp-uniform
+                const unsigned peers = __match_any_sync(0xffffffffu, key);
+                const unsigned sum = __reduce_add_sync(peers, cnt);
+                if (key != kNoVote && lane == __ffs(peers) - 1) atomicAdd(votes + key, sum);
+            }
         }
     }
     flush();
@@ -575,18 +620,85 @@ rle_block_mark_kernel(const BlkArgs a)
                 raw[rr] = __ldcs(reinterpret_cast<const uint4*>(v.codes + (size_t)(y0 + rr) * a.W + x0));
             if (edge && !eflagged && row_in) ecode[rr] = v.codes[(size_t)(y0 + rr) * a.W + ex];
         }
-        // ---- round trip 3: run keys of the codes that are neither void nor background
-        unsigned key[4][8], ekey[4];
+        if (key0 == 0u) {
+            // ---- common case (void is not a selected label): distinct codes never share a non-zero key, so run boundaries
+            // are code boundaries.  Two codes per 32-bit word are compared with their neighbours by the SIMD halfword
+            // instructions; keys are looked up only at boundary pixels, to drop runs of unselected codes.
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int y = y0 + rr;
+                if (y >= a.crop_h) break;                               // warp-uniform
+                unsigned w[4];
+                if (flagged || !inside) {
+                    w[0] = w[1] = w[2] = w[3] = kClsBase16 | (kClsBase16 << 16);       // outside: treated as background
+                } else if (a.vec) {
+                    w[0] = raw[rr].x; w[1] = raw[rr].y; w[2] = raw[rr].z; w[3] = raw[rr].w;
+                } else {
+                    const unsigned short* cp = v.codes + (size_t)y * a.W + x0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const unsigned c0 = (x0 + 2 * k < a.crop_w) ? cp[2 * k] : kClsBase16;
+                        const unsigned c1 = (x0 + 2 * k + 1 < a.crop_w) ? cp[2 * k + 1] : kClsBase16;
+                        w[k] = c0 | (c1 << 16);
+                    }
+                }
+                if (inside && x0 + 8 > a.crop_w && a.vec) {             // the crop ends inside this lane's 8 pixels
+#pragma unroll
+                    for (int p = 0; p < 8; ++p)
+                        if (x0 + p >= a.crop_w) w[p >> 1] = (p & 1) ? (w[p >> 1] & 0xFFFFu) | (kClsBase16 << 16) : (w[p >> 1] & 0xFFFF0000u) | kClsBase16;
+                }
+                unsigned left = __shfl_up_sync(0xffffffffu, w[3] >> 16, 1);
+                unsigned right = __shfl_down_sync(0xffffffffu, w[0] & 0xFFFFu, 1);
+                if (lane == 0) left = edge ? ecode[rr] : kClsBase16;    // outside the image: background, never selected
+                if (lane == 31) right = edge ? ecode[rr] : kClsBase16;
+                // bit p of sb / eb: pixel p differs from its left / right neighbour
+                unsigned sb = 0, eb = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned prev = k ? __funnelshift_l(w[k - 1], w[k], 16) : ((w[0] << 16) | left);
+                    const unsigned next = k < 3 ? __funnelshift_r(w[k], w[k + 1], 16) : ((w[3] >> 16) | (right << 16));
+                    const unsigned dp = __vcmpne2(w[k], prev), dn = __vcmpne2(w[k], next);
+                    sb |= ((dp & 1u) | ((dp >> 15) & 2u)) << (2 * k);
+                    eb |= ((dn & 1u) | ((dn >> 15) & 2u)) << (2 * k);
+                }
+                for (unsigned m = sb | eb; m; m &= m - 1) {             // boundary pixels: keep those of selected codes
+                    const int p = __ffs(m) - 1;
+                    const unsigned wp = p < 4 ? (p < 2 ? w[0] : w[1]) : (p < 6 ? w[2] : w[3]);   // no dynamic register index
+                    const unsigned code = (wp >> (16 * (p & 1))) & 0xFFFFu;
+                    const unsigned key = code == 0u ? 0u : code == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(code, a.cls_off));
+                    if (key == 0u) { sb &= ~(1u << p); eb &= ~(1u << p); }
+                }
+                if (!__any_sync(0xffffffffu, (sb | eb) != 0u)) continue;               // warp-uniform
+                const unsigned mine = sb | (eb << 8);
+                const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
+                               m3 = __shfl_down_sync(0xffffffffu, mine, 3);
+                unsigned cnt = 0;
+                if ((lane & 3) == 0) {
+                    const unsigned sw = (mine & 0xFFu) | ((m1 & 0xFFu) << 8) | ((m2 & 0xFFu) << 16) | ((m3 & 0xFFu) << 24);
+                    const unsigned ew = ((mine >> 8) & 0xFFu) | (((m1 >> 8) & 0xFFu) << 8) | (((m2 >> 8) & 0xFFu) << 16) | (((m3 >> 8) & 0xFFu) << 24);
+                    const int wi = g * 8 + (lane >> 2);
+                    if (wi < wd && (sw | ew)) {
+                        reinterpret_cast<uint32_t*>(rs + a.R.smask)[(size_t)y * wd + wi] = sw;
+                        reinterpret_cast<uint32_t*>(rs + a.R.emask)[(size_t)y * wd + wi] = ew;
+                    }
+                    cnt = (unsigned)__popc(sw);
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0 && cnt) atomicAdd(reinterpret_cast<uint32_t*>(rs + a.R.rowcnt) + y, cnt);
+            }
+            continue;
+        }
+        // ---- void is a selected label (it may share its key with a stuff class or an instance): compare keys, pixel by pixel
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const int y = y0 + rr;
+            if (y >= a.crop_h) break;                                   // warp-uniform
+            unsigned key[8];
 #pragma unroll
-            for (int p = 0; p < 8; ++p) key[rr][p] = 0u;
-            ekey[rr] = 0u;
-            if (y >= a.crop_h) continue;
+            for (int p = 0; p < 8; ++p) key[p] = 0u;
             if (flagged) {
 #pragma unroll
-                for (int p = 0; p < 8; ++p) key[rr][p] = (x0 + p < a.crop_w) ? bgkey : 0u;
+                for (int p = 0; p < 8; ++p) key[p] = (x0 + p < a.crop_w) ? bgkey : 0u;
             } else if (inside) {
                 unsigned code[8];
                 if (a.vec) {                                            // W % 8 == 0: the whole group lies inside the plane
@@ -605,33 +717,28 @@ rle_block_mark_kernel(const BlkArgs a)
                         prev_code = code[p];
                         prev_key = code[p] == 0u ? key0 : code[p] == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(code[p], a.cls_off));
                     }
-                    key[rr][p] = (x0 + p < a.crop_w) ? prev_key : 0u;
+                    key[p] = (x0 + p < a.crop_w) ? prev_key : 0u;
                 }
             }
+            unsigned ekey = 0u;
             if (edge) {
                 const unsigned c = ecode[rr];
-                ekey[rr] = c == 0u ? key0 : c == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(c, a.cls_off));
+                ekey = c == 0u ? key0 : c == kClsBase16 ? bgkey : __ldg(v.keylut + code_index(c, a.cls_off));
             }
-        }
-        // ---- start / end bits, gathered into mask words
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int y = y0 + rr;
-            if (y >= a.crop_h) break;                                   // warp-uniform
             unsigned any = 0;
 #pragma unroll
-            for (int p = 0; p < 8; ++p) any |= key[rr][p];
+            for (int p = 0; p < 8; ++p) any |= key[p];
             if (!__any_sync(0xffffffffu, any != 0u)) continue;          // warp-uniform: nothing selected in this row
-            unsigned left = __shfl_up_sync(0xffffffffu, key[rr][7], 1);
-            unsigned right = __shfl_down_sync(0xffffffffu, key[rr][0], 1);
-            if (lane == 0) left = ekey[rr];
-            if (lane == 31) right = ekey[rr];
+            unsigned left = __shfl_up_sync(0xffffffffu, key[7], 1);
+            unsigned right = __shfl_down_sync(0xffffffffu, key[0], 1);
+            if (lane == 0) left = ekey;
+            if (lane == 31) right = ekey;
             unsigned sb = 0, eb = 0;
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const unsigned l = p ? key[rr][p - 1] : left, rn = p < 7 ? key[rr][p + 1] : right;
-                sb |= (key[rr][p] != 0u && l != key[rr][p] ? 1u : 0u) << p;
-                eb |= (key[rr][p] != 0u && rn != key[rr][p] ? 1u : 0u) << p;
+                const unsigned l = p ? key[p - 1] : left, rn = p < 7 ? key[p + 1] : right;
+                sb |= (key[p] != 0u && l != key[p] ? 1u : 0u) << p;
+                eb |= (key[p] != 0u && rn != key[p] ? 1u : 0u) << p;
             }
             const unsigned mine = sb | (eb << 8);
             const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
@@ -1235,6 +1342,8 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         m.B = B; m.H = cfg->H; m.W = cfg->W; m.wc = cfg->w; m.shift = cfg->shift;
         m.blocks_x = (cfg->W + 63) / 64; m.blk_items = assign_block_items(cfg->H, cfg->W);
         m.T = P.th.n > 0 ? P.th.n : 1; m.thing_bits = thing_bits;
+        m.simple = (P.th.n == 1 && P.th.v[0] > 0 && cfg->shift >= 2) ? 1 : 0;
+        m.thing_class = P.th.n == 1 ? (unsigned)P.th.v[0] : 0u;
         const size_t items = (size_t)B * ((cfg->H + 3) / 4) * ((cfg->W + 511) / 512);
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 8));
         {

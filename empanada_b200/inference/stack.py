@@ -347,7 +347,7 @@ class StackShard:
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True, chain_chunk=4096, lanes=2):
+                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True, chain_chunk=4096, lanes=1):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
@@ -732,6 +732,10 @@ class StackShard:
 
     def finish(self):
         """Post-process + RLE-encode this rank's block.  Returns an RleStack ({z: rle_seg}, dicts built on access)."""
+        with _gc_paused():          # a cyclic collection over a previous block's ~10^5 dicts would stall the enqueue loop
+            return self._finish()
+
+    def _finish(self):
         from empanada_b200 import _cabi as C
         e = self.engine
         zs = list(range(self.z0, self.z1))
@@ -772,7 +776,7 @@ class StackShard:
                 # sees the same table, so all of them settle the carries with further rounds and redo the block.
                 self._settle = True
                 try:
-                    return self.finish()
+                    return self._finish()
                 finally:
                     self._settle = False
             per_class = table[:, :-1]
