@@ -132,7 +132,7 @@ def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=32, chain_chunk=4
         n_inst, n_runs = int(c[0]), int(c[1])
     sec = sum(times) / len(times)
     rec = {'metric': 'stack_postproc_throughput', 'value': depth * hw * hw / sec, 'unit': 'voxels/s', 'n_gpus': world,
-           'seconds': sec, 'seconds_best': min(times), 'repeats': repeats, 'ms_per_slice_per_rank': 1e3 * sec / max(len(out), 1),
+           'seconds': sec, 'seconds_best': min(times), 'seconds_all': [round(t, 5) for t in times], 'repeats': repeats, 'ms_per_slice_per_rank': 1e3 * sec / max(len(out), 1),
            'scaling': 'strong', 'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
            'stage_ms_and_launches': stages,
            'config': {'workload': f'stack_{depth}x{hw}x{hw}_coarse4_ks{ks}', 'slices_per_rank': len(out), 'block': block,

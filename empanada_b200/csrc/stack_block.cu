@@ -303,7 +303,7 @@ struct LeanArgs {
     const int32_t* ids; size_t ids_stride;
     char* ws; size_t ws_stride;
     size_t o_votes, o_areas, o_sflags, o_codes;
-    int B, H, W, wc, shift, blocks_x, blk_items, T;
+    int B, H, W, wc, shift, blocks_x, blk_shift, T;
     unsigned long long thing_bits;
     int simple;                 // one thing class (thing_class, != 0) and cells of >= 4 pixels: the byte-mask path applies
     unsigned thing_class;
@@ -313,31 +313,16 @@ __global__ void __launch_bounds__(256, 4)
 merge_lean_kernel(const LeanArgs a)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 2, q = lane & 3;
-    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
     const unsigned groups = (a.W + 511) / 512, srows = (a.H + 3) / 4;
-    const unsigned per_slice = srows * groups;
-    const unsigned items = per_slice * a.B;                             // host: < 2^31
+    const unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one item per warp, one slice per grid plane
+    if (item >= srows * groups) return;                                 // warp-uniform
     const bool class0_stuff = !(a.thing_bits & 1ull);
     const bool multi = a.T > 1;
-    int cur_b = -1;
-    unsigned deficit = 0;                                               // in-image pixels of the slice that are NOT class-0 stuff
-    char* ws = nullptr;
-    auto flush = [&]() {                                                // warp-uniform call sites
-        if (cur_b < 0) return;
-        const unsigned d = __reduce_add_sync(0xffffffffu, deficit);
-        if (d && lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(ws + a.o_areas) + kNumClasses, d);
-        deficit = 0;
-    };
-    for (unsigned it = warp_global; it < items; it += n_warps) {
-        const int b = (int)(it / per_slice);
-        const unsigned r = it - (unsigned)b * per_slice;
-        const int sy = (int)(r / groups), g = (int)(r % groups);
-        if (b != cur_b) {
-            flush();
-            cur_b = b;
-            ws = a.ws + (size_t)b * a.ws_stride;
-        }
+    unsigned deficit = 0;                                               // in-image pixels of the item that are NOT class-0 stuff
+    const int b = blockIdx.z;
+    char* ws = a.ws + (size_t)b * a.ws_stride;
+    const int sy = (int)(item / groups), g = (int)(item - (unsigned)sy * groups);
+    {
         // ---- streaming part: 4 rows x 512 columns, 16 bytes per lane and row; which of the 8 strips are pure background?
         const int y0 = sy * 4, xs = g * 512 + grp * 64;                 // the strip of this lane's group
         const int x0 = xs + q * 16;
@@ -355,8 +340,8 @@ merge_lean_kernel(const LeanArgs a)
         const unsigned gmask = 0xFu << (lane & ~3);
         const bool bg = full && class0_stuff && ((zero4 & gmask) == gmask);
         if (q == 0 && xs < a.W)
-            reinterpret_cast<unsigned char*>(ws + a.o_sflags)[((size_t)(y0 / (a.blk_items * 4)) * a.blocks_x + (xs >> 6)) * 16 +
-                                                              ((y0 >> 2) % a.blk_items)] = bg ? 1 : 0;
+            reinterpret_cast<unsigned char*>(ws + a.o_sflags)[((size_t)(y0 >> (a.blk_shift + 2)) * a.blocks_x + (xs >> 6)) * 16 +
+                                                              ((y0 >> 2) & ((1 << a.blk_shift) - 1))] = bg ? 1 : 0;
         unsigned todo = __ballot_sync(0xffffffffu, q == 0 && xs < a.W && !bg);
         // ---- strips that hold something: the whole warp takes one strip at a time, lane l 8 pixels of row l / 8
         uint32_t* votes = reinterpret_cast<uint32_t*>(ws + a.o_votes);
@@ -454,7 +439,8 @@ merge_lean_kernel(const LeanArgs a)
             }
         }
     }
-    flush();
+    const unsigned d = __reduce_add_sync(0xffffffffu, deficit);
+    if (d && lane == 0) atomicAdd(reinterpret_cast<uint32_t*>(ws + a.o_areas) + kNumClasses, d);
 }
 
 // =====================================================================================================
@@ -507,7 +493,7 @@ struct BlkArgs {
     BlkLayout R;
     RleClasses rc;
     int B, W, crop_h, crop_w;               // W: row pitch of the code map (the padded plane)
-    int blocks_x, blk_items;                // strip-flag geometry of the assign kernel
+    int blocks_x, blk_shift;                // strip-flag geometry of the assign kernel (1 << blk_shift strips per block)
     unsigned cls_off;
     int k_cap, run_cap, inst_cap;
     int vec;                                // 16-byte code loads allowed
@@ -536,7 +522,7 @@ struct CodeView {
     const unsigned short* codes;
     const unsigned char* sflags;
     const uint32_t* keylut;
-    int W, blocks_x, blk_items;
+    int W, blocks_x, blk_shift;      // strips per block of the assign geometry: 1 << blk_shift
     unsigned cls_off;
 };
 
@@ -547,7 +533,7 @@ __device__ __forceinline__ unsigned code_index(unsigned code, unsigned cls_off)
 
 __device__ __forceinline__ size_t flag_index(const CodeView& v, int y, int x)
 {
-    return ((size_t)(y / (v.blk_items * 4)) * v.blocks_x + (x >> 6)) * 16 + ((y >> 2) % v.blk_items);
+    return ((size_t)(y >> (v.blk_shift + 2)) * v.blocks_x + (x >> 6)) * 16 + ((y >> 2) & ((1 << v.blk_shift) - 1));
 }
 
 __device__ __forceinline__ unsigned key_at(const CodeView& v, int y, int x)
@@ -563,7 +549,7 @@ __device__ __forceinline__ CodeView code_view(const BlkArgs& a, int b)
     v.codes = reinterpret_cast<const unsigned short*>(ws + a.o_codes);
     v.sflags = reinterpret_cast<const unsigned char*>(ws + a.o_sflags);
     v.keylut = reinterpret_cast<const uint32_t*>(a.rs + (size_t)b * a.rs_stride + a.R.keylut);
-    v.W = a.W; v.blocks_x = a.blocks_x; v.blk_items = a.blk_items; v.cls_off = a.cls_off;
+    v.W = a.W; v.blocks_x = a.blocks_x; v.blk_shift = a.blk_shift; v.cls_off = a.cls_off;
     return v;
 }
 
@@ -576,28 +562,18 @@ __global__ void __launch_bounds__(256)
 rle_block_mark_kernel(const BlkArgs a)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
     const unsigned groups = (a.crop_w + 255) / 256;
     const unsigned srows = (a.crop_h + 3) / 4;
-    const unsigned per_slice = srows * groups;
-    const unsigned items = per_slice * a.B;                             // host: < 2^31
+    const unsigned item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // one item per warp, one slice per grid plane
+    if (item >= srows * groups) return;                                 // warp-uniform
     const int wd = a.R.wd;
-    int cur_b = -1;
-    unsigned bgkey = 0, key0 = 0;
-    CodeView v;
-    char* rs = nullptr;
-    for (unsigned it = warp_global; it < items; it += n_warps) {
-        const int b = (int)(it / per_slice);
-        const unsigned r = it - (unsigned)b * per_slice;
-        const int sy = (int)(r / groups), g = (int)(r % groups);
-        if (b != cur_b) {                                               // warp-uniform
-            cur_b = b;
-            v = code_view(a, b);
-            rs = a.rs + (size_t)b * a.rs_stride;
-            bgkey = __ldg(v.keylut + a.cls_off);                        // class-0 background
-            key0 = __ldg(v.keylut);                                     // void
-        }
+    const int b = blockIdx.z;
+    const CodeView v = code_view(a, b);
+    char* rs = a.rs + (size_t)b * a.rs_stride;
+    const unsigned bgkey = __ldg(v.keylut + a.cls_off);                 // class-0 background
+    const unsigned key0 = __ldg(v.keylut);                              // void
+    const int sy = (int)(item / groups), g = (int)(item - (unsigned)sy * groups);
+    {
         const int y0 = sy * 4;
         const int xb = g * 256, x0 = xb + lane * 8;
         const bool inside = x0 < a.crop_w;
@@ -607,7 +583,7 @@ rle_block_mark_kernel(const BlkArgs a)
         // ---- round trip 1: strip flags
         const bool flagged = inside && v.sflags[flag_index(v, y0, x0)] != 0;
         const bool eflagged = edge && v.sflags[flag_index(v, y0, ex)] != 0;
-        if (bgkey == 0u && __all_sync(0xffffffffu, flagged || !inside)) continue;      // nothing selected in this item
+        if (bgkey == 0u && __all_sync(0xffffffffu, flagged || !inside)) return;        // nothing selected in this item
         // ---- round trip 2: codes of the 4 rows (and of the edge pixels)
         uint4 raw[4];
         unsigned ecode[4];
@@ -651,6 +627,10 @@ rle_block_mark_kernel(const BlkArgs a)
                 unsigned right = __shfl_down_sync(0xffffffffu, w[0] & 0xFFFFu, 1);
                 if (lane == 0) left = edge ? ecode[rr] : kClsBase16;    // outside the image: background, never selected
                 if (lane == 31) right = edge ? ecode[rr] : kClsBase16;
+                // a row segment of one code (the inside of an instance, background between instances) has no boundary
+                const bool flat = w[0] == w[1] && w[1] == w[2] && w[2] == w[3] && w[0] == __funnelshift_l(w[0], w[0], 16) &&
+                                  left == (w[0] & 0xFFFFu) && right == (w[0] & 0xFFFFu);
+                if (__all_sync(0xffffffffu, flat)) continue;            // warp-uniform
                 // bit p of sb / eb: pixel p differs from its left / right neighbour
                 unsigned sb = 0, eb = 0;
 #pragma unroll
@@ -686,7 +666,7 @@ rle_block_mark_kernel(const BlkArgs a)
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 if (lane == 0 && cnt) atomicAdd(reinterpret_cast<uint32_t*>(rs + a.R.rowcnt) + y, cnt);
             }
-            continue;
+            return;
         }
         // ---- void is a selected label (it may share its key with a stuff class or an instance): compare keys, pixel by pixel
 #pragma unroll
@@ -1331,7 +1311,6 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         if (P.th.v[i] >= 0 && P.th.v[i] < 64) thing_bits |= 1ull << P.th.v[i];
         else things_small = false;
     }
-    const int sms = device_sm_count();
     if (things_small && cfg->W % 16 == 0 && (reinterpret_cast<uintptr_t>(sem8) & 15u) == 0 && sem8_stride % 16 == 0) {
         EMP_CUDA_CHECK(cudaMemset2DAsync(ws, P.Lm.total, 0, P.Lm.zero_bytes, (size_t)B, st));
         LeanArgs m;
@@ -1340,15 +1319,16 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         m.ws = ws; m.ws_stride = P.Lm.total;
         m.o_votes = P.Lm.votes; m.o_areas = P.Lm.areas; m.o_sflags = P.Lm.sflags; m.o_codes = P.Lm.codes;
         m.B = B; m.H = cfg->H; m.W = cfg->W; m.wc = cfg->w; m.shift = cfg->shift;
-        m.blocks_x = (cfg->W + 63) / 64; m.blk_items = assign_block_items(cfg->H, cfg->W);
+        m.blocks_x = (cfg->W + 63) / 64;
+        m.blk_shift = 0;
+        while ((1 << m.blk_shift) < assign_block_items(cfg->H, cfg->W)) ++m.blk_shift;     // strips per block: a power of two
         m.T = P.th.n > 0 ? P.th.n : 1; m.thing_bits = thing_bits;
         m.simple = (P.th.n == 1 && P.th.v[0] > 0 && cfg->shift >= 2) ? 1 : 0;
         m.thing_class = P.th.n == 1 ? (unsigned)P.th.v[0] : 0u;
-        const size_t items = (size_t)B * ((cfg->H + 3) / 4) * ((cfg->W + 511) / 512);
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 8));
+        const unsigned items = (unsigned)(((cfg->H + 3) / 4) * ((cfg->W + 511) / 512));
         {
             ProfScope ps(ST_ASSIGN, st);
-            merge_lean_kernel<<<grid, 256, 0, st>>>(m);
+            merge_lean_kernel<<<dim3((items + 7) / 8, 1, B), 256, 0, st>>>(m);
         }
         EMP_CUDA_CHECK(cudaGetLastError());
         if ((rc = build_luts_batched(B, cfg->H, cfg->W, P.th, cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev,
@@ -1366,7 +1346,8 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     a.cs = cs; a.cs_stride = P.Lc.total; a.o_cstatus = P.Lc.status;
     a.rs = rs; a.rs_stride = P.R.total; a.R = P.R; a.rc = P.rc;
     a.B = B; a.W = cfg->W; a.crop_h = cfg->crop_h; a.crop_w = cfg->crop_w;
-    a.blk_items = assign_block_items(cfg->H, cfg->W);
+    a.blk_shift = 0;
+    while ((1 << a.blk_shift) < assign_block_items(cfg->H, cfg->W)) ++a.blk_shift;
     a.blocks_x = (cfg->W + 63) / 64;
     a.cls_off = (unsigned)P.Lm.cls_off;
     a.k_cap = cfg->k_cap; a.run_cap = cfg->run_cap; a.inst_cap = cfg->inst_cap;
@@ -1382,10 +1363,9 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     {
-        const size_t items = (size_t)B * ((cfg->crop_h + 3) / 4) * ((cfg->crop_w + 255) / 256);
-        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((items + 7) / 8, (size_t)sms * 8));
+        const unsigned items = (unsigned)(((cfg->crop_h + 3) / 4) * ((cfg->crop_w + 255) / 256));
         ProfScope ps(ST_BLK_MARK, st);
-        rle_block_mark_kernel<<<grid, 256, 0, st>>>(a);
+        rle_block_mark_kernel<<<dim3((items + 7) / 8, 1, B), 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
     {
