@@ -409,9 +409,9 @@ def main():
         t0 = time.time()
         slices = bs.make_slices(dev, 2048)
         log(f'[rank {rank}] stack: {len(slices)} distinct slices ready in {time.time() - t0:.1f} s')
-        stack_rec, s_out_, _, _ = bs.run_stack(dev, rank, world, slices, 512, 2048, ks=3, repeats=3, profile=(world == 1))
+        stack_rec, s_out_, _, _ = bs.run_stack(dev, rank, world, slices, 512, 2048, ks=3, repeats=5, profile=(world == 1))
         if world > 1:
-            bs.add_parity(stack_rec, s_out_, dev, rank, world, slices, 512, 2048, 3, 32, 4096)
+            bs.add_parity(stack_rec, s_out_, dev, rank, world, slices, 512, 2048, 3, 0, 4096)
         peak_, _src = measured_peak()
         stack_rec['roofline'] = {'bound': 'hbm', 'alg_bytes_per_voxel': bs.ALG_BYTES_PER_VOXEL,
                                  'achieved': bs.ALG_BYTES_PER_VOXEL * stack_rec['value'] / 1e9 / world, 'peak': peak_, 'unit': 'GB/s per GPU',

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <vector>
 #include "rle_common.cuh"
 
 namespace emp {
@@ -499,6 +500,7 @@ struct BlkArgs {
     int vec;                                // 16-byte code loads allowed
     long long* packed;                      // EMP_BLK_* layout
     long long* runs3; size_t runs3_stride;  // optional (start, length, slot) row-runs per slice, int64 triples
+    long long* maxlab_all;                  // optional: per-class maxima accumulated over the blocks of a z-block
 };
 
 // label LUT -> run keys: 0 if the label belongs to no selected class, else (class index + 1) << 22 | (label - base)
@@ -1134,8 +1136,10 @@ rle_block_pack_kernel(const BlkArgs a)
             if (a.rc.label[ci] == cls) atomicMax(reinterpret_cast<unsigned long long*>(s_max + ci), (unsigned long long)(lab - a.rc.lo[ci]));
     }
     __syncthreads();
-    if (tid < a.rc.n && s_max[tid] > 0)
+    if (tid < a.rc.n && s_max[tid] > 0) {
         atomicMax(reinterpret_cast<unsigned long long*>(hdr + EMP_BLK_HDR_MAXLAB + tid), (unsigned long long)s_max[tid]);
+        if (a.maxlab_all) atomicMax(reinterpret_cast<unsigned long long*>(a.maxlab_all + tid), (unsigned long long)s_max[tid]);
+    }
     if (tid == 0) {
         const int32_t* cstat = reinterpret_cast<const int32_t*>(a.cs + (size_t)b * a.cs_stride + a.o_cstatus);
         const int32_t* mstat = reinterpret_cast<const int32_t*>(a.ws + (size_t)b * a.ws_stride + a.o_status);
@@ -1279,10 +1283,10 @@ EMP_API size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B)
            (size_t)B * (2 * (size_t)cfg->run_cap + (size_t)EMP_BLK_INST_WORDS * cfg->inst_cap);
 }
 
-EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
                             size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
                             void* scratch, size_t scratch_bytes, int64_t* packed_out, size_t packed_words, int64_t* runs3_out,
-                            void* stream)
+                            int64_t* maxlab_all, void* stream)
 {
     BlockPlan P;
     int rc = plan_block(cfg, B, &P);
@@ -1354,6 +1358,7 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     a.vec = (cfg->W % 8 == 0);
     a.packed = reinterpret_cast<long long*>(packed_out);
     a.runs3 = reinterpret_cast<long long*>(runs3_out); a.runs3_stride = 3 * (size_t)cfg->run_cap;
+    a.maxlab_all = reinterpret_cast<long long*>(maxlab_all);
 
     EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
     EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
@@ -1392,5 +1397,53 @@ EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         rle_block_pack_kernel<<<B, 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
+    return EMP_OK;
+}
+
+EMP_API int emp_stack_block(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+                            size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
+                            void* scratch, size_t scratch_bytes, int64_t* packed_out, size_t packed_words, int64_t* runs3_out,
+                            void* stream)
+{
+    return stack_block_impl(cfg, B, sem8, sem8_stride, hm, hm_stride, off, off_stride, need, need_stride, scratch, scratch_bytes,
+                            packed_out, packed_words, runs3_out, nullptr, stream);
+}
+
+// n slices as ceil(n / SB) blocks, each followed by the device -> host copy of the first host_words words of its packed
+// tables on copy_stream and by an 8-byte copy of its header word 0 (= B, never 0) into host_flags[block]: copies on
+// one stream land in order, so a host thread that sees host_flags[block] != 0 may parse host_out[block].
+EMP_API int emp_stack_blocks(const emp_stack_cfg* cfg, int n, int SB, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+                             size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
+                             void* scratch, size_t scratch_bytes, int64_t* packed_all, size_t packed_words, int64_t* runs3_all,
+                             int64_t* maxlab_all, int64_t* host_out, size_t host_stride, size_t host_words,
+                             int64_t* host_flags, void* stream, void* copy_stream)
+{
+    EMP_REQUIRE(n >= 1 && SB >= 1, EMP_ERR_INVALID, "bad block sizes (n=%d, SB=%d)", n, SB);
+    EMP_REQUIRE(packed_all && host_out && host_flags && copy_stream, EMP_ERR_INVALID, "null pointer");
+    EMP_REQUIRE(host_words >= (size_t)EMP_BLK_HDR_WORDS && host_words <= host_stride && host_words <= packed_words, EMP_ERR_INVALID,
+                "bad host copy size");
+    static thread_local std::vector<cudaEvent_t> events;        // reused from call to call; never destroyed
+    cudaStream_t st = static_cast<cudaStream_t>(stream), cs = static_cast<cudaStream_t>(copy_stream);
+    const int n_sub = (n + SB - 1) / SB;
+    while ((int)events.size() < n_sub) {
+        cudaEvent_t e;
+        EMP_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        events.push_back(e);
+    }
+    for (int bi = 0; bi < n_sub; ++bi) {
+        const int i0 = bi * SB, B = std::min(SB, n - i0);
+        int64_t* packed = packed_all + (size_t)bi * packed_words;
+        const int rc = stack_block_impl(cfg, B, sem8 + (size_t)i0 * sem8_stride, sem8_stride, hm + (size_t)i0 * hm_stride, hm_stride,
+                                        off + (size_t)i0 * off_stride, off_stride, need ? need + (size_t)i0 * need_stride : nullptr,
+                                        need_stride, scratch, scratch_bytes, packed, packed_words,
+                                        runs3_all ? runs3_all + (size_t)i0 * 3 * cfg->run_cap : nullptr, maxlab_all, stream);
+        if (rc) return rc;
+        EMP_CUDA_CHECK(cudaEventRecord(events[bi], st));
+        EMP_CUDA_CHECK(cudaStreamWaitEvent(cs, events[bi], 0));
+        const size_t full = emp_stack_block_packed_words(cfg, B);
+        EMP_CUDA_CHECK(cudaMemcpyAsync(host_out + (size_t)bi * host_stride, packed, sizeof(int64_t) * std::min(host_words, full),
+                                       cudaMemcpyDeviceToHost, cs));
+        EMP_CUDA_CHECK(cudaMemcpyAsync(host_flags + bi, packed, sizeof(int64_t), cudaMemcpyDeviceToHost, cs));
+    }
     return EMP_OK;
 }

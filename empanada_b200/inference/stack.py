@@ -62,16 +62,6 @@ _pinned = {}
 _words_per_slice = {}       # (device, H, W) -> packed words per slice seen so far (sizes the one D2H copy per sub-block)
 
 
-_lanes = {}
-
-
-def _lane_streams(device, n):
-    have = _lanes.setdefault(device.index, [])
-    while len(have) < n:
-        have.append(torch.cuda.Stream(device))
-    return have[:n]
-
-
 def _copy_stream(device):
     s = _copy_streams.get(device.index)
     if s is None:
@@ -347,7 +337,7 @@ class StackShard:
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True, chain_chunk=4096, lanes=1):
+                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True, chain_chunk=4096):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
@@ -366,7 +356,6 @@ class StackShard:
         self.block = max(1, int(block))
         self.keep_tables = bool(keep_tables)
         self.chain_chunk = max(1, int(chain_chunk))      # slices per emp_median_chain launch
-        self.lanes = max(1, int(lanes))                  # streams the sub-blocks alternate between
         self._settle = False
 
     def slices(self):
@@ -488,8 +477,8 @@ class StackShard:
         return sem8, flag
 
     def _enqueue_blocks(self, zs, sem8, dev, H, W, need=None):
-        """Phase A: one emp_stack_block call per sub-block on the current stream, each followed by ONE device->host
-        copy of its packed tables on the copy stream.  No host synchronisation."""
+        """Phase A: ONE emp_stack_blocks call for the whole z-block: per sub-block a dozen launches on the current stream
+        and one device->host copy of its packed tables on the copy stream.  No host synchronisation."""
         from empanada_b200 import _cabi as C
         from empanada_b200.inference import postprocess as pp
         e, L = self.engine, C.lib()
@@ -515,65 +504,36 @@ class StackShard:
         scratch_bytes = int(L.emp_stack_block_scratch_bytes(ctypes.byref(cfg), SB))
         if packed_words == 0 or scratch_bytes == 0:
             raise ValueError('bad arguments to emp_stack_block: ' + L.emp_last_error().decode(errors='replace'))
+        scratch = C.workspace(dev, scratch_bytes, 'stack_block')
         packed = torch.empty((n_sub, packed_words), dtype=torch.int64, device=dev)
         runs_all = torch.empty((n, run_cap, 3), dtype=torch.int64, device=dev) if self.keep_tables else None
-        main = torch.cuda.current_stream(dev)
-        side = _copy_stream(dev)
-        # Sub-blocks alternate between `lanes` streams, each with its own scratch: half of a sub-block's launches are
-        # small latency-bound kernels (centers, cell index, LUTs, the run-stage kernels) that leave the SMs mostly idle;
-        # the other lane's streaming kernels fill them.
-        lanes = _lane_streams(dev, min(self.lanes, n_sub))
-        start = torch.cuda.Event()
-        start.record(main)
-        counts = [torch.zeros((nl,), dtype=torch.int64, device=dev) for _ in lanes]
-        scratch = []
-        for st in lanes:
-            st.wait_event(start)
-            with torch.cuda.stream(st):
-                scratch.append(C.workspace(dev, scratch_bytes, 'stack_block'))
+        maxlab = torch.zeros((C.MAX_LABELS,), dtype=torch.int64, device=dev)
+        hm, hm_stride = _batched([_f32c(self.heads[z]['ctr_hmp']) for z in zs])          # one gather for the whole block
+        off, off_stride = _batched([_f32c(self.heads[z]['offsets']) for z in zs])
+        C.require_cuda(hm, off)
+        # one pinned buffer: n_sub table areas of host_words each (sized from what the data needed so far), then n_sub flags
         fixed = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * SB
         per_slice = _words_per_slice.get((dev.index, H, W), 1 << 14)
-        subs = []
+        host_words = min(packed_words, fixed + SB * int(per_slice * 1.25))
+        host = _pinned_words(dev, 'tables', n_sub * (host_words + 1))
+        flags = host[n_sub * host_words:n_sub * host_words + n_sub]
+        flags.zero_()
+        main = torch.cuda.current_stream(dev)
+        side = _copy_stream(dev)
+        vp = ctypes.c_void_p
         with torch.cuda.device(dev):
-            for bi in range(n_sub):
-                i0 = bi * SB
-                B = min(SB, n - i0)
-                li = bi % len(lanes)
-                st = lanes[li]
-                with torch.cuda.stream(st):
-                    hm, hm_stride = _batched([_f32c(self.heads[z]['ctr_hmp']) for z in zs[i0:i0 + B]])
-                    off, off_stride = _batched([_f32c(self.heads[z]['offsets']) for z in zs[i0:i0 + B]])
-                    C.require_cuda(hm, off)
-                    C.check(L.emp_stack_block(ctypes.byref(cfg), B, ctypes.c_void_p(sem8[i0].data_ptr()), H * W,
-                                              ctypes.c_void_p(hm.data_ptr()), hm_stride, ctypes.c_void_p(off.data_ptr()), off_stride,
-                                              ctypes.c_void_p(need[i0].data_ptr()) if need is not None else None,
-                                              need.shape[1] if need is not None else 0,
-                                              ctypes.c_void_p(scratch[li].data_ptr()), scratch[li].numel(),
-                                              ctypes.c_void_p(packed[bi].data_ptr()), packed_words,
-                                              ctypes.c_void_p(runs_all[i0].data_ptr()) if runs_all is not None else None,
-                                              ctypes.c_void_p(st.cuda_stream)))
-                    torch.maximum(counts[li], packed[bi, C.BLK_HDR_MAXLAB:C.BLK_HDR_MAXLAB + nl], out=counts[li])
-                    ready = torch.cuda.Event()
-                    ready.record(st)
-                guess = min(packed_words, fixed + B * int(per_slice * 1.25))
-                host = _pinned_words(dev, bi, guess)
-                done = torch.cuda.Event()
-                with torch.cuda.stream(side):
-                    side.wait_event(ready)
-                    host[:guess].copy_(packed[bi, :guess], non_blocking=True)
-                    done.record(side)
-                subs.append({'i0': i0, 'B': B, 'host': host, 'guess': guess, 'done': done, 'keep': (hm, off)})
-            for st in lanes:                                        # the block is complete when every lane is
-                fin = torch.cuda.Event()
-                fin.record(st)
-                main.wait_event(fin)
-            for c in counts[1:]:
-                torch.maximum(counts[0], c, out=counts[0])
-        counts = counts[0]
-        return subs, packed, runs_all, counts, cfg
+            C.check(L.emp_stack_blocks(ctypes.byref(cfg), n, SB, vp(sem8.data_ptr()), H * W, vp(hm.data_ptr()), hm_stride,
+                                       vp(off.data_ptr()), off_stride, vp(need.data_ptr()) if need is not None else None,
+                                       need.shape[1] if need is not None else 0, vp(scratch.data_ptr()), scratch.numel(),
+                                       vp(packed.data_ptr()), packed_words, vp(runs_all.data_ptr()) if runs_all is not None else None,
+                                       vp(maxlab.data_ptr()), vp(host.data_ptr()), host_words, host_words, vp(flags.data_ptr()),
+                                       vp(main.cuda_stream), vp(side.cuda_stream)))
+        subs = {'n_sub': n_sub, 'SB': SB, 'host': host, 'host_words': host_words, 'flags': flags.numpy(), 'keep': (hm, off, scratch)}
+        return subs, packed, runs_all, maxlab[:nl], cfg
 
     def _collect(self, zs, subs, packed, sem8, out):
-        """Phase B: wait for each sub-block's copy, take owned copies of its tables, register the slices with `out`."""
+        """Phase B: as each block's tables land in pinned memory (its flag word turns non-zero) take owned copies of them and
+        register the slices with `out` — while the GPU works on the blocks behind it."""
         from empanada_b200 import _cabi as C
         from empanada_b200.inference import postprocess as pp
         dev = packed.device
@@ -582,25 +542,33 @@ class StackShard:
         n_runs = np.zeros(n, dtype=np.int64)
         inst = [None] * n
         worst = 0
-        for bi, sb in enumerate(subs):
-            sb['done'].synchronize()
-            words = sb['host'].numpy()
-            need = _BlockTables.words_needed(words, sb['B'])
-            if need > sb['guess']:                                  # the guess was short: fetch the rest (rare)
-                host = _pinned_words(dev, bi, need)
-                host[:need].copy_(packed[bi, :need])
-                words = host.numpy()
-            t = _BlockTables(words, sb['B'])
-            worst = max(worst, (need - C.BLK_HDR_WORDS) // sb['B'] + 1)
-            for b in range(sb['B']):
-                i = sb['i0'] + b
-                flags = int(t.slices[b, 4])
-                if flags & (C.FLAG_K_OVERFLOW | C.FLAG_RLE_OVERFLOW):
+        SB, hw_, flags = subs['SB'], subs['host_words'], subs['flags']
+        host_np = subs['host'].numpy()
+        for bi in range(subs['n_sub']):
+            i0 = bi * SB
+            B = min(SB, n - i0)
+            spins = 0
+            while flags[bi] == 0:                                   # written by the copy engine after the block's tables
+                spins += 1
+                if spins % 4096 == 0 and _copy_stream(dev).query():  # the stream drained without the flag: a CUDA error
+                    torch.cuda.synchronize(dev)
+                    if flags[bi] == 0:
+                        raise RuntimeError('emp_stack_blocks: block tables never arrived')
+            words = host_np[bi * hw_:(bi + 1) * hw_]
+            need = _BlockTables.words_needed(words, B)
+            if need > hw_:                                          # the size guess was short: fetch the whole block (rare)
+                words = packed[bi, :need].cpu().numpy()
+            t = _BlockTables(words, B)
+            worst = max(worst, (need - C.BLK_HDR_WORDS) // B + 1)
+            for b in range(B):
+                i = i0 + b
+                fl = int(t.slices[b, 4])
+                if fl & (C.FLAG_K_OVERFLOW | C.FLAG_RLE_OVERFLOW):
                     bad[i] = True
                     out._add_dict(zs[i], _slice_sync(self.engine, self.heads[zs[i]], sem8[i].view(1, 1, *self._plane), self.labels,
                                                      self.upsampling, self.force_connected))
                     continue
-                pp._check_flags(flags)
+                pp._check_flags(fl)
                 out._add(zs[i], t, b)
                 n_runs[i] = int(t.slices[b, 3])
                 inst[i] = out.inst_rows(zs[i])
@@ -753,7 +721,9 @@ class StackShard:
             hh, ww, _ = self._geometry(H, W)
             need = torch.zeros((len(zs), hh * ww), dtype=torch.uint8, device=dev)
         sem8, changed = self._chain(planes, dev, H * W, Cn, need)
+        t_chain = time.perf_counter()
         subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W, need)
+        t_blocks = time.perf_counter()
         # instance counts per class (+ the "my outgoing carry moved" flag) over all ranks
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         table_h = None
@@ -761,7 +731,7 @@ class StackShard:
             mine = torch.cat([counts, (changed if changed is not None else torch.zeros((1,), dtype=torch.int32, device=dev)).to(torch.int64)])
             gathered = torch.empty((self.world, mine.numel()), dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(gathered, mine, group=self.group)
-            table_h = torch.empty(gathered.shape, dtype=torch.int64).pin_memory()
+            table_h = _pinned_words(dev, 'counts', gathered.numel())[:gathered.numel()].view(gathered.shape)
             table_h.copy_(gathered, non_blocking=True)
         t_b = time.perf_counter()
         out = RleStack(self.labels, e.thing_list, e.label_divisor)
@@ -792,7 +762,8 @@ class StackShard:
                     offs[c] = int(b)
         out.offsets = offs
         self.label_offsets_ = offs
-        self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b}
+        self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'enqueue_chain_s': t_chain - t_a, 'enqueue_blocks_s': t_blocks - t_chain,
+                        'enqueue_gather_s': t_b - t_blocks, 'after_s': time.perf_counter() - t_c}
         self.tables_shape_ = self._plane
         self.tables_ = {'runs_all': runs_all, 'n_runs': n_runs, 'bad': bad, 'inst': inst, 'zs': zs,
                         'slot_areas': [None if r is None else r[:, 8] for r in inst]}

@@ -289,6 +289,19 @@ int emp_rle_list_overlaps(const int64_t* runs_a, int n_a, int64_t lmax_a, const 
 int emp_fill_runs(const int64_t* runs, size_t run_stride, const int32_t* n_runs, int n_slices, int max_runs,
                   const int64_t* labels, size_t label_stride, void* out, int elem_bytes, size_t plane, void* stream);
 
+/* A whole z-block through emp_stack_block, SB slices at a time, in ONE call: block j = slices [j * SB, ...) writes its
+ * packed tables to packed_all + j * packed_words, and the first host_words words of them are copied to the PINNED host
+ * buffer host_out + j * host_stride on copy_stream while the next block runs on stream; then header word 0 of the block
+ * (its slice count, never 0) is copied to host_flags[j] (pinned, zeroed by the caller): copies on one stream land in
+ * order, so a host thread that reads host_flags[j] != 0 may parse block j.  If the header says the block holds more than
+ * host_words words, the caller fetches the rest from packed_all.  maxlab_all (device, EMP_MAX_LABELS words, zeroed by the
+ * caller; may be NULL) accumulates the per-class maxima of the blocks' headers — what the z-sharded stack all-gathers. */
+int emp_stack_blocks(const emp_stack_cfg* cfg, int n, int SB, const uint8_t* sem8, size_t sem8_stride, const float* hm,
+                     size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
+                     void* scratch, size_t scratch_bytes, int64_t* packed_all, size_t packed_words, int64_t* runs3_all,
+                     int64_t* maxlab_all, int64_t* host_out /* pinned host */, size_t host_stride, size_t host_words,
+                     int64_t* host_flags /* pinned host */, void* stream, void* copy_stream);
+
 #ifdef __cplusplus
 }
 #endif
