@@ -257,7 +257,7 @@ def main():
     ap.add_argument('--dense', action='store_true', help='BASELINE configs[4] as the main workload: ~5000 instances of semi-axes 4..12 px per tile')
     ap.add_argument('--no-stack', action='store_true', help='skip the configs[2] stack sub-record')
     ap.add_argument('--no-dense', action='store_true', help='skip the configs[4] dense sub-record (N = 1)')
-    ap.add_argument('--dense-tiles', type=int, default=4)
+    ap.add_argument('--dense-tiles', type=int, default=8)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -409,7 +409,7 @@ def main():
         t0 = time.time()
         slices = bs.make_slices(dev, 2048)
         log(f'[rank {rank}] stack: {len(slices)} distinct slices ready in {time.time() - t0:.1f} s')
-        stack_rec, s_out_, _, _ = bs.run_stack(dev, rank, world, slices, 512, 2048, ks=3, repeats=5, profile=(world == 1))
+        stack_rec, s_out_, _, _ = bs.run_stack(dev, rank, world, slices, 512, 2048, ks=3, repeats=5, warmup=4, profile=(world == 1))
         if world > 1:
             bs.add_parity(stack_rec, s_out_, dev, rank, world, slices, 512, 2048, 3, 0, 4096)
         peak_, _src = measured_peak()
