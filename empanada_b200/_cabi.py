@@ -42,6 +42,8 @@ _SIGNATURES = {
     'emp_host_sem_bytes_per_px': (ctypes.c_double, []),
     'emp_panoptic_batched_host': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
                                          _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
+    'emp_panoptic_batched_host_u8': (_i32, [_i32, _vp, _vp, _vp, _i32, _i32, _vp, _i32, _i64, _i64, _i64,
+                                            _f32, _i32, _vp, _vp, _vp, _i32, _vp, _sz]),
     'emp_median_harden': (_i32, [_vp, _i32, _i32, _i32, _i32, _f32, _vp, _vp, _i32, _vp]),
     'emp_median_chain': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _f32, _vp, _sz, _vp, _vp, _vp, _vp]),
     'emp_median_chain_repair': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _sz, _vp, _vp, _f32, _vp, _sz, _vp, _vp, _vp, _vp]),

@@ -87,11 +87,16 @@ fill_runs_kernel(const long long* __restrict__ runs, size_t run_stride, const in
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int j = warp_global; j < n; j += n_warps) {
-        const long long start = __ldg(R + 3 * (size_t)j), len = __ldg(R + 3 * (size_t)j + 1);
-        const long long v = __ldg(lab + __ldg(R + 3 * (size_t)j + 2));
+        long long start = __ldg(R + 3 * (size_t)j), end = start + __ldg(R + 3 * (size_t)j + 1);
+        const long long slot = __ldg(R + 3 * (size_t)j + 2);
+        if (slot < 0 || (size_t)slot >= label_stride) continue;            // no such instance: nothing to paint
+        const long long v = __ldg(lab + slot);
         if (v < 0) continue;
+        // numpy's volume[s:e] = id clips silently: so does this (runs of a tracker loaded for another shape ...)
+        start = max(start, 0ll);
+        end = min(end, (long long)plane);
         const T tv = (T)v;
-        for (long long i = lane; i < len; i += 32) dst[start + i] = tv;     // consecutive lanes, consecutive voxels
+        for (long long i = start + lane; i < end; i += 32) dst[i] = tv;     // consecutive lanes, consecutive voxels
     }
 }
 

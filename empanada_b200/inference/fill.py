@@ -17,7 +17,7 @@ import torch
 
 from empanada_b200 import _cabi as C
 
-__all__ = ['fill_instances', 'fill_block']
+__all__ = ['fill_instances', 'fill_slabs', 'fill_block']
 
 
 def _elem_bytes(t):
@@ -37,6 +37,35 @@ def _launch(runs, n_runs_dev, max_runs, labels, out2d, device):
                                       C.stream_ptr(device)))
 
 
+def _run_table(instances):
+    """(table (n, 3) int64 rows (start, length, slot), labels list) of a dict {label: {'starts', 'runs'}}; slots number
+    the instances in dict order."""
+    starts = [np.asarray(a['starts'], np.int64) for a in instances.values()]
+    lens = [np.asarray(a['runs'], np.int64) for a in instances.values()]
+    slot = np.repeat(np.arange(len(starts), dtype=np.int64), [len(s) for s in starts])
+    table = np.stack([np.concatenate(starts), np.concatenate(lens), slot], 1) if slot.size else np.zeros((0, 3), np.int64)
+    return table, [int(lab) for lab in instances.keys()]
+
+
+def _paint(flat, table, labels, dev):
+    """Paint the runs of `table` (flat indices into the (1, n) CUDA tensor `flat`) with labels[slot].  Runs outside the
+    tensor are clipped (the kernel clamps too).  Overlapping instances are painted in slot order, one launch per
+    instance, so that later ones win as in the reference's loop."""
+    if table.shape[0] == 0:
+        return
+    lab = torch.tensor([labels], dtype=torch.int64, device=dev)
+    s_sorted = np.argsort(table[:, 0], kind='stable')
+    ends = table[s_sorted, 0] + table[s_sorted, 1]
+    overlapping = bool((table[s_sorted, 0][1:] < np.maximum.accumulate(ends)[:-1]).any())
+    groups = [table] if not overlapping else [table[table[:, 2] == i] for i in range(len(labels))]
+    for g in groups:
+        if g.shape[0] == 0:
+            continue
+        runs = torch.from_numpy(np.ascontiguousarray(g[None])).to(dev)
+        n_runs = torch.tensor([g.shape[0]], dtype=torch.int32, device=dev)
+        _launch(runs, n_runs, g.shape[0], lab, flat, dev)
+
+
 def fill_instances(volume, instances):
     """Fill a CUDA tensor `volume` (any shape, int64 / int32 / uint32, contiguous) in place with run
     length encoded instances {label: {'starts': ..., 'runs': ...}} and return it.  Later instances
@@ -45,26 +74,55 @@ def fill_instances(volume, instances):
     assert volume.is_contiguous()
     if len(instances) == 0:
         return volume
-    flat = volume.view(1, -1)
-    order = {lab: i for i, lab in enumerate(instances.keys())}
-    starts = [np.asarray(a['starts'], np.int64) for a in instances.values()]
-    lens = [np.asarray(a['runs'], np.int64) for a in instances.values()]
-    slot = np.repeat(np.arange(len(starts), dtype=np.int64), [len(s) for s in starts])
-    table = np.stack([np.concatenate(starts), np.concatenate(lens), slot], 1) if slot.size else np.zeros((0, 3), np.int64)
+    table, labels = _run_table(instances)
+    _paint(volume.view(1, -1), table, labels, dev)
+    return volume
+
+
+def fill_slabs(volume, instances, max_slab_bytes=1 << 30, device=None):
+    """Fill a HOST-side (d, h, w) volume in place — a numpy array or anything sliceable along z the way a zarr array
+    is (``volume[z0:z1]`` reads / writes a slab; ``.chunks[0]`` gives the preferred slab height) — one z-slab at a
+    time: the slab's part of every run is painted in HBM (emp_fill_runs) and written back.  Only one slab is ever
+    resident, so volumes larger than the GPU's (or the host's) memory work, as with the reference's chunk-wise zarr
+    fill (zarr_utils.py:88-175)."""
+    if len(instances) == 0:
+        return volume
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    d, h, w = (int(v) for v in volume.shape)
+    plane = h * w
+    itemsize = np.dtype(volume.dtype).itemsize
+    dz = max(1, int(max_slab_bytes // max(plane * max(itemsize, 4), 1)))
+    zc = int(volume.chunks[0]) if hasattr(volume, 'chunks') else 1
+    if dz >= zc:
+        dz -= dz % zc                                              # whole chunks per slab: every chunk is written once
+    dz = max(1, min(dz, d))
+    table, labels = _run_table(instances)
     if table.shape[0] == 0:
         return volume
-    labels = torch.tensor([[int(lab) for lab in order]], dtype=torch.int64, device=dev)
-    # overlapping instances: paint in dict order, one launch per instance, only if any overlap exists
-    s_sorted = np.argsort(table[:, 0], kind='stable')
-    ends = table[s_sorted, 0] + table[s_sorted, 1]
-    overlapping = bool((table[s_sorted, 0][1:] < np.maximum.accumulate(ends)[:-1]).any())
-    groups = [table] if not overlapping else [table[slot == i] for i in range(len(starts))]
-    for g in groups:
-        if g.shape[0] == 0:
+    s_all, e_all = table[:, 0], table[:, 0] + table[:, 1]
+    for z0 in range(0, d, dz):
+        z1 = min(d, z0 + dz)
+        a, b = z0 * plane, z1 * plane
+        keep = (e_all > a) & (s_all < b)
+        if not keep.any():
             continue
-        runs = torch.from_numpy(np.ascontiguousarray(g[None])).to(dev)
-        n_runs = torch.tensor([g.shape[0]], dtype=torch.int32, device=dev)
-        _launch(runs, n_runs, g.shape[0], labels, flat, dev)
+        s_c = np.maximum(s_all[keep], a) - a
+        e_c = np.minimum(e_all[keep], b) - a
+        sub = np.stack([s_c, e_c - s_c, table[keep, 2]], 1)
+        slab = np.ascontiguousarray(volume[z0:z1])
+        kind = slab.dtype
+        if kind.kind not in 'iu':
+            raise Exception(f'Unsupported volume dtype {kind}')
+        if kind.itemsize >= 4:
+            carrier = np.int32 if kind.itemsize == 4 else np.int64
+            t = torch.from_numpy(slab.view(carrier)).to(device)
+            _paint(t.view(1, -1), sub, labels, device)
+            volume[z0:z1] = t.cpu().numpy().view(kind)
+        else:                                                       # narrow volumes are painted as int32 and narrowed back
+            t = torch.from_numpy(slab.astype(np.int32)).to(device)
+            _paint(t.view(1, -1), sub, labels, device)
+            volume[z0:z1] = t.cpu().numpy().astype(kind)
     return volume
 
 

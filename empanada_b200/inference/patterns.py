@@ -22,7 +22,7 @@ import torch.distributed as dist
 from empanada_b200.consensus import merge_objects_from_trackers, merge_semantic_from_trackers
 from empanada_b200.inference import filters
 from empanada_b200.inference.engines import _MedianQueue, median_harden
-from empanada_b200.inference.fill import fill_instances
+from empanada_b200.inference.fill import fill_instances, fill_slabs
 from empanada_b200.inference.matcher import RLEMatcher
 from empanada_b200.inference.postprocess import merge_semantic_and_instance
 from empanada_b200.inference.rle import pan_seg_to_rle_seg, rle_seg_to_pan_seg  # noqa: F401
@@ -143,30 +143,20 @@ def create_semantic_consensus(class_trackers, pixel_vote_thr=2):
 
 
 # ---- filling (patterns.py:204-222) ---------------------------------------------------------------------
-def _device_image(volume):
-    """numpy volume -> (CUDA tensor of a dtype emp_fill_runs paints, function mapping it back to volume.dtype).
-    4- and 8-byte integers travel as their own bit patterns, narrower ones are widened to int32."""
-    a = np.ascontiguousarray(volume)
-    if a.dtype.kind not in 'iu':
-        raise Exception(f'Unsupported volume dtype {a.dtype}')
-    if a.dtype.itemsize >= 4:
-        carrier = np.int32 if a.dtype.itemsize == 4 else np.int64
-        return torch.from_numpy(a.view(carrier)).cuda(), lambda t: t.cpu().numpy().view(a.dtype)
-    return torch.from_numpy(a.astype(np.int32)).cuda(), lambda t: t.cpu().numpy().astype(a.dtype)
-
-
 def fill_volume(volume, instances, processes=4):
-    """Paint run-length encoded instances into `volume` in place: a CUDA tensor is painted where it is; a
-    numpy array goes through HBM (upload, emp_fill_runs, download into the same array).  `processes` is
-    accepted for signature compatibility (the reference uses it for zarr stores only)."""
+    """Paint run-length encoded instances into `volume` in place (patterns.py:160-172 -> array_utils.numpy_fill_instances /
+    zarr_utils.zarr_fill_instances).  A CUDA tensor is painted where it is.  A numpy array or a zarr array (anything
+    with .shape / .dtype that reads and writes z-slabs by slicing) is filled one z-slab at a time through HBM, whole
+    z-chunks per slab for chunked stores, so the volume never has to fit into GPU memory.  `processes` (the
+    reference's pool size for zarr stores) is accepted and unused: the painting is one kernel launch per slab."""
     if torch.is_tensor(volume):
         fill_instances(volume, instances)
-    elif isinstance(volume, np.ndarray):
+    elif isinstance(volume, np.ndarray) or (hasattr(volume, 'shape') and hasattr(volume, 'dtype') and hasattr(volume, '__setitem__')):
         if len(instances) == 0:
             return
-        t, back = _device_image(volume)
-        fill_instances(t, instances)
-        volume[...] = back(t)
+        if len(volume.shape) != 3:
+            raise Exception(f'Expected a (d, h, w) volume, got shape {tuple(volume.shape)}')
+        fill_slabs(volume, instances)
     else:
         raise Exception(f'Unknown volume type of {type(volume)}')
 

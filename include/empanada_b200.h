@@ -141,9 +141,13 @@ int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float* hm, co
  * until the batch is complete.  k_out (host, B int32) receives K per tile, flags_out the flags.
  * The link is the bound of this entry, so sem is narrowed to one byte per pixel on the host (worker
  * threads, pinned staging owned by the library) before it crosses; a tile with a class id outside
- * [0, 255] travels as int64.  EMP_HOST_THREADS sets the worker count (0: no narrowing; default: host
- * threads / visible GPUs, at most 8).  emp_host_sem_bytes_per_px(): what the LAST call sent per sem
- * pixel on average (1.0 .. 8.0), for byte accounting. */
+ * [0, 255] travels as int64.  EMP_HOST_THREADS sets the worker count (0: no narrowing; default: the CPUs of
+ * the process's affinity mask — divided by the visible GPUs when the mask is the whole machine — at most 8);
+ * the workers live as long as the library.  One pipeline (streams, staging) exists per device and serves one
+ * caller at a time; on any error the call returns only after every copy it enqueued has finished.
+ * emp_host_sem_bytes_per_px(): what the LAST call sent per sem pixel on average (1.0 .. 8.0), for byte
+ * accounting.  emp_panoptic_batched_host_u8 is the same entry for callers that already hold the class map as
+ * bytes (nothing to narrow). */
 size_t emp_host_scratch_bytes(int H, int W, int k_cap, int n_things);
 double emp_host_sem_bytes_per_px(void);
 int emp_panoptic_batched_host(int B, const int64_t* sem_h, const float* hm_h, const float* off_h,
@@ -152,6 +156,12 @@ int emp_panoptic_batched_host(int B, const int64_t* sem_h, const float* hm_h, co
                               float threshold, int nms_kernel, int64_t* pan_out_h, int32_t* k_out,
                               int32_t* flags_out, int k_cap, void* dev_scratch,
                               size_t dev_scratch_bytes);
+int emp_panoptic_batched_host_u8(int B, const uint8_t* sem8_h, const float* hm_h, const float* off_h,
+                                 int H, int W, const int64_t* thing_list, int n_things,
+                                 int64_t label_divisor, int64_t stuff_area, int64_t void_label,
+                                 float threshold, int nms_kernel, int64_t* pan_out_h, int32_t* k_out,
+                                 int32_t* flags_out, int k_cap, void* dev_scratch,
+                                 size_t dev_scratch_bytes);
 
 /* _MedianQueue.get_median + _harden_seg — engines.py:59-66, :114-121.
  * Median (middle order statistic) over ks odd planes of (C,H,W) float32, optionally written back

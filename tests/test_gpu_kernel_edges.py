@@ -152,6 +152,62 @@ def test_dense_full_size_properties(cuda_device):
     np.testing.assert_array_equal(ctr[0].cpu().numpy(), oracle.find_instance_center(d['ctr_hmp'][0, 0], 0.1, 7))
 
 
+def test_dense_full_size_oracle(cuda_device):
+    """BASELINE config 5 at full size, bit for bit: one 4096^2 tile with ~5000 small instances against the oracle
+    (its masked brute-force search meets every one of the ~5000 centers at every thing pixel: ~10^10 distances)."""
+    H = W = 4096
+    d = synth_tile(H, W, 5000, seed=502, semi_axes=(4, 12), sigma=2.0)
+    want_pan, want_ctr = oracle.get_panoptic_segmentation(d['sem'], d['ctr_hmp'], d['offsets'], [1], 1000, 64, 0, 0.1, 7)
+    pan, ctr = pp.get_panoptic_segmentation(*(cu(d[k], cuda_device) for k in ('sem', 'ctr_hmp', 'offsets')), [1], 1000, 64, 0, 0.1, 7)
+    np.testing.assert_array_equal(ctr.cpu().numpy(), want_ctr)
+    assert ctr.shape[1] > 3000
+    np.testing.assert_array_equal(pan.cpu().numpy(), want_pan)
+
+
+def test_host_buffer_u8_entry_and_concurrent_callers(cuda_device):
+    """emp_panoptic_batched_host_u8 (class maps already bytes on the host) gives the int64 entry's result, and two host
+    threads calling the entry at once (the pipe serves one caller at a time) both get theirs."""
+    import ctypes
+    import threading
+    from empanada_b200 import _cabi as C
+    H, W, B = 192, 256, 4
+    tiles = [synth_tile(H, W, 20 + 5 * i, seed=800 + i, semi_axes=(5, 16), sigma=3.0) for i in range(B)]
+    sem_h = torch.from_numpy(np.stack([t['sem'][0, 0] for t in tiles])).pin_memory()
+    sem8_h = sem_h.to(torch.uint8).pin_memory()
+    hm_h = torch.from_numpy(np.stack([t['ctr_hmp'][0, 0] for t in tiles])).pin_memory()
+    off_h = torch.from_numpy(np.stack([t['offsets'][0] for t in tiles])).pin_memory()
+    L = C.lib()
+    things, nt = C.i64_array([1])
+    k_cap = 4096
+    nbytes = L.emp_host_scratch_bytes(H, W, k_cap, nt)
+    want = [oracle.get_panoptic_segmentation(t['sem'], t['ctr_hmp'], t['offsets'], [1], 1000, 64, 0, 0.1, 7)[0][0, 0] for t in tiles]
+    results, errors = {}, []
+
+    def call(name, fn, sem):
+        try:
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=cuda_device)
+            pan_h = torch.empty((B, H, W), dtype=torch.int64).pin_memory()
+            k_out, f_out = (ctypes.c_int32 * B)(), (ctypes.c_int32 * B)()
+            with torch.cuda.device(cuda_device):
+                for _ in range(3):
+                    C.check(fn(B, sem.data_ptr(), hm_h.data_ptr(), off_h.data_ptr(), H, W, things, nt, 1000, 64, 0, 0.1, 7,
+                               pan_h.data_ptr(), k_out, f_out, k_cap, scratch.data_ptr(), nbytes))
+            results[name] = pan_h.numpy().copy()
+        except Exception as e:                      # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=call, args=('i64', L.emp_panoptic_batched_host, sem_h)),
+               threading.Thread(target=call, args=('u8', L.emp_panoptic_batched_host_u8, sem8_h))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for name in ('i64', 'u8'):
+        for b in range(B):
+            np.testing.assert_array_equal(results[name][b], want[b])
+
+
 def test_host_buffer_entry_point(cuda_device):
     """emp_panoptic_batched_host — the end-to-end entry bench.py times: pageable AND pinned host buffers
     in, H2D / kernels / D2H pipelined over three slots, results identical to the resident path and

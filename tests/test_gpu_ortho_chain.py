@@ -172,3 +172,50 @@ def test_multigpu_worker_loop(cuda_device):
                 assert tuple(sa[c][lab]['box']) == tuple(sb[c][lab]['box'])
                 np.testing.assert_array_equal(sa[c][lab]['starts'], sb[c][lab]['starts'])
                 np.testing.assert_array_equal(sa[c][lab]['runs'], sb[c][lab]['runs'])
+
+
+
+class _FakeZarr:
+    """The slice of zarr.Array's interface fill_volume uses: shape, dtype, chunks, z-slab reads and writes."""
+
+    def __init__(self, shape, dtype, chunks):
+        self.a = np.zeros(shape, dtype)
+        self.shape, self.dtype, self.chunks = shape, np.dtype(dtype), chunks
+        self.writes = []
+
+    def __getitem__(self, k):
+        return self.a[k]
+
+    def __setitem__(self, k, v):
+        self.writes.append(k)
+        self.a[k] = v
+
+
+@pytest.mark.parametrize('dtype', [np.uint32, np.uint16, np.int64])
+def test_fill_volume_slabs_numpy_and_zarr_like(dtype, cuda_device, monkeypatch):
+    """fill_volume on host volumes goes slab by slab through HBM (array_utils.numpy_fill_instances :725-736 /
+    zarr_utils.zarr_fill_instances :88-175): same result as the reference's flat fill, runs that cross slab borders
+    are split, runs past the end of the volume are clipped like numpy slicing clips them."""
+    from empanada_b200.inference import fill as fl, patterns
+    rng = np.random.default_rng(4)
+    shape = (11, 24, 40)
+    n = int(np.prod(shape))
+    instances = {}
+    for lab in range(1, 30):
+        starts = np.sort(rng.choice(n - 400, size=12, replace=False)).astype(np.int64)
+        runs = rng.integers(1, 300, size=12).astype(np.int64)            # many cross plane (and slab) borders
+        instances[lab] = {'starts': starts, 'runs': runs}
+    instances[99] = {'starts': np.array([n - 7], np.int64), 'runs': np.array([50], np.int64)}     # runs off the end
+    want = np.zeros(n, dtype)
+    for lab, a in instances.items():
+        for s0, r in zip(a['starts'], a['runs']):
+            want[s0:s0 + r] = lab
+    want = want.reshape(shape)
+    monkeypatch.setattr(fl.fill_slabs, '__defaults__', (3 * 24 * 40 * 4, None))       # 3 planes per slab
+    vol = np.zeros(shape, dtype)
+    patterns.fill_volume(vol, instances)
+    np.testing.assert_array_equal(vol, want)
+    z = _FakeZarr(shape, dtype, (2, 8, 8))
+    patterns.fill_volume(z, instances, processes=3)
+    np.testing.assert_array_equal(z.a, want)
+    assert all(k.start % 2 == 0 for k in z.writes)                          # whole z-chunks per slab
