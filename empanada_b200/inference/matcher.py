@@ -102,9 +102,46 @@ def _flat_runs(starts_list, runs_list):
     return np.stack([st[order], ru[order], slot[order]], 1)
 
 
+def _disjoint(table):
+    """True if no two runs of the start-ordered (start, length, slot) table overlap."""
+    if table.shape[0] < 2:
+        return True
+    ends = table[:, 0] + table[:, 1]
+    return not bool((table[1:, 0] < np.maximum.accumulate(ends)[:-1]).any())
+
+
+def _list_overlap_rows(a, b, device):
+    """emp_rle_list_overlaps (instances of one list may overlap each other) -> summed (slot_a, slot_b, inter)."""
+    L = C.lib()
+    A, B = torch.from_numpy(np.ascontiguousarray(a)).to(device), torch.from_numpy(np.ascontiguousarray(b)).to(device)
+    cap = max(4096, 4 * max(a.shape[0], b.shape[0]))
+    while True:
+        out = torch.empty((cap, 4), dtype=torch.int32, device=device)
+        count = torch.zeros(1, dtype=torch.int32, device=device)
+        with torch.cuda.device(device):
+            C.check(L.emp_rle_list_overlaps(ctypes.c_void_p(A.data_ptr()), int(a.shape[0]), int(a[:, 1].max()),
+                                            ctypes.c_void_p(B.data_ptr()), int(b.shape[0]), ctypes.c_void_p(out.data_ptr()), cap,
+                                            ctypes.c_void_p(count.data_ptr()), C.stream_ptr(device)))
+        n = int(count.item())
+        if n <= cap:
+            break
+        cap = n
+    rows = out[:n].to(torch.int64)
+    if n == 0:
+        z = np.zeros(0, np.int64)
+        return z, z, z
+    key = (rows[:, 1] << 31) | rows[:, 2]
+    uniq, inv = torch.unique(key, return_inverse=True)
+    inter = torch.zeros(uniq.shape[0], dtype=torch.int64, device=device).index_add_(0, inv, rows[:, 3])
+    uniq, inter = uniq.cpu().numpy(), inter.cpu().numpy()
+    return uniq >> 31, uniq & ((1 << 31) - 1), inter
+
+
 def pair_overlaps(target_starts, target_runs, match_starts, match_runs, device=None):
-    """(n, m) int64 matrix of pixel intersections between two lists of run-length encoded instances
-    (each list's instances mutually disjoint, as instances of one slice are)."""
+    """(n, m) int64 matrix of pixel intersections between two lists of run-length encoded instances.  The instances of
+    one slice are mutually disjoint and take the pair kernel (binary search over the target's run ends); lists whose
+    instances overlap each other — the dict API accepts anything — go through the list kernel, which does not assume
+    disjointness (array_utils.rle_intersection treats every pair independently, :371-403)."""
     if device is None:
         device = torch.device('cuda', torch.cuda.current_device())
     n, m = len(target_starts), len(match_starts)
@@ -112,6 +149,12 @@ def pair_overlaps(target_starts, target_runs, match_starts, match_runs, device=N
     if n == 0 or m == 0:
         return inter
     a, b = _flat_runs(target_starts, target_runs), _flat_runs(match_starts, match_runs)
+    if a.shape[0] == 0 or b.shape[0] == 0:
+        return inter
+    if not (_disjoint(a) and _disjoint(b)):
+        sa, sb, ov = _list_overlap_rows(a, b, device)
+        inter[sa, sb] = ov
+        return inter
     stride = max(a.shape[0], b.shape[0], 1)
     both = np.zeros((2, stride, 3), np.int64)
     both[0, :a.shape[0]] = a

@@ -138,3 +138,23 @@ def test_merge_rles_host_semantics():
     np.testing.assert_array_equal(s, [0, 30, 50])
     np.testing.assert_array_equal(r, [17, 5, 2])
     assert mt.merge_boxes((1, 5, 9, 9), (0, 6, 4, 12)) == (0, 5, 9, 12)
+
+
+def test_pair_overlaps_with_overlapping_instances(cuda_device):
+    """The dict API takes any instance lists: instances that overlap each other (merged trackers, hand-made dicts) must
+    still give the reference's per-pair intersections (array_utils.rle_intersection :371-403 treats every pair alone)."""
+    from oracle import matcher as om
+    rng = np.random.default_rng(8)
+
+    def inst(n):
+        out = []
+        for _ in range(n):
+            s = np.sort(rng.choice(4000, size=9, replace=False)).astype(np.int64)
+            r = np.minimum(rng.integers(1, 120, size=9), np.append(np.diff(s), 200)).astype(np.int64)   # disjoint inside one instance
+            out.append((s, r))
+        return out
+    A, B = inst(7), inst(5)                         # instances of A overlap each other freely, so do B's
+    want = np.array([[om.rle_intersection(sa, ra, sb, rb) for sb, rb in B] for sa, ra in A], np.int64)
+    got = mt.pair_overlaps([s for s, _ in A], [r for _, r in A], [s for s, _ in B], [r for _, r in B], cuda_device)
+    np.testing.assert_array_equal(got, want)
+    assert (want > 0).sum() > 10

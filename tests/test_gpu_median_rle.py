@@ -100,3 +100,21 @@ def test_rle_capacity_retry_and_noise(cuda_device):
     got = rle.tables_to_rle_seg(inst, runs, [1, 2])
     for a, b in zip(_flatten(got), _flatten(want)):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize('ks,C', [(3, 1), (5, 1), (3, 3)])
+def test_median_harden_propagates_nan(ks, C, cuda_device):
+    """torch.median gives NaN for a window holding one (engines.py:59-66 runs it on the queued planes), argmax treats
+    NaN as the maximum, `>= thr` is false for it: the kernel must agree plane for plane."""
+    rng = np.random.default_rng(ks * 10 + C)
+    planes = [rng.random((1, C, 17, 23), dtype=np.float32) for _ in range(ks)]
+    planes[1][0, 0, 3, 4] = np.nan
+    planes[ks - 1][0, C - 1, 9, 9] = np.nan
+    planes[0][0, 0, 9, 9] = np.nan
+    t = [torch.from_numpy(p).to(cuda_device) for p in planes]
+    med, sem = eng.median_harden(t, 0.5, want_median=True, want_sem='i64')
+    want = torch.median(torch.cat(t, dim=0), dim=0, keepdim=True).values
+    assert torch.equal(torch.isnan(med), torch.isnan(want))
+    assert torch.equal(torch.nan_to_num(med, nan=-1.0), torch.nan_to_num(want, nan=-1.0))
+    want_sem = torch.argmax(want, dim=1, keepdim=True) if C > 1 else (want >= 0.5).long()
+    assert torch.equal(sem, want_sem)
