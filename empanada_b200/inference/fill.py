@@ -94,8 +94,7 @@ def fill_slabs(volume, instances, max_slab_bytes=1 << 30, device=None):
     itemsize = np.dtype(volume.dtype).itemsize
     dz = max(1, int(max_slab_bytes // max(plane * max(itemsize, 4), 1)))
     zc = int(volume.chunks[0]) if hasattr(volume, 'chunks') else 1
-    if dz >= zc:
-        dz -= dz % zc                                              # whole chunks per slab: every chunk is written once
+    dz = max(dz - dz % zc, zc)                                     # whole chunks per slab: every chunk is written once
     dz = max(1, min(dz, d))
     table, labels = _run_table(instances)
     if table.shape[0] == 0:
