@@ -252,6 +252,7 @@ def main():
     ap.add_argument('--thr', type=float, default=THR, help='center threshold (experiments; the workload uses 0.1)')
     ap.add_argument('--dense', action='store_true', help='BASELINE configs[4] as the main workload: ~5000 instances of semi-axes 4..12 px per tile')
     ap.add_argument('--no-stack', action='store_true', help='skip the configs[2] stack sub-record')
+    ap.add_argument('--no-cnn', action='store_true', help='skip the stack loop with the stand-in CNN in it')
     ap.add_argument('--no-dense', action='store_true', help='skip the configs[4] dense sub-record (N = 1)')
     ap.add_argument('--dense-tiles', type=int, default=8)
     args = ap.parse_args()
@@ -414,7 +415,10 @@ def main():
                                  'frac': bs.ALG_BYTES_PER_VOXEL * stack_rec['value'] / 1e9 / world / peak_,
                                  'note': 'host-visible time (enqueue, kernels, D2H of the tables, collectives) against the algorithmic bytes of '
                                          'SURVEY 8d; the fused path never writes or re-reads the int64 label map those bytes include'}
-        del slices, s_out_
+        del s_out_
+        if not args.no_cnn:
+            stack_rec['with_cnn'] = bs.run_stack_with_cnn(dev, rank, world, slices, 512, 2048, 3)
+        del slices
 
     # ---- BASELINE configs[4]: dense-instance stress, a few tiles through the same fused entry point ----
     dense_rec = None

@@ -143,6 +143,91 @@ def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=0, chain_chunk=40
     return rec, out, shard, matched
 
 
+class StandInNet:
+    """A small conv net with PanopticDeepLab's output contract (full-res semantic logits, quarter-res center heat-map and
+    offsets: quantization/panoptic_deeplab.py:238-250 with coarse boundaries): the unchanged-CNN side of the stack loop.
+    Random-init heads are constants, so the synthetic head tensors are ADDED to its outputs — the forward
+    still has to run, the post-processing still sees EM-shaped data."""
+
+    def __init__(self, dev, width=64):
+        import torch
+        import torch.nn as nn
+        torch.manual_seed(0)
+        self.body = nn.Sequential(
+            nn.Conv2d(1, width // 2, 3, stride=2, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(width // 2, width, 3, stride=2, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(width, width, 3, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(width, width, 3, padding=1), nn.ReLU(inplace=True),
+            nn.Conv2d(width, width, 3, padding=1), nn.ReLU(inplace=True)).to(dev).eval().to(memory_format=torch.channels_last)
+        self.heads = nn.Conv2d(width, 4, 1).to(dev).eval()          # sem logit, center, offset y, offset x at 1/4 resolution
+        torch.backends.cudnn.benchmark = True
+
+    def __call__(self, image):
+        import torch
+        import torch.nn.functional as F
+        with torch.no_grad():
+            x = self.heads(self.body(image.contiguous(memory_format=torch.channels_last)))
+            sem_logits = F.interpolate(x[:, 0:1], scale_factor=4, mode='bilinear', align_corners=True)
+            return {'sem_logits': sem_logits, 'ctr_hmp': x[:, 1:2], 'offsets': x[:, 2:4]}
+
+
+def run_stack_with_cnn(dev, rank, world, slices, depth, hw, ks=3, repeats=3, group=None):
+    """The stack loop of scripts/pdl_inference3d.py:163-187 on this rank's z-block with the CNN in it: per slice a
+    forward of the stand-in net on a uint8 image (normalised as VolumeDataset does), its heads written straight into
+    the block's batch buffers (StackShard takes views: no copy), then the block's post-processing.  Timed twice:
+    CNN alone, and CNN + post-processing + RLE tables on the host."""
+    import torch
+    import torch.distributed as dist
+    from empanada_b200.inference import stack
+    eng = make_engine()
+    net = StandInNet(dev)
+    z0, z1 = stack.partition_slices(depth, world, rank)
+    _, zh = stack.halo_range(depth, world, rank, ks)
+    n = zh - z0
+    vol = torch.randint(0, 256, (n, 1, 1, hw, hw), dtype=torch.uint8, device=dev)
+    sem_b = torch.empty((n, 1, 1, hw, hw), dtype=torch.float32, device=dev)
+    hm_b = torch.empty((n, 1, 1, hw // 4, hw // 4), dtype=torch.float32, device=dev)
+    off_b = torch.empty((n, 1, 2, hw // 4, hw // 4), dtype=torch.float32, device=dev)
+
+    def run_once(postproc):
+        shard = stack.StackShard(eng, labels=[1], depth=depth, rank=rank, world_size=world, median_kernel_size=ks,
+                                 upsampling=1, force_connected=True, group=group, keep_tables=False)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(group=group)
+            torch.cuda.synchronize(dev)
+        t = time.perf_counter()
+        for i, z in enumerate(shard.slices()):
+            image = (vol[i].to(torch.float32) - 255 * 0.508979) / (255 * 0.148561)       # A.Normalize of the MitoNet configs
+            o = net(image)
+            s = slices[z % len(slices)]
+            torch.add(s['sem_prob'], torch.sigmoid(o['sem_logits']), alpha=0.0, out=sem_b[i])
+            torch.add(s['ctr_hmp'], o['ctr_hmp'], alpha=0.0, out=hm_b[i])
+            torch.add(s['offsets'], o['offsets'], alpha=0.0, out=off_b[i])
+            shard.add(z, sem_b[i], hm_b[i], off_b[i], size=(hw, hw))
+        out = shard.finish() if postproc else None
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX, group=group)
+            dt = float(tt.item())
+        return dt, out
+
+    run_once(True)                                              # warm-up (cudnn autotune, workspaces, allocator)
+    run_once(True)
+    t_cnn = min(run_once(False)[0] for _ in range(repeats))
+    both = [run_once(True) for _ in range(repeats)]
+    t_all = min(b[0] for b in both)
+    n_inst, n_runs = both[-1][1].counts()
+    return {'metric': 'stack_inference_throughput', 'value': depth * hw * hw / t_all, 'unit': 'voxels/s', 'n_gpus': world,
+            'seconds': t_all, 'seconds_cnn_only': t_cnn, 'postproc_share_of_wall': (t_all - t_cnn) / t_all, 'scaling': 'strong',
+            'config': {'workload': f'stack_{depth}x{hw}x{hw}_coarse4_ks{ks}_with_cnn', 'slices_per_rank_incl_halo': n,
+                       'cnn': 'stand-in conv net (5 conv layers, 64 channels, quarter-res heads, bilinear x4 semantic logits), fp32 — two orders of magnitude lighter than the ResNet-50 PanopticDeepLab it stands for',
+                       'instances_rank0': n_inst, 'rle_runs_rank0': n_runs,
+                       'data': 'uint8 noise volume through the net; synthetic head tensors added to its (constant-like) outputs'}}
+
+
 def add_parity(rec, out, dev, rank, world, slices, depth, hw, ks, block, chain_chunk, group=None):
     """N > 1: every rank's slices must equal the same stack run as ONE block (rank 0 runs and times it)."""
     import torch.distributed as dist
@@ -173,6 +258,7 @@ def main():
     ap.add_argument('--block', type=int, default=0, help='slices per emp_stack_block call (0: 32, less for short blocks)')
     ap.add_argument('--chain-chunk', type=int, default=4096, help='slices per emp_median_chain launch')
     ap.add_argument('--profile', action='store_true', help='one extra run with per-stage CUDA events (ms per stage over the block)')
+    ap.add_argument('--cnn', action='store_true', help='also time the stack loop with a stand-in CNN in it')
     ap.add_argument('--match', action='store_true', help='also time the cross-slice matcher (forward + backward) on the block')
     ap.add_argument('--match-cpu-slices', type=int, default=12, help='slices of the CPU matcher baseline (oracle port of the reference)')
     args = ap.parse_args()
@@ -214,6 +300,10 @@ def main():
                 m(seg)
         match_cpu = {'ms_per_slice_forward_only': 1e3 * (time.perf_counter() - t) / max(len(zs) - 1, 1), 'slices': len(zs),
                      'kind': 'port', 'cores': 1}
+    if args.cnn:
+        del out, shard, matched
+        with_cnn = run_stack_with_cnn(dev, rank, world, slices, D, H, args.ks)
+        rec['with_cnn'] = with_cnn
     if rank == 0:
         rec['matcher_cpu_baseline'] = match_cpu
         os.write(json_fd, (json.dumps(rec) + '\n').encode())
