@@ -82,15 +82,22 @@ def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=0, chain_chunk=40
     from empanada_b200.inference import stack
     eng = make_engine()
     if not block:                                            # short blocks: smaller sub-blocks keep the copy / parse pipeline busy
-        per_rank = max(depth // world, 1)
-        block = 32 if per_rank >= 128 else 16 if per_rank >= 48 else 8
+        block = 128                                          # StackShard clips it to the block's length
+
+    # The heads of this rank's block (+ halo) as the inference loop leaves them: one batch buffer per head, slice z a
+    # view into it (run_stack_with_cnn shows the CNN writing them there) — StackShard then passes base + stride on.
+    z0, _ = stack.partition_slices(depth, world, rank)
+    _, zh = stack.halo_range(depth, world, rank, ks)
+    idx = torch.tensor([z % len(slices) for z in range(z0, zh)], device=dev)
+    sem_b = torch.stack([s['sem_prob'] for s in slices]).index_select(0, idx)
+    hm_b = torch.stack([s['ctr_hmp'] for s in slices]).index_select(0, idx)
+    off_b = torch.stack([s['offsets'] for s in slices]).index_select(0, idx)
 
     def run_once():
         shard = stack.StackShard(eng, labels=[1], depth=depth, rank=rank, world_size=world, median_kernel_size=ks,
                                  upsampling=1, force_connected=True, block=block, chain_chunk=chain_chunk, group=group)
-        for z in shard.slices():
-            s = slices[z % len(slices)]
-            shard.add(z, s['sem_prob'], s['ctr_hmp'], s['offsets'], size=(hw, hw))
+        for i, z in enumerate(shard.slices()):
+            shard.add(z, sem_b[i], hm_b[i], off_b[i], size=(hw, hw))
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier(group=group)
@@ -129,15 +136,19 @@ def run_stack(dev, rank, world, slices, depth, hw, ks=3, block=0, chain_chunk=40
         run_once()
         stages = {k: [round(v[0], 4), v[1]] for k, v in C.profile_read().items() if v[1]}
         C.profile_enable(False)
+    per_rank = None
     if world > 1:
         c = torch.tensor([n_inst, n_runs], device=dev, dtype=torch.int64)
         dist.all_reduce(c, group=group)
         n_inst, n_runs = int(c[0]), int(c[1])
+        gathered = [None] * world                           # the last repeat's host timeline of every rank
+        dist.all_gather_object(gathered, {k: round(v, 5) for k, v in timing.items()}, group=group)
+        per_rank = gathered
     sec = sorted(times)[len(times) // 2]                     # median: the caching allocator takes a few blocks to settle
     rec = {'metric': 'stack_postproc_throughput', 'value': depth * hw * hw / sec, 'unit': 'voxels/s', 'n_gpus': world,
            'seconds': sec, 'seconds_is': 'median of the repeats, max over ranks each', 'seconds_best': min(times), 'seconds_all': [round(t, 5) for t in times], 'repeats': repeats, 'ms_per_slice_per_rank': 1e3 * sec / max(len(out), 1),
            'scaling': 'strong', 'rank0_host_seconds': {k: round(v, 4) for k, v in timing.items()},
-           'stage_ms_and_launches': stages,
+           'per_rank_host_seconds': per_rank, 'stage_ms_and_launches': stages,
            'config': {'workload': f'stack_{depth}x{hw}x{hw}_coarse4_ks{ks}', 'slices_per_rank': len(out), 'block': block,
                       'instances': n_inst, 'rle_runs': n_runs, 'data': 'synthetic head tensors, CNN not included'}}
     return rec, out, shard, matched
@@ -255,7 +266,7 @@ def main():
     ap.add_argument('--distinct', type=int, default=12, help='distinct synthetic slices (cycled)')
     ap.add_argument('--blobs', type=int, default=400)
     ap.add_argument('--repeat', type=int, default=5)
-    ap.add_argument('--block', type=int, default=0, help='slices per emp_stack_block call (0: 32, less for short blocks)')
+    ap.add_argument('--block', type=int, default=0, help='slices per emp_stack_block call (0: 128)')
     ap.add_argument('--chain-chunk', type=int, default=4096, help='slices per emp_median_chain launch')
     ap.add_argument('--profile', action='store_true', help='one extra run with per-stage CUDA events (ms per stage over the block)')
     ap.add_argument('--cnn', action='store_true', help='also time the stack loop with a stand-in CNN in it')

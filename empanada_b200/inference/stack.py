@@ -69,6 +69,32 @@ def _copy_stream(device):
     return s
 
 
+class _PinnedPool:
+    """Pinned int64 buffers the packed tables land in.  A block's RleStack reads its arrays IN PLACE (views, no copy:
+    copying ~120 KB per slice out of the staging area cost more host time than the GPU needed for the slice), so a
+    buffer stays taken for as long as any of those views is alive and goes back to the pool when the last one dies —
+    the pool simply looks at reference counts.  Pinning is slow (milliseconds): buffers are kept and over-allocated."""
+
+    def __init__(self):
+        self.buffers = {}
+
+    def acquire(self, device, n_words):
+        import sys
+        have = self.buffers.setdefault(device.index, [])
+        for i in range(len(have)):
+            t = have[i]
+            # references when nobody else holds it: the list slot, `t`, and getrefcount's argument
+            if t.numel() >= n_words and sys.getrefcount(t) <= 3:
+                return t
+        have[:] = [t for t in have if sys.getrefcount(t) > 3 or t.numel() >= n_words][-4:]       # drop idle buffers that are too small
+        t = torch.empty(int(n_words * 1.5) + 1024, dtype=torch.int64).pin_memory()
+        have.append(t)
+        return t
+
+
+_table_pool = _PinnedPool()
+
+
 def _pinned_words(device, slot, n_words):
     """Pinned int64 staging buffer `slot` of this device, grown and never shrunk."""
     key = (device.index, slot)
@@ -199,11 +225,11 @@ class _BlockTables:
         from empanada_b200 import _cabi as C
         R, I = int(words[1]), int(words[2])
         s0 = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B
-        # owned copies: the pinned staging buffer is reused by the next block
-        self.slices = words[C.BLK_HDR_WORDS:s0].reshape(B, C.BLK_SLICE_WORDS).copy()
-        self.starts = words[s0:s0 + R].copy()
-        self.lens = words[s0 + R:s0 + 2 * R].copy()
-        self.inst = words[s0 + 2 * R:s0 + 2 * R + C.BLK_INST_WORDS * I].reshape(I, C.BLK_INST_WORDS).copy()
+        # views: `words` is a slice of a pooled pinned buffer that stays taken while these arrays live (_PinnedPool)
+        self.slices = words[C.BLK_HDR_WORDS:s0].reshape(B, C.BLK_SLICE_WORDS)
+        self.starts = words[s0:s0 + R]
+        self.lens = words[s0 + R:s0 + 2 * R]
+        self.inst = words[s0 + 2 * R:s0 + 2 * R + C.BLK_INST_WORDS * I].reshape(I, C.BLK_INST_WORDS)
 
     @staticmethod
     def words_needed(words, B):
@@ -337,7 +363,7 @@ class StackShard:
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, block=32, keep_tables=True, chain_chunk=4096):
+                 upsampling=1, force_connected=True, group=None, block=128, keep_tables=True, chain_chunk=4096):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
@@ -465,7 +491,9 @@ class StackShard:
             return changed
 
         def exchange():
+            t = time.perf_counter()
             exchange_planes(carry['out'], carry[state['new']], self.rank, self.world, self.group)
+            self._marks['exchange_call_s'] = self._marks.get('exchange_call_s', 0.0) + time.perf_counter() - t
 
         def any_changed(flag):
             t = (flag if flag is not None else torch.zeros((1,), dtype=torch.int32, device=dev)).to(torch.int64)
@@ -515,7 +543,7 @@ class StackShard:
         fixed = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * SB
         per_slice = _words_per_slice.get((dev.index, H, W), 1 << 14)
         host_words = min(packed_words, fixed + SB * int(per_slice * 1.25))
-        host = _pinned_words(dev, 'tables', n_sub * (host_words + 1))
+        host = _table_pool.acquire(dev, n_sub * (host_words + 1))
         flags = host[n_sub * host_words:n_sub * host_words + n_sub]
         flags.zero_()
         main = torch.cuda.current_stream(dev)
@@ -544,6 +572,7 @@ class StackShard:
         worst = 0
         SB, hw_, flags = subs['SB'], subs['host_words'], subs['flags']
         host_np = subs['host'].numpy()
+        t_first = time.perf_counter()
         for bi in range(subs['n_sub']):
             i0 = bi * SB
             B = min(SB, n - i0)
@@ -554,6 +583,8 @@ class StackShard:
                     torch.cuda.synchronize(dev)
                     if flags[bi] == 0:
                         raise RuntimeError('emp_stack_blocks: block tables never arrived')
+            if bi == 0:
+                self._marks['first_block_arrival_s'] = time.perf_counter() - t_first
             words = host_np[bi * hw_:(bi + 1) * hw_]
             need = _BlockTables.words_needed(words, B)
             if need > hw_:                                          # the size guess was short: fetch the whole block (rare)
@@ -705,6 +736,7 @@ class StackShard:
 
     def _finish(self):
         from empanada_b200 import _cabi as C
+        self._marks = {}
         e = self.engine
         zs = list(range(self.z0, self.z1))
         assert all(z in self.heads for z in range(self.z0, self.z_halo)), 'add() every slice of slices() first'
@@ -736,6 +768,7 @@ class StackShard:
         t_b = time.perf_counter()
         out = RleStack(self.labels, e.thing_list, e.label_divisor)
         bad, n_runs, inst = self._collect(zs, subs, packed, sem8, out)
+        self._marks['collect_s'] = time.perf_counter() - t_b
         torch.cuda.current_stream(dev).synchronize()
         t_c = time.perf_counter()
         offs = {c: 0 for c in self.labels}
@@ -764,6 +797,7 @@ class StackShard:
         self.label_offsets_ = offs
         self.timing_ = {'enqueue_s': t_b - t_a, 'wait_s': t_c - t_b, 'enqueue_chain_s': t_chain - t_a, 'enqueue_blocks_s': t_blocks - t_chain,
                         'enqueue_gather_s': t_b - t_blocks, 'after_s': time.perf_counter() - t_c}
+        self.timing_.update(self._marks)
         self.tables_shape_ = self._plane
         self.tables_ = {'runs_all': runs_all, 'n_runs': n_runs, 'bad': bad, 'inst': inst, 'zs': zs,
                         'slot_areas': [None if r is None else r[:, 8] for r in inst]}
