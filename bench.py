@@ -252,6 +252,7 @@ def main():
     ap.add_argument('--thr', type=float, default=THR, help='center threshold (experiments; the workload uses 0.1)')
     ap.add_argument('--dense', action='store_true', help='BASELINE configs[4] as the main workload: ~5000 instances of semi-axes 4..12 px per tile')
     ap.add_argument('--no-stack', action='store_true', help='skip the configs[2] stack sub-record')
+    ap.add_argument('--no-deep', action='store_true', help='skip the 2048-slice variant of the stack sub-record')
     ap.add_argument('--no-cnn', action='store_true', help='skip the stack loop with the stand-in CNN in it')
     ap.add_argument('--no-dense', action='store_true', help='skip the configs[4] dense sub-record (N = 1)')
     ap.add_argument('--dense-tiles', type=int, default=8)
@@ -416,6 +417,15 @@ def main():
                                  'note': 'host-visible time (enqueue, kernels, D2H of the tables, collectives) against the algorithmic bytes of '
                                          'SURVEY 8d; the fused path never writes or re-reads the int64 label map those bytes include'}
         del s_out_
+        if not args.no_deep:
+            # the same path on a 4 x deeper stack: per-rank work large enough that the fixed cost of a block
+            # (a few tenths of a millisecond of launches, carry exchange and table read-back) stops dominating at 8 ranks
+            deep, d_out, _, _ = bs.run_stack(dev, rank, world, slices, 2048, 2048, ks=3, repeats=3, warmup=2)
+            if world > 1:
+                bs.add_parity(deep, d_out, dev, rank, world, slices, 2048, 2048, 3, 0, 4096)
+            stack_rec['deep'] = {k: deep.get(k) for k in ('value', 'unit', 'seconds', 'seconds_all', 'parity', 'single_gpu_seconds_same_run',
+                                                         'speedup_vs_n1', 'config')}
+            del d_out
         if not args.no_cnn:
             stack_rec['with_cnn'] = bs.run_stack_with_cnn(dev, rank, world, slices, 512, 2048, 3)
         del slices

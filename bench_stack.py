@@ -287,6 +287,12 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        try:                                                # every rank on its own slice of the host's CPUs
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, cpus[local_rank * per:(local_rank + 1) * per] or cpus)
+        except OSError:
+            pass
     D, H = args.depth, args.hw
     t0 = time.time()
     slices = make_slices(dev, H, args.distinct, args.blobs)
