@@ -32,7 +32,10 @@ namespace emp {
 // 1. recursive median chain
 // =====================================================================================================
 constexpr unsigned kNoVote = 0xFFFFFFFFu;
-constexpr int kChainPf = 3;         // raw planes loaded ahead of the window (loads in flight per thread)
+#ifndef EMP_CHAIN_PF
+#define EMP_CHAIN_PF 3
+#endif
+constexpr int kChainPf = EMP_CHAIN_PF;   // raw planes loaded ahead of the window (loads in flight per thread)
 
 struct ChainArgs {
     const float* const* planes;     // device array: planes[j] = raw (C,H,W) probabilities of slice z0 + j, j < n_planes
