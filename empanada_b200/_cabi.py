@@ -55,6 +55,7 @@ _SIGNATURES = {
     'emp_stack_block': (_i32, [_vp, _i32, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     'emp_stack_blocks': (_i32, [_vp, _i32, _i32, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _sz,
                                 _vp, _vp, _vp]),
+    'emp_take_slices': (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     'emp_rle_pair_overlaps': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _i32, _vp, _vp]),
     'emp_rle_list_overlaps': (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _i32, _vp, _vp]),
     'emp_fill_runs': (_i32, [_vp, _sz, _vp, _i32, _i32, _vp, _sz, _vp, _i32, _sz, _vp]),

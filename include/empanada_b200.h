@@ -312,6 +312,13 @@ int emp_stack_blocks(const emp_stack_cfg* cfg, int n, int SB, const uint8_t* sem
                      int64_t* maxlab_all, int64_t* host_out /* pinned host */, size_t host_stride, size_t host_words,
                      int64_t* host_flags /* pinned host */, void* stream, void* copy_stream);
 
+/* Slices of a (D,H,W) volume resident in HBM — array_utils.take (array_utils.py:6-23) as data/volume_dataset.py:37-53
+ * calls it inside the stack / orthoplane loops of scripts/pdl_inference3d.py:110-176: the n slices i0 .. i0+n-1 along
+ * `axis` as one contiguous (n, A, B) batch, (A,B) = (H,W), (D,W), (D,H) for axis 0, 1, 2.  Elements of 1 byte (uint8
+ * images) or 4 bytes.  The axis-2 (yz) gather reads runs of n neighbouring slices and transposes them through shared
+ * memory, so taking slices in batches of >= 32 keeps it sector-efficient. */
+int emp_take_slices(const void* vol, int elem_bytes, int D, int H, int W, int axis, int i0, int n, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

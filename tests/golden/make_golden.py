@@ -704,8 +704,50 @@ def ortho_cases():
     save('ortho_chain', params=json.dumps(P), **res)
 
 
+def stack_rle_cases():
+    """The stack path end to end, by the reference alone: PanopticDeepLabRenderEngine3d over a replayed stack (recursive
+    median queue, coarse instance cells, merge, crop: engines.py:327-394), then pan_seg_to_rle_seg(force_connected) per
+    emitted slice (patterns.py:93-95) — inputs and every slice's RLE tables."""
+    for name, ks, up, D, size, things, ncls in (('stack_rle_ks3', 3, 1, 9, (60, 75), [1], 1),
+                                                ('stack_rle_ks5_up2', 5, 2, 8, (118, 150), [1], 1),
+                                                ('stack_rle_ks1_mc', 1, 1, 4, (64, 80), [1, 2], 3)):
+        H, W = 64, 80
+        base = stack_inputs(D, H * up, W * up, seed=52, coarse=1, n_classes=ncls)
+        ins = []
+        for z in range(D):
+            o = dict(base[z])
+            dd = synth_tile(H // 4, W // 4, 10, seed=53 + z // 3, semi_axes=(2, 4), sigma=1.2)
+            o['ctr_hmp'] = dd['ctr_hmp'].astype(np.float32)
+            o['offsets'] = (dd['offsets'] * 4).astype(np.float32)
+            ins.append(o)
+        model = ReplayModel([{k: t(v) for k, v in o.items()} for o in ins])
+        eng = reng.PanopticDeepLabRenderEngine3d(model, things, 20000, 32, 0, 0.1, 3, 0.3, ks, 16, coarse_boundaries=True)
+        pans = []
+        for z in range(D):
+            out = eng(torch.zeros(1, 1, size[0], size[1]), size, up)
+            if out is not None:
+                pans.append(out)
+        pans += eng.end(up)
+        assert len(pans) == D
+        labels = things + ([3] if ncls == 3 else [])
+        res = {}
+        for z, o in enumerate(ins):
+            for k, v in o.items():
+                res[f'in_{z}_{k}'] = v
+            seg = rrle.pan_seg_to_rle_seg(pans[z].squeeze().numpy(), labels, 20000, things, True)
+            inst, starts, runs = flatten_rle(seg)
+            res[f'out_{z}_inst'], res[f'out_{z}_starts'], res[f'out_{z}_runs'] = inst, starts, runs
+        n_inst = sum(res[f'out_{z}_inst'].shape[0] for z in range(D))
+        save(name, params=json.dumps(dict(thing_list=things, labels=labels, label_divisor=20000, stuff_area=32, void_label=0,
+                                          nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3, median_kernel_size=ks,
+                                          padding_factor=16, upsampling=up, size=list(size), n=D)), **res)
+        print(f'  {name}: {D} slices, {n_inst} instances')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker', 'consensus', 'ortho']
+    which = sys.argv[1:] or ['pp', 'merge', 'engine', 'rle', 'matcher', 'tracker', 'consensus', 'ortho', 'stack']
+    if 'stack' in which:
+        stack_rle_cases()
     if 'ortho' in which:
         ortho_cases()
     if 'pp' in which:

@@ -219,3 +219,22 @@ def test_fill_volume_slabs_numpy_and_zarr_like(dtype, cuda_device, monkeypatch):
     patterns.fill_volume(z, instances, processes=3)
     np.testing.assert_array_equal(z.a, want)
     assert all(k.start % 2 == 0 for k in z.writes)                          # whole z-chunks per slab
+
+
+@pytest.mark.parametrize('dtype', [torch.uint8, torch.int32, torch.float32])
+@pytest.mark.parametrize('shape', [(40, 50, 70), (33, 65, 31), (64, 64, 64)])
+def test_take_slices_matches_indexing(dtype, shape, cuda_device):
+    """emp_take_slices — array_utils.take (array_utils.py:6-23) for a batch of consecutive slices of an HBM-resident
+    volume — against plain indexing, along all three axes, at batch boundaries and odd sizes."""
+    from empanada_b200.inference.volume import take_slices
+    g = torch.Generator(device='cpu')
+    g.manual_seed(3)
+    vol = (torch.rand(shape, generator=g) * 250).to(dtype).to(cuda_device)
+    for axis in range(3):
+        n_ax = shape[axis]
+        for i0, n in ((0, n_ax), (3, 1), (n_ax - 7, 7), (5, min(33, n_ax - 5))):
+            got = take_slices(vol, axis, i0, n)
+            want = vol.narrow(axis, i0, n).movedim(axis, 0).contiguous()
+            assert got.shape == want.shape and torch.equal(got, want), (axis, i0, n)
+    with pytest.raises(IndexError):
+        take_slices(vol, 1, shape[1] - 2, 3)

@@ -241,3 +241,37 @@ def test_stack_block_vs_oracle_row_wrap(cuda_device):
         want = oracle.pan_seg_to_rle_seg(pan, [1], 1000, [1], True)
         _rle_equal(got[z], want, f'slice {z}')
         assert any(int(s % W + r) > W for a in got[z][1].values() for s, r in zip(a['starts'], a['runs']))   # a run crossing a row end
+
+
+@pytest.mark.parametrize('name', ['stack_rle_ks3', 'stack_rle_ks5_up2', 'stack_rle_ks1_mc'])
+@pytest.mark.parametrize('block', [128, 3])
+def test_stack_shard_vs_reference_stack_of_rle(name, block, cuda_device):
+    """StackShard against fixtures the REFERENCE produced for the whole stack path (tests/golden/make_golden.py stack:
+    its PanopticDeepLabRenderEngine3d over a replayed stack, then its pan_seg_to_rle_seg(force_connected=True) per
+    slice): every slice's labels, boxes, starts and runs."""
+    from conftest import load_golden
+    from empanada_b200.inference import engines as eng, stack
+    g = load_golden(name)
+    p = g['params']
+    D = p['n']
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=p['thing_list'], label_divisor=p['label_divisor'],
+                                        stuff_area=p['stuff_area'], void_label=p['void_label'], nms_threshold=p['nms_threshold'],
+                                        nms_kernel=p['nms_kernel'], confidence_thr=p['confidence_thr'], coarse_boundaries=True)
+    shard = stack.StackShard(e, labels=p['labels'], depth=D, median_kernel_size=p['median_kernel_size'], upsampling=p['upsampling'],
+                             force_connected=True, block=block)
+    for z in shard.slices():
+        prob = eng.logits_to_prob(torch.from_numpy(g[f'in_{z}_sem_logits']).to(cuda_device))
+        shard.add(z, prob, torch.from_numpy(g[f'in_{z}_ctr_hmp']).to(cuda_device), torch.from_numpy(g[f'in_{z}_offsets']).to(cuda_device),
+                  size=tuple(p['size']))
+    got = shard.finish()
+    total = 0
+    for z in range(D):
+        inst, starts, runs = g[f'out_{z}_inst'], g[f'out_{z}_starts'], g[f'out_{z}_runs']
+        want, at = {int(l): {} for l in p['labels']}, 0
+        for row in inst:
+            n = int(row[6])
+            want[int(row[0])][int(row[1])] = {'box': tuple(int(v) for v in row[2:6]), 'starts': starts[at:at + n], 'runs': runs[at:at + n]}
+            at += n
+        _rle_equal(got[z], want, f'{name} slice {z}')
+        total += inst.shape[0]
+    assert got.counts()[0] == total

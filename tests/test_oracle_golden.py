@@ -114,6 +114,53 @@ def test_render_engine3d(name):
         np.testing.assert_array_equal(o, g[f'out_{i}'])
 
 
+def _unflatten_labels(inst, starts, runs, labels):
+    seg, at = {int(l): {} for l in labels}, 0
+    for row in inst:
+        n = int(row[6])
+        seg[int(row[0])][int(row[1])] = {'box': tuple(int(v) for v in row[2:6]), 'starts': starts[at:at + n], 'runs': runs[at:at + n]}
+        at += n
+    return seg
+
+
+@pytest.mark.parametrize('name', golden_names('stack_rle_'))
+def test_stack_of_rle_matches_reference(name):
+    """The whole stack path — recursive median queue, harden, coarse cells, merge, crop, pan_seg_to_rle_seg with
+    force_connected — restated by the oracle against the reference's own RLE tables for every slice."""
+    g = load_golden(name)
+    p = g['params']
+    q = oracle.MedianQueue(p['median_kernel_size'])
+    up = p['upsampling']
+    h, w = p['size']
+    outs = []
+
+    def post(entry):
+        ctr = oracle.find_instance_center(entry['ctr_hmp'], p['nms_threshold'], p['nms_kernel'])
+        cells = np.zeros(entry['ctr_hmp'].shape[-2:], np.int64) if ctr.shape[0] == 0 else oracle.group_pixels(ctr, entry['offsets'], step=4.0)[0]
+        cells = oracle.nearest_upsample(cells, int(up * 4))
+        sem = oracle.harden_seg(entry['sem'], p['confidence_thr'])[0]
+        ins = np.where(np.isin(sem, p['thing_list']), cells[None], 0)
+        pan = oracle.merge_semantic_and_instance(sem, ins, p['label_divisor'], p['thing_list'], p['stuff_area'], p['void_label'])
+        return oracle.pan_seg_to_rle_seg(pan[0, :h, :w], p['labels'], p['label_divisor'], p['thing_list'], True)
+
+    for z in range(p['n']):
+        q.enqueue({'sem': _sigmoid_or_softmax(g[f'in_{z}_sem_logits']), 'ctr_hmp': g[f'in_{z}_ctr_hmp'], 'offsets': g[f'in_{z}_offsets']})
+        o = q.get_next(['sem'])
+        if o is not None:
+            outs.append(post(o))
+    outs += [post(e) for e in q.end()]
+    assert len(outs) == p['n']
+    for z, got in enumerate(outs):
+        want = _unflatten_labels(g[f"out_{z}_inst"], g[f"out_{z}_starts"], g[f"out_{z}_runs"], p["labels"])
+        assert list(got.keys()) == list(want.keys())
+        for c in want:
+            assert list(got[c].keys()) == list(want[c].keys()), f'slice {z} class {c}'
+            for lab in want[c]:
+                assert tuple(got[c][lab]['box']) == want[c][lab]['box']
+                np.testing.assert_array_equal(got[c][lab]['starts'], want[c][lab]['starts'])
+                np.testing.assert_array_equal(got[c][lab]['runs'], want[c][lab]['runs'])
+
+
 @pytest.mark.parametrize('name', golden_names('rle_'))
 def test_rle_matches_reference(name):
     g = load_golden(name)
