@@ -121,6 +121,16 @@ def main():
     sem_b = torch.empty((S + args.ks // 2, 1, 1, S, S), dtype=torch.float32, device=dev)
     hm_b = torch.empty((S, 1, 1, S // 4, S // 4), dtype=torch.float32, device=dev)
     off_b = torch.empty((S, 1, 2, S // 4, S // 4), dtype=torch.float32, device=dev)
+    # warm-up: library load, cuDNN autotune, allocator — a 4-slice stack along every axis
+    for axis in AXES.values():
+        w = stack.StackShard(eng, labels=[1], depth=4, median_kernel_size=args.ks)
+        img = take_slices(img_vol, axis, 0, 4)
+        sem, hm, off = heads_from_labels(take_slices(lab_vol, axis, 0, 4), args.blobs, gen)
+        for s in range(4):
+            net((img[s][None, None].to(torch.float32) - 130) / 38)
+            w.add(s, sem[s], hm[s], off[s], size=(S, S))
+        w.match(w.finish())
+    torch.cuda.synchronize()
     per_axis = {}
     for name, axis in AXES.items():
         tm = {}

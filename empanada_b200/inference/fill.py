@@ -57,7 +57,13 @@ def _paint(flat, table, labels, dev):
     s_sorted = np.argsort(table[:, 0], kind='stable')
     ends = table[s_sorted, 0] + table[s_sorted, 1]
     overlapping = bool((table[s_sorted, 0][1:] < np.maximum.accumulate(ends)[:-1]).any())
-    groups = [table] if not overlapping else [table[table[:, 2] == i] for i in range(len(labels))]
+    if not overlapping:
+        groups = [table]
+    else:                                                       # one group per instance, in slot order (one sort, not a mask per instance)
+        order = np.argsort(table[:, 2], kind='stable')
+        by_slot = table[order]
+        cuts = np.flatnonzero(np.diff(by_slot[:, 2])) + 1
+        groups = np.split(by_slot, cuts)
     for g in groups:
         if g.shape[0] == 0:
             continue
