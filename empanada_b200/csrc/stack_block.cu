@@ -1031,8 +1031,10 @@ rle_block_lists_kernel(const BlkArgs a)
     const int n = s.n, Wc = a.crop_w;
     const int n_inst = min(s.status[EMP_ST_NINST], a.inst_cap);
     const int my_off = s.status[kStBlkOff], total_rr = s.status[kStBlkTotal];
-    long long* starts_out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + my_off;
-    long long* lens_out = starts_out + total_rr;
+    // run lists as int32 pairs of planes (flat indices are < 2^31): half the bytes of the one copy that crosses PCIe
+    const int rr_even = (total_rr + 1) & ~1;
+    int* starts_out = reinterpret_cast<int*>(a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B) + my_off;
+    int* lens_out = starts_out + rr_even;
     for (int slot = warp; slot < n_inst; slot += n_warps) {
         const int ya = s.ymin[slot], yb = s.ymax[slot];
         const int base = s.cnt[slot];
@@ -1073,8 +1075,8 @@ rle_block_lists_kernel(const BlkArgs a)
             const unsigned above = m & ~(lanemask_lt() | (1u << lane));
             const int next_lane = above ? __ffs(above) - 1 : 32;
             const bool last_of_final = mine && (next_lane == 32 || ((hb >> next_lane) & 1u));
-            if (head) starts_out[base + fidx] = start;
-            if (last_of_final) lens_out[base + fidx] = end - fstart;
+            if (head) starts_out[base + fidx] = (int)start;
+            if (last_of_final) lens_out[base + fidx] = (int)(end - fstart);
             const int last_lane = 31 - __clz(m);                // carry: the slot's last row-run of this chunk
             carry_end = __shfl_sync(0xffffffffu, end, last_lane);
             carry_start = __shfl_sync(0xffffffffu, fstart, last_lane);
@@ -1127,7 +1129,7 @@ rle_block_pack_kernel(const BlkArgs a)
     const int n_inst = min(__ldcg(status + EMP_ST_NINST), a.inst_cap);
     const long long* inst = reinterpret_cast<const long long*>(rs + a.R.inst);
     long long* hdr = a.packed;
-    long long* out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + 2 * (size_t)total_rr +
+    long long* out = a.packed + EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * a.B + (size_t)((total_rr + 1) & ~1) +
                      (size_t)inst_off * EMP_BLK_INST_WORDS;
     for (int i = tid; i < n_inst * EMP_BLK_INST_WORDS; i += blockDim.x) out[i] = inst[i];
     // largest label - class base per class over the block (the z-sharded stack's label offsets)
@@ -1283,7 +1285,7 @@ EMP_API size_t emp_stack_block_packed_words(const emp_stack_cfg* cfg, int B)
 {
     if (!cfg || B < 1 || cfg->run_cap < 1 || cfg->inst_cap < 1) return 0;
     return (size_t)EMP_BLK_HDR_WORDS + (size_t)EMP_BLK_SLICE_WORDS * B +
-           (size_t)B * (2 * (size_t)cfg->run_cap + (size_t)EMP_BLK_INST_WORDS * cfg->inst_cap);
+           (size_t)B * ((size_t)cfg->run_cap + 1 + (size_t)EMP_BLK_INST_WORDS * cfg->inst_cap);
 }
 
 static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8, size_t sem8_stride, const float* hm,

@@ -33,6 +33,7 @@ import contextlib
 import ctypes
 import gc
 import math
+import os
 import time
 
 import numpy as np
@@ -251,17 +252,19 @@ class _BlockTables:
     def __init__(self, words, B):
         from empanada_b200 import _cabi as C
         R, I = int(words[1]), int(words[2])
+        Rp = (R + 1) & ~1
         s0 = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B
         # views: `words` is a slice of a pooled pinned buffer that stays taken while these arrays live (_PinnedPool)
         self.slices = words[C.BLK_HDR_WORDS:s0].reshape(B, C.BLK_SLICE_WORDS)
-        self.starts = words[s0:s0 + R]
-        self.lens = words[s0 + R:s0 + 2 * R]
-        self.inst = words[s0 + 2 * R:s0 + 2 * R + C.BLK_INST_WORDS * I].reshape(I, C.BLK_INST_WORDS)
+        runs32 = words[s0:s0 + Rp].view(np.int32)              # the run lists cross PCIe as int32 (flat indices < 2^31)
+        self.starts = runs32[:R]
+        self.lens = runs32[Rp:Rp + R]
+        self.inst = words[s0 + Rp:s0 + Rp + C.BLK_INST_WORDS * I].reshape(I, C.BLK_INST_WORDS)
 
     @staticmethod
     def words_needed(words, B):
         from empanada_b200 import _cabi as C
-        return C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B + 2 * int(words[1]) + C.BLK_INST_WORDS * int(words[2])
+        return C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B + ((int(words[1]) + 1) & ~1) + C.BLK_INST_WORDS * int(words[2])
 
 
 class RleStack(collections.abc.Mapping):
@@ -328,7 +331,11 @@ class RleStack(collections.abc.Mapping):
                 boxes = rows[:, 2:6].tolist()
                 cnt = rows[:, 6].tolist()
                 first = rows[:, 7].tolist()
-                starts, lens = t.starts, t.lens
+                # the slice's run lists widened to the reference's int64 once; the instances' arrays are views into them
+                lo = first[0]
+                hi = first[-1] + cnt[-1]
+                starts, lens = t.starts[lo:hi].astype(np.int64), t.lens[lo:hi].astype(np.int64)
+                first = [f - lo for f in first]
                 offs = {c: (int(self.offsets.get(c, 0)) if c in self.thing_list else 0) for c in self.labels}
                 for i in range(len(cls)):
                     c = cls[i]
@@ -527,6 +534,17 @@ class StackShard:
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
             return bool(t.item())
 
+        if os.environ.get('EMP_STACK_DEBUG_SYNC'):                     # diagnostic: device time of each step of the hand-over
+            def timed(name, fn):
+                def run(*a):
+                    torch.cuda.synchronize(dev)
+                    t = time.perf_counter()
+                    r = fn(*a)
+                    torch.cuda.synchronize(dev)
+                    self._marks['dbg_' + name] = self._marks.get('dbg_' + name, 0.0) + time.perf_counter() - t
+                    return r
+                return run
+            chain, repair, exchange = timed('chain_s', chain), timed('repair_s', repair), timed('exchange_s', exchange)
         flag = carry_rounds(self.rank, self.world, lambda: chain(at['guess'] if self.rank > 0 else None), repair, exchange,
                             any_changed if self._settle else None)
         return sem8, flag
@@ -570,7 +588,7 @@ class StackShard:
         t_1 = time.perf_counter()
         # one pinned buffer: n_sub table areas of host_words each (sized from what the data needed so far), then n_sub flags
         fixed = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * SB
-        per_slice = _words_per_slice.get((dev.index, H, W), 1 << 14)
+        per_slice = _words_per_slice.get((dev.index, H, W), 1 << 13)
         host_words = min(packed_words, fixed + SB * int(per_slice * 1.25))
         host = _table_pool.acquire(dev, n_sub * (host_words + 1))
         flags = host[n_sub * host_words:n_sub * host_words + n_sub]

@@ -241,9 +241,10 @@ int emp_rle(const int64_t* pan, int H, int W, const int64_t* labels /* host */, 
  *       [EMP_BLK_HDR_MAXLAB + i]  largest (label - labels[i] * label_divisor) in the block
  *       per slice b at EMP_BLK_HDR_WORDS + EMP_BLK_SLICE_WORDS * b:
  *           n instances, first instance row, first run row, row-runs, OR of the EMP_FLAG_* bits, K (centers found)
- *       starts[R], lengths[R] (flat indices into the crop_h x crop_w map; grouped by instance, ascending inside one)
- *       I instance rows of EMP_BLK_INST_WORDS: class label, instance label, y0, x0, y1, x1, n runs, first run row
- *           (into starts / lengths), area — slices in order, instances in the reference's dict order
+ *       starts[R'], lengths[R'] as INT32 (R' = R rounded up to even, so R' / 2 words each; flat indices into the
+ *           crop_h x crop_w map, which is < 2^31 pixels; grouped by instance, ascending inside one)
+ *       I instance rows of EMP_BLK_INST_WORDS int64: class label, instance label, y0, x0, y1, x1, n runs, first run
+ *           row (into starts / lengths), area — slices in order, instances in the reference's dict order
  *   runs3_out  optional device (B, run_cap, 3) int64: (start, length, instance slot) of every row-run in ascending
  *              start order — the layout emp_rle_pair_overlaps / emp_fill_runs consume. */
 typedef struct emp_stack_cfg {
