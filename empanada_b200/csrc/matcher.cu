@@ -22,6 +22,7 @@ rle_pair_overlaps_kernel(const long long* __restrict__ runs, size_t run_stride, 
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nB; j += gridDim.x * blockDim.x) {
         const long long bs = B[3 * (size_t)j], be = bs + B[3 * (size_t)j + 1];
         const int slot_b = (int)B[3 * (size_t)j + 2];
+        if (slot_b < 0) continue;                               // a run of a label that is not selected
         int lo = 0, hi = nA;                                    // first A run with end > bs (ends ascend too)
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -32,7 +33,7 @@ rle_pair_overlaps_kernel(const long long* __restrict__ runs, size_t run_stride, 
             if (as >= be) break;
             const long long ae = as + A[3 * (size_t)i + 1];
             const long long ov = min(ae, be) - max(as, bs);
-            if (ov > 0) {
+            if (ov > 0 && A[3 * (size_t)i + 2] >= 0) {
                 const int pos = atomicAdd(count, 1);
                 if (pos < cap) {
                     int4 row = make_int4(p, (int)A[3 * (size_t)i + 2], slot_b, (int)ov);
@@ -143,6 +144,7 @@ rle_list_overlaps_kernel(const long long* __restrict__ A, int nA, long long lmax
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nB; j += gridDim.x * blockDim.x) {
         const long long bs = B[3 * (size_t)j], be = bs + B[3 * (size_t)j + 1];
         const int slot_b = (int)B[3 * (size_t)j + 2];
+        if (slot_b < 0) continue;                               // a run of a label that is not selected
         int lo = 0, hi = nA;                                    // first A run with start > bs - lmax_a
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;

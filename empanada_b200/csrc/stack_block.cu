@@ -311,7 +311,21 @@ struct LeanArgs {
     unsigned long long thing_bits;
     int simple;                 // one thing class (thing_class, != 0) and cells of >= 4 pixels: the byte-mask path applies
     unsigned thing_class;
+    // mark != 0: also write the RLE encoder's run start / end masks and row counts (possible when the void label is not
+    // a selected label: then distinct codes other than void / class-0 background never share a label, so run boundaries
+    // are code boundaries; runs of codes whose label turns out not to be selected are dropped at run level)
+    int mark;
+    char* rs; size_t rs_stride; size_t o_smask, o_emask, o_rowcnt;
+    int wd, crop_h, crop_w;
 };
+
+// the code merge_lean gives pixel (y, x): instance id (0: none -> void) on thing pixels, class code elsewhere
+__device__ __forceinline__ unsigned lean_code_at(const LeanArgs& a, const unsigned char* plane, const int32_t* ids, int y, int x)
+{
+    const unsigned c = plane[(size_t)y * a.W + x];
+    if (c < 64u && ((a.thing_bits >> c) & 1ull)) return (unsigned)__ldg(ids + (y >> a.shift) * a.wc + (x >> a.shift));
+    return kClsBase16 + c;
+}
 
 __global__ void __launch_bounds__(256, 4)
 merge_lean_kernel(const LeanArgs a)
@@ -432,6 +446,47 @@ merge_lean_kernel(const LeanArgs a)
                 if (acnt) atomicAdd(areas + akey, acnt);
             }
             if (valid) *reinterpret_cast<uint4*>(codes + (size_t)y * a.W + x) = make_uint4(out[0], out[1], out[2], out[3]);
+            if (a.mark) {
+                // ---- run boundaries of this strip row: a pixel starts (ends) a run if its code is neither void nor class-0
+                // background and differs from its left (right) neighbour's; pixels outside the crop count as background
+                const bool row_in = valid && y < a.crop_h;
+                unsigned c8[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const unsigned v = (out[p >> 1] >> (16 * (p & 1))) & 0xFFFFu;
+                    c8[p] = (row_in && x + p < a.crop_w) ? v : kClsBase16;
+                }
+                unsigned left = __shfl_up_sync(0xffffffffu, c8[7], 1);
+                unsigned right = __shfl_down_sync(0xffffffffu, c8[0], 1);
+                if ((lane & 7) == 0) left = (row_in && x > 0) ? lean_code_at(a, plane, ids, y, x - 1) : kClsBase16;
+                if ((lane & 7) == 7) right = (row_in && x + 8 < a.crop_w) ? lean_code_at(a, plane, ids, y, x + 8) : kClsBase16;
+                unsigned sb = 0, eb = 0;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    const unsigned l = p ? c8[p - 1] : left, rn = p < 7 ? c8[p + 1] : right;
+                    const bool sel = c8[p] != 0u && c8[p] != kClsBase16;
+                    sb |= (sel && l != c8[p] ? 1u : 0u) << p;
+                    eb |= (sel && rn != c8[p] ? 1u : 0u) << p;
+                }
+                const unsigned mine = sb | (eb << 8);
+                const unsigned m1 = __shfl_down_sync(0xffffffffu, mine, 1), m2 = __shfl_down_sync(0xffffffffu, mine, 2),
+                               m3 = __shfl_down_sync(0xffffffffu, mine, 3);
+                unsigned cnt = 0;
+                if ((lane & 3) == 0 && row_in) {
+                    const unsigned sw = (mine & 0xFFu) | ((m1 & 0xFFu) << 8) | ((m2 & 0xFFu) << 16) | ((m3 & 0xFFu) << 24);
+                    const unsigned ew = ((mine >> 8) & 0xFFu) | (((m1 >> 8) & 0xFFu) << 8) | (((m2 >> 8) & 0xFFu) << 16) | (((m3 >> 8) & 0xFFu) << 24);
+                    const int wi = (x >> 5);
+                    if (wi < a.wd && (sw | ew)) {
+                        char* rsb = a.rs + (size_t)b * a.rs_stride;
+                        reinterpret_cast<uint32_t*>(rsb + a.o_smask)[(size_t)y * a.wd + wi] = sw;
+                        reinterpret_cast<uint32_t*>(rsb + a.o_emask)[(size_t)y * a.wd + wi] = ew;
+                    }
+                    cnt = (unsigned)__popc(sw);
+                }
+                cnt += __shfl_down_sync(0xffffffffu, cnt, 4);           // the row's two words
+                if ((lane & 7) == 0 && cnt)
+                    atomicAdd(reinterpret_cast<uint32_t*>(a.rs + (size_t)b * a.rs_stride + a.o_rowcnt) + y, cnt);
+            }
             // votes: lanes holding the same key (the rows of a strip share their cells) add up first
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
@@ -1314,6 +1369,14 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
                                  ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st, need, need_stride)))
         return rc;
     const int32_t* k_dev = reinterpret_cast<const int32_t*>(cs + P.Lc.status) + EMP_ST_K;
+    EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
+    EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
+    // is the void label itself a selected label?  (then it may share its label with a stuff class or an instance, and run
+    // boundaries have to be decided on labels, by rle_block_mark, not on codes inside the merge kernel)
+    bool void_selected = false;
+    for (int i = 0; i < P.rc.n; ++i)
+        void_selected |= cfg->void_label != 0 && cfg->void_label >= P.rc.lo[i] && cfg->void_label < P.rc.lo[i] + P.rc.L;
+    bool marked = false;
     unsigned long long thing_bits = 0ull;
     bool things_small = true;
     for (int i = 0; i < P.th.n; ++i) {
@@ -1334,6 +1397,10 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         m.T = P.th.n > 0 ? P.th.n : 1; m.thing_bits = thing_bits;
         m.simple = (P.th.n == 1 && P.th.v[0] > 0 && cfg->shift >= 2) ? 1 : 0;
         m.thing_class = P.th.n == 1 ? (unsigned)P.th.v[0] : 0u;
+        m.mark = void_selected ? 0 : 1;
+        m.rs = rs; m.rs_stride = P.R.total; m.o_smask = P.R.smask; m.o_emask = P.R.emask; m.o_rowcnt = P.R.rowcnt;
+        m.wd = P.R.wd; m.crop_h = cfg->crop_h; m.crop_w = cfg->crop_w;
+        marked = m.mark != 0;
         const unsigned items = (unsigned)(((cfg->H + 3) / 4) * ((cfg->W + 511) / 512));
         {
             ProfScope ps(ST_ASSIGN, st);
@@ -1365,14 +1432,12 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
     a.runs3 = reinterpret_cast<long long*>(runs3_out); a.runs3_stride = 3 * (size_t)cfg->run_cap;
     a.maxlab_all = reinterpret_cast<long long*>(maxlab_all);
 
-    EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
-    EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
     {
         ProfScope ps(ST_BLK_KEYS, st);
         rle_block_keys_kernel<<<dim3(8, 1, B), 256, 0, st>>>(a);
     }
     EMP_CUDA_CHECK(cudaGetLastError());
-    {
+    if (!marked) {                                              // else merge_lean has written the masks already
         const unsigned items = (unsigned)(((cfg->crop_h + 3) / 4) * ((cfg->crop_w + 255) / 256));
         ProfScope ps(ST_BLK_MARK, st);
         rle_block_mark_kernel<<<dim3((items + 7) / 8, 1, B), 256, 0, st>>>(a);
