@@ -29,7 +29,7 @@ def main():
         out['dram_bytes_per_px'][key] = (d['dram__bytes_read.sum'] + d['dram__bytes_write.sum']) / px
         out['ncu_time_us'][key] = d['gpu__time_duration.sum']
     vox = 64 * 2048 * 2048
-    for prefix in ('median_chain_kernel', 'merge_lean_kernel', 'rle_block_mark_kernel', 'rle_block_emit_kernel', 'assign_kernel<2, 0, 3, 1>',
+    for prefix in ('median_chain_kernel', 'merge_lean_kernel', 'rle_block_emit_kernel', 'assign_kernel<2, 0, 3, 1>',
                    'rle_block_union_kernel', 'rle_block_flags_kernel', 'rle_block_slots_kernel', 'rle_block_assign_kernel',
                    'rle_block_offsets_kernel', 'rle_block_lists_kernel', 'rle_block_pack_kernel', 'rle_block_keys_kernel'):
         d = biggest(allk, prefix)
