@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include "common.cuh"
 
@@ -40,13 +42,15 @@ void set_error(const char* fmt, ...)
 // per-stage timing
 // ---------------------------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int stage; };
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mutex;                 // the record list is shared by every thread that launches kernels
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
 
 ProfScope::ProfScope(int stage, cudaStream_t s) : idx(-1), st(s)
 {
-    if (!g_prof_on) return;
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     if (g_prof_used == g_prof.size()) {
         ProfRec r;
         if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
@@ -60,7 +64,9 @@ ProfScope::ProfScope(int stage, cudaStream_t s) : idx(-1), st(s)
 
 ProfScope::~ProfScope()
 {
-    if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if ((size_t)idx < g_prof.size()) cudaEventRecord(g_prof[idx].b, st);
 }
 
 int make_things(const int64_t* list, int n, Things* out)
@@ -1504,13 +1510,13 @@ apply_lut_staged_kernel(const __grid_constant__ ApplyArgs a)
 // ---------------------------------------------------------------------------------------------
 static int sm_count()
 {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        n = v;
-    }
-    return n;
+    static std::atomic<int> cached[64];         // per device ordinal; 0 = not asked yet
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && (v = cached[dev].load(std::memory_order_relaxed)) > 0) return v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    if (dev >= 0 && dev < 64) cached[dev].store(v, std::memory_order_relaxed);
+    return v;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -1851,7 +1857,8 @@ EMP_API int emp_version(void) { return 100; }
 
 EMP_API int emp_profile_enable(int on)
 {
-    g_prof_on = on != 0;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_on.store(on != 0);
     g_prof_used = 0;
     return EMP_OK;
 }
@@ -1859,6 +1866,7 @@ EMP_API int emp_profile_enable(int on)
 EMP_API int emp_profile_read(double* ms_per_stage, int* launches_per_stage)
 {
     for (int i = 0; i < ST_COUNT; ++i) { ms_per_stage[i] = 0.0; launches_per_stage[i] = 0; }   // ST_COUNT == EMP_PROFILE_STAGES
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (size_t i = 0; i < g_prof_used; ++i) {
         EMP_CUDA_CHECK(cudaEventSynchronize(g_prof[i].b));
         float ms = 0.f;

@@ -275,3 +275,18 @@ def test_stack_shard_vs_reference_stack_of_rle(name, block, cuda_device):
         _rle_equal(got[z], want, f'{name} slice {z}')
         total += inst.shape[0]
     assert got.counts()[0] == total
+
+
+def test_sharded_stack_on_two_gpus_matches_single_block():
+    """tests/mp_stack_match.py under torchrun on 2 GPUs (NCCL): every rank's finish + match + fill must equal the single
+    block.  Skipped on boxes with one GPU (the bench lines carry the same check at every N)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29541', os.path.join(root, 'tests', 'mp_stack_match.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert 'mp_stack_match world=2: OK' in r.stdout
