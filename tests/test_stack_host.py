@@ -200,3 +200,78 @@ def test_matching_chain_continues_across_blocks(name):
             np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg({1: got}, (p['H'], p['W'])), g[f'fwd_{z}'])
         for z, got in enumerate(b_a + b_b):
             np.testing.assert_array_equal(oracle.rle_seg_to_pan_seg({1: got}, (p['H'], p['W'])), g[f'bwd_{z}'])
+
+
+# ---- host side of the batched stack path: packed tables -> RleStack (no GPU needed) ------------------------------
+def _packed_block(slices):
+    """Packs per-slice instance lists [(class, label, box, starts, lens), ...] the way emp_stack_block does
+    (include/empanada_b200.h, EMP_BLK_*): header | per-slice rows | int32 starts | int32 lengths | int64 instance rows."""
+    from empanada_b200 import _cabi as C
+    B = len(slices)
+    starts, lens, inst, rows = [], [], [], []
+    for sl in slices:
+        first_inst, first_run = len(inst), len(starts)
+        for cls, lab, box, s, l in sl:
+            inst.append([cls, lab, *box, len(s), len(starts), int(np.sum(l))])
+            starts += list(s)
+            lens += list(l)
+        rows.append([len(sl), first_inst, first_run, len(starts) - first_run, 0, len(sl)])
+    R, Rp = len(starts), (len(starts) + 1) & ~1
+    words = np.zeros(C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B + Rp + C.BLK_INST_WORDS * len(inst), np.int64)
+    words[0], words[1], words[2], words[3] = B, R, len(inst), C.BLK_INST_WORDS
+    s0 = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * B
+    words[C.BLK_HDR_WORDS:s0] = np.asarray(rows, np.int64).reshape(-1)
+    r32 = words[s0:s0 + Rp].view(np.int32)
+    r32[:R] = starts
+    r32[Rp:Rp + R] = lens
+    words[s0 + Rp:] = np.asarray(inst, np.int64).reshape(-1)
+    return words
+
+
+def test_rle_stack_reads_packed_tables():
+    slices = [
+        [(1, 20001, (0, 0, 2, 9), [0, 12], [3, 2]), (1, 20002, (3, 1, 4, 4), [31], [3]), (2, 40000, (0, 5, 6, 10), [5, 15, 25], [5, 5, 5])],
+        [],
+        [(1, 20001, (1, 1, 2, 2), [11], [1])],
+    ]
+    words = _packed_block(slices)
+    assert stack._BlockTables.words_needed(words, 3) == words.size
+    t = stack._BlockTables(words, 3)
+    out = stack.RleStack([1, 2], [1], 20000)
+    for b, z in enumerate((7, 8, 9)):
+        out._add(z, t, b)
+    out._add_dict(10, {1: {20003: {'box': (0, 0, 1, 1), 'starts': np.array([0]), 'runs': np.array([1])}}, 2: {}})
+    out.offsets = {1: 40, 2: 0}                         # this rank's label offset: thing classes only
+    assert list(out) == [7, 8, 9, 10] and len(out) == 4
+    assert out.counts() == (5, 8)
+    seg = out[7]
+    assert list(seg) == [1, 2] and list(seg[1]) == [20041, 20042] and list(seg[2]) == [40000]
+    assert seg[1][20041]['box'] == (0, 0, 2, 9)
+    np.testing.assert_array_equal(seg[1][20041]['starts'], [0, 12])
+    np.testing.assert_array_equal(seg[1][20041]['runs'], [3, 2])
+    np.testing.assert_array_equal(seg[2][40000]['starts'], [5, 15, 25])
+    assert seg[1][20041]['starts'].dtype == np.int64 and seg[1][20041]['runs'].dtype == np.int64
+    assert out[8] == {1: {}, 2: {}}
+    assert list(out[9][1]) == [20041] and list(out[10][1]) == [20043]
+    assert out[7] is seg                                # materialised once
+    assert out.inst_rows(10) is None and out.inst_rows(7).shape == (3, 9)
+    out.offsets = {1: 19999}
+    out._cache.clear()
+    with pytest.raises(ValueError):
+        out[7]                                          # 20001 + 19999 leaves class 1's label range
+
+
+def test_pinned_pool_hands_out_idle_buffers_only():
+    """The pool looks at reference counts: a buffer whose views are still alive is not handed out again."""
+    if not torch.cuda.is_available():
+        pytest.skip('pinned memory needs a CUDA runtime')
+    pool = stack._PinnedPool()
+    dev = torch.device('cuda', 0)
+    a = pool.acquire(dev, 1000)
+    view = a.numpy()[:10]
+    del a
+    b = pool.acquire(dev, 500)
+    assert b.data_ptr() != view.ctypes.data             # the first buffer is still referenced by `view`
+    del view, b
+    c = pool.acquire(dev, 800)
+    assert len(pool.buffers[0]) == 2 and c.numel() >= 800
