@@ -138,10 +138,10 @@ class ClockSampler:
 
 
 def reference_postprocess():
-    """The reference's own post-processing module when build() staged it (oracle/_ref/postprocess.py: the unmodified
+    """The reference's own post-processing module when build() staged it (oracle/_ref/empanada_inference_postprocess.py: the unmodified
     file, copied from /root/reference in the build container; git-ignored, it travels with the snapshot), else the
     oracle's op-sequence port.  Returns (find_instance_center, group_pixels, merge_semantic_and_instance, kind)."""
-    path = os.path.join(ROOT, 'oracle', '_ref', 'postprocess.py')
+    path = os.path.join(ROOT, 'oracle', '_ref', 'empanada_inference_postprocess.py')
     if os.path.exists(path):
         import importlib.util
         spec = importlib.util.spec_from_file_location('empanada_reference_postprocess', path)
