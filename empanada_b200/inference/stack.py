@@ -397,7 +397,7 @@ class StackShard:
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, block=128, keep_tables=True, chain_chunk=4096):
+                 upsampling=1, force_connected=True, group=None, block=128, keep_tables=True, chain_chunk=4096, run_cap=None, inst_cap=None):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
@@ -416,6 +416,7 @@ class StackShard:
         self.block = max(1, int(block))
         self.keep_tables = bool(keep_tables)
         self.chain_chunk = max(1, int(chain_chunk))      # slices per emp_median_chain launch
+        self.run_cap, self.inst_cap = run_cap, inst_cap  # deferred table capacities per slice (None: from the plane size)
         self._settle = False
 
     def slices(self):
@@ -564,8 +565,9 @@ class StackShard:
         step = 4 if e.coarse_boundaries else 1
         things, nt = C.i64_array(e.thing_list)
         labels, nl = C.i64_array(self.labels)
-        run_cap = max(1 << 14, (H * W) // 256)
-        inst_cap = max(1 << 12, run_cap // 4)
+        # a slice that overflows either table is redone synchronously with tables grown to fit (_slice_sync)
+        run_cap = int(self.run_cap) if self.run_cap else max(1 << 14, (H * W) // 256)
+        inst_cap = int(self.inst_cap) if self.inst_cap else max(1 << 12, run_cap // 4)
         cfg = C.StackCfg(H=H, W=W, h=hh, w=ww, shift=shift, nms_kernel=int(e.nms_kernel), k_cap=min(pp.DEFAULT_K_CAP, hh * ww),
                          crop_h=crop[0], crop_w=crop[1], n_things=nt, n_labels=nl, force_connected=int(bool(self.force_connected)),
                          run_cap=run_cap, inst_cap=inst_cap, nms_threshold=float(e.nms_threshold), step=float(step),

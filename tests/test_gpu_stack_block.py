@@ -211,6 +211,33 @@ def test_stack_block_matches_per_slice_path(case, cuda_device):
         np.testing.assert_array_equal(vol[z], rle.rle_seg_to_pan_seg(want[z], size).astype(np.int64))
 
 
+@pytest.mark.parametrize('caps', [(40, 4096), (16384, 3)])
+def test_stack_block_table_overflow_falls_back_per_slice(caps, cuda_device):
+    """A slice with more row-runs / instances than the deferred tables hold is flagged by the kernels and redone
+    synchronously through the per-slice path (tables grown to fit); the other slices of the block keep their batched
+    results.  Everything must still equal the per-slice reference path."""
+    from empanada_b200.inference import engines as eng, stack
+    from empanada_b200.synth import synth_stack_slices
+    dev = cuda_device
+    D, H, W = 6, 128, 192
+    sl = list(synth_stack_slices(D, H, W, 30, seed=15, coarse=4, sigma=4.0, z_extent=(3, 9), semi_axes=(5, 16)))
+    heads = [{k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')} for s in sl]
+    heads[2]['sem_prob'] = torch.full_like(heads[2]['sem_prob'], 0.1)         # one slice with nothing in it stays under any capacity
+    probs = [h['sem_prob'] for h in heads]
+    kw = dict(thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3,
+              confidence_thr=0.3, coarse_boundaries=True)
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), **kw)
+    want = _per_slice_reference(e, probs, heads, (H, W), 1, D, [1], True)
+    shard = stack.StackShard(e, labels=[1], depth=D, median_kernel_size=1, run_cap=caps[0], inst_cap=caps[1])
+    for z in shard.slices():
+        shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=(H, W))
+    got = shard.finish()
+    assert shard.tables_['bad'].any() and not shard.tables_['bad'].all()
+    for z in range(D):
+        _rle_equal(got[z], want[z], f'slice {z}')
+    assert got.counts()[0] == sum(len(v) for w in want for v in w.values())
+
+
 def test_stack_block_vs_oracle_row_wrap(cuda_device):
     """Runs that reach the last column continue in column 0 of the next row (array_utils.rle_encode): full-width
     things, checked against the oracle's restatement of rle.py on the oracle's own panoptic maps."""
