@@ -317,3 +317,51 @@ def test_sharded_stack_on_two_gpus_matches_single_block():
                         '--master-port', '29541', os.path.join(root, 'tests', 'mp_stack_match.py')], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'mp_stack_match world=2: OK' in r.stdout
+
+
+def test_stack_block_degenerate_slices(cuda_device):
+    """Slices with nothing in them (all background: every strip flagged), with thing pixels but no center (ids 0 -> void),
+    and a normal one, in one block."""
+    from empanada_b200.inference import engines as eng, stack
+    from empanada_b200.synth import synth_stack_slices
+    dev = cuda_device
+    D, H, W = 4, 128, 192
+    sl = list(synth_stack_slices(D, H, W, 25, seed=33, coarse=4, sigma=4.0, z_extent=(3, 9), semi_axes=(5, 16)))
+    heads = [{k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')} for s in sl]
+    heads[0]['sem_prob'] = torch.full_like(heads[0]['sem_prob'], 0.1)
+    heads[1]['ctr_hmp'] = torch.zeros_like(heads[1]['ctr_hmp'])              # things, but no center anywhere
+    heads[2]['sem_prob'] = torch.full_like(heads[2]['sem_prob'], 0.9)        # every pixel a thing pixel: no strip is flagged
+    probs = [h['sem_prob'] for h in heads]
+    kw = dict(thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3,
+              confidence_thr=0.3, coarse_boundaries=True)
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), **kw)
+    want = _per_slice_reference(e, probs, heads, (H, W), 1, D, [1], True)
+    shard = stack.StackShard(e, labels=[1], depth=D, median_kernel_size=1)
+    for z in shard.slices():
+        shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=(H, W))
+    got = shard.finish()
+    assert got[0] == {1: {}} and got[1] == {1: {}}
+    for z in range(D):
+        _rle_equal(got[z], want[z], f'slice {z}')
+
+
+def test_stack_block_4096_plane(cuda_device):
+    """A 4096 x 4096 plane (coarse 1024 x 1024): 65536-entry run tables, 32-bit flat indices near their upper half."""
+    from empanada_b200.inference import engines as eng, stack
+    from empanada_b200.synth import synth_stack_slices
+    dev = cuda_device
+    D, H, W = 2, 4096, 4096
+    sl = list(synth_stack_slices(D, H, W, 300, seed=44, coarse=4, z_extent=(2, 6)))
+    heads = [{k: torch.from_numpy(s[k]).to(dev) for k in ('sem_prob', 'ctr_hmp', 'offsets')} for s in sl]
+    probs = [h['sem_prob'] for h in heads]
+    kw = dict(thing_list=[1], label_divisor=20000, stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=3,
+              confidence_thr=0.3, coarse_boundaries=True)
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), **kw)
+    want = _per_slice_reference(e, probs, heads, (H, W), 1, D, [1], True)
+    shard = stack.StackShard(e, labels=[1], depth=D, median_kernel_size=1)
+    for z in shard.slices():
+        shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=(H, W))
+    got = shard.finish()
+    assert sum(len(w[1]) for w in want) > 50
+    for z in range(D):
+        _rle_equal(got[z], want[z], f'slice {z}')
