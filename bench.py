@@ -204,6 +204,49 @@ def cpu_reference_sample(seed=0, win_centers=1024, win_group=160, win_merge=512)
     return n_px / t_tile / 1e6, t_c + t_g + t_m, K, torch.get_num_threads(), desc, kind
 
 
+def run_config1(dev, reps=50):
+    """BASELINE configs[0]: the 1024 x 1024 tile the reference itself was run on (tests/golden/make_config1.py: its
+    ResNet-50 PanopticDeepLab + engine on the CPU) through this package's PanopticDeepLabEngine (engines.py:92-160 of the
+    reference: sigmoid, harden, get_panoptic_segmentation), the CNN replaced by its recorded outputs.  Latency per tile
+    as a caller sees it (Python API, synchronised), checked against the reference's panoptic map."""
+    import torch
+    from empanada_b200.inference import engines as eng
+    from empanada_b200.synth import CONFIG1, CONFIG1_TILE, config1_heads
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'config1.npz'))
+    heads = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in config1_heads(g['consts']).items()}
+
+    class RecordedHeads(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.anchor = torch.nn.Parameter(torch.zeros(1, device=dev))       # the engine asks the model for its device
+
+        def forward(self, x):
+            return dict(heads)
+
+    engine = eng.PanopticDeepLabEngine(RecordedHeads(), **CONFIG1)
+    hw = CONFIG1_TILE[0]
+    image = torch.zeros((1, 1, hw, hw), device=dev)
+    for _ in range(5):
+        pan = engine(image)
+    torch.cuda.synchronize(dev)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        pan = engine(image)
+        torch.cuda.synchronize(dev)
+        times.append(time.perf_counter() - t0)
+    ms = statistics.median(times) * 1e3
+    rec = {'workload': f'postproc_1x{hw}x{hw}_k{CONFIG1_TILE[1]}_engine2d', 'ms_per_tile': ms, 'value': hw * hw / (ms * 1e-3) / 1e6, 'unit': UNIT,
+           'what': 'PanopticDeepLabEngine.__call__ minus the CNN: sigmoid + harden + fused post-processing, one synchronised Python call per tile',
+           'matches_reference_run': bool(np.array_equal(pan.cpu().numpy().reshape(hw, hw), g['pan'].reshape(hw, hw)))}
+    ref = os.path.join(ROOT, 'profiles', 'r2_config1_cpu.json')
+    if os.path.exists(ref):
+        with open(ref) as f:
+            r = json.load(f)
+        rec['reference_cpu_build_container'] = {k: r[k] for k in ('threads', 'seconds_cnn_forward', 'seconds_postprocess', 'postprocess_mpix_per_s')}
+    return rec
+
+
 def workload_config(world, B, Ks, dense=False):
     return {'workload': WORKLOAD if not dense else 'postproc_16x4096x4096_dense_k5000', 'tiles_per_gpu': B, 'tile': [H, W],
             'centers_per_tile': Ks, 'thing_list': THINGS, 'label_divisor': LABEL_DIVISOR, 'nms_kernel': NMS_K,
@@ -256,6 +299,7 @@ def main():
     ap.add_argument('--no-cnn', action='store_true', help='skip the stack loop with the stand-in CNN in it')
     ap.add_argument('--no-dense', action='store_true', help='skip the configs[4] dense sub-record (N = 1)')
     ap.add_argument('--dense-tiles', type=int, default=8)
+    ap.add_argument('--no-config1', action='store_true', help='skip the configs[0] sub-record (one 1024^2 tile through the 2D engine, N = 1)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -462,6 +506,11 @@ def main():
                      'hbm_frac_of_measured': ALG_BYTES_PER_PX * Bd * n_px / (dms * 1e-3) / 1e9 / measured_peak()[0]}
         del sem_d, hm_d, off_d
 
+    # ---- BASELINE configs[0]: the reference's CPU-runnable case — one 1024^2 tile through PanopticDeepLabEngine ----
+    config1_rec = None
+    if world == 1 and not args.no_config1:
+        config1_rec = run_config1(dev)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         dom = max(STAGE_ALG_BYTES_PER_PX, key=lambda k: prof[k][0])          # the kernel that takes the most time
@@ -501,6 +550,7 @@ def main():
             'clocks': clocks,
             'stack': stack_rec,
             'dense': dense_rec,
+            'config1': config1_rec,
         }
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)

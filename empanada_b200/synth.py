@@ -220,3 +220,23 @@ def synth_blob_volume(shape, n_blobs, seed, radii=(4.0, 9.0)):
         m = ((zz - c[i, 0]) / rad[i, 0]) ** 2 + ((yy - c[i, 1]) / rad[i, 1]) ** 2 + ((xx - c[i, 2]) / rad[i, 2]) ** 2 <= 1
         vol[m] = i + 1
     return vol
+
+
+# BASELINE configs[0] ("config 1"): the reference's own CPU-runnable case — one 1024 x 1024 tile, PanopticDeepLabEngine
+# defaults (engines.py:92-112), ~60 instances.  tests/golden/make_config1.py runs the reference on it.
+CONFIG1 = dict(thing_list=[1], label_divisor=1000, stuff_area=64, void_label=0, nms_threshold=0.1, nms_kernel=7, confidence_thr=0.5)
+CONFIG1_TILE = (1024, 60, 0)            # side, instances, seed
+
+
+def config1_heads(consts):
+    """Config 1's head tensors as float32 numpy arrays: the random-initialised network's per-channel constants
+    (consts: sem logit, heat-map, dy, dx — stored in tests/golden/config1.npz) + seeded synthetic heads.  No
+    transcendental function on the way, so the values are the same bits on any host."""
+    hw, n, seed = CONFIG1_TILE
+    d = synth_tile(hw, hw, n, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    logit = np.where(d['ins'] > 0, np.float32(2.0), np.float32(-2.0)).astype(np.float32)
+    logit += rng.uniform(-0.5, 0.5, logit.shape).astype(np.float32)
+    c = np.asarray(consts, np.float32)
+    return {'sem_logits': (logit + c[0])[None, None], 'ctr_hmp': d['ctr_hmp'] + c[1],
+            'offsets': d['offsets'] + c[2:4].reshape(1, 2, 1, 1)}

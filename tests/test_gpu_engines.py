@@ -46,6 +46,27 @@ def test_engine2d(cuda_device):
         assert _mismatch(out, g[f'out_{z}']) == 0
 
 
+def test_config1_tile_matches_reference_run(cuda_device):
+    """BASELINE configs[0]: the 1024^2 tile the reference's ResNet-50 PDL + PanopticDeepLabEngine was run on
+    (tests/golden/make_config1.py); the CNN's outputs are regenerated from the recorded constants + seed."""
+    from empanada_b200.synth import CONFIG1, config1_heads
+    g = load_golden('config1')
+    heads = {k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda_device) for k, v in config1_heads(g['consts']).items()}
+
+    class Recorded(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.anchor = torch.nn.Parameter(torch.zeros(1, device=cuda_device))       # the engine asks the model for its device
+
+        def forward(self, x):
+            return dict(heads)
+
+    e = eng.PanopticDeepLabEngine(Recorded(), **CONFIG1)
+    out = e(torch.zeros(1, 1, 1024, 1024, device=cuda_device))
+    assert out.dtype == torch.int64 and tuple(out.shape) == (1, 1, 1024, 1024)
+    assert _mismatch(out, g['pan'].astype(np.int64)) == 0
+
+
 @pytest.mark.parametrize('name', golden_names('engine3d_'))
 def test_engine3d(name, cuda_device):
     g = load_golden(name)

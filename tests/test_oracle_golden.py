@@ -268,3 +268,17 @@ def test_matcher_oracle_stack(name):
         else:
             seg = mat(seg)
         _same_rles(seg, g[f'bwd_inst_{z}'], g[f'bwd_starts_{z}'], g[f'bwd_runs_{z}'])
+
+
+def test_config1_matches_reference_run():
+    """BASELINE configs[0]: the oracle on the 1024^2 tile the reference's own engine (ResNet-50 PDL + post-processing,
+    tests/golden/make_config1.py) was run on."""
+    import torch
+    from empanada_b200.synth import CONFIG1 as p, config1_heads
+    g = load_golden('config1')
+    h = config1_heads(g['consts'])
+    sem = oracle.harden_seg(torch.sigmoid(torch.from_numpy(h['sem_logits'])).numpy(), p['confidence_thr'])
+    pan, _ = oracle.get_panoptic_segmentation(sem, h['ctr_hmp'], h['offsets'], p['thing_list'], p['label_divisor'],
+                                              p['stuff_area'], p['void_label'], p['nms_threshold'], p['nms_kernel'])
+    assert np.unique(g['pan']).size > 50
+    np.testing.assert_array_equal(pan.reshape(g['pan'].shape), g['pan'])
