@@ -520,7 +520,7 @@ def main():
         dom_ms = a_ms / max(a_n, 1)
         achieved = STAGE_ALG_BYTES_PER_PX[dom] * px_per_launch / (dom_ms * 1e-3) / 1e9
         stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
-        launches = sum(v[1] for v in prof.values())
+        launches = sum(v[1] for k, v in prof.items() if k != 'memset')          # the clears are not kernels of this library
         pipeline_gbs = ALG_BYTES_PER_PX * B * n_px / (ms_step * 1e-3) / 1e9
         tpp = ncu_traffic(dom)
         traffic = tpp * px_per_launch if tpp is not None else None

@@ -98,7 +98,7 @@ class NeedMap(ctypes.Structure):
 
 STAGES = ('nms_peaks', 'emit_centers', 'assign', 'build_lut', 'apply_lut', 'median_harden', 'rle_mark', 'rle_runs',
           'bin_centers', 'median_chain', 'rle_block_keys', 'rle_block_mark', 'rle_block_emit', 'rle_block_runs',
-          'rle_block_pack')
+          'rle_block_pack', 'memset')
 
 
 def profile_enable(on):

@@ -90,7 +90,7 @@ int make_things(const int64_t* list, int n, Things* out);
 // around each kernel launch on the launching stream.  Off by default (no events recorded).
 enum { ST_NMS = 0, ST_EMIT = 1, ST_ASSIGN = 2, ST_LUT = 3, ST_APPLY = 4, ST_MEDIAN = 5, ST_RLE_MARK = 6,
        ST_RLE_RUNS = 7, ST_BIN = 8, ST_CHAIN = 9, ST_BLK_KEYS = 10, ST_BLK_MARK = 11, ST_BLK_EMIT = 12, ST_BLK_RUNS = 13,
-       ST_BLK_PACK = 14, ST_COUNT = EMP_PROFILE_STAGES };
+       ST_BLK_PACK = 14, ST_MEMSET = 15, ST_COUNT = EMP_PROFILE_STAGES };
 struct ProfScope {
     ProfScope(int stage, cudaStream_t st);
     ~ProfScope();

@@ -1564,8 +1564,10 @@ int launch_centers(int B, const float* hm, int H, int W, float thr, int k, float
     n.ws = ws; n.ws_stride = ws_stride; n.o_mask = L.mask; n.o_rowcnt = L.rowcnt;
     n.B = B; n.H = H; n.W = W; n.wd = L.wd; n.lo = k / 2; n.hi = k - 1 - n.lo; n.thr = thr;
     n.blocks_x = (W + kNmsItemW - 1) / kNmsItemW;
-    n.blk_items = kNmsBlkItems;                 // shorter strips for small planes, so that every warp has work
-    while (n.blk_items > 1 && (long long)((H + n.blk_items * kNmsRows - 1) / (n.blk_items * kNmsRows)) * n.blocks_x * B < 2048) n.blk_items >>= 1;
+    n.blk_items = kNmsBlkItems;                 // shorter strips for small batches: at least ~4 strips per resident warp, so the
+                                                // warps that draw one strip more than the others do not set the launch's time
+    const long long want_strips = 4ll * sm_count() * kNmsCtasPerSm * kNmsWarps;
+    while (n.blk_items > 1 && (long long)((H + n.blk_items * kNmsRows - 1) / (n.blk_items * kNmsRows)) * n.blocks_x * B < want_strips) n.blk_items >>= 1;
     n.blocks_y = (H + n.blk_items * kNmsRows - 1) / (n.blk_items * kNmsRows);
     const long long n_blocks = (long long)n.blocks_x * n.blocks_y * B;
     EMP_REQUIRE(n_blocks < (1ll << 30), EMP_ERR_INVALID, "batch too large for one launch");
@@ -1788,7 +1790,10 @@ int coarse_ids_batched(int B, const float* hm, size_t hm_stride, const float* of
 {
     const WsLayout L = ws_layout(h, w, k_cap, 1);
     EMP_REQUIRE(ws_stride >= L.total && ws_stride % 256 == 0, EMP_ERR_WORKSPACE, "coarse workspace stride too small");
-    EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    {
+        ProfScope ps(ST_MEMSET, st);
+        EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    }
     int rc;
     if ((rc = launch_centers(B, hm, h, w, threshold, nms_kernel, step, L, ws, ws_stride, k_cap, nullptr, 0, st, hm_stride))) return rc;
     if ((rc = launch_bin(B, L, ws, ws_stride, h, w, k_cap, -1, step, st))) return rc;
@@ -1822,7 +1827,10 @@ int merge_codes_batched(int B, const unsigned char* sem8, size_t sem_stride, con
     const WsLayout L = ws_layout(H, W, k_cap, th.n);
     EMP_REQUIRE(L.code16, EMP_ERR_INVALID, "the stack block needs 16-bit codes (k_cap < %u)", kClsBase16);
     EMP_REQUIRE(ws_stride >= L.total && ws_stride % 256 == 0, EMP_ERR_WORKSPACE, "merge workspace stride too small");
-    EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    {
+        ProfScope ps(ST_MEMSET, st);
+        EMP_CUDA_CHECK(cudaMemset2DAsync(ws, ws_stride, 0, L.zero_bytes, (size_t)B, st));
+    }
     AssignArgs a;
     memset(&a, 0, sizeof(a));
     a.sem = sem8; a.sem_stride = sem_stride;
@@ -2056,7 +2064,10 @@ EMP_API int emp_panoptic_batched(int B, const void* sem, int sem_u8, const float
     char* wsb = static_cast<char*>(ws);
     const size_t n_px = (size_t)H * W;
 
-    EMP_CUDA_CHECK(cudaMemset2DAsync(wsb, ws_bytes_per_tile, 0, L.zero_bytes, (size_t)B, st));
+    {
+        ProfScope ps(ST_MEMSET, st);
+        EMP_CUDA_CHECK(cudaMemset2DAsync(wsb, ws_bytes_per_tile, 0, L.zero_bytes, (size_t)B, st));
+    }
     if ((rc = launch_centers(B, hm, H, W, threshold, nms_kernel, 1.0f, L, wsb, ws_bytes_per_tile, k_cap, ctr_out, cap, st))) return rc;
     if ((rc = launch_bin(B, L, wsb, ws_bytes_per_tile, H, W, k_cap, -1, 1.0f, st))) return rc;
 

@@ -327,7 +327,11 @@ __device__ __forceinline__ unsigned lean_code_at(const LeanArgs& a, const unsign
     return kClsBase16 + c;
 }
 
-__global__ void __launch_bounds__(256, 4)
+#ifndef EMP_LEAN_WARPS
+#define EMP_LEAN_WARPS 2
+#endif
+constexpr int kLeanWarps = EMP_LEAN_WARPS;              // warps per CTA: each takes one item, a CTA lives as long as its slowest warp
+__global__ void __launch_bounds__(kLeanWarps * 32, 32 / kLeanWarps)
 merge_lean_kernel(const LeanArgs a)
 {
     const int lane = threadIdx.x & 31, grp = lane >> 2, q = lane & 3;
@@ -1369,8 +1373,11 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
                                  ids, P.ids_stride, cfg->k_cap, cs, P.Lc.total, st, need, need_stride)))
         return rc;
     const int32_t* k_dev = reinterpret_cast<const int32_t*>(cs + P.Lc.status) + EMP_ST_K;
-    EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
-    EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
+    {
+        ProfScope ps(ST_MEMSET, st);
+        EMP_CUDA_CHECK(cudaMemset2DAsync(rs, P.R.total, 0, P.R.zero_bytes, (size_t)B, st));
+        EMP_CUDA_CHECK(cudaMemsetAsync(packed_out, 0, sizeof(int64_t) * EMP_BLK_HDR_WORDS, st));
+    }
     // is the void label itself a selected label?  (then it may share its label with a stuff class or an instance, and run
     // boundaries have to be decided on labels, by rle_block_mark, not on codes inside the merge kernel)
     bool void_selected = false;
@@ -1384,7 +1391,10 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         else things_small = false;
     }
     if (things_small && cfg->W % 16 == 0 && (reinterpret_cast<uintptr_t>(sem8) & 15u) == 0 && sem8_stride % 16 == 0) {
-        EMP_CUDA_CHECK(cudaMemset2DAsync(ws, P.Lm.total, 0, P.Lm.zero_bytes, (size_t)B, st));
+        {
+            ProfScope ps(ST_MEMSET, st);
+            EMP_CUDA_CHECK(cudaMemset2DAsync(ws, P.Lm.total, 0, P.Lm.zero_bytes, (size_t)B, st));
+        }
         LeanArgs m;
         memset(&m, 0, sizeof(m));
         m.sem8 = sem8; m.sem_stride = sem8_stride; m.ids = ids; m.ids_stride = P.ids_stride;
@@ -1404,7 +1414,7 @@ static int stack_block_impl(const emp_stack_cfg* cfg, int B, const uint8_t* sem8
         const unsigned items = (unsigned)(((cfg->H + 3) / 4) * ((cfg->W + 511) / 512));
         {
             ProfScope ps(ST_ASSIGN, st);
-            merge_lean_kernel<<<dim3((items + 7) / 8, 1, B), 256, 0, st>>>(m);
+            merge_lean_kernel<<<dim3((items + kLeanWarps - 1) / kLeanWarps, 1, B), kLeanWarps * 32, 0, st>>>(m);
         }
         EMP_CUDA_CHECK(cudaGetLastError());
         if ((rc = build_luts_batched(B, cfg->H, cfg->W, P.th, cfg->label_divisor, cfg->stuff_area, cfg->void_label, cfg->k_cap, k_dev,

@@ -50,7 +50,7 @@ extern "C" {
 #define EMP_ST_GSHIFT 5     /* internal: log2 of the center-index cell size in pixels */
 #define EMP_ST_TICKET 6     /* internal: block hand-out counter of the assign kernel */
 #define EMP_ST_WORDS 16
-#define EMP_PROFILE_STAGES 15
+#define EMP_PROFILE_STAGES 16
 
 #define EMP_FLAG_K_OVERFLOW 1     /* more centers than k_cap: result invalid, retry with larger cap */
 #define EMP_FLAG_CLASS_RANGE 2    /* a semantic class id outside [0, EMP_MAX_CLASSES) was seen */
@@ -64,7 +64,7 @@ const char* emp_last_error(void);
  * bracketed by a CUDA event pair on its stream.  emp_profile_read() waits for the recorded events
  * and returns, per stage (0 nms_peaks, 1 emit_centers, 2 assign, 3 build_lut, 4 apply_lut,
  * 5 median_harden, 6 rle_mark, 7 rle run kernels, 8 bin_centers, 9 median_chain, 10..14 the stack block's
- * rle keys / mark / emit / runs / pack), the summed milliseconds and the
+ * rle keys / mark / emit / runs / pack, 15 the workspace clears of the batched entry points), the summed milliseconds and the
  * number of launches since the last read.  Both arrays have EMP_PROFILE_STAGES entries (host). */
 int emp_profile_enable(int on);
 int emp_profile_read(double* ms_per_stage, int* launches_per_stage);
