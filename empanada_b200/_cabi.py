@@ -17,6 +17,7 @@ FLAG_K_OVERFLOW, FLAG_CLASS_RANGE, FLAG_ID_RANGE, FLAG_RLE_OVERFLOW = 1, 2, 4, 8
 MAX_THINGS, MAX_CLASSES, MAX_LABELS = 16, 4096, 64
 # packed output of emp_stack_block (include/empanada_b200.h: EMP_BLK_*)
 BLK_HDR_MAXLAB, BLK_HDR_WORDS, BLK_SLICE_WORDS, BLK_INST_WORDS = 4, 4 + 64, 6, 9
+BLK_MAXLAB_OVERFLOW = 1 << 62           # emp_stack_blocks raises maxlab_all[0] to this if a slice overflowed a table
 
 _lib = None
 

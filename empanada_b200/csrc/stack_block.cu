@@ -1222,8 +1222,13 @@ rle_block_pack_kernel(const BlkArgs a)
         s[1] = inst_off;
         s[2] = rr_off;
         s[3] = min(__ldcg(status + EMP_ST_NROWRUNS), a.run_cap);
-        s[4] = (long long)(__ldcg(cstat + EMP_ST_FLAGS) | __ldcg(mstat + EMP_ST_FLAGS) | __ldcg(status + EMP_ST_FLAGS));
+        const int fl = __ldcg(cstat + EMP_ST_FLAGS) | __ldcg(mstat + EMP_ST_FLAGS) | __ldcg(status + EMP_ST_FLAGS);
+        s[4] = (long long)fl;
         s[5] = __ldcg(cstat + EMP_ST_K);
+        // a slice that overflowed a table is not in the maxima: poison them, so that every rank of a sharded stack learns
+        // of it from the gathered maxima (EMP_BLK_MAXLAB_OVERFLOW) and all of them fail together
+        if ((fl & (EMP_FLAG_K_OVERFLOW | EMP_FLAG_RLE_OVERFLOW)) && a.maxlab_all)
+            atomicMax(reinterpret_cast<unsigned long long*>(a.maxlab_all), (unsigned long long)EMP_BLK_MAXLAB_OVERFLOW);
         if (b == 0) { hdr[0] = a.B; hdr[1] = total_rr; hdr[2] = total_inst; hdr[3] = EMP_BLK_INST_WORDS; }
     }
 }

@@ -834,8 +834,12 @@ class StackShard:
                 finally:
                     self._settle = False
             per_class = table[:, :-1]
-            if bad.any():                                           # a slice redone synchronously is not in the device counts
-                raise RuntimeError('a slice overflowed the deferred tables on a multi-rank stack; raise the capacities')
+            if bad.any() or (per_class >= C.BLK_MAXLAB_OVERFLOW).any():
+                # a slice redone synchronously is not in the device counts.  The overflowing rank poisoned its row of the
+                # gathered table (EMP_BLK_MAXLAB_OVERFLOW), so every rank raises here and nobody is left in a collective.
+                ranks = np.flatnonzero((per_class >= C.BLK_MAXLAB_OVERFLOW).any(1)).tolist()
+                raise RuntimeError(f'a slice overflowed the deferred tables on rank(s) {ranks} of a multi-rank stack; '
+                                   f'raise run_cap / inst_cap')
             before = per_class[:self.rank].sum(0)
             worst = per_class.sum(0)
             for c, b, w in zip(self.labels, before.tolist(), worst.tolist()):

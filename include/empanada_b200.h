@@ -260,6 +260,7 @@ typedef struct emp_stack_cfg {
     const int64_t* labels;              /* host */
 } emp_stack_cfg;
 #define EMP_BLK_HDR_MAXLAB 4
+#define EMP_BLK_MAXLAB_OVERFLOW (1ll << 62)   /* emp_stack_blocks: maxlab_all[0] is raised to this if any slice overflowed a table */
 #define EMP_BLK_HDR_WORDS (4 + EMP_MAX_LABELS)
 #define EMP_BLK_SLICE_WORDS 6
 #define EMP_BLK_INST_WORDS 9
@@ -306,7 +307,8 @@ int emp_fill_runs(const int64_t* runs, size_t run_stride, const int32_t* n_runs,
  * (its slice count, never 0) is copied to host_flags[j] (pinned, zeroed by the caller): copies on one stream land in
  * order, so a host thread that reads host_flags[j] != 0 may parse block j.  If the header says the block holds more than
  * host_words words, the caller fetches the rest from packed_all.  maxlab_all (device, EMP_MAX_LABELS words, zeroed by the
- * caller; may be NULL) accumulates the per-class maxima of the blocks' headers — what the z-sharded stack all-gathers. */
+ * caller; may be NULL) accumulates the per-class maxima of the blocks' headers — what the z-sharded stack all-gathers;
+ * a slice whose EMP_FLAG_K_OVERFLOW / EMP_FLAG_RLE_OVERFLOW bit is set raises maxlab_all[0] to EMP_BLK_MAXLAB_OVERFLOW. */
 int emp_stack_blocks(const emp_stack_cfg* cfg, int n, int SB, const uint8_t* sem8, size_t sem8_stride, const float* hm,
                      size_t hm_stride, const float* off, size_t off_stride, const uint8_t* need, size_t need_stride,
                      void* scratch, size_t scratch_bytes, int64_t* packed_all, size_t packed_words, int64_t* runs3_all,

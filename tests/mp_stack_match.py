@@ -61,6 +61,24 @@ def main():
                     ok = False
                     print(f'MISMATCH at slice {z}: {sorted(a)[:6]} vs {sorted(b)[:6]}')
         print(f'mp_stack_match world={world}: {"OK" if ok else "FAILED"} — {D} slices, {len(n_obj)} tracked objects')
+    # a table overflow on ANY rank must surface on EVERY rank (the gathered maxima carry it), or the others would
+    # wait in the matcher's hand-over: rank 0 alone gets capacities too small for its slices
+    eng = engines.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=[1], label_divisor=20000, stuff_area=64,
+                                              void_label=0, nms_threshold=0.1, nms_kernel=3, confidence_thr=0.3)
+    shard = stack.StackShard(eng, labels=[1], depth=D, rank=rank, world_size=world, median_kernel_size=ks,
+                             run_cap=8 if rank == 0 else None, inst_cap=4 if rank == 0 else None)
+    for z in shard.slices():
+        shard.add(z, heads[z]['sem_prob'], heads[z]['ctr_hmp'], heads[z]['offsets'], size=(H, W))
+    raised = False
+    try:
+        shard.finish()
+    except RuntimeError as err:
+        raised = 'overflowed' in str(err)
+    flags = [None] * world
+    dist.all_gather_object(flags, raised)
+    if rank == 0:
+        print(f'overflow on rank 0 raised on every rank: {all(flags)} {flags}')
+        ok = ok and all(flags)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
