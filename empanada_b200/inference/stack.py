@@ -394,10 +394,13 @@ class StackShard:
     are used; its own median queue is bypassed in favour of the sharded chain above).
     block: slices per emp_stack_block call (sub-block); keep_tables: keep the (start, length, slot) row-run tables
     in HBM for match() / fill().
+    stream: an optional torch.cuda.Stream for advance(): the streamed sub-blocks then run beside the producer of the
+    heads (the CNN on the current stream) instead of between its kernels.
     """
 
     def __init__(self, engine, labels, depth, rank=0, world_size=1, median_kernel_size=3,
-                 upsampling=1, force_connected=True, group=None, block=128, keep_tables=True, chain_chunk=4096, run_cap=None, inst_cap=None):
+                 upsampling=1, force_connected=True, group=None, block=128, keep_tables=True, chain_chunk=4096, run_cap=None, inst_cap=None,
+                 stream=None):
         assert median_kernel_size % 2 == 1, "Kernel size must be odd integer!"
         assert math.log(upsampling, 2).is_integer(), "Upsampling factor not log base 2!"
         self.engine, self.labels, self.depth = engine, list(labels), depth
@@ -418,6 +421,9 @@ class StackShard:
         self.chain_chunk = max(1, int(chain_chunk))      # slices per emp_median_chain launch
         self.run_cap, self.inst_cap = run_cap, inst_cap  # deferred table capacities per slice (None: from the plane size)
         self._settle = False
+        self._stream = None                               # None: not begun; False: not streamable; dict: state of advance()
+        self.side_stream = stream                         # advance() enqueues here (None: on the current stream)
+        self._geom = None
 
     def slices(self):
         """z indices this rank must run the CNN on, in order."""
@@ -432,11 +438,14 @@ class StackShard:
     # ------------------------------------------------------------------------------------------------------
     def _geometry(self, H, W):
         """(coarse h, w, shift) of the block: the coarse maps are 2^shift times smaller than the H x W planes."""
+        if self._geom is not None:                                  # streamed blocks forget their first slices' heads
+            return self._geom
         hh, ww = self.heads[self.z0]['ctr_hmp'].shape[-2:]
         s_up = int(self.upsampling * (4 if self.engine.coarse_boundaries else 1))
         shift = int(math.log2(s_up))
         assert (1 << shift) == s_up
-        return int(hh), int(ww), shift
+        self._geom = (int(hh), int(ww), shift)
+        return self._geom
 
     def _chain(self, planes, dev, hw, Cn, need=None):
         """Recursive median + harden over the rank's block: sem8 (n, hw) uint8 in HBM.  Multi-rank blocks start from a
@@ -550,9 +559,9 @@ class StackShard:
                             any_changed if self._settle else None)
         return sem8, flag
 
-    def _enqueue_blocks(self, zs, sem8, dev, H, W, need=None):
-        """Phase A: ONE emp_stack_blocks call for the whole z-block: per sub-block a dozen launches on the current stream
-        and one device->host copy of its packed tables on the copy stream.  No host synchronisation."""
+    def _blocks_prepare(self, zs, dev, H, W):
+        """Everything the block launches of this rank's z-block share: the configuration, the device scratch and packed
+        tables, the pinned landing area with one arrival flag per sub-block."""
         from empanada_b200 import _cabi as C
         from empanada_b200.inference import postprocess as pp
         e, L = self.engine, C.lib()
@@ -560,7 +569,7 @@ class StackShard:
         h0 = self.heads[zs[0]]
         hh, ww, shift = self._geometry(H, W)
         size = h0['size']
-        assert all(self.heads[z]['size'] == size for z in zs), 'slices of one block must share their unpadded size'
+        self._size0 = size
         crop = (H, W) if size is None else (min(int(size[0]), H), min(int(size[1]), W))
         step = 4 if e.coarse_boundaries else 1
         things, nt = C.i64_array(e.thing_list)
@@ -579,15 +588,10 @@ class StackShard:
         scratch_bytes = int(L.emp_stack_block_scratch_bytes(ctypes.byref(cfg), SB))
         if packed_words == 0 or scratch_bytes == 0:
             raise ValueError('bad arguments to emp_stack_block: ' + L.emp_last_error().decode(errors='replace'))
-        t_0 = time.perf_counter()
         scratch = C.workspace(dev, scratch_bytes, 'stack_block')
         packed = _device_pool.acquire(dev, (n_sub, packed_words), torch.int64)
         runs_all = _device_pool.acquire(dev, (n, run_cap, 3), torch.int64) if self.keep_tables else None
         maxlab = torch.zeros((C.MAX_LABELS,), dtype=torch.int64, device=dev)
-        hm, hm_stride = _batched([_f32c(self.heads[z]['ctr_hmp']) for z in zs])          # one gather for the whole block
-        off, off_stride = _batched([_f32c(self.heads[z]['offsets']) for z in zs])
-        C.require_cuda(hm, off)
-        t_1 = time.perf_counter()
         # one pinned buffer: n_sub table areas of host_words each (sized from what the data needed so far), then n_sub flags
         fixed = C.BLK_HDR_WORDS + C.BLK_SLICE_WORDS * SB
         per_slice = _words_per_slice.get((dev.index, H, W), 1 << 13)
@@ -595,22 +599,53 @@ class StackShard:
         host = _table_pool.acquire(dev, n_sub * (host_words + 1))
         flags = host[n_sub * host_words:n_sub * host_words + n_sub]
         flags.zero_()
+        return {'cfg': cfg, 'n': n, 'n_sub': n_sub, 'SB': SB, 'H': H, 'W': W, 'packed_words': packed_words, 'scratch': scratch,
+                'packed': packed, 'runs_all': runs_all, 'run_cap': run_cap, 'maxlab': maxlab, 'nl': nl, 'host': host,
+                'host_words': host_words, 'flags_t': flags, 'flags': flags.numpy(), 'keep': [things, labels]}
+
+    def _blocks_launch(self, prep, zs, sem8, need, i0=0, m=None):
+        """ONE emp_stack_blocks call for slices [i0, i0 + m) of the z-block (default: all of it): per sub-block a dozen
+        launches on the current stream and one device->host copy of its packed tables on the copy stream.  No host
+        synchronisation.  i0 must be a multiple of the sub-block size."""
+        from empanada_b200 import _cabi as C
+        L = C.lib()
+        n = prep['n']
+        m = n - i0 if m is None else m
+        SB, H, W = prep['SB'], prep['H'], prep['W']
+        assert i0 % SB == 0 and 0 < m <= n - i0
+        bi0 = i0 // SB
+        dev = sem8.device
+        zs_g = zs[i0:i0 + m]
+        assert all(self.heads[z]['size'] == self._size0 for z in zs_g), 'slices of one block must share their unpadded size'
+        hm, hm_stride = _batched([_f32c(self.heads[z]['ctr_hmp']) for z in zs_g])        # one gather for the whole block
+        off, off_stride = _batched([_f32c(self.heads[z]['offsets']) for z in zs_g])
+        C.require_cuda(hm, off)
         main = torch.cuda.current_stream(dev)
         side = _copy_stream(dev)
         vp = ctypes.c_void_p
-        t_2 = time.perf_counter()
+        packed, runs_all, host, hw_ = prep['packed'], prep['runs_all'], prep['host'], prep['host_words']
+        scratch = prep['scratch']
         with torch.cuda.device(dev):
-            C.check(L.emp_stack_blocks(ctypes.byref(cfg), n, SB, vp(sem8.data_ptr()), H * W, vp(hm.data_ptr()), hm_stride,
-                                       vp(off.data_ptr()), off_stride, vp(need.data_ptr()) if need is not None else None,
+            C.check(L.emp_stack_blocks(ctypes.byref(prep['cfg']), m, SB, vp(sem8.data_ptr() + i0 * H * W), H * W, vp(hm.data_ptr()), hm_stride,
+                                       vp(off.data_ptr()), off_stride,
+                                       vp(need.data_ptr() + i0 * need.shape[1]) if need is not None else None,
                                        need.shape[1] if need is not None else 0, vp(scratch.data_ptr()), scratch.numel(),
-                                       vp(packed.data_ptr()), packed_words, vp(runs_all.data_ptr()) if runs_all is not None else None,
-                                       vp(maxlab.data_ptr()), vp(host.data_ptr()), host_words, host_words, vp(flags.data_ptr()),
-                                       vp(main.cuda_stream), vp(side.cuda_stream)))
-        self._marks.update(blocks_alloc_s=t_1 - t_0, blocks_pinned_s=t_2 - t_1, blocks_c_call_s=time.perf_counter() - t_2)
-        subs = {'n_sub': n_sub, 'SB': SB, 'host': host, 'host_words': host_words, 'flags': flags.numpy(), 'keep': (hm, off, scratch)}
-        return subs, packed, runs_all, maxlab[:nl], cfg
+                                       vp(packed.data_ptr() + 8 * bi0 * prep['packed_words']), prep['packed_words'],
+                                       vp(runs_all.data_ptr() + 8 * 3 * prep['run_cap'] * i0) if runs_all is not None else None,
+                                       vp(prep['maxlab'].data_ptr()), vp(host.data_ptr() + 8 * bi0 * hw_), hw_, hw_,
+                                       vp(prep['flags_t'].data_ptr() + 8 * bi0), vp(main.cuda_stream), vp(side.cuda_stream)))
+        prep['keep'].append((hm, off))
 
-    def _collect(self, zs, subs, packed, sem8, out):
+    def _enqueue_blocks(self, zs, sem8, dev, H, W, need=None):
+        """Phase A: the whole z-block in one emp_stack_blocks call."""
+        t_0 = time.perf_counter()
+        prep = self._blocks_prepare(zs, dev, H, W)
+        t_1 = time.perf_counter()
+        self._blocks_launch(prep, zs, sem8, need)
+        self._marks.update(blocks_alloc_s=t_1 - t_0, blocks_pinned_s=0.0, blocks_c_call_s=time.perf_counter() - t_1)
+        return prep, prep['packed'], prep['runs_all'], prep['maxlab'][:prep['nl']], prep['cfg']
+
+    def _collect(self, zs, subs, packed, sem8, out, streamed=False):
         """Phase B: as each block's tables land in pinned memory (its flag word turns non-zero) take owned copies of them and
         register the slices with `out` — while the GPU works on the blocks behind it."""
         from empanada_b200 import _cabi as C
@@ -646,6 +681,9 @@ class StackShard:
                 i = i0 + b
                 fl = int(t.slices[b, 4])
                 if fl & (C.FLAG_K_OVERFLOW | C.FLAG_RLE_OVERFLOW):
+                    if streamed:                                    # the slice's heads are gone: nothing to redo it from
+                        raise RuntimeError(f'slice {zs[i]} overflowed the deferred tables of a streamed stack; raise run_cap / '
+                                           f'inst_cap, or finish() without advance()')
                     bad[i] = True
                     out._add_dict(zs[i], _slice_sync(self.engine, self.heads[zs[i]], sem8[i].view(1, 1, *self._plane), self.labels,
                                                      self.upsampling, self.force_connected))
@@ -783,11 +821,14 @@ class StackShard:
     def finish(self):
         """Post-process + RLE-encode this rank's block.  Returns an RleStack ({z: rle_seg}, dicts built on access)."""
         with _gc_paused():          # a cyclic collection over a previous block's ~10^5 dicts would stall the enqueue loop
+            if self._stream:
+                return self._finish_streamed()
             return self._finish()
 
     def _finish(self):
         from empanada_b200 import _cabi as C
         self._marks = {}
+        self._geom = None
         e = self.engine
         zs = list(range(self.z0, self.z1))
         assert all(z in self.heads for z in range(self.z0, self.z_halo)), 'add() every slice of slices() first'
@@ -807,6 +848,15 @@ class StackShard:
         t_chain = time.perf_counter()
         subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W, need)
         t_blocks = time.perf_counter()
+        return self._complete(zs, dev, subs, sem8, changed, (t_a, t_chain, t_blocks), streamed=False)
+
+    def _complete(self, zs, dev, subs, sem8, changed, t_marks, streamed):
+        """The tail every finish shares: all-gather of the label maxima (+ the carry flag), collection of the sub-blocks'
+        tables as they land, label offsets."""
+        from empanada_b200 import _cabi as C
+        e = self.engine
+        t_a, t_chain, t_blocks = t_marks
+        packed, runs_all, counts = subs['packed'], subs['runs_all'], subs['maxlab'][:subs['nl']]
         # instance counts per class (+ the "my outgoing carry moved" flag) over all ranks
         multi = self.world > 1 and dist.is_available() and dist.is_initialized()
         table_h = None
@@ -818,13 +868,18 @@ class StackShard:
             table_h.copy_(gathered, non_blocking=True)
         t_b = time.perf_counter()
         out = RleStack(self.labels, e.thing_list, e.label_divisor)
-        bad, n_runs, inst = self._collect(zs, subs, packed, sem8, out)
+        bad, n_runs, inst = self._collect(zs, subs, packed, sem8, out, streamed)
         self._marks['collect_s'] = time.perf_counter() - t_b
         torch.cuda.current_stream(dev).synchronize()
         t_c = time.perf_counter()
         offs = {c: 0 for c in self.labels}
         if multi:
             table = table_h.numpy()
+            if table[:, -1].any() and streamed:
+                # every rank sees the same table: all of them raise
+                ranks = np.flatnonzero(table[:, -1]).tolist()
+                raise RuntimeError(f'streamed stack: the median carry of rank(s) {ranks} did not settle inside their first '
+                                   f'sub-block of {self.block} slices; use a larger `block`, or finish() without advance()')
             if table[:, -1].any() and not self._settle:
                 # some rank's repair reached the end of its block: its neighbour's carry was not final.  Every rank
                 # sees the same table, so all of them settle the carries with further rounds and redo the block.
@@ -858,3 +913,186 @@ class StackShard:
                         'slot_areas': [None if r is None else r[:, 8] for r in inst]}
         self._keep = None
         return out
+
+    # ------------------------------------------------------------------------------------------------------
+    # streaming: sub-blocks are chained and post-processed while later slices are still being produced
+    # ------------------------------------------------------------------------------------------------------
+    def advance(self):
+        """Optional, between add() calls: run the median chain and the post-processing of every sub-block (`block`
+        slices) whose slices and `median_kernel_size // 2` look-ahead slices have been add()ed, on the current stream,
+        and drop this object's references to their head tensors — the reference's slice-by-slice loop
+        (engines.py:363-394, pdl_inference3d.py:163-187) at sub-block granularity: the work hides behind the CNN of the
+        following slices, and only one sub-block of heads (plus a byte per voxel of hardened classes) stays resident.
+        finish() then only has the tail left.  Returns the number of sub-blocks enqueued by this call.
+
+        On ranks > 0 of a multi-rank stack the first sub-block waits for the block's end: it is chained from the guessed
+        carry at once (the following sub-blocks continue from its end state), but its tables are cut after the true carry
+        has arrived and the sub-block has been repaired — the call that reaches the block's last sub-block exchanges the
+        carries with the neighbour ranks (a collective: every rank must get there); a carry that does not settle inside
+        that first sub-block raises on every rank at finish().  Not streamed (advance() returns 0 and finish() does everything): blocks of a single sub-block, and
+        multi-class probabilities on a multi-rank stack (their carry is handed over rank after rank)."""
+        with _gc_paused():
+            return self._advance(final=False)
+
+    def _on_side(self, dev):
+        """Context of the streamed launches: the side stream (after it has caught up with the producer of the heads) or
+        the current stream."""
+        if self.side_stream is None:
+            return contextlib.nullcontext()
+        self.side_stream.wait_stream(torch.cuda.current_stream(dev))
+        return torch.cuda.stream(self.side_stream)
+
+    def _forget(self, zs):
+        """Drop the references to the heads of slices whose launches are enqueued."""
+        for z in zs:
+            h = self.heads[z]
+            if self.side_stream is not None:                        # the allocator must not reuse them before the side stream is done
+                for k in ('sem', 'ctr_hmp', 'offsets'):
+                    if isinstance(h.get(k), torch.Tensor) and h[k].is_cuda:
+                        h[k].record_stream(self.side_stream)
+            self.heads[z] = {'size': h['size']}
+
+    def _stream_begin(self):
+        from empanada_b200 import _cabi as C
+        e = self.engine
+        first = _f32c(self.heads[self.z0]['sem'])
+        if not first.is_cuda:
+            raise RuntimeError('StackShard runs on CUDA tensors only (there is no CPU fallback)')
+        dev = C.require_cuda(first)
+        assert first.dim() == 4 and first.size(0) == 1
+        Cn, H, W = (int(v) for v in first.shape[1:])
+        n, mid = self.z1 - self.z0, self.mid
+        multi = self.world > 1 and mid > 0 and dist.is_available() and dist.is_initialized()
+        if n <= self.block or (multi and Cn > 1):
+            self._stream = False                                    # not streamable: finish() does everything
+            return
+        self._marks = {}
+        self._geom = None
+        self._plane = (H, W)
+        hw = H * W
+        zs = list(range(self.z0, self.z1))
+        need = None
+        if all(0 <= int(c) < 64 for c in e.thing_list):
+            hh, ww, _ = self._geometry(H, W)
+            need = _device_pool.acquire(dev, (n, hh * ww), torch.uint8).zero_()
+        carry = {}
+        if mid > 0:
+            for name in ('out', 'a', 'b', 'p0', 'p1'):
+                carry[name] = [torch.empty((Cn * hw,), dtype=torch.float32, device=dev) for _ in range(mid)]
+            carry['guess'] = [first.reshape(-1).clone()] * mid      # this rank's first raw plane
+        self._stream = {
+            'dev': dev, 'Cn': Cn, 'H': H, 'W': W, 'hw': hw, 'multi': multi, 'zs': zs, 'need': need, 'carry': carry,
+            'sem8': _device_pool.acquire(dev, (n, hw), torch.uint8),
+            'best': torch.empty((n, hw), dtype=torch.float32, device=dev) if Cn > 1 else None,
+            'prep': self._blocks_prepare(zs, dev, H, W), 'next': 0, 'state': None, 'keep': [], 'group0': None,
+            't_a': time.perf_counter(),
+        }
+
+    def _carry_table(self, st, name):
+        """Device array of the `mid` plane pointers of one carry buffer (what the chain kernels take)."""
+        t = torch.tensor([p.data_ptr() for p in st['carry'][name]], dtype=torch.int64).to(st['dev'])
+        st['keep'].append(t)
+        return t.data_ptr()
+
+    def _advance(self, final):
+        from empanada_b200 import _cabi as C
+        if self._stream is None:
+            if self.z0 not in self.heads:
+                return 0
+            self._stream_begin()
+        st = self._stream
+        if st is False:
+            return 0
+        with self._on_side(st['dev']):
+            return self._advance_groups(st, final)
+
+    def _advance_groups(self, st, final):
+        from empanada_b200 import _cabi as C
+        e, L = self.engine, C.lib()
+        dev, hw, Cn, mid, ks = st['dev'], st['hw'], st['Cn'], self.mid, self.ks
+        prep = st['prep']
+        SB, n, n_sub = prep['SB'], prep['n'], prep['n_sub']
+        stream = C.stream_ptr(dev)
+        vp = ctypes.c_void_p
+        thr = float(e.confidence_thr)
+        done = 0
+        while st['next'] < n_sub:
+            g = st['next']
+            i0 = g * SB
+            m = min(SB, n - i0)
+            z_need = min(self.z0 + i0 + m + mid, self.z_halo)       # the group's slices + the chain's look-ahead
+            if not all(z in self.heads for z in range(self.z0 + i0, z_need)):
+                assert not final, 'add() every slice of slices() first'
+                break
+            planes = [_f32c(self.heads[z]['sem']) for z in range(self.z0 + i0, z_need)]
+            C.require_cuda(*planes)
+            assert all(p.shape == (1, Cn, st['H'], st['W']) for p in planes)
+            tab = torch.tensor([p.data_ptr() for p in planes], dtype=torch.int64).to(dev)
+            st['keep'].append((tab, planes if (g == 0 and st['multi'] and self.rank > 0) else None))
+            # carry in: the stack's start (none), the guess (first group of a rank > 0), else the previous group's end state
+            if g == 0:
+                cin = self._carry_table(st, 'guess') if (st['multi'] and self.rank > 0) else None
+            else:
+                cin = st['state']
+            cout = None
+            if mid > 0:
+                cout = self._carry_table(st, 'out' if g + 1 == n_sub else ('p0' if g % 2 == 0 else 'p1'))
+            nm = None
+            if st['need'] is not None:
+                hh, ww, shift = self._geometry(st['H'], st['W'])
+                bits = 0
+                for c in e.thing_list:
+                    bits |= 1 << int(c)
+                nm = C.NeedMap(map=st['need'].data_ptr() + i0 * st['need'].shape[1], stride=st['need'].shape[1], W=st['W'],
+                               shift=shift, wc=ww, thing_bits=bits)
+            with torch.cuda.device(dev):
+                C.check(L.emp_median_chain(vp(tab.data_ptr()), m, len(planes), self.z0 + i0, self.depth, ks, Cn, hw,
+                                           vp(cin) if cin else None, thr, vp(st['sem8'].data_ptr() + i0 * hw), hw,
+                                           vp(st['best'].data_ptr() + 4 * i0 * hw) if st['best'] is not None else None,
+                                           vp(cout) if cout else None, ctypes.byref(nm) if nm is not None else None, stream))
+            st['state'] = cout
+            if g + 1 == n_sub and st['multi']:
+                # the block's end state exists: hand it to rank + 1, take rank - 1's, repair the first sub-block from it and
+                # cut its tables — before this sub-block's own launches, so that the hand-over does not queue behind them
+                self._stream_carry(st)
+            if g == 0 and st['multi'] and self.rank > 0:
+                st['group0'] = (tab, len(planes), m, nm)             # repaired and cut into tables once the true carry is here
+            else:
+                self._blocks_launch(prep, st['zs'], st['sem8'], st['need'], i0, m)
+                self._forget(range(self.z0 + i0, self.z0 + i0 + m))
+            st['next'] += 1
+            done += 1
+        return done
+
+    def _stream_carry(self, st):
+        from empanada_b200 import _cabi as C
+        L = C.lib()
+        dev, hw = st['dev'], st['hw']
+        vp = ctypes.c_void_p
+        exchange_planes(st['carry']['out'], st['carry']['a'], self.rank, self.world, self.group)
+        if self.rank == 0:
+            return
+        tab, n_planes, m, nm = st['group0']
+        st['changed'] = torch.zeros((1,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            C.check(L.emp_median_chain_repair(vp(tab.data_ptr()), m, n_planes, self.z0, self.depth, self.ks, hw,
+                                              vp(self._carry_table(st, 'guess')), vp(self._carry_table(st, 'a')),
+                                              float(self.engine.confidence_thr), vp(st['sem8'].data_ptr()), hw,
+                                              vp(self._carry_table(st, 'b')), vp(st['changed'].data_ptr()),
+                                              ctypes.byref(nm) if nm is not None else None, C.stream_ptr(dev)))
+        self._blocks_launch(st['prep'], st['zs'], st['sem8'], st['need'], 0, m)
+        self._forget(range(self.z0, self.z0 + m))
+
+    def _finish_streamed(self):
+        st = self._stream
+        self._advance(final=True)
+        if self.side_stream is not None:
+            torch.cuda.current_stream(st['dev']).wait_stream(self.side_stream)
+        t_blocks = time.perf_counter()
+        self._keep = st                                              # alive until the stream has run
+        self._stream = None
+        try:
+            return self._complete(st['zs'], st['dev'], st['prep'], st['sem8'], st.get('changed'), (st['t_a'], t_blocks, t_blocks),
+                                  streamed=True)
+        finally:
+            self._keep = None

@@ -149,8 +149,9 @@ def _per_slice_reference(e, probs, heads, sizes, ks, depth, labels, force_connec
     return out
 
 
+@pytest.mark.parametrize('streamed', [False, True, 'side'])
 @pytest.mark.parametrize('case', ['plain', 'crop', 'odd', 'multiclass', 'noccl', 'void7', 'block1', 'up2'])
-def test_stack_block_matches_per_slice_path(case, cuda_device):
+def test_stack_block_matches_per_slice_path(case, streamed, cuda_device):
     from empanada_b200.inference import engines as eng, stack
     from empanada_b200.synth import synth_stack_slices
     dev = cuda_device
@@ -193,9 +194,19 @@ def test_stack_block_matches_per_slice_path(case, cuda_device):
         probs = new
     e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), **kw)
     want = _per_slice_reference(e, probs, heads, size, ks, D, labels, fc, up)
-    shard = stack.StackShard(e, labels=labels, depth=D, median_kernel_size=ks, upsampling=up, force_connected=fc, block=block)
+    shard = stack.StackShard(e, labels=labels, depth=D, median_kernel_size=ks, upsampling=up, force_connected=fc, block=block,
+                             stream=torch.cuda.Stream(dev) if streamed == 'side' else None)
+    early = 0
     for z in shard.slices():
-        shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=size)
+        # streamed: sub-blocks are chained and cut into tables as soon as their slices (+ look-ahead) are in, and their heads
+        # forgotten (fresh tensors per slice, so that a premature release would show)
+        if streamed:
+            shard.add(z, probs[z].clone(), heads[z]['ctr_hmp'].clone(), heads[z]['offsets'].clone(), size=size)
+            early += shard.advance()
+        else:
+            shard.add(z, probs[z], heads[z]['ctr_hmp'], heads[z]['offsets'], size=size)
+    if streamed:
+        assert early >= (D - 1) // block - 1 and 'sem' not in shard.heads[0]
     got = shard.finish()
     assert sorted(got.keys()) == list(range(D))
     assert sum(len(v) for w in want for v in w.values()) > 20
