@@ -367,8 +367,24 @@ def _slice_sync(engine, head, sem8, labels, upsampling, force_connected):
 
 
 def _f32c(t):
-    t = t.detach()
-    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+    # only data pointers are taken from these tensors (no autograd graph is touched): the common case costs two checks
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _same_planes(planes):
+    """All planes on one CUDA device, (1, C, H, W), equal in shape — checked cheaply: a block has hundreds of them and
+    this runs before the first launch."""
+    from empanada_b200 import _cabi as C
+    p0 = planes[0]
+    dev = C.require_cuda(p0, planes[-1])
+    assert p0.dim() == 4 and p0.size(0) == 1 and planes[-1].shape == p0.shape
+    idx, numel = p0.get_device(), p0.numel()
+    for p in planes:
+        if p.get_device() != idx or p.numel() != numel:
+            raise RuntimeError('the slices of a block must be CUDA tensors of one device and one shape')
+    return dev
 
 
 def _batched(tensors):
@@ -835,8 +851,7 @@ class StackShard:
         planes = [_f32c(self.heads[z]['sem']) for z in range(self.z0, self.z_halo)]
         if not planes[0].is_cuda:
             raise RuntimeError('StackShard runs on CUDA tensors only (there is no CPU fallback)')
-        dev = C.require_cuda(*planes)
-        assert all(p.dim() == 4 and p.size(0) == 1 and p.shape == planes[0].shape for p in planes)
+        dev = _same_planes(planes)
         Cn, H, W = planes[0].shape[1:]
         self._plane = (int(H), int(W))
         t_a = time.perf_counter()
@@ -1025,8 +1040,7 @@ class StackShard:
                 assert not final, 'add() every slice of slices() first'
                 break
             planes = [_f32c(self.heads[z]['sem']) for z in range(self.z0 + i0, z_need)]
-            C.require_cuda(*planes)
-            assert all(p.shape == (1, Cn, st['H'], st['W']) for p in planes)
+            assert _same_planes(planes) == dev and planes[0].shape == (1, Cn, st['H'], st['W'])
             tab = torch.tensor([p.data_ptr() for p in planes], dtype=torch.int64).to(dev)
             st['keep'].append((tab, planes if (g == 0 and st['multi'] and self.rank > 0) else None))
             # carry in: the stack's start (none), the guess (first group of a rank > 0), else the previous group's end state
