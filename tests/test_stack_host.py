@@ -275,3 +275,22 @@ def test_pinned_pool_hands_out_idle_buffers_only():
     del view, b
     c = pool.acquire(dev, 800)
     assert len(pool.buffers[0]) == 2 and c.numel() >= 800
+
+
+def test_shard_has_no_cpu_path_and_streams_nothing_before_a_slice_is_in():
+    """finish() and advance() on CPU tensors fail loudly (no fallback); advance() before any add() is a no-op."""
+    import torch
+    from empanada_b200.inference import engines as eng
+    e = eng.PanopticDeepLabRenderEngine(torch.nn.Identity(), thing_list=[1], label_divisor=20000, nms_kernel=3, confidence_thr=0.3)
+    D, H, W = 6, 32, 48
+    shard = stack.StackShard(e, labels=[1], depth=D, median_kernel_size=3, block=2)
+    assert shard.advance() == 0
+    for z in shard.slices():
+        shard.add(z, torch.rand(1, 1, H, W), torch.rand(1, 1, H // 4, W // 4), torch.zeros(1, 2, H // 4, W // 4), size=(H, W))
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        shard.advance()
+    shard = stack.StackShard(e, labels=[1], depth=D, median_kernel_size=3)
+    for z in shard.slices():
+        shard.add(z, torch.rand(1, 1, H, W), torch.rand(1, 1, H // 4, W // 4), torch.zeros(1, 2, H // 4, W // 4), size=(H, W))
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        shard.finish()
