@@ -475,7 +475,7 @@ class StackShard:
         sem8 = _device_pool.acquire(dev, (n, hw), torch.uint8)
         need_arg = need_map = None
         if need is not None:
-            hh, ww, shift = self._geometry(*self._plane)
+            _, ww, shift = self._geometry(*self._plane)
             bits = 0
             for c in e.thing_list:
                 bits |= 1 << int(c)
@@ -659,7 +659,7 @@ class StackShard:
         t_1 = time.perf_counter()
         self._blocks_launch(prep, zs, sem8, need)
         self._marks.update(blocks_alloc_s=t_1 - t_0, blocks_pinned_s=0.0, blocks_c_call_s=time.perf_counter() - t_1)
-        return prep, prep['packed'], prep['runs_all'], prep['maxlab'][:prep['nl']], prep['cfg']
+        return prep
 
     def _collect(self, zs, subs, packed, sem8, out, streamed=False):
         """Phase B: as each block's tables land in pinned memory (its flag word turns non-zero) take owned copies of them and
@@ -861,7 +861,7 @@ class StackShard:
             need = _device_pool.acquire(dev, (len(zs), hh * ww), torch.uint8).zero_()
         sem8, changed = self._chain(planes, dev, H * W, Cn, need)
         t_chain = time.perf_counter()
-        subs, packed, runs_all, counts, cfg = self._enqueue_blocks(zs, sem8, dev, H, W, need)
+        subs = self._enqueue_blocks(zs, sem8, dev, H, W, need)
         t_blocks = time.perf_counter()
         return self._complete(zs, dev, subs, sem8, changed, (t_a, t_chain, t_blocks), streamed=False)
 
@@ -1053,7 +1053,7 @@ class StackShard:
                 cout = self._carry_table(st, 'out' if g + 1 == n_sub else ('p0' if g % 2 == 0 else 'p1'))
             nm = None
             if st['need'] is not None:
-                hh, ww, shift = self._geometry(st['H'], st['W'])
+                _, ww, shift = self._geometry(st['H'], st['W'])
                 bits = 0
                 for c in e.thing_list:
                     bits |= 1 << int(c)
